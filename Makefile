@@ -1,0 +1,51 @@
+# Build of the B200-native GAF->PAF path.  Everything is compiled in-tree so that the
+# binaries travel to the GPU box with the repository snapshot.
+#
+#   make            libg2p.so + gaf2paf + gaf2unstable (sm_100a) + test/bench helpers
+#   make oracle     oracle restatement + (when /root/reference exists) oracle/_ref
+#   make hostsim    CPU instantiation of the device code (test infrastructure)
+NVCC      ?= /usr/local/cuda/bin/nvcc
+CXX       ?= g++
+PKG       := cactus-gfa-tools_b200
+CSRC      := $(PKG)/csrc
+BUILD     := build
+NVFLAGS   := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function
+CXXFLAGS  := -O2 -std=c++17 -Wall -fPIC
+LIB       := $(PKG)/lib/libg2p.so
+HDRS      := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.hpp include/*.h)
+
+all: $(LIB) $(PKG)/bin/gaf2paf $(BUILD)/libgafgen.so $(BUILD)/gafgen hostsim
+
+$(LIB): $(CSRC)/g2p_capi.cu $(HDRS)
+	@mkdir -p $(PKG)/lib
+	$(NVCC) $(NVFLAGS) -Xptxas -v -shared -o $@ $(CSRC)/g2p_capi.cu $(wildcard $(CSRC)/g2u_capi.cu) -lcudart 2> $(BUILD)/ptxas.log || (cat $(BUILD)/ptxas.log; false)
+	@grep -E "error|warning" $(BUILD)/ptxas.log || true
+
+$(PKG)/bin/gaf2paf: $(CSRC)/gaf2paf_main.cpp $(LIB) include/g2p.h
+	@mkdir -p $(PKG)/bin
+	$(CXX) $(CXXFLAGS) -o $@ $(CSRC)/gaf2paf_main.cpp -L$(PKG)/lib -lg2p -Wl,-rpath,'$$ORIGIN/../lib'
+
+$(PKG)/bin/gaf2unstable: $(CSRC)/gaf2unstable_main.cpp $(LIB) include/g2p.h
+	@mkdir -p $(PKG)/bin
+	$(CXX) $(CXXFLAGS) -o $@ $(CSRC)/gaf2unstable_main.cpp -L$(PKG)/lib -lg2p -Wl,-rpath,'$$ORIGIN/../lib'
+
+$(BUILD)/libgafgen.so: tools/gafgen.cpp
+	@mkdir -p $(BUILD)
+	$(CXX) $(CXXFLAGS) -shared -pthread -o $@ $<
+
+$(BUILD)/gafgen: tools/gafgen.cpp
+	@mkdir -p $(BUILD)
+	$(CXX) $(CXXFLAGS) -DGAFGEN_MAIN -pthread -o $@ $<
+
+hostsim: $(BUILD)/g2p_hostsim
+$(BUILD)/g2p_hostsim: tests/hostsim/g2p_hostsim.cpp $(HDRS)
+	@mkdir -p $(BUILD)
+	$(CXX) $(CXXFLAGS) -ffp-contract=off -o $@ $<
+
+oracle:
+	$(MAKE) -C oracle
+
+clean:
+	rm -rf $(BUILD) $(PKG)/lib $(PKG)/bin
+
+.PHONY: all oracle hostsim clean

@@ -1,0 +1,237 @@
+"""cactus-gfa-tools_b200 — B200-native GAF -> PAF conversion (gaf2paf / gaf2unstable path).
+
+Thin ctypes binding over the C-ABI of ``lib/libg2p.so`` (``include/g2p.h``).  The
+reference (ComparativeGenomicsToolkit/cactus-gfa-tools) exposes this path only as the
+``gaf2paf`` / ``gaf2unstable`` executables; the functions here mirror those two command
+lines (``gaf2paf(gaf, lengths)`` ~ ``gaf2paf -l lengths.tsv in.gaf``) so that parity
+tests read like the reference's ``test/gaf2paf.t``.
+
+There is no CPU fallback: importing works anywhere (so that CPU-only CI can check the
+exported symbols), but creating a :class:`Converter` without a CUDA device raises
+:class:`G2PError`, and a missing ``libg2p.so`` raises at import.
+
+The directory name contains a hyphen (it is the name the build contract fixes), so
+import it through the ``cactus_gfa_tools_b200`` shim module at the repository root.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libg2p.so")
+BIN_DIR = os.path.join(_HERE, "bin")
+
+# include/g2p.h
+G2P_OK = 0
+G2P_E_NO_DEVICE = -1
+G2P_E_CUDA = -2
+G2P_E_ARG = -3
+G2P_E_TABLE = -4
+G2P_E_NOTABLE = -5
+G2P_E_TOOBIG = -6
+
+REC_OK = 0
+REC_ERR_NAME = 1
+REC_ERR_NOCG = 2
+REC_ABORT = 16
+
+EXPORTED_SYMBOLS = (
+    "g2p_create", "g2p_destroy", "g2p_last_error", "g2p_host_alloc", "g2p_host_free", "g2p_load_lengths",
+    "g2p_table_entries", "g2p_copy_to_device", "g2p_copy_to_host", "g2p_convert_device", "g2p_convert_host", "g2p_index_lines", "g2p_format_error",
+)
+
+
+class G2PError(RuntimeError):
+    pass
+
+
+class Result(ctypes.Structure):
+    """struct g2p_result (include/g2p.h)."""
+    _fields_ = [
+        ("n_records", ctypes.c_uint64),
+        ("out_bytes", ctypes.c_uint64),
+        ("rec_status", ctypes.c_uint32),
+        ("rec_aux", ctypes.c_uint32),
+        ("err_record", ctypes.c_uint64),
+        ("err_name_off", ctypes.c_uint64),
+        ("err_name_len", ctypes.c_uint32),
+        ("gpu_launches", ctypes.c_uint32),
+        ("device_ms", ctypes.c_float),
+        ("emit_ms", ctypes.c_float),
+        ("size_ms", ctypes.c_float),
+        ("index_ms", ctypes.c_float),
+    ]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise G2PError(
+            "%s is missing: build it with `make` (nvcc, sm_100a). There is no CPU fallback for this path." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, cp, sz = ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t
+    lib.g2p_create.argtypes = [ctypes.c_int, ctypes.POINTER(vp)]
+    lib.g2p_create.restype = ctypes.c_int
+    lib.g2p_destroy.argtypes = [vp]
+    lib.g2p_destroy.restype = None
+    lib.g2p_last_error.argtypes = [vp]
+    lib.g2p_last_error.restype = cp
+    lib.g2p_host_alloc.argtypes = [sz]
+    lib.g2p_host_alloc.restype = vp
+    lib.g2p_host_free.argtypes = [vp]
+    lib.g2p_host_free.restype = None
+    lib.g2p_copy_to_device.argtypes = [vp, vp, sz]
+    lib.g2p_copy_to_device.restype = ctypes.c_int
+    lib.g2p_copy_to_host.argtypes = [vp, vp, sz]
+    lib.g2p_copy_to_host.restype = ctypes.c_int
+    lib.g2p_load_lengths.argtypes = [vp, vp, sz]
+    lib.g2p_load_lengths.restype = ctypes.c_int
+    lib.g2p_table_entries.argtypes = [vp]
+    lib.g2p_table_entries.restype = ctypes.c_uint64
+    lib.g2p_convert_device.argtypes = [vp, vp, sz, ctypes.POINTER(vp), ctypes.POINTER(Result), vp]
+    lib.g2p_convert_device.restype = ctypes.c_int
+    lib.g2p_convert_host.argtypes = [vp, vp, sz, ctypes.POINTER(vp), ctypes.POINTER(Result)]
+    lib.g2p_convert_host.restype = ctypes.c_int
+    lib.g2p_index_lines.argtypes = [vp, vp, sz, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_uint64), vp]
+    lib.g2p_index_lines.restype = ctypes.c_int
+    lib.g2p_format_error.argtypes = [ctypes.POINTER(Result), vp, sz, vp, sz]
+    lib.g2p_format_error.restype = ctypes.c_int
+    return lib
+
+
+lib = _load()
+
+
+def _buf_ptr(b):
+    """(address, length, keepalive) of a bytes / bytearray / memoryview / (addr, n) pair."""
+    if isinstance(b, tuple):
+        return int(b[0]), int(b[1]), None
+    if isinstance(b, bytes):
+        return ctypes.cast(ctypes.c_char_p(b), ctypes.c_void_p).value or 0, len(b), b
+    mv = memoryview(b).cast("B")
+    if mv.readonly:
+        bb = bytes(mv)
+        return ctypes.cast(ctypes.c_char_p(bb), ctypes.c_void_p).value or 0, len(bb), bb
+    arr = (ctypes.c_char * len(mv)).from_buffer(mv)
+    return ctypes.addressof(arr), len(mv), arr
+
+
+class Converter:
+    """One conversion context bound to one GPU (g2p_ctx)."""
+
+    def __init__(self, device=0):
+        h = ctypes.c_void_p()
+        rc = lib.g2p_create(int(device), ctypes.byref(h))
+        if rc != G2P_OK:
+            raise G2PError("g2p_create(device=%d) failed with %d: no usable CUDA device; this library has no CPU path" % (device, rc))
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.g2p_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc != G2P_OK:
+            raise G2PError("libg2p error %d: %s" % (rc, lib.g2p_last_error(self._h).decode("latin-1")))
+
+    def load_lengths(self, tsv):
+        """get_len_map (reference gaf2paf_main.cpp:22-45).  Returns False where the reference would abort."""
+        addr, n, keep = _buf_ptr(tsv)
+        rc = lib.g2p_load_lengths(self._h, addr, n)
+        if rc == G2P_E_TABLE:
+            return False
+        self._check(rc)
+        return True
+
+    @property
+    def table_entries(self):
+        return lib.g2p_table_entries(self._h)
+
+    def convert_host(self, gaf):
+        """GAF text in host memory -> (paf bytes, Result).  H2D, device pipeline, D2H."""
+        addr, n, keep = _buf_ptr(gaf)
+        out = ctypes.c_void_p()
+        res = Result()
+        self._check(lib.g2p_convert_host(self._h, addr, n, ctypes.byref(out), ctypes.byref(res)))
+        return ctypes.string_at(out.value, res.out_bytes) if res.out_bytes else b"", res
+
+    def convert_host_raw(self, addr, n):
+        """Like convert_host for a raw (pinned) host address; returns (out address, Result) without copying."""
+        out = ctypes.c_void_p()
+        res = Result()
+        self._check(lib.g2p_convert_host(self._h, addr, n, ctypes.byref(out), ctypes.byref(res)))
+        return out.value, res
+
+    def convert_device(self, d_ptr, n, stream=0):
+        """Device-resident GAF (16-byte aligned device address) -> (device address of PAF, Result)."""
+        out = ctypes.c_void_p()
+        res = Result()
+        self._check(lib.g2p_convert_device(self._h, d_ptr, n, ctypes.byref(out), ctypes.byref(res), stream or None))
+        return out.value, res
+
+    def index_lines(self, d_ptr, n, stream=0):
+        """Line index only -> (device address of uint32 starts[n_lines+1], n_lines)."""
+        starts = ctypes.c_void_p()
+        nl = ctypes.c_uint64()
+        self._check(lib.g2p_index_lines(self._h, d_ptr, n, ctypes.byref(starts), ctypes.byref(nl), stream or None))
+        return starts.value, nl.value
+
+    @staticmethod
+    def format_error(res, gaf):
+        addr, n, keep = _buf_ptr(gaf)
+        buf = ctypes.create_string_buffer(2048)
+        lib.g2p_format_error(ctypes.byref(res), addr, n, buf, len(buf))
+        return buf.value.decode("latin-1")
+
+
+def copy_to_host(d_ptr, n):
+    """Device address -> bytes (cudaMemcpy through the C-ABI)."""
+    buf = ctypes.create_string_buffer(max(1, n))
+    if n and lib.g2p_copy_to_host(buf, d_ptr, n) != G2P_OK:
+        raise G2PError("g2p_copy_to_host failed")
+    return buf.raw[:n]
+
+
+def copy_to_device(d_ptr, data):
+    addr, n, keep = _buf_ptr(data)
+    if n and lib.g2p_copy_to_device(d_ptr, addr, n) != G2P_OK:
+        raise G2PError("g2p_copy_to_device failed")
+
+
+def exit_code(res):
+    """Process exit status of the reference for this result (0, 1 or 134)."""
+    if res.rec_status == REC_OK:
+        return 0
+    return 134 if res.rec_status >= REC_ABORT else 1
+
+
+def gaf2paf(gaf, lengths, device=0, converter=None):
+    """``gaf2paf -l <lengths> <gaf>``: returns (stdout bytes, exit code, stderr text)."""
+    cv = converter or Converter(device)
+    try:
+        if not cv.load_lengths(lengths):
+            return b"", 134, "terminate called after throwing an instance of 'std::invalid_argument'\n  what():  stol\n"
+        out, res = cv.convert_host(gaf)
+        rc = exit_code(res)
+        err = Converter.format_error(res, gaf) if rc else ""
+        return out, rc, err
+    finally:
+        if converter is None:
+            cv.close()
+
+
+def shard_ranges(buf, n_shards):
+    """Newline-aligned byte ranges [(a, b), ...] covering ``buf`` (multi-GPU sharding):
+    cut the byte range into n contiguous pieces and move every cut forward to just after the next newline."""
+    n = len(buf)
+    cuts = [0]
+    for i in range(1, n_shards):
+        p = max(cuts[-1], n * i // n_shards)
+        if p > 0 and p < n and buf[p - 1:p] != b"\n":
+            q = buf.find(b"\n", p)
+            p = n if q < 0 else q + 1
+        cuts.append(min(p, n))
+    cuts.append(n)
+    return [(cuts[i], cuts[i + 1]) for i in range(n_shards)]

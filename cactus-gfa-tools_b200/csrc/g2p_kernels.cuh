@@ -1,0 +1,333 @@
+// g2p_kernels.cuh — sm_100a kernels of the GAF -> PAF pipeline.
+//
+//   k_count_lines / k_scan_tiles / k_fill_lines   newline index (record start offsets)
+//   k_convert<false>                               pass 1: per-record PAF byte length + status
+//   k_scan_*                                       exclusive scan of the lengths -> output offsets
+//   k_convert<true>                                pass 2: write the PAF bytes
+//   k_diagnose                                     details of the first failing record
+//
+// All work is byte / integer; the pipeline is bound by HBM traffic and by the
+// latency of serial per-record parsing, so the kernels stage contiguous record
+// batches through shared memory with 128-bit coalesced accesses in both directions.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "g2p_core.cuh"
+
+namespace g2p {
+
+struct PipelineMeta {
+    u32 n_lines;       // '\n' count
+    u32 n_records;     // lines incl. an unterminated last one
+    u32 first_err;     // smallest failing record index (0xFFFFFFFF = none)
+    u32 pad;
+    u64 out_total;     // bytes of PAF for all records
+    // k_diagnose
+    u32 err_status;
+    u32 err_a, err_b;  // name span relative to the record start
+    u32 err_rec_start;
+    u64 err_out_end;   // output offset just after the failing record's (partial) output
+};
+
+// ------------------------------------------------------------------------------
+// Line index.  A tile is 256 threads x 4 x 16 B = 16 KiB, loaded as coalesced
+// 128-bit vectors (vector v = k*256 + t).  Newlines are found with per-byte SIMD
+// compares; ranks come from one block scan over four packed 16-bit counters.
+// ------------------------------------------------------------------------------
+constexpr int kIdxThreads = 256;
+constexpr int kIdxVec = 4;
+constexpr u32 kIdxTile = kIdxThreads * kIdxVec * 16;
+
+__device__ __forceinline__ uint4 load_vec_guarded(const u8* base, u64 off, u64 n) {
+    if (off + 16 <= n) return __ldg(reinterpret_cast<const uint4*>(base + off));
+    u32 w[4] = {0, 0, 0, 0};
+    for (u32 i = 0; i < 16; ++i)
+        if (off + i < n) w[i >> 2] |= (u32)base[off + i] << (8 * (i & 3));
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__device__ __forceinline__ u32 nl_bits(u32 w) { return __vcmpeq4(w, 0x0A0A0A0Au) & 0x80808080u; }
+
+__global__ void __launch_bounds__(kIdxThreads) k_count_lines(const u8* __restrict__ text, u64 n, u32* __restrict__ tile_count) {
+    const u64 base = (u64)blockIdx.x * kIdxTile;
+    u32 cnt = 0;
+#pragma unroll
+    for (int k = 0; k < kIdxVec; ++k) {
+        u64 off = base + ((u64)k * kIdxThreads + threadIdx.x) * 16;
+        if (off < n) {
+            uint4 v = load_vec_guarded(text, off, n);
+            cnt += __popc(nl_bits(v.x)) + __popc(nl_bits(v.y)) + __popc(nl_bits(v.z)) + __popc(nl_bits(v.w));
+        }
+    }
+    // block reduce
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    __shared__ u32 wsum[kIdxThreads / 32];
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 s = 0;
+        for (int i = 0; i < kIdxThreads / 32; ++i) s += wsum[i];
+        tile_count[blockIdx.x] = s;
+    }
+}
+
+// One CTA: exclusive scan of the per-tile counts in place; fills the meta record.
+__global__ void __launch_bounds__(1024) k_scan_tiles(u32* __restrict__ tile_count, u32 ntiles, const u8* __restrict__ text, u64 n,
+                                                     PipelineMeta* __restrict__ meta) {
+    __shared__ u32 part[1024];
+    const u32 per = (ntiles + 1023) / 1024;
+    const u32 a = threadIdx.x * per;
+    const u32 b = min(a + per, ntiles);
+    u32 s = 0;
+    for (u32 i = a; i < b; ++i) s += tile_count[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    // Hillis-Steele over 1024 partials
+    for (u32 o = 1; o < 1024; o <<= 1) {
+        u32 v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    u32 run = threadIdx.x ? part[threadIdx.x - 1] : 0;
+    for (u32 i = a; i < b; ++i) { u32 c = tile_count[i]; tile_count[i] = run; run += c; }
+    if (threadIdx.x == 1023) {
+        u32 lines = part[1023];
+        meta->n_lines = lines;
+        meta->n_records = lines + ((n > 0 && text[n - 1] != '\n') ? 1u : 0u);
+        meta->first_err = 0xFFFFFFFFu;
+        meta->out_total = 0;
+        meta->err_status = 0;
+    }
+}
+
+__global__ void __launch_bounds__(kIdxThreads) k_fill_lines(const u8* __restrict__ text, u64 n, const u32* __restrict__ tile_off,
+                                                            u32* __restrict__ rec_start, const PipelineMeta* __restrict__ meta) {
+    const u64 base = (u64)blockIdx.x * kIdxTile;
+    uint4 v[kIdxVec];
+    u64 packed = 0;   // four 16-bit counters, one per k
+#pragma unroll
+    for (int k = 0; k < kIdxVec; ++k) {
+        u64 off = base + ((u64)k * kIdxThreads + threadIdx.x) * 16;
+        v[k] = make_uint4(0, 0, 0, 0);
+        if (off < n) v[k] = load_vec_guarded(text, off, n);
+        u32 c = __popc(nl_bits(v[k].x)) + __popc(nl_bits(v[k].y)) + __popc(nl_bits(v[k].z)) + __popc(nl_bits(v[k].w));
+        packed |= (u64)c << (16 * k);
+    }
+    // block exclusive scan of `packed`
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u64 incl = packed;
+    for (int o = 1; o < 32; o <<= 1) {
+        u64 up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (u32)o) incl += up;
+    }
+    __shared__ u64 wtot[kIdxThreads / 32];
+    if (lane == 31) wtot[warp] = incl;
+    __syncthreads();
+    u64 wpre = 0, total = 0;
+    for (int i = 0; i < kIdxThreads / 32; ++i) { if (i < (int)warp) wpre += wtot[i]; total += wtot[i]; }
+    const u64 excl = wpre + incl - packed;
+    u32 kbase = tile_off[blockIdx.x];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (n > 0) rec_start[0] = 0;
+        if (meta->n_records != meta->n_lines) rec_start[meta->n_records] = (u32)n + 1;   // unterminated last line
+    }
+#pragma unroll
+    for (int k = 0; k < kIdxVec; ++k) {
+        u32 rank = kbase + (u32)((excl >> (16 * k)) & 0xffff);
+        const u64 off = base + ((u64)k * kIdxThreads + threadIdx.x) * 16;
+        const u32 w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            u32 m = nl_bits(w[j]);
+            while (m) {
+                u32 bit = __ffs(m) - 1;
+                m &= m - 1;
+                u64 p = off + j * 4 + (bit >> 3);
+                rec_start[rank + 1] = (u32)(p + 1);
+                ++rank;
+            }
+        }
+        kbase += (u32)((total >> (16 * k)) & 0xffff);
+    }
+}
+
+// ------------------------------------------------------------------------------
+// Exclusive scan of u64 values in place (three small kernels).
+// ------------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr u32 kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ u64 block_excl_scan_u64(u64 v, u64& total) {
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u64 incl = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        u64 up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (u32)o) incl += up;
+    }
+    __shared__ u64 wt[kScanThreads / 32];
+    __syncthreads();
+    if (lane == 31) wt[warp] = incl;
+    __syncthreads();
+    u64 pre = 0, tot = 0;
+    for (int i = 0; i < kScanThreads / 32; ++i) { if (i < (int)warp) pre += wt[i]; tot += wt[i]; }
+    total = tot;
+    return pre + incl - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_reduce(const u64* __restrict__ x, u32 n, u64* __restrict__ block_sum) {
+    const u32 base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    u64 s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) if (base + i < n) s += x[base + i];
+    u64 total;
+    block_excl_scan_u64(s, total);
+    if (threadIdx.x == 0) block_sum[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_blocks(u64* __restrict__ block_sum, u32 nblocks, PipelineMeta* __restrict__ meta) {
+    __shared__ u64 part[1024];
+    const u32 per = (nblocks + 1023) / 1024;
+    const u32 a = threadIdx.x * per, b = min(a + per, nblocks);
+    u64 s = 0;
+    for (u32 i = a; i < b; ++i) s += block_sum[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (u32 o = 1; o < 1024; o <<= 1) {
+        u64 v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    u64 run = threadIdx.x ? part[threadIdx.x - 1] : 0;
+    for (u32 i = a; i < b; ++i) { u64 c = block_sum[i]; block_sum[i] = run; run += c; }
+    if (threadIdx.x == 1023) meta->out_total = part[1023];
+}
+
+// x[0..n) lengths -> exclusive offsets; x[n] = total
+__global__ void __launch_bounds__(kScanThreads) k_scan_apply(u64* __restrict__ x, u32 n, const u64* __restrict__ block_off,
+                                                             const PipelineMeta* __restrict__ meta) {
+    const u32 base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    u64 v[kScanItems];
+    u64 s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) { v[i] = base + i < n ? x[base + i] : 0; s += v[i]; }
+    u64 total;
+    u64 run = block_off[blockIdx.x] + block_excl_scan_u64(s, total);
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        if (base + i < n) x[base + i] = run;
+        run += v[i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) x[n] = meta->out_total;
+}
+
+// ------------------------------------------------------------------------------
+// Record conversion.  One warp owns 32 consecutive records; their bytes form one
+// contiguous input range that is staged into the warp's shared-memory slice with
+// 128-bit coalesced loads, and (pass 2) one contiguous output range that is
+// assembled in shared memory and flushed with 128-bit coalesced stores.  Batches
+// that do not fit the slices fall back to direct global access for that warp.
+// ------------------------------------------------------------------------------
+constexpr int kCvtWarps = 4;
+constexpr int kCvtThreads = kCvtWarps * 32;
+constexpr u32 kInCap = 8 * 1024;     // bytes of staged input per warp
+constexpr u32 kOutCap = 16 * 1024;   // bytes of staged output per warp
+
+template <class Sink>
+__device__ __noinline__ u32 convert_record_global(const u8* r, u32 len, const LenTableView& T, Sink& S, u32& ea, u32& eb) {
+    return convert_record(r, len, T, S, ea, eb);
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(kCvtThreads) k_convert(const u8* __restrict__ gaf, u64 n, const u32* __restrict__ rec_start, u32 nrec,
+                                                         LenTableView T, u64* __restrict__ out_off, u32* __restrict__ status,
+                                                         u8* __restrict__ out, PipelineMeta* __restrict__ meta) {
+    extern __shared__ __align__(16) u8 smem[];
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u8* sm_in = smem + (size_t)warp * (EMIT ? (kInCap + kOutCap) : kInCap);
+    u8* sm_out = sm_in + kInCap;
+    const u32 R0 = (blockIdx.x * kCvtWarps + warp) * 32;
+    if (R0 >= nrec) return;
+    const u32 Rend = min(R0 + 32, nrec);
+    const u32 r = R0 + lane;
+    const bool valid = r < nrec;
+    const u32 s = valid ? rec_start[r] : 0;
+    const u32 e = valid ? rec_start[r + 1] : 0;
+    const u32 len = valid ? e - s - 1 : 0;
+    const u32 s0 = __shfl_sync(0xffffffffu, s, 0);
+    u32 s1 = rec_start[Rend];
+    if ((u64)s1 > n) s1 = (u32)n;
+
+    // ---- stage input
+    const u32 A = s0 & ~15u;
+    const u32 nvec = (s1 - A + 15) >> 4;
+    const bool in_staged = nvec * 16 <= kInCap;
+    if (in_staged) {
+        for (u32 v = lane; v < nvec; v += 32)
+            reinterpret_cast<uint4*>(sm_in)[v] = load_vec_guarded(gaf, (u64)A + (u64)v * 16, n);
+        __syncwarp();
+    }
+
+    u32 ea = 0, eb = 0;
+    if (!EMIT) {
+        u32 st = ST_OK;
+        u64 bytes = 0;
+        if (valid) {
+            CountSink cs;
+            st = in_staged ? convert_record(sm_in + (s - A), len, T, cs, ea, eb)
+                           : convert_record_global(gaf + s, len, T, cs, ea, eb);
+            bytes = (st_is_abort(st) || st == ST_SKIP) ? 0 : cs.n;
+            out_off[r] = bytes;
+            status[r] = st;
+            if (st_is_error(st)) atomicMin(&meta->first_err, r);
+        }
+    } else {
+        const u64 o = valid ? out_off[r] : 0;
+        const u64 o0 = __shfl_sync(0xffffffffu, o, 0);
+        const u64 o1 = out_off[Rend];
+        const u32 st_prev = valid ? status[r] : (u32)ST_SKIP;
+        const bool active = valid && !st_is_abort(st_prev) && st_prev != ST_SKIP;
+        const bool out_staged = (o1 - o0) + 32 <= kOutCap;
+        const u32 pad = (u32)(o0 & 15);
+        if (active) {
+            u8* dst = out_staged ? sm_out + pad + (u32)(o - o0) : out + o;
+            StoreSink ss(dst);
+            if (in_staged) convert_record(sm_in + (s - A), len, T, ss, ea, eb);
+            else convert_record_global(gaf + s, len, T, ss, ea, eb);
+        }
+        if (out_staged) {
+            __syncwarp();
+            const u64 ga = (o0 + 15) & ~15ULL, gb = o1 & ~15ULL;
+            if (ga >= gb) {
+                for (u64 g = o0 + lane; g < o1; g += 32) out[g] = sm_out[pad + (u32)(g - o0)];
+            } else {
+                for (u64 g = o0 + lane; g < ga; g += 32) out[g] = sm_out[pad + (u32)(g - o0)];
+                for (u64 g = gb + lane; g < o1; g += 32) out[g] = sm_out[pad + (u32)(g - o0)];
+                const uint4* src = reinterpret_cast<const uint4*>(sm_out + pad + (u32)(ga - o0));
+                uint4* dstv = reinterpret_cast<uint4*>(out + ga);
+                const u32 nv = (u32)((gb - ga) >> 4);
+                for (u32 v = lane; v < nv; v += 32) dstv[v] = src[v];
+            }
+        }
+    }
+}
+
+// Details of the first failing record (one thread; runs only on error).
+__global__ void k_diagnose(const u8* __restrict__ gaf, const u32* __restrict__ rec_start, LenTableView T,
+                           const u64* __restrict__ out_off, PipelineMeta* __restrict__ meta) {
+    const u32 r = meta->first_err;
+    if (r == 0xFFFFFFFFu) return;
+    const u32 s = rec_start[r], e = rec_start[r + 1];
+    CountSink cs;
+    u32 ea = 0, eb = 0;
+    u32 st = convert_record_global(gaf + s, e - s - 1, T, cs, ea, eb);
+    meta->err_status = st;
+    meta->err_a = ea;
+    meta->err_b = eb;
+    meta->err_rec_start = s;
+    meta->err_out_end = out_off[r + 1];
+}
+
+}  // namespace g2p

@@ -1,0 +1,113 @@
+/* g2p.h — C-ABI of the B200 GAF->PAF conversion library (libg2p.so).
+ *
+ * The reference (cactus-gfa-tools) has no library / plugin / FFI surface: its only
+ * stable interface is the process boundary of the `gaf2paf` and `gaf2unstable`
+ * executables.  This header is therefore the boundary the new
+ * build defines between the C++ host drivers (same argv, same stdout/stderr/exit
+ * codes as the reference) and the CUDA side.  Each entry point names the reference
+ * code it replaces.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or
+ * a negative G2P_E_* code (no exceptions cross the boundary); the caller owns host
+ * buffers it passes in; the library owns every device buffer and the pinned result
+ * buffers it hands back (valid until the next call on the same context or
+ * g2p_destroy).  One context per GPU; calls on one context must be serialised by the
+ * caller; different contexts may be driven from different host threads.
+ *
+ * There is no CPU fallback: without a CUDA device g2p_create fails with
+ * G2P_E_NO_DEVICE and nothing else can be called.
+ */
+#ifndef G2P_H
+#define G2P_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct g2p_ctx g2p_ctx;
+
+enum {
+    G2P_OK = 0,
+    G2P_E_NO_DEVICE = -1,   /* no usable CUDA device / driver */
+    G2P_E_CUDA = -2,        /* a CUDA call failed; see g2p_last_error */
+    G2P_E_ARG = -3,         /* bad argument */
+    G2P_E_TABLE = -4,       /* lengths table could not be parsed (reference would abort in std::stol) */
+    G2P_E_NOTABLE = -5,     /* convert called before g2p_load_lengths */
+    G2P_E_TOOBIG = -6       /* a single call is limited to < 4 GiB of GAF text: split at a newline */
+};
+
+/* Status of the first failing record in input order, mirroring the reference's two
+ * error classes: */
+enum {
+    G2P_REC_OK = 0,
+    G2P_REC_ERR_NAME = 1,   /* "[gaf2paf] error: unable to find X in lengths map", exit 1 (gaf2paf_main.cpp:118,163) */
+    G2P_REC_ERR_NOCG = 2,   /* "[gaf2paf] error: cg cigar not found…", exit 1 (gaf2paf_main.cpp:365-368) */
+    G2P_REC_ABORT = 16      /* >= 16: the reference dies with SIGABRT (assert / uncaught exception), rc 134 */
+};
+
+typedef struct g2p_result {
+    uint64_t n_records;     /* GAF lines seen (including skipped '*' lines) */
+    uint64_t out_bytes;     /* bytes of PAF produced; on error: everything the reference would have flushed */
+    uint32_t rec_status;    /* G2P_REC_* of the first failing record (0 = none) */
+    uint32_t rec_aux;       /* GAF column number for column parse errors */
+    uint64_t err_record;    /* index of the failing record */
+    uint64_t err_name_off;  /* byte offset in the input of the missing name (G2P_REC_ERR_NAME) */
+    uint32_t err_name_len;
+    uint32_t gpu_launches;  /* kernels launched by this call */
+    float device_ms;        /* CUDA-event time of the device pipeline (index .. emit) */
+    float emit_ms;          /* CUDA-event time of the emit kernel alone */
+    float size_ms;          /* CUDA-event time of the size kernel alone */
+    float index_ms;         /* CUDA-event time of the line index kernels */
+} g2p_result;
+
+/* Context bound to one CUDA device. */
+int g2p_create(int device, g2p_ctx** out);
+void g2p_destroy(g2p_ctx* ctx);
+const char* g2p_last_error(const g2p_ctx* ctx);
+
+/* Pinned host memory helpers (cudaHostAlloc) so that callers can read files straight
+ * into DMA-able memory. */
+void* g2p_host_alloc(size_t bytes);
+void g2p_host_free(void* p);
+
+/* Synchronous copies between host and device memory (cudaMemcpy) for callers that hold raw
+ * device addresses but do not link the CUDA runtime themselves (tests, bench harness). */
+int g2p_copy_to_device(void* d_dst, const void* h_src, size_t bytes);
+int g2p_copy_to_host(void* h_dst, const void* d_src, size_t bytes);
+
+/* Replaces get_len_map (gaf2paf_main.cpp:22-45): parse a "name<TAB>length…" table held
+ * in host memory and upload the open-addressing name->length table. */
+int g2p_load_lengths(g2p_ctx* ctx, const char* tsv, size_t n);
+uint64_t g2p_table_entries(const g2p_ctx* ctx);
+
+/* Replaces the record loop of gaf2paf main() (gaf2paf_main.cpp:357-373) with
+ * parse_gaf_record / flip_gaf / gaf2paf (gafkluge.hpp:84-204, gaf2paf_main.cpp:92-264)
+ * for a newline-delimited block of GAF text already resident in device memory.
+ *   d_gaf   device pointer, 16-byte aligned; n < 4 GiB bytes; whole lines (a final
+ *           line may lack its '\n').
+ *   d_out   receives a library-owned device pointer to the PAF bytes.
+ *   stream  a cudaStream_t (NULL = default stream).  The call returns after the
+ *           stream has been synchronised. */
+int g2p_convert_device(g2p_ctx* ctx, const void* d_gaf, size_t n, void** d_out, g2p_result* res, void* stream);
+
+/* Same conversion for GAF text in host memory: host->device copy, device pipeline,
+ * device->host copy into a library-owned pinned buffer returned in *out.  This is the
+ * call the gaf2paf executable makes for every input chunk. */
+int g2p_convert_host(g2p_ctx* ctx, const char* gaf, size_t n, const char** out, g2p_result* res);
+
+/* The line index on its own (first kernel of the pipeline): offsets of line starts of a
+ * device-resident text block.  *d_starts receives a library-owned device array of
+ * n_lines+1 uint32 offsets (last = n, or n+1 when the final line lacks '\n'). */
+int g2p_index_lines(g2p_ctx* ctx, const void* d_text, size_t n, const uint32_t** d_starts, uint64_t* n_lines, void* stream);
+
+/* Formats the stderr line the reference prints for a failed record (empty for aborts,
+ * whose text comes from the C++ runtime).  `gaf` is the host copy of the input. */
+int g2p_format_error(const g2p_result* res, const char* gaf, size_t n, char* buf, size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* G2P_H */

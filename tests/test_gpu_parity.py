@@ -1,0 +1,221 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the
+C-ABI of libg2p.so; the CPU oracle (oracle/_ref reference build when present, else the
+restatement) is only the checker.  Bar: byte-identical PAF, same exit code, same stderr
+line for the reference's exit(1) errors."""
+import ctypes
+import hashlib
+import os
+import subprocess
+import tempfile
+
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def test_native_library_is_what_runs(g2p, converter):
+    """The extension in-tree is loaded and a conversion launches kernels."""
+    maps = open("/proc/self/maps").read()
+    assert "libg2p.so" in maps
+    d = H.golden("gaf2paf_kat.json")
+    assert converter.load_lengths(d["lengths"].encode())
+    out, res = converter.convert_host((d["vectors"][0]["in"] + "\n").encode("latin-1"))
+    assert res.gpu_launches >= 5
+    assert out.decode("latin-1") == d["vectors"][0]["out"]
+
+
+def test_golden_vectors(g2p, converter):
+    d = H.golden("gaf2paf_kat.json")
+    assert converter.load_lengths(d["lengths"].encode())
+    for v in d["vectors"]:
+        gaf = (v["in"] + "\n").encode("latin-1")
+        out, res = converter.convert_host(gaf)
+        rc = g2p.exit_code(res)
+        assert rc == v["rc"], v["name"]
+        if rc != 134:
+            assert out.decode("latin-1") == v["out"], v["name"]
+        if rc == 1:
+            assert g2p.Converter.format_error(res, gaf) == v["err"], v["name"]
+    out, res = converter.convert_host(("\n".join(d["stream"]["in"]) + "\n").encode("latin-1"))
+    assert g2p.exit_code(res) == 0 and out.decode("latin-1") == d["stream"]["out"]
+    # unterminated last line
+    out, res = converter.convert_host("\n".join(d["stream"]["in"]).encode("latin-1"))
+    assert g2p.exit_code(res) == 0 and out.decode("latin-1") == d["stream"]["out"]
+
+
+def test_error_in_the_middle_keeps_earlier_output(g2p, converter):
+    d = H.golden("gaf2paf_kat.json")
+    assert converter.load_lengths(d["lengths"].encode())
+    vec = {v["name"]: v for v in d["vectors"]}
+    good = [v for v in d["vectors"] if v["rc"] == 0 and v["out"]]
+    for bad_name in ("X7-unknown-name-second-step-partial-output", "K21-no-cg-exit1", "K19-cigar-too-short-abort"):
+        bad = vec[bad_name]
+        lines = [g["in"] for g in good[:40]] + [bad["in"]] + [g["in"] for g in good[:5]]
+        gaf = ("\n".join(lines) + "\n").encode("latin-1")
+        out, res = converter.convert_host(gaf)
+        rc, ref_out, ref_err, kind = H.run_gaf2paf_cpu(gaf, d["lengths"].encode())
+        assert g2p.exit_code(res) == rc == bad["rc"]
+        assert res.err_record == 40
+        if rc == 1:
+            assert out == ref_out
+            assert g2p.Converter.format_error(res, gaf) == ref_err
+        else:
+            assert out.decode("latin-1") == "".join(g["out"] for g in good[:40])
+
+
+def test_empty_and_degenerate_inputs(g2p, converter):
+    d = H.golden("gaf2paf_kat.json")
+    assert converter.load_lengths(d["lengths"].encode())
+    out, res = converter.convert_host(b"")
+    assert out == b"" and res.n_records == 0 and g2p.exit_code(res) == 0
+    out, res = converter.convert_host(b"*\t>s43\t97\t12\t0\t6\t92\n" * 3)
+    assert out == b"" and res.n_records == 3 and g2p.exit_code(res) == 0
+    out, res = converter.convert_host(b"\n")           # blank line: the reference aborts in parse_gaf_record
+    assert g2p.exit_code(res) == 134
+
+
+@pytest.mark.parametrize("name,count,over", [
+    ("short", 200000, {"pct_star": 2}),
+    ("short_eqx", 50000, {}),
+    ("stable", 3000, {}),
+    ("medium", 3000, {}),
+    ("asm", 24, {}),
+    ("asm", 3, {"steps_lo": 30000, "steps_hi": 40000}),
+])
+def test_synthetic_parity(g2p, name, count, over):
+    p = H.preset(name, seed=21, **over)
+    lengths = H.gen_lengths(p)
+    gaf = H.gen_records(p, 0, count)
+    cv = g2p.Converter(0)
+    try:
+        assert cv.load_lengths(lengths)
+        out, res = cv.convert_host(gaf)
+    finally:
+        cv.close()
+    rc, ref, err, kind = H.run_gaf2paf_cpu(gaf, lengths)
+    assert rc == 0 and g2p.exit_code(res) == 0
+    assert res.n_records == gaf.count(b"\n")
+    assert len(out) == len(ref)
+    assert out == ref, "PAF differs from the %s oracle" % kind
+
+
+def test_mixed_skew_parity(g2p):
+    """Short and assembly-scale records interleaved in one buffer (config 5 shape)."""
+    ps, pa = H.preset("short", seed=31), H.preset("asm", seed=31, n_nodes=200000, node_len_lo=20, node_len_hi=400)
+    lengths = H.gen_lengths(ps)    # same node-length function and seed -> one table serves both
+    parts = []
+    for i in range(6):
+        parts.append(H.gen_records(ps, i * 5000, 5000))
+        parts.append(H.gen_records(pa, i, 1))
+    gaf = b"".join(parts)
+    cv = g2p.Converter(0)
+    try:
+        assert cv.load_lengths(lengths)
+        out, res = cv.convert_host(gaf)
+    finally:
+        cv.close()
+    rc, ref, err, kind = H.run_gaf2paf_cpu(gaf, lengths)
+    assert rc == 0 and g2p.exit_code(res) == 0 and out == ref
+
+
+def test_sharded_equals_whole(g2p):
+    """Newline-aligned byte-range shards converted independently and concatenated in
+    order reproduce the unsharded output (the multi-GPU scheme, on one device)."""
+    p = H.preset("short", seed=41)
+    lengths = H.gen_lengths(p)
+    gaf = H.gen_records(p, 0, 60000)
+    cv = g2p.Converter(0)
+    try:
+        assert cv.load_lengths(lengths)
+        whole, res = cv.convert_host(gaf)
+        for n in (2, 3, 8):
+            parts = [cv.convert_host(gaf[a:b])[0] for a, b in g2p.shard_ranges(gaf, n)]
+            assert b"".join(parts) == whole
+    finally:
+        cv.close()
+
+
+def test_full_size_properties(g2p):
+    """BASELINE config 3 scale (reduced to what one test may take): properties that do not
+    need the oracle — determinism, line accounting, and a sampled slice checked exactly."""
+    import torch
+    p = H.preset("short", seed=51)
+    lengths = H.gen_lengths(p)
+    count = 2_000_000
+    gaf = H.gen_records(p, 0, count)
+    cv = g2p.Converter(0)
+    try:
+        assert cv.load_lengths(lengths)
+        out1, res1 = cv.convert_host(gaf)
+        out2, res2 = cv.convert_host(gaf)
+        assert res1.n_records == count and g2p.exit_code(res1) == 0
+        assert hashlib.md5(out1).digest() == hashlib.md5(out2).digest()
+        assert out1.endswith(b"\n")
+        # every PAF line carries the 12 columns + gm/gl/gi/cg tags
+        sample = out1[:2_000_000]
+        for line in sample.split(b"\n")[:-1][:2000]:
+            f = line.split(b"\t")
+            assert len(f) >= 16 and f[-1].startswith(b"cg:Z:") and f[4] in (b"+", b"-")
+        # sampled newline-aligned slice against the oracle
+        a, b = g2p.shard_ranges(gaf, 200)[77]
+        rc, ref, err, kind = H.run_gaf2paf_cpu(gaf[a:b], lengths)
+        got, r = cv.convert_host(gaf[a:b])
+        assert rc == 0 and got == ref
+    finally:
+        cv.close()
+
+
+def test_device_resident_entry_point(g2p):
+    import torch
+    p = H.preset("short", seed=61)
+    lengths = H.gen_lengths(p)
+    gaf = H.gen_records(p, 0, 30000)
+    cv = g2p.Converter(0)
+    try:
+        assert cv.load_lengths(lengths)
+        t = torch.empty(len(gaf) + 16, dtype=torch.uint8, device="cuda")
+        g2p.copy_to_device(t.data_ptr(), gaf)
+        torch.cuda.synchronize()
+        d_out, res = cv.convert_device(t.data_ptr(), len(gaf), torch.cuda.current_stream().cuda_stream)
+        ref_out, _ = cv.convert_host(gaf)
+        assert g2p.copy_to_host(d_out, res.out_bytes) == ref_out
+        # line index on its own
+        starts, nl = cv.index_lines(t.data_ptr(), len(gaf), torch.cuda.current_stream().cuda_stream)
+        assert nl == 30000
+        import numpy as np
+        got = np.frombuffer(g2p.copy_to_host(starts, 4 * (nl + 1)), dtype=np.uint32)
+        exp = np.flatnonzero(np.frombuffer(gaf, dtype=np.uint8) == 10) + 1
+        assert got[0] == 0 and (got[1:] == exp).all()
+    finally:
+        cv.close()
+
+
+def test_cli_end_to_end(g2p):
+    """The drop-in executable: same stdout / exit code as the CPU oracle, incl. stdin and two files."""
+    exe = os.path.join(g2p.BIN_DIR, "gaf2paf")
+    p = H.preset("short", seed=71)
+    lengths = H.gen_lengths(p)
+    gaf = H.gen_records(p, 0, 20000)
+    binary, kind = H.oracle_path()
+    with tempfile.TemporaryDirectory() as td:
+        lp, a, b = os.path.join(td, "l.tsv"), os.path.join(td, "a.gaf"), os.path.join(td, "b.gaf")
+        open(lp, "wb").write(lengths)
+        half = gaf.rfind(b"\n", 0, len(gaf) // 2) + 1
+        open(a, "wb").write(gaf[:half - 1])     # first file without trailing newline
+        open(b, "wb").write(gaf[half:])
+        rc, out, err = H.run_tool(exe, [a, b, "-l", lp])
+        rrc, rout, rerr = H.run_tool(binary, [a, b, "-l", lp])
+        assert rc == rrc == 0 and out == rout
+        rc, out, err = H.run_tool(exe, ["-l", lp, "-"], gaf)
+        assert rc == 0 and out == rout
+        # small chunks force the newline-aligned carry logic
+        env = dict(os.environ, G2P_CHUNK_MB="1")
+        pr = subprocess.run([exe, "-l", lp, a, b], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+        assert pr.returncode == 0 and pr.stdout == rout
+        # error path: unknown name -> message + exit 1, earlier output kept
+        bad = gaf[:half] + b"q\t100\t0\t15\t+\t>zzz:0-15\t15\t0\t15\t15\t15\t60\tcg:Z:15M\n" + gaf[half:]
+        rc, out, err = H.run_tool(exe, ["-", "-l", lp], bad)
+        rrc, rout2, rerr = H.run_tool(binary, ["-", "-l", lp], bad)
+        assert rc == rrc == 1 and out == rout2 and err == rerr

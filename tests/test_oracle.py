@@ -1,0 +1,82 @@
+"""CPU tests: the oracle restatement (and the host instantiation of the device code)
+against the committed golden vectors and, where the reference build is present,
+against the reference binary on seeded synthetic inputs."""
+import os
+import tempfile
+
+import pytest
+
+import helpers as H
+
+PORT = os.path.join(H.ORACLE_BIN, "gaf2paf_oracle")
+HOSTSIM = os.path.join(H.BUILD, "g2p_hostsim")
+REF = os.path.join(H.REF_BIN, "gaf2paf")
+
+
+def _run_vectors(binary):
+    d = H.golden("gaf2paf_kat.json")
+    with tempfile.TemporaryDirectory() as td:
+        lp = os.path.join(td, "l.tsv")
+        open(lp, "w").write(d["lengths"])
+        for v in d["vectors"]:
+            rc, out, err = H.run_tool(binary, ["-", "-l", lp], (v["in"] + "\n").encode("latin-1"))
+            assert rc == v["rc"], v["name"]
+            if rc != 134:
+                assert out.decode("latin-1") == v["out"], v["name"]
+            if rc == 1:
+                assert err == v["err"], v["name"]
+        rc, out, err = H.run_tool(binary, ["-", "-l", lp], ("\n".join(d["stream"]["in"]) + "\n").encode("latin-1"))
+        assert rc == 0 and out.decode("latin-1") == d["stream"]["out"]
+
+
+def test_oracle_port_matches_golden():
+    _run_vectors(PORT)
+
+
+def test_device_code_on_host_matches_golden():
+    _run_vectors(HOSTSIM)
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference build (oracle/_ref) not present")
+def test_reference_binary_matches_golden():
+    _run_vectors(REF)
+
+
+@pytest.mark.parametrize("name,count,over", [
+    ("short", 3000, {"pct_star": 3}),
+    ("short_eqx", 2000, {}),
+    ("stable", 300, {}),
+    ("medium", 300, {}),
+    ("asm", 2, {"steps_lo": 800, "steps_hi": 1500}),
+])
+def test_differential_synthetic(name, count, over):
+    """port == hostsim (== reference when built) on seeded synthetic records."""
+    p = H.preset(name, seed=11, **over)
+    lengths = H.gen_lengths(p)
+    gaf = H.gen_records(p, 0, count, threads=4)
+    with tempfile.TemporaryDirectory() as td:
+        lp = os.path.join(td, "l.tsv")
+        open(lp, "wb").write(lengths)
+        rc_p, out_p, _ = H.run_tool(PORT, ["-", "-l", lp], gaf)
+        rc_h, out_h, _ = H.run_tool(HOSTSIM, ["-", "-l", lp], gaf)
+        assert rc_p == 0 and rc_h == 0
+        assert out_p == out_h
+        assert out_p.count(b"\n") > 0
+        if os.path.exists(REF):
+            rc_r, out_r, _ = H.run_tool(REF, ["-", "-l", lp], gaf)
+            assert rc_r == 0 and out_r == out_p
+
+
+def test_unterminated_last_line_and_two_files():
+    d = H.golden("gaf2paf_kat.json")
+    lines = d["stream"]["in"]
+    with tempfile.TemporaryDirectory() as td:
+        lp = os.path.join(td, "l.tsv")
+        open(lp, "w").write(d["lengths"])
+        a, b = os.path.join(td, "a.gaf"), os.path.join(td, "b.gaf")
+        half = len(lines) // 2
+        open(a, "w").write("\n".join(lines[:half]))          # no trailing newline
+        open(b, "w").write("\n".join(lines[half:]) + "\n")
+        for binary in (PORT, HOSTSIM):
+            rc, out, err = H.run_tool(binary, [a, b, "-l", lp])
+            assert rc == 0 and out.decode("latin-1") == d["stream"]["out"], binary

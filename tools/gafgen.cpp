@@ -226,6 +226,39 @@ size_t gafgen_records(const gafgen_params* P, uint64_t first, uint64_t count, ch
     return total;
 }
 
+// Generates records [first, first+count) once and returns a malloc'd buffer (free with
+// gafgen_free); *size receives the byte count.
+char* gafgen_records_alloc(const gafgen_params* P, uint64_t first, uint64_t count, int threads, size_t* size) {
+    if (threads < 1) threads = 1;
+    if ((uint64_t)threads > count) threads = count ? (int)count : 1;
+    std::vector<std::string> parts(threads);
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; ++t) {
+        th.emplace_back([&, t]() {
+            u64 a = first + count * t / threads, b = first + count * (t + 1) / threads;
+            std::string& o = parts[t];
+            o.reserve((size_t)((b - a) * 160));
+            for (u64 i = a; i < b; ++i) gen_record(*P, i, o);
+        });
+    }
+    for (auto& x : th) x.join();
+    size_t total = 0;
+    for (auto& p : parts) total += p.size();
+    char* buf = static_cast<char*>(std::malloc(total ? total : 1));
+    if (!buf) { *size = 0; return nullptr; }
+    size_t off = 0;
+    std::vector<std::thread> cp;
+    for (int t = 0; t < threads; ++t) {
+        char* dst = buf + off;
+        off += parts[t].size();
+        cp.emplace_back([&, t, dst]() { std::memcpy(dst, parts[t].data(), parts[t].size()); });
+    }
+    for (auto& x : cp) x.join();
+    *size = total;
+    return buf;
+}
+void gafgen_free(char* p) { std::free(p); }
+
 void gafgen_preset(const char* name, gafgen_params* P) {
     std::memset(P, 0, sizeof *P);
     P->seed = 1;
