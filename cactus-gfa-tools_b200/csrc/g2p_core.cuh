@@ -57,7 +57,10 @@ enum : u32 {
     ST_SKIP = 255             // '*' line (gaf2paf_main.cpp:360): no output, not an error
 };
 G2P_HD bool st_is_abort(u32 st) { return (st & 0xff) >= 16 && (st & 0xff) != ST_SKIP; }
-G2P_HD bool st_is_error(u32 st) { return (st & 0xff) != ST_OK && (st & 0xff) != ST_SKIP; }
+G2P_HD bool st_is_error(u32 st) {   // code 3 is gaf2unstable's multi-contig warning, not an error
+    const u32 c = st & 0xff;
+    return c == ST_ERR_NAME || c == ST_ERR_NOCG || (c >= 16 && c != ST_SKIP);
+}
 
 // ---------------------------------------------------------------------------------
 // name -> length table (reference: unordered_map<string,int64_t>, gaf2paf_main.cpp:22-45).
