@@ -59,6 +59,8 @@ class Result(ctypes.Structure):
         ("emit_ms", ctypes.c_float),
         ("size_ms", ctypes.c_float),
         ("index_ms", ctypes.c_float),
+        ("n_delegated", ctypes.c_uint32),
+        ("reserved", ctypes.c_uint32),
     ]
 
 

@@ -6,6 +6,7 @@
 // every byte of PAF is produced by k_convert<true>.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -60,7 +61,8 @@ struct g2p_ctx {
     uint64_t table_entries = 0;
     bool have_table = false;
     // work buffers
-    DevBuf d_in, d_tiles, d_rec, d_status, d_off, d_blocks, d_out, d_meta;
+    DevBuf d_in, d_tiles, d_rec, d_status, d_off, d_blocks, d_out, d_meta, d_list;
+    int n_sm = 148;
     PinBuf h_out, h_meta;
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev[8] = {};
@@ -89,8 +91,9 @@ int g2p_create(int device, g2p_ctx** out) {
     ctx->device = device;
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return G2P_E_NO_DEVICE; }
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
-    cudaFuncSetAttribute(k_convert<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCvtWarps * (kInCap + kOutCap));
-    cudaFuncSetAttribute(k_convert<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCvtWarps * kInCap);
+    cudaFuncSetAttribute(k_short<kSG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShortSmem);
+    cudaFuncSetAttribute(k_short<kSG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShortSmem);
+    cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
     if (ctx->d_meta.ensure(sizeof(PipelineMeta)) != cudaSuccess || ctx->h_meta.ensure(sizeof(PipelineMeta)) != cudaSuccess) {
         delete ctx;
         return G2P_E_NO_DEVICE;
@@ -104,7 +107,7 @@ void g2p_destroy(g2p_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (DevBuf* b : {&ctx->d_slots, &ctx->d_arena, &ctx->d_in, &ctx->d_tiles, &ctx->d_rec, &ctx->d_status, &ctx->d_off, &ctx->d_blocks,
-                      &ctx->d_out, &ctx->d_meta})
+                      &ctx->d_out, &ctx->d_meta, &ctx->d_list})
         b->release();
     ctx->h_out.release();
     ctx->h_meta.release();
@@ -219,11 +222,16 @@ int g2p_convert_device(g2p_ctx* ctx, const void* d_gaf_v, size_t n, void** d_out
     u32* d_status = static_cast<u32*>(ctx->d_status.p);
     u64* d_off = static_cast<u64*>(ctx->d_off.p);
     u64* d_blocks = static_cast<u64*>(ctx->d_blocks.p);
-    const u32 ncta = (nrec + kCvtThreads - 1) / kCvtThreads;
+    G2P_CUDA(ctx->d_list.ensure((size_t)nrec * sizeof(u32)));
+    u32* d_list = static_cast<u32*>(ctx->d_list.p);
+    const u32 ncta = (nrec + kShortRecsPerCta - 1) / kShortRecsPerCta;
+    const u32 nlist = std::min<u32>((nrec + kListThreads - 1) / kListThreads, (u32)ctx->n_sm * 16u);
+    ShortArgs sa{d_gaf, (u64)n, d_rec, nrec, ctx->table, d_off, d_status, nullptr, d_list, &d_meta->n_deleg};
 
-    // pass 1: sizes + status
-    k_convert<false><<<ncta, kCvtThreads, kCvtWarps * kInCap, st>>>(d_gaf, n, d_rec, nrec, ctx->table, d_off, d_status, nullptr, d_meta);
-    ++launches;
+    // pass 1: sizes + status (fast kernel, then the general kernel on what it delegated)
+    k_short<kSG, false><<<ncta, kSThreads, kShortSmem, st>>>(sa);
+    k_convert_list<false><<<nlist, kListThreads, 0, st>>>(d_gaf, d_rec, ctx->table, d_off, d_status, nullptr, d_meta, d_list);
+    launches += 2;
     G2P_CUDA(cudaEventRecord(ctx->ev[2], st));
     // exclusive scan -> offsets
     k_scan_reduce<<<nscan, kScanThreads, 0, st>>>(d_off, nrec, d_blocks);
@@ -233,12 +241,18 @@ int g2p_convert_device(g2p_ctx* ctx, const void* d_gaf_v, size_t n, void** d_out
     G2P_CUDA(cudaMemcpyAsync(hm, d_meta, sizeof(PipelineMeta), cudaMemcpyDeviceToHost, st));
     G2P_CUDA(cudaStreamSynchronize(st));
     const u64 out_total = hm->out_total;
+    res->n_delegated = hm->n_deleg;
     G2P_CUDA(ctx->d_out.ensure(out_total + 256));
     u8* d_o = static_cast<u8*>(ctx->d_out.p);
     // pass 2: emit
     G2P_CUDA(cudaEventRecord(ctx->ev[3], st));
-    k_convert<true><<<ncta, kCvtThreads, kCvtWarps * (kInCap + kOutCap), st>>>(d_gaf, n, d_rec, nrec, ctx->table, d_off, d_status, d_o, d_meta);
+    sa.out = d_o;
+    k_short<kSG, true><<<ncta, kSThreads, kShortSmem, st>>>(sa);
     ++launches;
+    if (hm->n_deleg) {
+        k_convert_list<true><<<nlist, kListThreads, 0, st>>>(d_gaf, d_rec, ctx->table, d_off, d_status, d_o, d_meta, d_list);
+        ++launches;
+    }
     G2P_CUDA(cudaEventRecord(ctx->ev[4], st));
     res->out_bytes = out_total;
     if (hm->first_err != 0xFFFFFFFFu) {

@@ -31,6 +31,7 @@
 namespace g2p {
 
 typedef uint8_t u8;
+typedef uint16_t u16;
 typedef uint32_t u32;
 typedef uint64_t u64;
 typedef int64_t i64;
@@ -111,9 +112,39 @@ G2P_HD void name_key(const u8* s, u32 len, u64& k0, u64& k1) {
     k0 = a; k1 = b;
 }
 
+// Slot of a key: 32-bit multiply/xor-shift mixing (cheap on the device: the probe, not the
+// hash, should dominate a lookup).
 G2P_HD u32 slot_index(u64 k0, u64 k1, u32 len, u32 nslots) {
-    u64 h = mix64(k0 ^ mix64(k1 + 0x9e3779b97f4a7c15ULL * (u64)(len + 1)));
-    return (u32)(((h >> 32) * (u64)nslots) >> 32);
+    u32 x = (u32)k0 * 0x9E3779B1u ^ (u32)(k0 >> 32) * 0x85EBCA77u ^ (u32)k1 * 0xC2B2AE3Du ^ (u32)(k1 >> 32) * 0x27D4EB2Fu ^
+            (len * 0x165667B1u);
+    x ^= x >> 15; x *= 0x2C1B3C6Du;
+    x ^= x >> 12; x *= 0x297A2D39u;
+    x ^= x >> 15;
+    return (u32)(((u64)x * (u64)nslots) >> 32);
+}
+
+// Probe with a ready key for names of <= 16 bytes (the key is the name itself, so no arena
+// compare is needed).  Returns true and the length when present.
+G2P_HD bool table_lookup_key16(const LenTableView& T, u64 k0, u64 k1, u32 len, i64& length) {
+    if (T.nslots == 0) return false;
+    u32 idx = slot_index(k0, k1, len, T.nslots);
+    for (;;) {
+        const LenSlot* sl = T.slots + idx;
+#if defined(__CUDA_ARCH__)
+        const ulonglong2 lo = __ldg(reinterpret_cast<const ulonglong2*>(sl));
+        const ulonglong2 hi = __ldg(reinterpret_cast<const ulonglong2*>(sl) + 1);
+        const u64 s_k0 = lo.x, s_k1 = lo.y;
+        const i64 s_len = (i64)hi.x;
+        const u32 s_nlen = (u32)(hi.y >> 32);
+#else
+        const u64 s_k0 = sl->k0, s_k1 = sl->k1;
+        const i64 s_len = sl->length;
+        const u32 s_nlen = sl->name_len;
+#endif
+        if (s_nlen == kEmptySlot) return false;
+        if (s_nlen == len && s_k0 == k0 && s_k1 == k1) { length = s_len; return true; }
+        idx = idx + 1 == T.nslots ? 0 : idx + 1;
+    }
 }
 
 // Returns true and the length when `name` is in the table.

@@ -1,18 +1,24 @@
 // g2p_kernels.cuh — sm_100a kernels of the GAF -> PAF pipeline.
 //
 //   k_count_lines / k_scan_tiles / k_fill_lines   newline index (record start offsets)
-//   k_convert<false>                               pass 1: per-record PAF byte length + status
+//   k_short<G,false> + k_convert_list<false>       pass 1: per-record PAF byte length + status
 //   k_scan_*                                       exclusive scan of the lengths -> output offsets
-//   k_convert<true>                                pass 2: write the PAF bytes
+//   k_short<G,true> + k_convert_list<true>         pass 2: write the PAF bytes
 //   k_diagnose                                     details of the first failing record
 //
 // All work is byte / integer; the pipeline is bound by HBM traffic and by the
 // latency of serial per-record parsing, so the kernels stage contiguous record
 // batches through shared memory with 128-bit coalesced accesses in both directions.
 #pragma once
+#if defined(G2P_HOSTSIM)
+#include "cuda_shim.hpp"
+#else
 #include <cuda_runtime.h>
+#define G2P_NOINLINE __noinline__
+#endif
 
 #include "g2p_core.cuh"
+#include "g2p_short.cuh"
 
 namespace g2p {
 
@@ -27,6 +33,8 @@ struct PipelineMeta {
     u32 err_a, err_b;  // name span relative to the record start
     u32 err_rec_start;
     u64 err_out_end;   // output offset just after the failing record's (partial) output
+    u32 n_deleg;       // records k_short left to the general kernel
+    u32 pad2;
 };
 
 // ------------------------------------------------------------------------------
@@ -38,15 +46,9 @@ constexpr int kIdxThreads = 256;
 constexpr int kIdxVec = 4;
 constexpr u32 kIdxTile = kIdxThreads * kIdxVec * 16;
 
-__device__ __forceinline__ uint4 load_vec_guarded(const u8* base, u64 off, u64 n) {
-    if (off + 16 <= n) return __ldg(reinterpret_cast<const uint4*>(base + off));
-    u32 w[4] = {0, 0, 0, 0};
-    for (u32 i = 0; i < 16; ++i)
-        if (off + i < n) w[i >> 2] |= (u32)base[off + i] << (8 * (i & 3));
-    return make_uint4(w[0], w[1], w[2], w[3]);
-}
+__device__ __forceinline__ uint4 load_vec_guarded(const u8* base, u64 off, u64 n) { return ldg_vec_guarded(base, off, n); }
 
-__device__ __forceinline__ u32 nl_bits(u32 w) { return __vcmpeq4(w, 0x0A0A0A0Au) & 0x80808080u; }
+__device__ __forceinline__ u32 nl_bits(u32 w) { return zero_bytes(w ^ 0x0A0A0A0Au); }
 
 __global__ void __launch_bounds__(kIdxThreads) k_count_lines(const u8* __restrict__ text, u64 n, u32* __restrict__ tile_count) {
     const u64 base = (u64)blockIdx.x * kIdxTile;
@@ -98,6 +100,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(u32* __restrict__ tile_coun
         meta->first_err = 0xFFFFFFFFu;
         meta->out_total = 0;
         meta->err_status = 0;
+        meta->n_deleg = 0;
     }
 }
 
@@ -224,92 +227,37 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_apply(u64* __restrict__ x
 }
 
 // ------------------------------------------------------------------------------
-// Record conversion.  One warp owns 32 consecutive records; their bytes form one
-// contiguous input range that is staged into the warp's shared-memory slice with
-// 128-bit coalesced loads, and (pass 2) one contiguous output range that is
-// assembled in shared memory and flushed with 128-bit coalesced stores.  Batches
-// that do not fit the slices fall back to direct global access for that warp.
+// General per-record conversion: one thread walks one record with the streaming state
+// machine of g2p_core.cuh (any record length, every error path of the reference).  It
+// runs over the list of records that k_short (g2p_short.cuh) delegated.
 // ------------------------------------------------------------------------------
-constexpr int kCvtWarps = 4;
-constexpr int kCvtThreads = kCvtWarps * 32;
-constexpr u32 kInCap = 8 * 1024;     // bytes of staged input per warp
-constexpr u32 kOutCap = 16 * 1024;   // bytes of staged output per warp
+constexpr int kListThreads = 64;
 
 template <class Sink>
-__device__ __noinline__ u32 convert_record_global(const u8* r, u32 len, const LenTableView& T, Sink& S, u32& ea, u32& eb) {
+__device__ G2P_NOINLINE u32 convert_record_global(const u8* r, u32 len, const LenTableView& T, Sink& S, u32& ea, u32& eb) {
     return convert_record(r, len, T, S, ea, eb);
 }
 
 template <bool EMIT>
-__global__ void __launch_bounds__(kCvtThreads) k_convert(const u8* __restrict__ gaf, u64 n, const u32* __restrict__ rec_start, u32 nrec,
-                                                         LenTableView T, u64* __restrict__ out_off, u32* __restrict__ status,
-                                                         u8* __restrict__ out, PipelineMeta* __restrict__ meta) {
-    extern __shared__ __align__(16) u8 smem[];
-    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    u8* sm_in = smem + (size_t)warp * (EMIT ? (kInCap + kOutCap) : kInCap);
-    u8* sm_out = sm_in + kInCap;
-    const u32 R0 = (blockIdx.x * kCvtWarps + warp) * 32;
-    if (R0 >= nrec) return;
-    const u32 Rend = min(R0 + 32, nrec);
-    const u32 r = R0 + lane;
-    const bool valid = r < nrec;
-    const u32 s = valid ? rec_start[r] : 0;
-    const u32 e = valid ? rec_start[r + 1] : 0;
-    const u32 len = valid ? e - s - 1 : 0;
-    const u32 s0 = __shfl_sync(0xffffffffu, s, 0);
-    u32 s1 = rec_start[Rend];
-    if ((u64)s1 > n) s1 = (u32)n;
-
-    // ---- stage input
-    const u32 A = s0 & ~15u;
-    const u32 nvec = (s1 - A + 15) >> 4;
-    const bool in_staged = nvec * 16 <= kInCap;
-    if (in_staged) {
-        for (u32 v = lane; v < nvec; v += 32)
-            reinterpret_cast<uint4*>(sm_in)[v] = load_vec_guarded(gaf, (u64)A + (u64)v * 16, n);
-        __syncwarp();
-    }
-
-    u32 ea = 0, eb = 0;
-    if (!EMIT) {
-        u32 st = ST_OK;
-        u64 bytes = 0;
-        if (valid) {
+__global__ void __launch_bounds__(kListThreads) k_convert_list(const u8* __restrict__ gaf, const u32* __restrict__ rec_start, LenTableView T,
+                                                               u64* __restrict__ out_off, u32* __restrict__ status, u8* __restrict__ out,
+                                                               PipelineMeta* __restrict__ meta, const u32* __restrict__ list) {
+    const u32 nd = meta->n_deleg;
+    for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < nd; k += gridDim.x * blockDim.x) {
+        const u32 r = list[k];
+        const u32 s = rec_start[r], len = rec_start[r + 1] - s - 1;
+        u32 ea = 0, eb = 0;
+        if (!EMIT) {
             CountSink cs;
-            st = in_staged ? convert_record(sm_in + (s - A), len, T, cs, ea, eb)
-                           : convert_record_global(gaf + s, len, T, cs, ea, eb);
-            bytes = (st_is_abort(st) || st == ST_SKIP) ? 0 : cs.n;
-            out_off[r] = bytes;
+            const u32 st = convert_record_global(gaf + s, len, T, cs, ea, eb);
+            out_off[r] = (st_is_abort(st) || (st & 0xff) == ST_SKIP) ? 0 : cs.n;
             status[r] = st;
             if (st_is_error(st)) atomicMin(&meta->first_err, r);
-        }
-    } else {
-        const u64 o = valid ? out_off[r] : 0;
-        const u64 o0 = __shfl_sync(0xffffffffu, o, 0);
-        const u64 o1 = out_off[Rend];
-        const u32 st_prev = valid ? status[r] : (u32)ST_SKIP;
-        const bool active = valid && !st_is_abort(st_prev) && st_prev != ST_SKIP;
-        const bool out_staged = (o1 - o0) + 32 <= kOutCap;
-        const u32 pad = (u32)(o0 & 15);
-        if (active) {
-            u8* dst = out_staged ? sm_out + pad + (u32)(o - o0) : out + o;
-            StoreSink ss(dst);
-            if (in_staged) convert_record(sm_in + (s - A), len, T, ss, ea, eb);
-            else convert_record_global(gaf + s, len, T, ss, ea, eb);
-        }
-        if (out_staged) {
-            __syncwarp();
-            const u64 ga = (o0 + 15) & ~15ULL, gb = o1 & ~15ULL;
-            if (ga >= gb) {
-                for (u64 g = o0 + lane; g < o1; g += 32) out[g] = sm_out[pad + (u32)(g - o0)];
-            } else {
-                for (u64 g = o0 + lane; g < ga; g += 32) out[g] = sm_out[pad + (u32)(g - o0)];
-                for (u64 g = gb + lane; g < o1; g += 32) out[g] = sm_out[pad + (u32)(g - o0)];
-                const uint4* src = reinterpret_cast<const uint4*>(sm_out + pad + (u32)(ga - o0));
-                uint4* dstv = reinterpret_cast<uint4*>(out + ga);
-                const u32 nv = (u32)((gb - ga) >> 4);
-                for (u32 v = lane; v < nv; v += 32) dstv[v] = src[v];
-            }
+        } else {
+            const u32 st = status[r];
+            if (st_is_abort(st) || (st & 0xff) == ST_SKIP) continue;
+            StoreSink ss(out + out_off[r]);
+            convert_record_global(gaf + s, len, T, ss, ea, eb);
         }
     }
 }

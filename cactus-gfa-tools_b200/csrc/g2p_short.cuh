@@ -1,0 +1,607 @@
+// g2p_short.cuh — the short-record conversion kernel (SURVEY.md §8a rows a2-a10 for records
+// of up to kSLimit bytes: short reads, 1..G-1 path steps, <= kSMaxOps CIGAR operations).
+//
+// G lanes (G = 8: four records per warp) own one GAF record.  The record is staged into
+// shared memory with 128-bit coalesced loads and classified 16 bytes per lane with SWAR byte
+// compares (tab / '>' '<' / non-digit bit masks); ranks come from shuffle prefix sums and the
+// token positions are scattered to small shared arrays.  After that every phase is
+// item-parallel inside the group:
+//   columns + tags   one lane per field        (parse_gaf_record, gafkluge.hpp:84-204)
+//   path steps       one lane per step         (gafkluge.hpp:118-158; table probe = gaf2paf_main.cpp:162-167)
+//   cg operations    one lane per op + four shuffle prefix sums (for_each_cg, gafkluge.hpp:226-239)
+//   split            one lane per step boundary: lower_bound of the cumulative step quota in the
+//                    cumulative target length of the ops (cigar_next_by_target, gaf2paf_main.cpp:71-90,
+//                    closed form in SURVEY.md Appendix B.3-B.5)
+//   emit             one lane per PAF line into a shared staging buffer, flushed with 128-bit stores
+//
+// '-' strand records (flip_gaf, gaf2paf_main.cpp:92-131) are handled by index arithmetic: steps
+// and ops are visited in reverse order, nothing is physically reversed.
+//
+// The kernel only converts records it can prove canonical (plain decimal columns of <= 9
+// digits, names of <= 16 bytes present in the table, XX:T:value tags, strict CIGAR syntax...).
+// Anything else -- including every record the reference would reject -- is *delegated*: its
+// index is appended to a list that the general per-record kernel (k_convert_list, the
+// streaming state machine of g2p_core.cuh) converts.  Results are identical either way; the
+// delegate path is simply slower.
+#pragma once
+#include "g2p_core.cuh"
+
+namespace g2p {
+
+enum : u32 {
+    ST_F_FAST = 0x10000u   // status flag: record was converted by k_short (else by the general kernel)
+};
+
+constexpr int kSG = 8;                 // lanes per record
+constexpr int kSThreads = 256;         // 32 records per CTA
+constexpr u32 kSLimit = 240;           // longest record (bytes, without '\n') taken by the fast path
+constexpr u32 kSMaxTabs = 31;          // 12 columns + up to 20 tags
+constexpr u32 kSMaxTags = 20;
+constexpr u32 kSMaxOps = 24;
+constexpr u32 kSOutCap = 1024;         // staged PAF bytes per record; larger outputs are written directly
+
+// header slots (u32 / i32) in shared memory
+enum { H_QN_B = 0, H_QLEN = 1, H_QS = 2, H_QE = 3, H_MINUS = 4, H_PATH_A = 5, H_PLEN = 6, H_PS = 7, H_PE = 8, H_M = 9, H_B = 10,
+       H_MAPQ = 11, H_CG_A = 12, H_CG_B = 13, H_TP_A = 14, H_TP_B = 15, H_RC_A = 16, H_RC_B = 17, H_PATH_B = 18, H_N = 20 };
+
+struct __align__(16) SGroupMem {
+    u8 text[288];                  // the record, staged at its global 16-byte phase
+    u16 spos[16];                  // path-step marker positions (+ end); tag keys alias spos..opos
+    u16 opos[kSMaxOps];            // positions of the CIGAR op letters
+    u32 hdr[H_N];
+    union {
+        struct {
+            u16 tabs[32];
+            u32 pEnd[kSMaxOps], pQ[kSMaxOps], pNM[kSMaxOps], pNB[kSMaxOps];   // inclusive prefix sums, normalised op order
+        } w;
+        u8 out[kSOutCap + 16];
+    };
+};
+constexpr u32 kShortRecsPerCta = kSThreads / kSG;
+constexpr size_t kShortSmem = sizeof(SGroupMem) * kShortRecsPerCta;
+static_assert(sizeof(SGroupMem) % 16 == 0, "group slices must keep 16-byte alignment");
+
+template <int G>
+struct Grp {
+    u32 gl, gbase, gmask;
+    __device__ __forceinline__ Grp() {
+        const u32 lane = threadIdx.x & 31u;
+        gl = lane & (u32)(G - 1);
+        gbase = lane - gl;
+        gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << gbase);
+    }
+    __device__ __forceinline__ bool any(bool p) const { return __any_sync(gmask, p) != 0; }
+    template <class T> __device__ __forceinline__ T shfl(T v, int src) const { return __shfl_sync(gmask, v, src, G); }
+    template <class T> __device__ __forceinline__ T up(T v, int d) const { return __shfl_up_sync(gmask, v, d, G); }
+    template <class T> __device__ __forceinline__ T down(T v, int d) const { return __shfl_down_sync(gmask, v, d, G); }
+    __device__ __forceinline__ void sync() const { __syncwarp(gmask); }
+    __device__ __forceinline__ u32 incl_scan(u32 v) const {
+#pragma unroll
+        for (int d = 1; d < G; d <<= 1) { const u32 t = up(v, d); if (gl >= (u32)d) v += t; }
+        return v;
+    }
+    __device__ __forceinline__ u32 excl_scan(u32 v, u32& total) const {
+        const u32 incl = incl_scan(v);
+        total = shfl(incl, G - 1);
+        return incl - v;
+    }
+};
+
+// ---- SWAR byte classification ------------------------------------------------------------
+__device__ __forceinline__ u32 zero_bytes(u32 x) { return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u; }
+__device__ __forceinline__ u32 movemask4(u32 m) { return ((m >> 7) * 0x01020408u) >> 24; }   // bit7 of byte k -> bit k
+__device__ __forceinline__ u32 nondigit_bytes(u32 w) {
+    const u32 hi3 = zero_bytes((w & 0xF0F0F0F0u) ^ 0x30303030u);            // high nibble == 3
+    const u32 gt9 = (((w & 0x0F0F0F0Fu) + 0x06060606u) & 0x10101010u) << 3;   // low nibble >= 10
+    return ~(hi3 & ~gt9) & 0x80808080u;
+}
+__device__ __forceinline__ u32 range16(int lo, int hi) {   // bits [lo, hi) of a 16-bit chunk mask
+    lo = lo < 0 ? 0 : (lo > 16 ? 16 : lo);
+    hi = hi < 0 ? 0 : (hi > 16 ? 16 : hi);
+    return hi > lo ? (((1u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u;
+}
+
+// 16 bytes from an arbitrarily aligned shared-memory address.
+__device__ __forceinline__ void lds16_unaligned(const u8* p, u32& w0, u32& w1, u32& w2, u32& w3) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const u32* q = reinterpret_cast<const u32*>(a & ~(uintptr_t)3);
+    const u32 sh = (u32)(a & 3) * 8;
+    const u32 x0 = q[0], x1 = q[1], x2 = q[2], x3 = q[3], x4 = q[4];
+    w0 = __funnelshift_r(x0, x1, sh); w1 = __funnelshift_r(x1, x2, sh);
+    w2 = __funnelshift_r(x2, x3, sh); w3 = __funnelshift_r(x3, x4, sh);
+}
+__device__ __forceinline__ u32 keep_bytes(u32 w, int n) {   // keep the n lowest bytes of w (n may be <0 or >4)
+    return n >= 4 ? w : (n <= 0 ? 0u : (w & ((1u << (8 * n)) - 1u)));
+}
+
+// ---- decimal helpers (32-bit) -------------------------------------------------------------
+__device__ __forceinline__ u32 dlen_u32(u32 v, const u32* p10) {
+    const u32 t = ((32u - (u32)__clz((int)(v | 1u))) * 1233u) >> 12;   // floor(log10) or one more
+    return t + 1u - (u32)((v | 1u) < p10[t]);
+}
+__device__ __forceinline__ u32 dlen_i32(i32 v, const u32* p10) { return v < 0 ? 1u + dlen_u32(0u - (u32)v, p10) : dlen_u32((u32)v, p10); }
+__device__ __forceinline__ u8* put_u32(u8* p, u32 v, const u32* p10) {
+    const u32 n = dlen_u32(v, p10);
+    for (u32 k = n; k-- > 0;) { const u32 q = v / 10u; p[k] = (u8)('0' + (v - q * 10u)); v = q; }
+    return p + n;
+}
+__device__ __forceinline__ u8* put_i32(u8* p, i32 v, const u32* p10) {
+    if (v < 0) { *p++ = '-'; return put_u32(p, 0u - (u32)v, p10); }
+    return put_u32(p, (u32)v, p10);
+}
+__device__ __forceinline__ u8* put_bytes(u8* p, const u8* s, u32 n) {
+    for (u32 i = 0; i < n; ++i) p[i] = s[i];
+    return p + n;
+}
+__device__ __forceinline__ u8* put_tag(u8* p, u8 a, u8 b, u8 t) {   // "\tab:t:"
+    p[0] = '\t'; p[1] = a; p[2] = b; p[3] = ':'; p[4] = t; p[5] = ':';
+    return p + 6;
+}
+
+// gi:f: text for 0 <= floor(m/b*1000+0.5) <= 1000 (gaf2paf_main.cpp:248-253); returns 0 if outside.
+__device__ __forceinline__ u32 gi_fast(i32 m, i32 b, u8* out) {
+    if (b <= 0) { out[0] = '0'; return 1; }
+    const double x = __ddiv_rn((double)m, (double)b);
+    const double k = floor(__dadd_rn(__dmul_rn(x, 1000.0), 0.5));
+    if (!(k >= 0.0 && k <= 1000.0)) return 0;
+    const u32 ki = (u32)k;
+    if (ki == 0) { out[0] = '0'; return 1; }
+    if (ki == 1000) { out[0] = '1'; return 1; }
+    const u32 d0 = ki / 100, d1 = (ki / 10) % 10, d2 = ki % 10;
+    out[0] = '0'; out[1] = '.';
+    out[2] = (u8)('0' + d0); out[3] = (u8)('0' + d1); out[4] = (u8)('0' + d2);
+    return d2 ? 5 : (d1 ? 4 : 3);
+}
+
+__device__ __forceinline__ uint4 ldg_vec_guarded(const u8* base, u64 off, u64 n) {
+    if (off + 16 <= n) return __ldg(reinterpret_cast<const uint4*>(base + off));
+    u32 w[4] = {0, 0, 0, 0};
+    for (u32 i = 0; i < 16; ++i)
+        if (off + i < n) w[i >> 2] |= (u32)base[off + i] << (8 * (i & 3));
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+#if defined(G2P_HOSTSIM)
+#define G2P_DYN_SMEM(name) u8* name = hs::g_dyn_smem
+#else
+#define G2P_DYN_SMEM(name) extern __shared__ __align__(16) u8 name[]
+#endif
+
+struct ShortArgs {
+    const u8* gaf;
+    u64 n;
+    const u32* rec_start;
+    u32 nrec;
+    LenTableView T;
+    u64* out_off;        // size pass: per-record byte count; emit pass: exclusive offsets
+    u32* status;
+    u8* out;
+    u32* deleg_list;     // size pass: indices of records left to the general kernel
+    u32* n_deleg;
+};
+
+// One record per G-lane group.  EMIT=false: size + status (or delegate).  EMIT=true: write PAF.
+template <int G, bool EMIT>
+__global__ void __launch_bounds__(kSThreads, 4) k_short(const ShortArgs a) {
+    G2P_DYN_SMEM(smem);
+    __shared__ u32 p10[10];
+    if (threadIdx.x < 10) {
+        u32 v = 1;
+        for (u32 i = 0; i < threadIdx.x; ++i) v *= 10u;
+        p10[threadIdx.x] = v;
+    }
+    __syncthreads();
+
+    const Grp<G> g;
+    const u32 gid = threadIdx.x / G;
+    SGroupMem* gm = reinterpret_cast<SGroupMem*>(smem) + gid;
+    const u32 r = blockIdx.x * (kSThreads / G) + gid;
+    if (r >= a.nrec) return;
+    const u32 s = a.rec_start[r], e = a.rec_start[r + 1];
+    const u32 len = e - s - 1;
+    u64 o = 0;
+    u32 osize = 0;
+    if (EMIT) {
+        if (!(a.status[r] & ST_F_FAST)) return;
+        o = a.out_off[r];
+        osize = (u32)(a.out_off[r + 1] - o);
+        if (osize == 0) return;
+    }
+
+    bool deleg = false;      // group-uniform
+    u32 size = 0;
+    u32 status = ST_OK | ST_F_FAST;
+    do {
+        if (len == 0 || len > kSLimit) { deleg = true; break; }
+        // ---------------- phase 0: stage + classify
+        const u32 A = s & ~15u, sh = s - A;
+        const u32 nchunks = (sh + len + 15) >> 4;   // <= 16
+        const u8* rt = gm->text + sh;
+        constexpr int NIT = (16 + G - 1) / G;
+        u32 tabm[NIT], mrkm[NIT], ndgm[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const u32 c = it * G + g.gl;
+            tabm[it] = mrkm[it] = ndgm[it] = 0;
+            if (c < nchunks) {
+                const uint4 v = ldg_vec_guarded(a.gaf, (u64)A + 16u * c, a.n);
+                reinterpret_cast<uint4*>(gm->text)[c] = v;
+                const u32 w[4] = {v.x, v.y, v.z, v.w};
+                u32 t = 0, m = 0, d = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    t |= movemask4(zero_bytes(w[k] ^ 0x09090909u)) << (4 * k);
+                    m |= movemask4(zero_bytes((w[k] & 0xFDFDFDFDu) ^ 0x3C3C3C3Cu)) << (4 * k);
+                    d |= movemask4(nondigit_bytes(w[k])) << (4 * k);
+                }
+                const u32 vm = range16((int)sh - 16 * (int)c, (int)(sh + len) - 16 * (int)c);
+                tabm[it] = t & vm; mrkm[it] = m & vm; ndgm[it] = d & vm;
+            }
+        }
+        if (g.gl < 6) gm->hdr[H_CG_A + g.gl] = 0;
+        u32 nt = 0;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            u32 tot;
+            u32 k = nt + g.excl_scan((u32)__popc(tabm[it]), tot);
+            u32 m = tabm[it];
+            const u32 base = 16u * (it * G + g.gl) - sh;
+            while (m) {
+                const u32 b = (u32)__ffs((int)m) - 1u;
+                m &= m - 1u;
+                if (k < 32) gm->w.tabs[k] = (u16)(base + b);
+                ++k;
+            }
+            nt += tot;
+        }
+        g.sync();
+        if (rt[0] == '*') { status = ST_SKIP | ST_F_FAST; break; }   // gaf2paf_main.cpp:360
+        if (nt < 11 || nt > kSMaxTabs) { deleg = true; break; }
+        const u16* tabs = gm->w.tabs;
+
+        // ---------------- phase 1: columns 1..12 and tags, one lane per field
+        u32 lbad = 0;
+        for (u32 f = g.gl; f < 12; f += G) {
+            const u32 fa = f ? tabs[f - 1] + 1u : 0u;
+            const u32 fb = f < nt ? tabs[f] : len;
+            const u32 fl = fb - fa;
+            if (fl == 0) { lbad = 1; continue; }
+            if (f == 0) { gm->hdr[H_QN_B] = fb; }
+            else if (f == 4) {
+                const u8 c = rt[fa];
+                if (fl != 1 || (c != '+' && c != '-')) lbad = 1;
+                gm->hdr[H_MINUS] = c == '-';
+            } else if (f == 5) { gm->hdr[H_PATH_A] = fa; gm->hdr[H_PATH_B] = fb; }
+            else {
+                i32 v = 0;
+                if (fl == 1 && rt[fa] == '*') v = -1;
+                else if (fl > 9) lbad = 1;
+                else {
+                    u32 x = 0;
+                    for (u32 k = fa; k < fb; ++k) { const u32 d = (u32)rt[k] - '0'; if (d > 9) lbad = 1; x = x * 10u + d; }
+                    v = (i32)x;
+                    if (f == 11 && v >= 255) v = -1;   // gafkluge.hpp:176-183
+                }
+                gm->hdr[f] = (u32)v;
+            }
+        }
+        const u32 ntf = nt - 11;   // tag fields (possibly empty ones)
+        u32* tkeys = reinterpret_cast<u32*>(gm->spos);
+        for (u32 t0 = 0; t0 < ntf; t0 += G) {
+            const u32 ti = t0 + g.gl;
+            if (ti < ntf) {
+                const u32 f = 12 + ti;
+                const u32 fa = tabs[f - 1] + 1u, fb = f < nt ? tabs[f] : len, fl = fb - fa;
+                u32 key = 0x10000u + ti;   // empty field: unique non-key
+                if (fl) {
+                    if (fl < 5 || rt[fa + 2] != ':' || rt[fa + 4] != ':') lbad = 1;
+                    else {
+                        key = (u32)rt[fa] | ((u32)rt[fa + 1] << 8);
+                        if (key == ((u32)'c' | ((u32)'g' << 8))) { gm->hdr[H_CG_A] = fa + 5; gm->hdr[H_CG_B] = fb; }
+                        else if (key == ((u32)'t' | ((u32)'p' << 8))) { gm->hdr[H_TP_A] = fa + 3; gm->hdr[H_TP_B] = fb; }
+                        else if (key == ((u32)'r' | ((u32)'c' << 8))) { gm->hdr[H_RC_A] = fa + 3; gm->hdr[H_RC_B] = fb; }
+                    }
+                }
+                tkeys[ti] = key;
+            }
+        }
+        g.sync();
+        for (u32 t0 = 0; t0 < ntf; t0 += G) {   // duplicate tags (gafkluge.hpp:195-198)
+            const u32 ti = t0 + g.gl;
+            if (ti < ntf) {
+                const u32 key = tkeys[ti];
+                for (u32 j = 0; j < ti; ++j) if (tkeys[j] == key) lbad = 1;
+            }
+        }
+        if (g.any(lbad != 0)) { deleg = true; break; }   // also orders the tkeys reads before the scatter below
+
+        const bool minus = gm->hdr[H_MINUS] != 0;
+        const i32 qs = (i32)gm->hdr[H_QS], ps = (i32)gm->hdr[H_PS], pe = (i32)gm->hdr[H_PE];
+        const u32 ca = gm->hdr[H_CG_A], cb = gm->hdr[H_CG_B];
+        const u32 pa = gm->hdr[H_PATH_A], pb = gm->hdr[H_PATH_B];
+        if (cb == 0 || ca >= cb || qs < 0 || ps < 0 || pe < 0) { deleg = true; break; }
+        const u8 c0 = rt[pa];
+        const bool prefixed = c0 == '>' || c0 == '<';
+        const bool empty_path = !prefixed && pb - pa == 1 && c0 == '*';
+
+        // ---------------- phase 2: step markers and op letters -> positions
+        u32 ns = 0, no = 0;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int base = 16 * (it * G + (int)g.gl) - (int)sh;
+            u32 mm = prefixed ? (mrkm[it] & range16((int)pa - base, (int)pb - base)) : 0u;
+            u32 dm = ndgm[it] & range16((int)ca - base, (int)cb - base);
+            u32 tot;
+            const u32 ex = g.excl_scan((u32)__popc(mm) | ((u32)__popc(dm) << 16), tot);
+            u32 k = ns + (ex & 0xffffu);
+            while (mm) {
+                const u32 b = (u32)__ffs((int)mm) - 1u;
+                mm &= mm - 1u;
+                if (k < 15) gm->spos[k] = (u16)(base + (int)b);
+                ++k;
+            }
+            k = no + (ex >> 16);
+            while (dm) {
+                const u32 b = (u32)__ffs((int)dm) - 1u;
+                dm &= dm - 1u;
+                if (k < kSMaxOps) gm->opos[k] = (u16)(base + (int)b);
+                ++k;
+            }
+            ns += tot & 0xffffu;
+            no += tot >> 16;
+        }
+        if (!prefixed) ns = empty_path ? 0u : 1u;
+        if (ns > (u32)(G - 1) || no == 0 || no > kSMaxOps) { deleg = true; break; }
+        if (prefixed && g.gl == 0) gm->spos[ns] = (u16)pb;
+        g.sync();
+        if (gm->opos[no - 1] != cb - 1) { deleg = true; break; }   // digits after the last op letter
+
+        // ---------------- phase 3: one lane per path step
+        const u32 i = g.gl;             // normalised step index (and boundary index)
+        const bool is_step = i < ns;
+        u32 name_a = 0, nl = 0;
+        i32 tlen = 0, sa = 0, se = 0;
+        bool rev = false;
+        if (is_step) {
+            const u32 so_ = minus ? ns - 1 - i : i;
+            u32 p, q;
+            if (prefixed) { p = gm->spos[so_]; q = gm->spos[so_ + 1]; } else { p = pa - 1; q = pb; }
+            rev = (prefixed && rt[p] == '<') != minus;
+            name_a = p + 1;
+            const u32 tl = q - name_a;
+            u32 w0, w1, w2, w3;
+            lds16_unaligned(rt + name_a, w0, w1, w2, w3);
+            bool interval = false;
+            nl = tl;
+            if (prefixed) {
+                u32 cm = movemask4(zero_bytes(w0 ^ 0x3A3A3A3Au)) | (movemask4(zero_bytes(w1 ^ 0x3A3A3A3Au)) << 4) |
+                         (movemask4(zero_bytes(w2 ^ 0x3A3A3A3Au)) << 8) | (movemask4(zero_bytes(w3 ^ 0x3A3A3A3Au)) << 12);
+                cm &= tl >= 16 ? 0xffffu : ((1u << tl) - 1u);
+                if (cm) { nl = (u32)__ffs((int)cm) - 1u; interval = true; }
+            }
+            if (nl == 0 || nl > 16) lbad = 1;
+            else {
+                w0 = keep_bytes(w0, (int)nl); w1 = keep_bytes(w1, (int)nl - 4);
+                w2 = keep_bytes(w2, (int)nl - 8); w3 = keep_bytes(w3, (int)nl - 12);
+                i64 tl64 = 0;
+                if (!table_lookup_key16(a.T, (u64)w0 | ((u64)w1 << 32), (u64)w2 | ((u64)w3 << 32), nl, tl64)) lbad = 1;
+                else if (tl64 < 0 || tl64 > 0x7fffffffLL) lbad = 1;
+                tlen = (i32)tl64;
+                se = tlen;
+                if (interval) {   // ":start-end" (gafkluge.hpp:131-146), plain digits only
+                    u32 k = name_a + nl + 1, x = 0, nd = 0;
+                    while (k < q && nd < 10) { const u32 d = (u32)rt[k] - '0'; if (d > 9) break; x = x * 10u + d; ++nd; ++k; }
+                    if (nd == 0 || nd > 9 || k >= q || rt[k] != '-') lbad = 1;
+                    sa = (i32)x;
+                    ++k; x = 0; nd = 0;
+                    while (k < q && nd < 10) { const u32 d = (u32)rt[k] - '0'; if (d > 9) break; x = x * 10u + d; ++nd; ++k; }
+                    if (nd == 0 || nd > 9 || k != q) lbad = 1;
+                    se = (i32)x;
+                }
+            }
+        }
+        const i32 slen = se - sa;
+        if (is_step && slen < 0) lbad = 1;
+        // flip_gaf: mirror the path interval about the summed step lengths (gaf2paf_main.cpp:111-131)
+        i32 ps2 = ps, pe2 = pe;
+        if (minus) {
+            u32 lo = is_step && !lbad ? (u32)slen : 0u, hi = 0;   // 64-bit sum in two halves
+#pragma unroll
+            for (int d = 1; d < G; d <<= 1) {
+                const u32 tlo = g.up(lo, d), thi = g.up(hi, d);
+                if (g.gl >= (u32)d) { const u32 nlo = lo + tlo; hi += thi + (nlo < lo); lo = nlo; }
+            }
+            lo = g.shfl(lo, G - 1); hi = g.shfl(hi, G - 1);
+            if (hi != 0 || lo > 0x7fffffffu) lbad = 1;
+            ps2 = (i32)lo - pe; pe2 = (i32)lo - ps;
+        }
+        // quotas (gaf2paf_main.cpp:176-182) and cumulative boundaries B_i (Appendix B.3)
+        const i32 W = pe2 - ps2;
+        const i32 so = (i == 0) ? ps2 : 0;
+        const bool is_last = is_step && i + 1 == ns;
+        u32 tbc;
+        u32 B = g.excl_scan(is_step && !is_last ? (u32)(slen - so) : 0u, tbc);
+        i32 quota = slen - so, eo = 0;
+        if (is_last) { quota = W - (i32)tbc; eo = slen - so - quota; }
+        if (is_step && (so < 0 || quota < 0 || eo < 0)) lbad = 1;   // :178 assert / negative quota
+        if (!is_step) { quota = 0; if (i == ns) B = (u32)W; }
+        if (g.any(lbad != 0)) { deleg = true; break; }
+
+        // ---------------- phase 4: one lane per CIGAR op, inclusive prefix sums
+        {
+            u32 cE = 0, cQ = 0, cM = 0, cB = 0;
+            for (u32 j0 = 0; j0 < no; j0 += G) {
+                const u32 j = j0 + g.gl;
+                u32 vE = 0, vQ = 0, vM = 0, vB = 0;
+                if (j < no) {
+                    const u32 oo = minus ? no - 1 - j : j;
+                    const u32 lp = gm->opos[oo];
+                    const u32 ds = oo ? gm->opos[oo - 1] + 1u : ca;
+                    const u32 nd = lp - ds;
+                    const u32 k = (u32)rt[lp] - '=';
+                    if (k >= 28 || !((kOpMask >> k) & 1u) || nd == 0 || nd > 7 || (nd > 1 && rt[ds] == '0')) lbad = 1;
+                    else {
+                        u32 x = 0;
+                        for (u32 t = ds; t < lp; ++t) x = x * 10u + ((u32)rt[t] - '0');
+                        if (x == 0) lbad = 1;
+                        vB = x;
+                        vE = ((kTargetMask >> k) & 1u) ? x : 0u;
+                        vQ = ((kQueryMask >> k) & 1u) ? x : 0u;
+                        vM = ((kMatchMask >> k) & 1u) ? x : 0u;
+                    }
+                }
+                vE = g.incl_scan(vE) + cE; vQ = g.incl_scan(vQ) + cQ; vM = g.incl_scan(vM) + cM; vB = g.incl_scan(vB) + cB;
+                if (j < no) { gm->w.pEnd[j] = vE; gm->w.pQ[j] = vQ; gm->w.pNM[j] = vM; gm->w.pNB[j] = vB; }
+                cE = g.shfl(vE, G - 1); cQ = g.shfl(vQ, G - 1); cM = g.shfl(vM, G - 1); cB = g.shfl(vB, G - 1);
+            }
+        }
+        if (g.any(lbad != 0)) { deleg = true; break; }   // (also a group barrier for the prefix arrays)
+
+        // ---------------- phase 5: boundary i -> position in the op stream (lanes 0..ns)
+        u32 bj = 0, bt = 0, bCQ = 0, bCM = 0, bCB = 0;
+        bool bcut = false, bexh = false;
+        if (i <= ns && B != 0) {
+            u32 lo = 0, hi = no;
+            while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (gm->w.pEnd[mid] >= B) hi = mid; else lo = mid + 1; }
+            bj = lo;
+            if (bj == no) bexh = true;
+            else {
+                const u32 Ej = gm->w.pEnd[bj];
+                bt = bj ? gm->w.pEnd[bj - 1] : 0u;
+                const u32 off = B - bt;
+                const u32 k = (u32)rt[gm->opos[minus ? no - 1 - bj : bj]] - '=';
+                bCQ = (bj ? gm->w.pQ[bj - 1] : 0u) + (((kQueryMask >> k) & 1u) ? off : 0u);
+                bCM = (bj ? gm->w.pNM[bj - 1] : 0u) + (((kMatchMask >> k) & 1u) ? off : 0u);
+                bCB = (bj ? gm->w.pNB[bj - 1] : 0u) + off;
+                bcut = Ej > B;
+            }
+        }
+        // the end boundary of step i is the start boundary of step i+1
+        const u32 ej = g.down(bj, 1), et = g.down(bt, 1), eCQ = g.down(bCQ, 1), eCM = g.down(bCM, 1), eCB = g.down(bCB, 1);
+        const u32 eB = g.down(B, 1);
+        const bool eexh = g.down((u32)bexh, 1) != 0;
+        const bool live = is_step && quota > 0;
+        if (live && eexh) lbad = 1;   // :80 assert(cur_len > target_len): CIGAR shorter than the path
+        if (g.any(lbad != 0)) { deleg = true; break; }
+        const u32 q = live ? eCQ - bCQ : 0u, nm = live ? eCM - bCM : 0u, nb = live ? eCB - bCB : 0u;
+        u32 qtot;
+        const u32 qex = g.excl_scan(q, qtot);
+        const bool emit_line = live && nm > 0;   // :225
+
+        // pieces of the step: ops jS..jE (normalised order)
+        const u32 jS = (B == 0) ? 0u : (bcut ? bj : bj + 1u);
+        const bool cutS = B != 0 && bcut;
+        const u32 jE = ej;
+        const u32 lenE = eB - (et > B ? et : B);
+        u32 lenS = 0, mS = jS, mE = jE;   // verbatim middle tokens: [mS, mE)
+        u32 cglen = 0;
+        u32 mid_a = 0, mid_b = 0;         // their bytes in the record text
+        if (emit_line) {
+            if (jS < jE) {
+                if (cutS) { lenS = gm->w.pEnd[jS] - B; mS = jS + 1; cglen += dlen_u32(lenS, p10) + 1u; }
+                if (mS < mE) {
+                    const u32 o1 = minus ? no - mE : mS, o2 = minus ? no - 1 - mS : mE - 1;   // original index range [o1, o2]
+                    mid_a = o1 ? gm->opos[o1 - 1] + 1u : ca;
+                    mid_b = gm->opos[o2] + 1u;
+                    cglen += mid_b - mid_a;
+                }
+            }
+            cglen += dlen_u32(lenE, p10) + 1u;
+        }
+
+        // PAF columns (gaf2paf_main.cpp:214-217) and the line length
+        const i32 qlen = (i32)gm->hdr[H_QLEN], m_ = (i32)gm->hdr[H_M], b_ = (i32)gm->hdr[H_B], mapq = (i32)gm->hdr[H_MAPQ];
+        const u32 qn_b = gm->hdr[H_QN_B];
+        const u32 tp_a = gm->hdr[H_TP_A], tp_b = gm->hdr[H_TP_B], rc_a = gm->hdr[H_RC_A], rc_b = gm->hdr[H_RC_B];
+        u8 gi[8];
+        const u32 gi_n = gi_fast(m_, b_, gi);
+        if (gi_n == 0) { deleg = true; break; }   // uniform: same m, b in the whole group
+        const i32 so2 = rev ? eo : so, eo2 = rev ? so : eo;
+        const u32 q0 = (u32)qs + qex, q1 = q0 + q;
+        const u32 ts = (u32)(sa + so2), te = (u32)(se - eo2);
+        u32 line = 0;
+        if (emit_line) {
+            line = qn_b + dlen_i32(qlen, p10) + 12u + dlen_i32(mapq, p10) + (tp_b ? 4u + (tp_b - tp_a) : 0u) + (rc_b ? 4u + (rc_b - rc_a) : 0u) +
+                   6u + dlen_i32(m_, p10) + 6u + dlen_i32(b_, p10) + 6u + gi_n + 6u + 1u +
+                   nl + cglen + dlen_u32(q0, p10) + dlen_u32(q1, p10) + dlen_u32((u32)tlen, p10) + dlen_u32(ts, p10) + dlen_u32(te, p10) +
+                   dlen_u32(nm, p10) + dlen_u32(nb, p10);
+        }
+        const u32 loff = g.excl_scan(line, size);
+
+        if (EMIT) {
+            if (size != osize) break;   // cannot happen: both passes run the same code
+            const bool staged = size <= kSOutCap;
+            const u32 pad = (u32)(o & 15u);
+            g.sync();   // the staging buffer aliases tabs / prefix arrays: everyone is done reading them
+            if (emit_line) {
+                u8* p = staged ? gm->out + pad + loff : a.out + o + loff;
+                p = put_bytes(p, rt, qn_b); *p++ = '\t';
+                p = put_i32(p, qlen, p10); *p++ = '\t';
+                p = put_u32(p, q0, p10); *p++ = '\t';
+                p = put_u32(p, q1, p10); *p++ = '\t';
+                *p++ = rev ? '-' : '+'; *p++ = '\t';
+                p = put_bytes(p, rt + name_a, nl); *p++ = '\t';
+                p = put_u32(p, (u32)tlen, p10); *p++ = '\t';
+                p = put_u32(p, ts, p10); *p++ = '\t';
+                p = put_u32(p, te, p10); *p++ = '\t';
+                p = put_u32(p, nm, p10); *p++ = '\t';
+                p = put_u32(p, nb, p10); *p++ = '\t';
+                p = put_i32(p, mapq, p10);
+                if (tp_b) { p[0] = '\t'; p[1] = 't'; p[2] = 'p'; p[3] = ':'; p = put_bytes(p + 4, rt + tp_a, tp_b - tp_a); }
+                if (rc_b) { p[0] = '\t'; p[1] = 'r'; p[2] = 'c'; p[3] = ':'; p = put_bytes(p + 4, rt + rc_a, rc_b - rc_a); }
+                p = put_tag(p, 'g', 'm', 'i'); p = put_i32(p, m_, p10);
+                p = put_tag(p, 'g', 'l', 'i'); p = put_i32(p, b_, p10);
+                p = put_tag(p, 'g', 'i', 'f'); p = put_bytes(p, gi, gi_n);
+                p = put_tag(p, 'c', 'g', 'Z');
+                // pieces, reversed for '<' steps (gaf2paf_main.cpp:184-211)
+                const u8 codeE = rt[gm->opos[minus ? no - 1 - jE : jE]];
+                const u8 codeS = cutS && jS < jE ? rt[gm->opos[minus ? no - 1 - jS : jS]] : 0;
+                if (!rev) {
+                    if (codeS) { p = put_u32(p, lenS, p10); *p++ = codeS; }
+                } else {
+                    p = put_u32(p, lenE, p10); *p++ = codeE;
+                }
+                if (mid_b > mid_a) {
+                    if (rev == minus) p = put_bytes(p, rt + mid_a, mid_b - mid_a);   // text order == output order
+                    else {
+                        u32 t1 = mid_b;   // token by token, backwards
+                        while (t1 > mid_a) {
+                            u32 t0 = t1 - 1;
+                            while (t0 > mid_a && rt[t0 - 1] <= '9') --t0;
+                            p = put_bytes(p, rt + t0, t1 - t0);
+                            t1 = t0;
+                        }
+                    }
+                }
+                if (!rev) { p = put_u32(p, lenE, p10); *p++ = codeE; }
+                else if (codeS) { p = put_u32(p, lenS, p10); *p++ = codeS; }
+                *p++ = '\n';
+            }
+            if (staged) {
+                g.sync();
+                const u32 total = pad + size;
+                u8* gbase = a.out + (o - pad);
+                const u32 full_b = total >> 4;
+                for (u32 u = (pad ? 1u : 0u) + g.gl; u < full_b; u += G)
+                    reinterpret_cast<uint4*>(gbase)[u] = reinterpret_cast<const uint4*>(gm->out)[u];
+                const u32 head_end = pad ? (total < 16u ? total : 16u) : 0u;
+                for (u32 b = pad + g.gl; b < head_end; b += G) gbase[b] = gm->out[b];
+                const u32 tail_a = full_b * 16u > head_end ? full_b * 16u : head_end;
+                for (u32 b = tail_a + g.gl; b < total; b += G) gbase[b] = gm->out[b];
+            }
+        }
+    } while (0);
+
+    if (!EMIT && g.gl == 0) {
+        if (deleg) {
+            a.status[r] = ST_OK;   // overwritten by the general kernel
+            a.out_off[r] = 0;
+            a.deleg_list[atomicAdd(a.n_deleg, 1u)] = r;
+        } else {
+            a.status[r] = status;
+            a.out_off[r] = size;
+        }
+    }
+}
+
+}  // namespace g2p

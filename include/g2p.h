@@ -61,6 +61,8 @@ typedef struct g2p_result {
     float emit_ms;          /* CUDA-event time of the emit kernel alone */
     float size_ms;          /* CUDA-event time of the size kernel alone */
     float index_ms;         /* CUDA-event time of the line index kernels */
+    uint32_t n_delegated;   /* records converted by the general (slow) kernel instead of the short-record kernel */
+    uint32_t reserved;
 } g2p_result;
 
 /* Context bound to one CUDA device. */

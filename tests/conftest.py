@@ -21,6 +21,7 @@ def _built():
         os.path.join(ROOT, "cactus-gfa-tools_b200", "lib", "libg2p.so"),
         os.path.join(ROOT, "build", "libgafgen.so"),
         os.path.join(ROOT, "build", "g2p_hostsim"),
+        os.path.join(ROOT, "build", "g2p_simt"),
     ]
     if not all(os.path.exists(p) for p in need):
         subprocess.check_call(["make", "-C", ROOT], stdout=subprocess.DEVNULL)

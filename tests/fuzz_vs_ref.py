@@ -105,7 +105,10 @@ def mutate(rnd, line):
 
 
 def run(binary, lp, data):
-    p = subprocess.run([binary, "-", "-l", lp], input=data, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    try:
+        p = subprocess.run([binary, "-", "-l", lp], input=data, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=20)
+    except subprocess.TimeoutExpired:
+        return 999, b"", b"TIMEOUT"
     rc = p.returncode
     if rc < 0:
         rc = 128 - rc

@@ -1,0 +1,107 @@
+// g2p_simt — the device pipeline (line index, k_short, k_convert_list, scan, emit) executed on
+// the CPU by the SIMT emulator in cuda_shim.hpp.
+//
+// TEST INFRASTRUCTURE ONLY (never linked into libg2p.so or the executables).  The launch
+// sequence below mirrors g2p_convert_device (g2p_capi.cu); the kernels are the product's own
+// sources compiled for the host.  It lets CPU-only CI run the warp-cooperative kernels against
+// the oracle, and lets a kernel bug be debugged with gdb/ASan instead of GPU round trips.
+//
+// usage: g2p_simt -l lengths.tsv <gaf|-> [gaf2 ...]     (stdout / exit code as gaf2paf)
+//        G2P_SIMT_STATS=1 prints "records delegated" to stderr
+#define HS_IMPLEMENTATION
+#include "cuda_shim.hpp"
+
+#include <string>
+
+#include "../../cactus-gfa-tools_b200/csrc/g2p_kernels.cuh"
+#include "../../cactus-gfa-tools_b200/csrc/g2p_table.hpp"
+
+using namespace g2p;
+
+static bool slurp(const char* path, std::string& out) {
+    FILE* f = std::strcmp(path, "-") == 0 ? stdin : std::fopen(path, "rb");
+    if (!f) return false;
+    char buf[1 << 16];
+    size_t k;
+    while ((k = std::fread(buf, 1, sizeof buf, f)) > 0) out.append(buf, k);
+    if (f != stdin) std::fclose(f);
+    return true;
+}
+
+int main(int argc, char** argv) {
+    const char* lengths = nullptr;
+    std::vector<const char*> inputs;
+    for (int i = 1; i < argc; ++i) {
+        if (!std::strcmp(argv[i], "-l") && i + 1 < argc) lengths = argv[++i];
+        else inputs.push_back(argv[i]);
+    }
+    if (!lengths || inputs.empty()) { std::fprintf(stderr, "usage: g2p_simt -l lengths.tsv <gaf> ...\n"); return 1; }
+    std::string tsv;
+    if (!slurp(lengths, tsv)) { std::fprintf(stderr, "[gaf2paf] error: unable to open %s\n", lengths); return 1; }
+    HostLenTable table;
+    if (build_len_table(tsv.data(), tsv.size(), table) != ST_OK) { std::fprintf(stderr, "abort: lengths table\n"); return 134; }
+    const LenTableView T = table.view();
+
+    std::string gaf_s;
+    for (const char* p : inputs) {
+        if (!slurp(p, gaf_s)) { std::fprintf(stderr, "[gaf2paf] error: unable to open input: %s\n", p); return 1; }
+        if (!gaf_s.empty() && gaf_s.back() != '\n') gaf_s.push_back('\n');
+    }
+    const u64 n = gaf_s.size();
+    // 16-byte aligned copy with slack, like a device allocation
+    std::vector<uint4> gaf_buf((n + 15) / 16 + 4);
+    u8* gaf = reinterpret_cast<u8*>(gaf_buf.data());
+    std::memcpy(gaf, gaf_s.data(), n);
+
+    PipelineMeta meta;
+    std::memset(&meta, 0, sizeof meta);
+    const u32 ntiles = (u32)((n + kIdxTile - 1) / kIdxTile);
+    std::vector<u32> tiles(ntiles + 1);
+    if (ntiles) hs::launch(dim3(ntiles), dim3(kIdxThreads), 0, [&] { k_count_lines(gaf, n, tiles.data()); });
+    hs::launch(dim3(1), dim3(1024), 0, [&] { k_scan_tiles(tiles.data(), ntiles, gaf, n, &meta); });
+    const u32 nrec = meta.n_records;
+    std::vector<u32> rec(nrec + 2);
+    if (ntiles) hs::launch(dim3(ntiles), dim3(kIdxThreads), 0, [&] { k_fill_lines(gaf, n, tiles.data(), rec.data(), &meta); });
+    if (nrec == 0) return 0;
+
+    std::vector<u32> status(nrec), list(nrec);
+    std::vector<u64> off(nrec + 1);
+    const u32 nscan = (nrec + kScanTile - 1) / kScanTile;
+    std::vector<u64> blocks(nscan);
+    const u32 ncta = (nrec + kShortRecsPerCta - 1) / kShortRecsPerCta;
+    const u32 nlist = std::min<u32>((nrec + kListThreads - 1) / kListThreads, 8u);
+    ShortArgs sa{gaf, n, rec.data(), nrec, T, off.data(), status.data(), nullptr, list.data(), &meta.n_deleg};
+    hs::launch(dim3(ncta), dim3(kSThreads), kShortSmem, [&] { k_short<kSG, false>(sa); });
+    hs::launch(dim3(nlist), dim3(kListThreads), 0, [&] { k_convert_list<false>(gaf, rec.data(), T, off.data(), status.data(), nullptr, &meta, list.data()); });
+    hs::launch(dim3(nscan), dim3(kScanThreads), 0, [&] { k_scan_reduce(off.data(), nrec, blocks.data()); });
+    hs::launch(dim3(1), dim3(1024), 0, [&] { k_scan_blocks(blocks.data(), nscan, &meta); });
+    hs::launch(dim3(nscan), dim3(kScanThreads), 0, [&] { k_scan_apply(off.data(), nrec, blocks.data(), &meta); });
+    std::vector<u8> out(meta.out_total + 256, 0xEE);
+    sa.out = out.data();
+    hs::launch(dim3(ncta), dim3(kSThreads), kShortSmem, [&] { k_short<kSG, true>(sa); });
+    if (meta.n_deleg)
+        hs::launch(dim3(nlist), dim3(kListThreads), 0, [&] { k_convert_list<true>(gaf, rec.data(), T, off.data(), status.data(), out.data(), &meta, list.data()); });
+    u64 out_bytes = meta.out_total;
+    if (meta.first_err != 0xFFFFFFFFu) {
+        hs::launch(dim3(1), dim3(1), 0, [&] { k_diagnose(gaf, rec.data(), T, off.data(), &meta); });
+        out_bytes = meta.err_out_end;
+    }
+    if (std::getenv("G2P_SIMT_STATS")) std::fprintf(stderr, "g2p_simt: %u records, %u delegated, %llu bytes out\n", nrec, meta.n_deleg, (unsigned long long)out_bytes);
+    std::fwrite(out.data(), 1, out_bytes, stdout);
+    std::fflush(stdout);
+    if (meta.first_err != 0xFFFFFFFFu) {
+        const u32 st = meta.err_status & 0xff;
+        if (st == ST_ERR_NAME) {
+            std::string nm((const char*)gaf + meta.err_rec_start + meta.err_a, meta.err_b - meta.err_a);
+            std::fprintf(stderr, "[gaf2paf] error: unable to find %s in lengths map\n", nm.c_str());
+            return 1;
+        }
+        if (st == ST_ERR_NOCG) {
+            std::fprintf(stderr, "[gaf2paf] error: cg cigar not found. This tool only works on output of minigraph -c\n");
+            return 1;
+        }
+        std::fprintf(stderr, "abort: record %u status %u aux %u\n", meta.first_err, st, (meta.err_status >> 8) & 0xff);
+        return 134;
+    }
+    return 0;
+}

@@ -10,6 +10,7 @@ import helpers as H
 
 PORT = os.path.join(H.ORACLE_BIN, "gaf2paf_oracle")
 HOSTSIM = os.path.join(H.BUILD, "g2p_hostsim")
+SIMT = os.path.join(H.BUILD, "g2p_simt")   # the CUDA kernels themselves, run by the SIMT emulator (tests/hostsim/cuda_shim.hpp)
 REF = os.path.join(H.REF_BIN, "gaf2paf")
 
 
@@ -37,6 +38,11 @@ def test_device_code_on_host_matches_golden():
     _run_vectors(HOSTSIM)
 
 
+def test_kernels_under_simt_emulator_match_golden():
+    """k_short / k_convert_list / scans / index kernels, executed warp-accurately on the CPU."""
+    _run_vectors(SIMT)
+
+
 @pytest.mark.skipif(not os.path.exists(REF), reason="reference build (oracle/_ref) not present")
 def test_reference_binary_matches_golden():
     _run_vectors(REF)
@@ -61,6 +67,8 @@ def test_differential_synthetic(name, count, over):
         rc_h, out_h, _ = H.run_tool(HOSTSIM, ["-", "-l", lp], gaf)
         assert rc_p == 0 and rc_h == 0
         assert out_p == out_h
+        rc_s, out_s, _ = H.run_tool(SIMT, ["-", "-l", lp], gaf)
+        assert rc_s == 0 and out_s == out_p
         assert out_p.count(b"\n") > 0
         if os.path.exists(REF):
             rc_r, out_r, _ = H.run_tool(REF, ["-", "-l", lp], gaf)
