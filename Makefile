@@ -37,7 +37,10 @@ $(BUILD)/gafgen: tools/gafgen.cpp
 	@mkdir -p $(BUILD)
 	$(CXX) $(CXXFLAGS) -DGAFGEN_MAIN -pthread -o $@ $<
 
-hostsim: $(BUILD)/g2p_hostsim $(BUILD)/g2p_simt
+hostsim: $(BUILD)/g2p_hostsim $(BUILD)/g2p_simt $(BUILD)/g2p_simt_long
+$(BUILD)/g2p_simt_long: tests/hostsim/g2p_simt.cpp tests/hostsim/cuda_shim.hpp $(HDRS)
+	@mkdir -p $(BUILD)
+	$(CXX) -O1 -g -std=c++17 -ffp-contract=off -Wall -Wno-unused-function -Wno-unknown-pragmas -DG2P_S_LIMIT=0 -Itests/hostsim -o $@ $<
 $(BUILD)/g2p_simt: tests/hostsim/g2p_simt.cpp tests/hostsim/cuda_shim.hpp $(HDRS)
 	@mkdir -p $(BUILD)
 	$(CXX) -O1 -g -std=c++17 -ffp-contract=off -Wall -Wno-unused-function -Wno-unknown-pragmas -Itests/hostsim -o $@ $<

@@ -60,7 +60,7 @@ class Result(ctypes.Structure):
         ("size_ms", ctypes.c_float),
         ("index_ms", ctypes.c_float),
         ("n_delegated", ctypes.c_uint32),
-        ("reserved", ctypes.c_uint32),
+        ("n_long", ctypes.c_uint32),
     ]
 
 

@@ -61,7 +61,7 @@ struct g2p_ctx {
     uint64_t table_entries = 0;
     bool have_table = false;
     // work buffers
-    DevBuf d_in, d_tiles, d_rec, d_status, d_off, d_blocks, d_out, d_meta, d_list;
+    DevBuf d_in, d_tiles, d_rec, d_status, d_off, d_blocks, d_out, d_meta, d_list, d_list2;
     int n_sm = 148;
     PinBuf h_out, h_meta;
     cudaStream_t own_stream = nullptr;
@@ -93,6 +93,8 @@ int g2p_create(int device, g2p_ctx** out) {
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
     cudaFuncSetAttribute(k_short<kSG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShortSmem);
     cudaFuncSetAttribute(k_short<kSG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShortSmem);
+    cudaFuncSetAttribute(k_long<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmem);
+    cudaFuncSetAttribute(k_long<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmem);
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
     if (ctx->d_meta.ensure(sizeof(PipelineMeta)) != cudaSuccess || ctx->h_meta.ensure(sizeof(PipelineMeta)) != cudaSuccess) {
         delete ctx;
@@ -107,7 +109,7 @@ void g2p_destroy(g2p_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (DevBuf* b : {&ctx->d_slots, &ctx->d_arena, &ctx->d_in, &ctx->d_tiles, &ctx->d_rec, &ctx->d_status, &ctx->d_off, &ctx->d_blocks,
-                      &ctx->d_out, &ctx->d_meta, &ctx->d_list})
+                      &ctx->d_out, &ctx->d_meta, &ctx->d_list, &ctx->d_list2})
         b->release();
     ctx->h_out.release();
     ctx->h_meta.release();
@@ -223,15 +225,21 @@ int g2p_convert_device(g2p_ctx* ctx, const void* d_gaf_v, size_t n, void** d_out
     u64* d_off = static_cast<u64*>(ctx->d_off.p);
     u64* d_blocks = static_cast<u64*>(ctx->d_blocks.p);
     G2P_CUDA(ctx->d_list.ensure((size_t)nrec * sizeof(u32)));
+    G2P_CUDA(ctx->d_list2.ensure((size_t)nrec * sizeof(u32)));
     u32* d_list = static_cast<u32*>(ctx->d_list.p);
+    u32* d_list2 = static_cast<u32*>(ctx->d_list2.p);
     const u32 ncta = (nrec + kShortRecsPerCta - 1) / kShortRecsPerCta;
+    const u32 nlong = (u32)ctx->n_sm * 4u;
     const u32 nlist = std::min<u32>((nrec + kListThreads - 1) / kListThreads, (u32)ctx->n_sm * 16u);
     ShortArgs sa{d_gaf, (u64)n, d_rec, nrec, ctx->table, d_off, d_status, nullptr, d_list, &d_meta->n_deleg};
+    LongArgs la{d_gaf, (u64)n, d_rec, ctx->table, d_off, d_status, nullptr, d_list, &d_meta->n_deleg, d_list2, &d_meta->n_deleg2};
 
-    // pass 1: sizes + status (fast kernel, then the general kernel on what it delegated)
+    // pass 1: sizes + status.  k_short takes the short canonical records, k_long what it left,
+    // the general kernel what neither converts (non-canonical or erroneous records).
     k_short<kSG, false><<<ncta, kSThreads, kShortSmem, st>>>(sa);
-    k_convert_list<false><<<nlist, kListThreads, 0, st>>>(d_gaf, d_rec, ctx->table, d_off, d_status, nullptr, d_meta, d_list);
-    launches += 2;
+    k_long<false><<<nlong, kLThreads, kLongSmem, st>>>(la);
+    k_convert_list<false><<<nlist, kListThreads, 0, st>>>(d_gaf, d_rec, ctx->table, d_off, d_status, nullptr, d_meta, d_list2, &d_meta->n_deleg2);
+    launches += 3;
     G2P_CUDA(cudaEventRecord(ctx->ev[2], st));
     // exclusive scan -> offsets
     k_scan_reduce<<<nscan, kScanThreads, 0, st>>>(d_off, nrec, d_blocks);
@@ -241,16 +249,22 @@ int g2p_convert_device(g2p_ctx* ctx, const void* d_gaf_v, size_t n, void** d_out
     G2P_CUDA(cudaMemcpyAsync(hm, d_meta, sizeof(PipelineMeta), cudaMemcpyDeviceToHost, st));
     G2P_CUDA(cudaStreamSynchronize(st));
     const u64 out_total = hm->out_total;
-    res->n_delegated = hm->n_deleg;
+    res->n_long = hm->n_deleg;
+    res->n_delegated = hm->n_deleg2;
     G2P_CUDA(ctx->d_out.ensure(out_total + 256));
     u8* d_o = static_cast<u8*>(ctx->d_out.p);
     // pass 2: emit
     G2P_CUDA(cudaEventRecord(ctx->ev[3], st));
     sa.out = d_o;
+    la.out = d_o;
     k_short<kSG, true><<<ncta, kSThreads, kShortSmem, st>>>(sa);
     ++launches;
     if (hm->n_deleg) {
-        k_convert_list<true><<<nlist, kListThreads, 0, st>>>(d_gaf, d_rec, ctx->table, d_off, d_status, d_o, d_meta, d_list);
+        k_long<true><<<nlong, kLThreads, kLongSmem, st>>>(la);
+        ++launches;
+    }
+    if (hm->n_deleg2) {
+        k_convert_list<true><<<nlist, kListThreads, 0, st>>>(d_gaf, d_rec, ctx->table, d_off, d_status, d_o, d_meta, d_list2, &d_meta->n_deleg2);
         ++launches;
     }
     G2P_CUDA(cudaEventRecord(ctx->ev[4], st));

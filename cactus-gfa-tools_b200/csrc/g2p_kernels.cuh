@@ -1,9 +1,9 @@
 // g2p_kernels.cuh — sm_100a kernels of the GAF -> PAF pipeline.
 //
 //   k_count_lines / k_scan_tiles / k_fill_lines   newline index (record start offsets)
-//   k_short<G,false> + k_convert_list<false>       pass 1: per-record PAF byte length + status
+//   k_short / k_long / k_convert_list <false>      pass 1: per-record PAF byte length + status
 //   k_scan_*                                       exclusive scan of the lengths -> output offsets
-//   k_short<G,true> + k_convert_list<true>         pass 2: write the PAF bytes
+//   k_short / k_long / k_convert_list <true>       pass 2: write the PAF bytes
 //   k_diagnose                                     details of the first failing record
 //
 // All work is byte / integer; the pipeline is bound by HBM traffic and by the
@@ -19,6 +19,7 @@
 
 #include "g2p_core.cuh"
 #include "g2p_short.cuh"
+#include "g2p_long.cuh"
 
 namespace g2p {
 
@@ -33,8 +34,8 @@ struct PipelineMeta {
     u32 err_a, err_b;  // name span relative to the record start
     u32 err_rec_start;
     u64 err_out_end;   // output offset just after the failing record's (partial) output
-    u32 n_deleg;       // records k_short left to the general kernel
-    u32 pad2;
+    u32 n_deleg;       // records k_short left to k_long
+    u32 n_deleg2;      // records k_long left to the general kernel
 };
 
 // ------------------------------------------------------------------------------
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(u32* __restrict__ tile_coun
         meta->out_total = 0;
         meta->err_status = 0;
         meta->n_deleg = 0;
+        meta->n_deleg2 = 0;
     }
 }
 
@@ -229,7 +231,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_apply(u64* __restrict__ x
 // ------------------------------------------------------------------------------
 // General per-record conversion: one thread walks one record with the streaming state
 // machine of g2p_core.cuh (any record length, every error path of the reference).  It
-// runs over the list of records that k_short (g2p_short.cuh) delegated.
+// runs over the list of records that k_short / k_long (g2p_short.cuh, g2p_long.cuh) delegated.
 // ------------------------------------------------------------------------------
 constexpr int kListThreads = 64;
 
@@ -241,8 +243,8 @@ __device__ G2P_NOINLINE u32 convert_record_global(const u8* r, u32 len, const Le
 template <bool EMIT>
 __global__ void __launch_bounds__(kListThreads) k_convert_list(const u8* __restrict__ gaf, const u32* __restrict__ rec_start, LenTableView T,
                                                                u64* __restrict__ out_off, u32* __restrict__ status, u8* __restrict__ out,
-                                                               PipelineMeta* __restrict__ meta, const u32* __restrict__ list) {
-    const u32 nd = meta->n_deleg;
+                                                               PipelineMeta* __restrict__ meta, const u32* __restrict__ list, const u32* __restrict__ n_list) {
+    const u32 nd = *n_list;
     for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < nd; k += gridDim.x * blockDim.x) {
         const u32 r = list[k];
         const u32 s = rec_start[r], len = rec_start[r + 1] - s - 1;

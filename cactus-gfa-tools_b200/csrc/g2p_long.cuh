@@ -1,0 +1,518 @@
+// g2p_long.cuh — the streaming conversion kernel for records k_short does not take: anything
+// longer than kSLimit bytes or with more steps / ops than fit one 8-lane group, up to
+// chromosome-scale assembly records (10^4 path steps, 10^5 CIGAR ops, hundreds of kB of text).
+//
+// One warp owns one record and never materialises it.  Two token streams run over the record
+// text in global memory, forwards for '+' records and backwards for '-' records (flip_gaf,
+// gaf2paf_main.cpp:92-131, becomes a change of direction):
+//   step stream   '>' / '<' markers of the path column  (gafkluge.hpp:118-158)
+//   op stream     op letters of the cg:Z: value          (for_each_cg, gafkluge.hpp:226-239)
+// Each refill classifies 512 bytes (16 per lane, SWAR compares), ranks the hits with a shuffle
+// prefix sum and scatters their positions into a shared ring.  Steps are consumed 31 at a time
+// (one lane per step: token parse, table probe, quota), ops 32 at a time (one lane per op, four
+// 64-bit shuffle prefix sums carried from window to window).  The split of the CIGAR at step
+// boundaries (cigar_next_by_target, gaf2paf_main.cpp:71-90) is a
+// merge of two sorted sequences: a boundary B is resolved by a shuffle binary search in the
+// first op window whose cumulative target length reaches it; the window only advances when an
+// unresolved boundary lies beyond it.  State carried between windows / batches is O(1).
+// PAF lines of a batch are formatted one per lane into a shared staging buffer and flushed with
+// 128-bit stores.
+//
+// Like k_short, the kernel converts only canonical records and delegates everything else
+// (including every error path of the reference) to the general kernel k_convert_list.
+#pragma once
+#include "g2p_short.cuh"
+
+namespace g2p {
+
+enum : u32 { ST_F_LONG = 0x20000u };   // status flag: record was converted by k_long
+
+constexpr int kLWarps = 4;
+constexpr int kLThreads = kLWarps * 32;
+constexpr u32 kLRing = 512;      // ring entries (power of two, >= 33 + 256)
+constexpr u32 kLChunk = 512;     // bytes classified per refill
+constexpr u32 kLBatch = 31;      // steps per batch; the next lane holds the batch's end boundary
+constexpr u32 kLOutCap = 8192;   // staged PAF bytes per batch
+
+struct __align__(16) LWarpMem {
+    u32 sring[kLRing];
+    u32 oring[kLRing];
+    u32 tabs[32];
+    u32 hdr[H_N];
+    u32 tkeys[kSMaxTags];
+    u8 out[kLOutCap + 16];
+};
+static_assert(sizeof(LWarpMem) % 16 == 0, "warp slices must keep 16-byte alignment");
+constexpr size_t kLongSmem = sizeof(LWarpMem) * kLWarps;
+
+__device__ __forceinline__ u32 range16u(u32 lo, u32 hi) {   // bits [lo, hi), both clamped to 16
+    lo = lo > 16u ? 16u : lo;
+    hi = hi > 16u ? 16u : hi;
+    return hi > lo ? (((1u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u;
+}
+__device__ __forceinline__ u32 wscan32(u32 v, u32 lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= (u32)d) v += t; }
+    return v;
+}
+__device__ __forceinline__ u64 wscan64(u64 v, u32 lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const u64 t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= (u32)d) v += t; }
+    return v;
+}
+
+// 16 bytes of global text from an arbitrary offset (gaf itself is 16-byte aligned).
+__device__ __forceinline__ void ldg16_unaligned(const u8* gaf, u32 off, u32& w0, u32& w1, u32& w2, u32& w3) {
+    const u32* q = reinterpret_cast<const u32*>(gaf + (off & ~3u));
+    const u32 sh = (off & 3u) * 8u;
+    const u32 x0 = __ldg(q), x1 = __ldg(q + 1), x2 = __ldg(q + 2), x3 = __ldg(q + 3), x4 = __ldg(q + 4);
+    w0 = __funnelshift_r(x0, x1, sh); w1 = __funnelshift_r(x1, x2, sh);
+    w2 = __funnelshift_r(x2, x3, sh); w3 = __funnelshift_r(x3, x4, sh);
+}
+
+// Positions (absolute offsets into the GAF buffer) of the marker / non-digit bytes of a text span,
+// produced chunk by chunk in stream order into a shared ring.  All members are warp-uniform.
+template <bool MARKERS>
+struct TokStream {
+    u32* ring;
+    u32 lo, hi;        // span [lo, hi)
+    u32 cur;           // base of the next chunk (multiple of kLChunk)
+    u32 head, count;
+    bool bwd, done;
+
+    __device__ __forceinline__ void init(u32* ring_, u32 lo_, u32 hi_, bool bwd_) {
+        ring = ring_; lo = lo_; hi = hi_; bwd = bwd_;
+        head = count = 0;
+        done = hi_ <= lo_;
+        cur = done ? 0u : (bwd_ ? ((hi_ - 1u) & ~(kLChunk - 1u)) : (lo_ & ~(kLChunk - 1u)));
+    }
+    __device__ __forceinline__ void refill(const u8* gaf, u64 n, u32 lane) {
+        const u32 off = cur + 16u * lane;
+        u32 m = 0;
+        if (off < hi && off + 16u > lo) {
+            const uint4 v = ldg_vec_guarded(gaf, off, n);
+            const u32 w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                m |= movemask4(MARKERS ? zero_bytes((w[k] & 0xFDFDFDFDu) ^ 0x3C3C3C3Cu) : nondigit_bytes(w[k])) << (4 * k);
+            m &= range16u(lo > off ? lo - off : 0u, hi - off);
+        }
+        const u32 cnt = (u32)__popc(m);
+        const u32 incl = wscan32(cnt, lane);
+        const u32 total = __shfl_sync(0xffffffffu, incl, 31);
+        if (!bwd) {
+            u32 k = head + count + incl - cnt;
+            while (m) { const u32 b = (u32)__ffs((int)m) - 1u; m &= m - 1u; ring[k & (kLRing - 1u)] = off + b; ++k; }
+        } else {
+            u32 k = head + count + (total - incl);
+            while (m) { const u32 b = 31u - (u32)__clz((int)m); m &= ~(1u << b); ring[k & (kLRing - 1u)] = off + b; ++k; }
+        }
+        count += total;
+        if (!bwd) { if (hi - cur <= kLChunk) done = true; else cur += kLChunk; }
+        else { if (cur <= lo) done = true; else cur -= kLChunk; }
+        __syncwarp();
+    }
+    __device__ __forceinline__ void ensure(u32 need, const u8* gaf, u64 n, u32 lane) {
+        while (count < need && !done) refill(gaf, n, lane);
+    }
+    __device__ __forceinline__ u32 at(u32 k) const { return ring[(head + k) & (kLRing - 1u)]; }
+    __device__ __forceinline__ void pop(u32 k) { head = (head + k) & (kLRing - 1u); count -= k; }
+};
+
+struct StepTok2 {
+    u32 name_a, nl;   // absolute offset / length of the name
+    i32 tlen, sa, se;
+};
+
+// One path step token [p, q) (p = its marker, or pa-1 for an unprefixed path): name, optional
+// ":start-end", table probe.  Returns the lane's "not canonical" flag.
+__device__ __forceinline__ u32 parse_step_global(const u8* gaf, u64 n, const LenTableView& T, u32 p, u32 q, bool prefixed, StepTok2& t) {
+    t.name_a = p + 1;
+    const u32 tl = q - t.name_a;
+    t.nl = tl; t.tlen = 0; t.sa = 0; t.se = 0;
+    if ((u64)t.name_a + 24 > n) return 1;
+    u32 w0, w1, w2, w3;
+    ldg16_unaligned(gaf, t.name_a, w0, w1, w2, w3);
+    bool interval = false;
+    if (prefixed) {
+        u32 cm = movemask4(zero_bytes(w0 ^ 0x3A3A3A3Au)) | (movemask4(zero_bytes(w1 ^ 0x3A3A3A3Au)) << 4) |
+                 (movemask4(zero_bytes(w2 ^ 0x3A3A3A3Au)) << 8) | (movemask4(zero_bytes(w3 ^ 0x3A3A3A3Au)) << 12);
+        cm &= tl >= 16 ? 0xffffu : ((1u << tl) - 1u);
+        if (cm) { t.nl = (u32)__ffs((int)cm) - 1u; interval = true; }
+    }
+    if (t.nl == 0 || t.nl > 16) return 1;
+    const int nl = (int)t.nl;
+    w0 = keep_bytes(w0, nl); w1 = keep_bytes(w1, nl - 4); w2 = keep_bytes(w2, nl - 8); w3 = keep_bytes(w3, nl - 12);
+    i64 tl64 = 0;
+    if (!table_lookup_key16(T, (u64)w0 | ((u64)w1 << 32), (u64)w2 | ((u64)w3 << 32), t.nl, tl64)) return 1;
+    if (tl64 < 0 || tl64 > 0x7fffffffLL) return 1;
+    t.tlen = (i32)tl64;
+    t.se = t.tlen;
+    if (interval) {
+        u32 k = t.name_a + t.nl + 1, x = 0, nd = 0;
+        while (k < q && nd < 10) { const u32 d = (u32)gaf[k] - '0'; if (d > 9) break; x = x * 10u + d; ++nd; ++k; }
+        if (nd == 0 || nd > 9 || k >= q || gaf[k] != '-') return 1;
+        t.sa = (i32)x;
+        ++k; x = 0; nd = 0;
+        while (k < q && nd < 10) { const u32 d = (u32)gaf[k] - '0'; if (d > 9) break; x = x * 10u + d; ++nd; ++k; }
+        if (nd == 0 || nd > 9 || k != q) return 1;
+        t.se = (i32)x;
+    }
+    return t.se < t.sa ? 1u : 0u;
+}
+
+struct LongArgs {
+    const u8* gaf;
+    u64 n;
+    const u32* rec_start;
+    LenTableView T;
+    u64* out_off;
+    u32* status;
+    u8* out;
+    const u32* list;       // records to convert (delegated by k_short)
+    const u32* n_list;
+    u32* deleg_list;       // size pass: records left to the general kernel
+    u32* n_deleg;
+};
+
+template <bool EMIT>
+__device__ __forceinline__ void long_record(const LongArgs& a, LWarpMem* wm, const u32 r, const u32 lane, const u32* p10) {
+    const u32 FULL = 0xffffffffu;
+    const Grp<32> g;
+    const u8* gaf = a.gaf;
+    const u32 s = a.rec_start[r], len = a.rec_start[r + 1] - s - 1;
+    const u8* rt = gaf + s;
+    u64 o = 0, osize = 0;
+    if (EMIT) {
+        if (!(a.status[r] & ST_F_LONG)) return;
+        o = a.out_off[r];
+        osize = a.out_off[r + 1] - o;
+        if (osize == 0) return;
+    }
+    bool deleg = false;
+    u64 size = 0;
+    u32 status = ST_OK | ST_F_LONG;
+    do {
+        if (len == 0) { deleg = true; break; }
+        if (rt[0] == '*') { status = ST_SKIP | ST_F_LONG; break; }
+        // ---------------- tabs
+        u32 nt = 0;
+        {
+            const u64 end = (u64)s + len;
+            for (u64 base = s & ~(kLChunk - 1u); base < end; base += kLChunk) {
+                const u64 off = base + 16u * lane;
+                u32 m = 0;
+                if (off < end && off + 16 > s) {
+                    const uint4 v = ldg_vec_guarded(gaf, off, a.n);
+                    const u32 w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) m |= movemask4(zero_bytes(w[k] ^ 0x09090909u)) << (4 * k);
+                    m &= range16u(s > off ? (u32)(s - off) : 0u, (u32)(end - off > 16 ? 16 : end - off));
+                }
+                if (!__any_sync(FULL, m != 0)) continue;
+                const u32 cnt = (u32)__popc(m);
+                const u32 incl = wscan32(cnt, lane);
+                u32 k = nt + incl - cnt;
+                while (m) { const u32 b = (u32)__ffs((int)m) - 1u; m &= m - 1u; if (k < 32) wm->tabs[k] = (u32)(off - s) + b; ++k; }
+                nt += __shfl_sync(FULL, incl, 31);
+                if (nt > kSMaxTabs) break;
+            }
+        }
+        if (lane < 6) wm->hdr[H_CG_A + lane] = 0;
+        __syncwarp();
+        if (nt < 11 || nt > kSMaxTabs) { deleg = true; break; }
+        u32 lbad = parse_fields<32>(g, rt, wm->tabs, nt, len, wm->hdr, wm->tkeys);
+        if (__any_sync(FULL, lbad != 0)) { deleg = true; break; }
+        const bool minus = wm->hdr[H_MINUS] != 0;
+        const i32 qs = (i32)wm->hdr[H_QS], ps = (i32)wm->hdr[H_PS], pe = (i32)wm->hdr[H_PE];
+        if (wm->hdr[H_CG_B] == 0 || wm->hdr[H_CG_A] >= wm->hdr[H_CG_B] || qs < 0 || ps < 0 || pe < 0) { deleg = true; break; }
+        const u32 cA = s + wm->hdr[H_CG_A], cB = s + wm->hdr[H_CG_B];
+        const u32 pA = s + wm->hdr[H_PATH_A], pB = s + wm->hdr[H_PATH_B];
+        const u8 c0 = gaf[pA];
+        const bool prefixed = c0 == '>' || c0 == '<';
+        const bool empty_path = !prefixed && pB - pA == 1 && c0 == '*';
+
+        LineRec R;
+        R.qn_b = wm->hdr[H_QN_B];
+        R.qlen = (i32)wm->hdr[H_QLEN]; R.m = (i32)wm->hdr[H_M]; R.b = (i32)wm->hdr[H_B]; R.mapq = (i32)wm->hdr[H_MAPQ];
+        R.tp_a = wm->hdr[H_TP_A]; R.tp_b = wm->hdr[H_TP_B]; R.rc_a = wm->hdr[H_RC_A]; R.rc_b = wm->hdr[H_RC_B];
+        R.gi_n = gi_fast(R.m, R.b, R.gi);
+        if (R.gi_n == 0) { deleg = true; break; }
+        const u32 const_len = line_const_len(R, p10);
+
+        TokStream<true> ss;
+        TokStream<false> os;
+        // ---------------- '-' records: path length from the steps (flip_gaf, gaf2paf_main.cpp:111-131)
+        i32 ps2 = ps, pe2 = pe;
+        if (minus) {
+            u64 L = 0;
+            if (prefixed) {
+                ss.init(wm->sring, pA, pB, false);
+                for (;;) {
+                    ss.ensure(33, gaf, a.n, lane);
+                    const u32 nb_ = ss.count < 32u ? ss.count : 32u;
+                    if (nb_ == 0) break;
+                    u64 v = 0;
+                    if (lane < nb_) {
+                        const u32 p = ss.at(lane), q = lane + 1 < ss.count ? ss.at(lane + 1) : pB;
+                        StepTok2 t;
+                        lbad |= parse_step_global(gaf, a.n, a.T, p, q, true, t);
+                        v = (u64)(u32)(t.se - t.sa);
+                    }
+                    v = wscan64(v, lane);
+                    L += __shfl_sync(FULL, v, 31);
+                    __syncwarp();
+                    ss.pop(nb_);
+                }
+            } else if (!empty_path) {
+                StepTok2 t;
+                lbad |= parse_step_global(gaf, a.n, a.T, pA - 1, pB, false, t);
+                L = (u64)(u32)(t.se - t.sa);
+            }
+            if (__any_sync(FULL, lbad != 0) || L > 0x7fffffffULL) { deleg = true; break; }
+            ps2 = (i32)L - pe; pe2 = (i32)L - ps;
+        }
+        const i32 W = pe2 - ps2;
+        if (ps2 < 0 || W < 0) { deleg = true; break; }
+
+        // ---------------- streams
+        ss.init(wm->sring, prefixed ? pA : 0u, prefixed ? pB : 0u, minus);
+        os.init(wm->oring, cA, cB, minus);
+        // op window (one op per lane, inclusive prefixes carried across windows)
+        u64 wEND = 0, wQ = 0, wM = 0, wNB = 0, cE = 0, cQ = 0, cM = 0, cNB = 0;
+        u32 wlen = 0, wlp = 0, wds = 0, wk = 0, nwin = 0;
+        u32 last_lp = cA - 1;          // fwd: letter position of the previous op
+        u32 top_lp = 0;                // largest letter position seen (must be cB-1)
+        bool win_valid = false, ops_done = false;
+        u64 win_last = 0;              // cumulative target length at the end of the window
+        auto load_window = [&]() {
+            os.ensure(33, gaf, a.n, lane);
+            nwin = os.count < 32u ? os.count : 32u;
+            if (nwin == 0) { win_valid = false; ops_done = true; return; }
+            u64 vE = 0, vQ = 0, vM = 0, vB = 0;
+            wlen = 0; wlp = 0; wds = 0; wk = 0;
+            const u32 mylp = lane < nwin ? os.at(lane) : 0u;
+            u32 prev = __shfl_up_sync(FULL, mylp, 1);
+            if (lane == 0) prev = last_lp;
+            if (lane < nwin) {
+                wlp = mylp;
+                if (!minus) wds = prev + 1u;
+                else wds = lane + 1 < os.count ? os.at(lane + 1) + 1u : cA;
+                const u32 nd = wlp - wds;
+                wk = (u32)gaf[wlp] - '=';
+                if (wk >= 28 || !((kOpMask >> wk) & 1u) || nd == 0 || nd > 9 || (nd > 1 && gaf[wds] == '0')) lbad = 1;
+                else {
+                    u32 x = 0;
+                    for (u32 t = wds; t < wlp; ++t) x = x * 10u + ((u32)gaf[t] - '0');
+                    if (x == 0) lbad = 1;
+                    wlen = x;
+                    vB = x;
+                    vE = ((kTargetMask >> wk) & 1u) ? x : 0u;
+                    vQ = ((kQueryMask >> wk) & 1u) ? x : 0u;
+                    vM = ((kMatchMask >> wk) & 1u) ? x : 0u;
+                }
+            }
+            wEND = wscan64(vE, lane) + cE; wQ = wscan64(vQ, lane) + cQ; wM = wscan64(vM, lane) + cM; wNB = wscan64(vB, lane) + cNB;
+            cE = __shfl_sync(FULL, wEND, nwin - 1); cQ = __shfl_sync(FULL, wQ, nwin - 1);
+            cM = __shfl_sync(FULL, wM, nwin - 1); cNB = __shfl_sync(FULL, wNB, nwin - 1);
+            win_last = cE;
+            if (lane >= nwin) wEND = ~0ULL;
+            const u32 hi_lp = __shfl_sync(FULL, wlp, minus ? 0 : (int)nwin - 1);
+            if (hi_lp > top_lp) top_lp = hi_lp;
+            last_lp = __shfl_sync(FULL, wlp, nwin - 1);
+            __syncwarp();
+            os.pop(nwin);
+            win_valid = true;
+        };
+
+        // ---------------- merge of step boundaries and op windows
+        u32 tbc = 0;                   // cumulative quota of the steps before the batch
+        u32 prev_p = pB;               // bwd: marker position of the previous (text-later) step
+        bool first_batch = true, steps_done = empty_path;
+        u64 run = 0;                   // PAF bytes of the record so far
+        bool fail = false;
+        while (!steps_done) {
+            // --- next batch of steps
+            u32 nsb;
+            bool has_last;
+            if (prefixed) {
+                ss.ensure(kLBatch + 1, gaf, a.n, lane);
+                nsb = ss.count < kLBatch ? ss.count : kLBatch;
+                has_last = ss.done && ss.count == nsb;
+            } else { nsb = 1; has_last = true; }
+            if (nsb == 0) { fail = true; break; }   // prefixed path without a marker cannot happen
+            const bool is_step = lane < nsb;
+            StepTok2 t;
+            t.name_a = 0; t.nl = 0; t.tlen = 0; t.sa = 0; t.se = 0;
+            bool rev = false;
+            {
+                u32 p = 0, q = 0;
+                if (prefixed) {
+                    const u32 myp = is_step ? ss.at(lane) : 0u;
+                    if (!minus) q = lane + 1 < ss.count ? ss.at(lane + 1) : pB;
+                    else { q = __shfl_up_sync(FULL, myp, 1); if (lane == 0) q = prev_p; }
+                    p = myp;
+                    prev_p = __shfl_sync(FULL, myp, (int)nsb - 1);
+                } else { p = pA - 1; q = pB; }
+                if (is_step) {
+                    rev = (prefixed && gaf[p] == '<') != minus;
+                    lbad |= parse_step_global(gaf, a.n, a.T, p, q, prefixed, t);
+                }
+            }
+            __syncwarp();
+            if (prefixed) ss.pop(nsb);
+            const i32 slen = t.se - t.sa;
+            const i32 so = (first_batch && lane == 0) ? ps2 : 0;
+            const bool is_last = has_last && lane + 1 == nsb;
+            const u32 qsum = wscan32(is_step && !is_last ? (u32)(slen - so) : 0u, lane);
+            u32 B = tbc + qsum - (is_step && !is_last ? (u32)(slen - so) : 0u);
+            i32 quota = slen - so, eo = 0;
+            if (is_last) { quota = W - (i32)B; eo = slen - so - quota; }
+            if (is_step && (quota < 0 || eo < 0)) lbad = 1;
+            {   // end boundary of the batch on lane nsb
+                const u32 endB = __shfl_sync(FULL, B + (u32)quota, (int)nsb - 1);
+                if (lane == nsb) B = endB;
+                tbc = endB;
+            }
+            if (!is_step) quota = 0;
+            if (__any_sync(FULL, lbad != 0)) { fail = true; break; }
+            if ((u32)W > 0x7fffffffu || tbc > (u32)W) { fail = true; break; }
+
+            // --- resolve boundaries (lanes 0..nsb) against the op windows
+            bool need = lane <= nsb && B != 0;
+            u32 r_lp = 0, r_ds = 0, r_code = 0, r_rem = 0, r_t = 0;
+            bool r_cut = false;
+            u64 rCQ = 0, rCM = 0, rCB = 0;
+            while (__any_sync(FULL, need)) {
+                if (!win_valid && !ops_done) load_window();
+                if (__any_sync(FULL, lbad != 0)) { fail = true; break; }
+                if (!win_valid) { fail = true; break; }   // CIGAR shorter than the path (:80 assert)
+                const bool mine = need && (u64)B <= win_last;
+                u32 lo = 0, hi = nwin - 1;
+#pragma unroll
+                for (int it = 0; it < 5; ++it) {
+                    const u32 mid = (lo + hi) >> 1;
+                    const u64 v = __shfl_sync(FULL, wEND, (int)mid);
+                    if (lo < hi) { if (v >= (u64)B) hi = mid; else lo = mid + 1; }
+                }
+                const u64 jE_ = __shfl_sync(FULL, wEND, (int)lo), jQ = __shfl_sync(FULL, wQ, (int)lo), jM = __shfl_sync(FULL, wM, (int)lo),
+                          jB = __shfl_sync(FULL, wNB, (int)lo);
+                const u32 jl = __shfl_sync(FULL, wlen, (int)lo), jlp = __shfl_sync(FULL, wlp, (int)lo), jds = __shfl_sync(FULL, wds, (int)lo),
+                          jk = __shfl_sync(FULL, wk, (int)lo);
+                if (mine) {
+                    const u64 tj = jE_ - jl;   // e(B) always consumes target
+                    const u64 off = (u64)B - tj;
+                    rCQ = jQ - (((kQueryMask >> jk) & 1u) ? (u64)jl - off : 0ULL);
+                    rCM = jM - (((kMatchMask >> jk) & 1u) ? (u64)jl - off : 0ULL);
+                    rCB = jB - ((u64)jl - off);
+                    r_cut = jE_ > (u64)B;
+                    r_rem = (u32)(jE_ - (u64)B);
+                    r_t = (u32)tj;
+                    r_lp = jlp; r_ds = jds; r_code = jk;
+                    need = false;
+                }
+                if (__any_sync(FULL, need)) { win_valid = false; if (ops_done) { fail = true; break; } }
+            }
+            if (fail) break;
+
+            // --- per-step values
+            const bool zeroS = B == 0;
+            const u32 eB = __shfl_down_sync(FULL, B, 1);
+            const u32 e_lp = __shfl_down_sync(FULL, r_lp, 1), e_ds = __shfl_down_sync(FULL, r_ds, 1), e_code = __shfl_down_sync(FULL, r_code, 1),
+                      e_t = __shfl_down_sync(FULL, r_t, 1);
+            const u64 eCQ = __shfl_down_sync(FULL, rCQ, 1), eCM = __shfl_down_sync(FULL, rCM, 1), eCB = __shfl_down_sync(FULL, rCB, 1);
+            const bool live = is_step && quota > 0;
+            const u64 q64 = live ? eCQ - rCQ : 0ULL, nm64 = live ? eCM - rCM : 0ULL, nb64 = live ? eCB - rCB : 0ULL;
+            const u64 q0_64 = (u64)(u32)qs + rCQ;
+            if (live && (q0_64 + q64 > 0x7fffffffULL || nm64 > 0x7fffffffULL || nb64 > 0x7fffffffULL)) lbad = 1;
+            if (__any_sync(FULL, lbad != 0)) { fail = true; break; }
+            const bool emit_line = live && nm64 > 0;
+            LineStep Ls;
+            Ls.rev = rev;
+            Ls.q0 = (u32)q0_64; Ls.q1 = (u32)(q0_64 + q64);
+            Ls.name_a = t.name_a - s; Ls.nl = t.nl; Ls.tlen = (u32)t.tlen;
+            Ls.ts = (u32)(t.sa + (rev ? eo : so)); Ls.te = (u32)(t.se - (rev ? so : eo));
+            Ls.nm = (u32)nm64; Ls.nb = (u32)nb64;
+            Ls.lenS = 0; Ls.codeS = 0; Ls.codeE = (u8)('=' + e_code); Ls.mid_a = Ls.mid_b = 0;
+            Ls.mid_fwd = rev == minus;
+            Ls.lenE = eB - (e_t > B ? e_t : B);
+            u32 line = 0;
+            if (emit_line) {
+                const bool cutS = !zeroS && r_cut;
+                const bool single = cutS && r_lp == e_lp;
+                if (!single) {
+                    if (cutS) { Ls.lenS = r_rem; Ls.codeS = (u8)('=' + r_code); }
+                    u32 ma, mb;
+                    if (!minus) { ma = zeroS ? cA : r_lp + 1u; mb = e_ds; }
+                    else { ma = e_lp + 1u; mb = zeroS ? cB : r_ds; }
+                    if (mb > ma) { Ls.mid_a = ma - s; Ls.mid_b = mb - s; }
+                }
+                line = const_len + line_step_len(Ls, p10);
+            }
+            const u32 lincl = wscan32(line, lane);
+            const u32 btot = __shfl_sync(FULL, lincl, 31);
+            if (EMIT && btot) {
+                const u64 ob = o + run;
+                const bool staged = btot <= kLOutCap;
+                const u32 pad = (u32)(ob & 15u);
+                if (emit_line) write_line(staged ? wm->out + pad + (lincl - line) : a.out + ob + (lincl - line), rt, R, Ls, p10);
+                if (staged) {
+                    __syncwarp();
+                    const u32 total = pad + btot;
+                    u8* gb = a.out + (ob - pad);
+                    const u32 full_b = total >> 4;
+                    for (u32 u = (pad ? 1u : 0u) + lane; u < full_b; u += 32) reinterpret_cast<uint4*>(gb)[u] = reinterpret_cast<const uint4*>(wm->out)[u];
+                    const u32 head_end = pad ? (total < 16u ? total : 16u) : 0u;
+                    for (u32 b = pad + lane; b < head_end; b += 32) gb[b] = wm->out[b];
+                    const u32 tail_a = full_b * 16u > head_end ? full_b * 16u : head_end;
+                    for (u32 b = tail_a + lane; b < total; b += 32) gb[b] = wm->out[b];
+                    __syncwarp();
+                }
+            }
+            run += btot;
+            first_batch = false;
+            if (has_last) steps_done = true;
+        }
+        if (fail) { deleg = true; break; }
+        // ---------------- the rest of the CIGAR is still validated (for_each_cg parses all of it)
+        while (!ops_done) {
+            load_window();
+            if (__any_sync(FULL, lbad != 0)) break;
+        }
+        if (__any_sync(FULL, lbad != 0) || top_lp != cB - 1) { deleg = true; break; }
+        size = run;
+    } while (0);
+    __syncwarp();
+    if (!EMIT && lane == 0) {
+        if (deleg) {
+            a.status[r] = ST_OK;   // overwritten by the general kernel
+            a.out_off[r] = 0;
+            a.deleg_list[atomicAdd(a.n_deleg, 1u)] = r;
+        } else {
+            a.status[r] = status;
+            a.out_off[r] = size;
+        }
+    }
+    (void)osize;
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(kLThreads) k_long(const LongArgs a) {
+    G2P_DYN_SMEM(smem);
+    __shared__ u32 p10[10];
+    if (threadIdx.x < 10) {
+        u32 v = 1;
+        for (u32 i = 0; i < threadIdx.x; ++i) v *= 10u;
+        p10[threadIdx.x] = v;
+    }
+    __syncthreads();
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    LWarpMem* wm = reinterpret_cast<LWarpMem*>(smem) + warp;
+    const u32 nl = *a.n_list;
+    for (u32 k = blockIdx.x * kLWarps + warp; k < nl; k += gridDim.x * kLWarps) {
+        long_record<EMIT>(a, wm, a.list[k], lane, p10);
+        __syncwarp();
+    }
+}
+
+}  // namespace g2p

@@ -34,7 +34,10 @@ enum : u32 {
 
 constexpr int kSG = 8;                 // lanes per record
 constexpr int kSThreads = 256;         // 32 records per CTA
-constexpr u32 kSLimit = 240;           // longest record (bytes, without '\n') taken by the fast path
+#ifndef G2P_S_LIMIT
+#define G2P_S_LIMIT 240   /* tests build a variant with 0 to push every record through k_long */
+#endif
+constexpr u32 kSLimit = G2P_S_LIMIT;   // longest record (bytes, without '\n') taken by the fast path
 constexpr u32 kSMaxTabs = 31;          // 12 columns + up to 20 tags
 constexpr u32 kSMaxTags = 20;
 constexpr u32 kSMaxOps = 24;
@@ -153,6 +156,139 @@ __device__ __forceinline__ u32 gi_fast(i32 m, i32 b, u8* out) {
     return d2 ? 5 : (d1 ? 4 : 3);
 }
 
+
+// ---- record header: columns 1..12 and the optional tags, one lane per field ---------------
+// (parse_gaf_record, gafkluge.hpp:84-204).  `rt` is the record text (shared or global memory),
+// tabs[nt] its tab positions (11 <= nt <= kSMaxTabs), tkeys a scratch of kSMaxTags words.
+// Results go to hdr[]; the return value is this lane's "not canonical" flag.  The caller must
+// have zeroed hdr[H_CG_A..H_RC_B] and synchronised the group.  Ends with hdr/tkeys written but
+// not yet synchronised for other lanes: the caller's next group vote orders them.
+template <int G, class TabT>
+__device__ __forceinline__ u32 parse_fields(const Grp<G>& g, const u8* rt, const TabT* tabs, u32 nt, u32 len, u32* hdr, u32* tkeys) {
+    u32 lbad = 0;
+    for (u32 f = g.gl; f < 12; f += G) {
+        const u32 fa = f ? (u32)tabs[f - 1] + 1u : 0u;
+        const u32 fb = f < nt ? (u32)tabs[f] : len;
+        const u32 fl = fb - fa;
+        if (fl == 0) { lbad = 1; continue; }
+        if (f == 0) { hdr[H_QN_B] = fb; }
+        else if (f == 4) {
+            const u8 c = rt[fa];
+            if (fl != 1 || (c != '+' && c != '-')) lbad = 1;
+            hdr[H_MINUS] = c == '-';
+        } else if (f == 5) { hdr[H_PATH_A] = fa; hdr[H_PATH_B] = fb; }
+        else {
+            i32 v = 0;
+            if (fl == 1 && rt[fa] == '*') v = -1;
+            else if (fl > 9) lbad = 1;
+            else {
+                u32 x = 0;
+                for (u32 k = fa; k < fb; ++k) { const u32 d = (u32)rt[k] - '0'; if (d > 9) lbad = 1; x = x * 10u + d; }
+                v = (i32)x;
+                if (f == 11 && v >= 255) v = -1;   // gafkluge.hpp:176-183
+            }
+            hdr[f] = (u32)v;
+        }
+    }
+    const u32 ntf = nt - 11;   // tag fields (possibly empty ones)
+    for (u32 t0 = 0; t0 < ntf; t0 += G) {
+        const u32 ti = t0 + g.gl;
+        if (ti < ntf) {
+            const u32 f = 12 + ti;
+            const u32 fa = (u32)tabs[f - 1] + 1u, fb = f < nt ? (u32)tabs[f] : len, fl = fb - fa;
+            u32 key = 0x10000u + ti;   // empty field: unique non-key
+            if (fl) {
+                if (fl < 5 || rt[fa + 2] != ':' || rt[fa + 4] != ':') lbad = 1;
+                else {
+                    key = (u32)rt[fa] | ((u32)rt[fa + 1] << 8);
+                    if (key == ((u32)'c' | ((u32)'g' << 8))) { hdr[H_CG_A] = fa + 5; hdr[H_CG_B] = fb; }
+                    else if (key == ((u32)'t' | ((u32)'p' << 8))) { hdr[H_TP_A] = fa + 3; hdr[H_TP_B] = fb; }
+                    else if (key == ((u32)'r' | ((u32)'c' << 8))) { hdr[H_RC_A] = fa + 3; hdr[H_RC_B] = fb; }
+                }
+            }
+            tkeys[ti] = key;
+        }
+    }
+    g.sync();
+    for (u32 t0 = 0; t0 < ntf; t0 += G) {   // duplicate tags (gafkluge.hpp:195-198)
+        const u32 ti = t0 + g.gl;
+        if (ti < ntf) {
+            const u32 key = tkeys[ti];
+            for (u32 j = 0; j < ti; ++j) if (tkeys[j] == key) lbad = 1;
+        }
+    }
+    return lbad;
+}
+
+// ---- one PAF line (paf.hpp:83-95 + gaf2paf_main.cpp:228-256) -------------------------------
+struct LineRec {    // constant over the lines of one record
+    u32 qn_b;
+    i32 qlen, mapq, m, b;
+    u32 tp_a, tp_b, rc_a, rc_b;   // "type:value" spans of the tp / rc tags (b == 0: absent)
+    u32 gi_n;
+    u8 gi[8];
+};
+struct LineStep {
+    u32 q0, q1, name_a, nl, tlen, ts, te, nm, nb;
+    u32 lenS, lenE;        // explicit first / last piece lengths
+    u32 mid_a, mid_b;      // text span of the pieces copied verbatim (empty if mid_b <= mid_a)
+    u8 codeS, codeE;       // codeS == 0: no explicit first piece
+    bool rev, mid_fwd;     // mid_fwd: the verbatim span is printed in text order
+};
+__device__ __forceinline__ u32 line_const_len(const LineRec& R, const u32* p10) {
+    return R.qn_b + dlen_i32(R.qlen, p10) + 12u + dlen_i32(R.mapq, p10) + (R.tp_b ? 4u + (R.tp_b - R.tp_a) : 0u) +
+           (R.rc_b ? 4u + (R.rc_b - R.rc_a) : 0u) + 6u + dlen_i32(R.m, p10) + 6u + dlen_i32(R.b, p10) + 6u + R.gi_n + 6u + 1u;
+}
+__device__ __forceinline__ u32 line_step_len(const LineStep& L, const u32* p10) {
+    u32 n = L.nl + dlen_u32(L.q0, p10) + dlen_u32(L.q1, p10) + dlen_u32(L.tlen, p10) + dlen_u32(L.ts, p10) + dlen_u32(L.te, p10) +
+            dlen_u32(L.nm, p10) + dlen_u32(L.nb, p10) + dlen_u32(L.lenE, p10) + 1u;
+    if (L.codeS) n += dlen_u32(L.lenS, p10) + 1u;
+    if (L.mid_b > L.mid_a) n += L.mid_b - L.mid_a;
+    return n;
+}
+__device__ __forceinline__ u8* write_line(u8* p, const u8* rt, const LineRec& R, const LineStep& L, const u32* p10) {
+    p = put_bytes(p, rt, R.qn_b); *p++ = '\t';
+    p = put_i32(p, R.qlen, p10); *p++ = '\t';
+    p = put_u32(p, L.q0, p10); *p++ = '\t';
+    p = put_u32(p, L.q1, p10); *p++ = '\t';
+    *p++ = L.rev ? '-' : '+'; *p++ = '\t';
+    p = put_bytes(p, rt + L.name_a, L.nl); *p++ = '\t';
+    p = put_u32(p, L.tlen, p10); *p++ = '\t';
+    p = put_u32(p, L.ts, p10); *p++ = '\t';
+    p = put_u32(p, L.te, p10); *p++ = '\t';
+    p = put_u32(p, L.nm, p10); *p++ = '\t';
+    p = put_u32(p, L.nb, p10); *p++ = '\t';
+    p = put_i32(p, R.mapq, p10);
+    if (R.tp_b) { p[0] = '\t'; p[1] = 't'; p[2] = 'p'; p[3] = ':'; p = put_bytes(p + 4, rt + R.tp_a, R.tp_b - R.tp_a); }
+    if (R.rc_b) { p[0] = '\t'; p[1] = 'r'; p[2] = 'c'; p[3] = ':'; p = put_bytes(p + 4, rt + R.rc_a, R.rc_b - R.rc_a); }
+    p = put_tag(p, 'g', 'm', 'i'); p = put_i32(p, R.m, p10);
+    p = put_tag(p, 'g', 'l', 'i'); p = put_i32(p, R.b, p10);
+    p = put_tag(p, 'g', 'i', 'f'); p = put_bytes(p, R.gi, R.gi_n);
+    p = put_tag(p, 'c', 'g', 'Z');
+    // pieces, reversed for '<' steps (gaf2paf_main.cpp:184-211)
+    if (!L.rev) {
+        if (L.codeS) { p = put_u32(p, L.lenS, p10); *p++ = L.codeS; }
+    } else {
+        p = put_u32(p, L.lenE, p10); *p++ = L.codeE;
+    }
+    if (L.mid_b > L.mid_a) {
+        if (L.mid_fwd) p = put_bytes(p, rt + L.mid_a, L.mid_b - L.mid_a);
+        else {
+            u32 t1 = L.mid_b;   // token by token, backwards
+            while (t1 > L.mid_a) {
+                u32 t0 = t1 - 1;
+                while (t0 > L.mid_a && rt[t0 - 1] <= '9') --t0;
+                p = put_bytes(p, rt + t0, t1 - t0);
+                t1 = t0;
+            }
+        }
+    }
+    if (!L.rev) { p = put_u32(p, L.lenE, p10); *p++ = L.codeE; }
+    else if (L.codeS) { p = put_u32(p, L.lenS, p10); *p++ = L.codeS; }
+    *p++ = '\n';
+    return p;
+}
+
 __device__ __forceinline__ uint4 ldg_vec_guarded(const u8* base, u64 off, u64 n) {
     if (off + 16 <= n) return __ldg(reinterpret_cast<const uint4*>(base + off));
     u32 w[4] = {0, 0, 0, 0};
@@ -257,62 +393,8 @@ __global__ void __launch_bounds__(kSThreads, 4) k_short(const ShortArgs a) {
         g.sync();
         if (rt[0] == '*') { status = ST_SKIP | ST_F_FAST; break; }   // gaf2paf_main.cpp:360
         if (nt < 11 || nt > kSMaxTabs) { deleg = true; break; }
-        const u16* tabs = gm->w.tabs;
-
         // ---------------- phase 1: columns 1..12 and tags, one lane per field
-        u32 lbad = 0;
-        for (u32 f = g.gl; f < 12; f += G) {
-            const u32 fa = f ? tabs[f - 1] + 1u : 0u;
-            const u32 fb = f < nt ? tabs[f] : len;
-            const u32 fl = fb - fa;
-            if (fl == 0) { lbad = 1; continue; }
-            if (f == 0) { gm->hdr[H_QN_B] = fb; }
-            else if (f == 4) {
-                const u8 c = rt[fa];
-                if (fl != 1 || (c != '+' && c != '-')) lbad = 1;
-                gm->hdr[H_MINUS] = c == '-';
-            } else if (f == 5) { gm->hdr[H_PATH_A] = fa; gm->hdr[H_PATH_B] = fb; }
-            else {
-                i32 v = 0;
-                if (fl == 1 && rt[fa] == '*') v = -1;
-                else if (fl > 9) lbad = 1;
-                else {
-                    u32 x = 0;
-                    for (u32 k = fa; k < fb; ++k) { const u32 d = (u32)rt[k] - '0'; if (d > 9) lbad = 1; x = x * 10u + d; }
-                    v = (i32)x;
-                    if (f == 11 && v >= 255) v = -1;   // gafkluge.hpp:176-183
-                }
-                gm->hdr[f] = (u32)v;
-            }
-        }
-        const u32 ntf = nt - 11;   // tag fields (possibly empty ones)
-        u32* tkeys = reinterpret_cast<u32*>(gm->spos);
-        for (u32 t0 = 0; t0 < ntf; t0 += G) {
-            const u32 ti = t0 + g.gl;
-            if (ti < ntf) {
-                const u32 f = 12 + ti;
-                const u32 fa = tabs[f - 1] + 1u, fb = f < nt ? tabs[f] : len, fl = fb - fa;
-                u32 key = 0x10000u + ti;   // empty field: unique non-key
-                if (fl) {
-                    if (fl < 5 || rt[fa + 2] != ':' || rt[fa + 4] != ':') lbad = 1;
-                    else {
-                        key = (u32)rt[fa] | ((u32)rt[fa + 1] << 8);
-                        if (key == ((u32)'c' | ((u32)'g' << 8))) { gm->hdr[H_CG_A] = fa + 5; gm->hdr[H_CG_B] = fb; }
-                        else if (key == ((u32)'t' | ((u32)'p' << 8))) { gm->hdr[H_TP_A] = fa + 3; gm->hdr[H_TP_B] = fb; }
-                        else if (key == ((u32)'r' | ((u32)'c' << 8))) { gm->hdr[H_RC_A] = fa + 3; gm->hdr[H_RC_B] = fb; }
-                    }
-                }
-                tkeys[ti] = key;
-            }
-        }
-        g.sync();
-        for (u32 t0 = 0; t0 < ntf; t0 += G) {   // duplicate tags (gafkluge.hpp:195-198)
-            const u32 ti = t0 + g.gl;
-            if (ti < ntf) {
-                const u32 key = tkeys[ti];
-                for (u32 j = 0; j < ti; ++j) if (tkeys[j] == key) lbad = 1;
-            }
-        }
+        u32 lbad = parse_fields<G>(g, rt, gm->w.tabs, nt, len, gm->hdr, reinterpret_cast<u32*>(gm->spos));
         if (g.any(lbad != 0)) { deleg = true; break; }   // also orders the tkeys reads before the scatter below
 
         const bool minus = gm->hdr[H_MINUS] != 0;
@@ -484,47 +566,42 @@ __global__ void __launch_bounds__(kSThreads, 4) k_short(const ShortArgs a) {
         if (live && eexh) lbad = 1;   // :80 assert(cur_len > target_len): CIGAR shorter than the path
         if (g.any(lbad != 0)) { deleg = true; break; }
         const u32 q = live ? eCQ - bCQ : 0u, nm = live ? eCM - bCM : 0u, nb = live ? eCB - bCB : 0u;
-        u32 qtot;
-        const u32 qex = g.excl_scan(q, qtot);
         const bool emit_line = live && nm > 0;   // :225
 
-        // pieces of the step: ops jS..jE (normalised order)
-        const u32 jS = (B == 0) ? 0u : (bcut ? bj : bj + 1u);
-        const bool cutS = B != 0 && bcut;
-        const u32 jE = ej;
-        const u32 lenE = eB - (et > B ? et : B);
-        u32 lenS = 0, mS = jS, mE = jE;   // verbatim middle tokens: [mS, mE)
-        u32 cglen = 0;
-        u32 mid_a = 0, mid_b = 0;         // their bytes in the record text
-        if (emit_line) {
-            if (jS < jE) {
-                if (cutS) { lenS = gm->w.pEnd[jS] - B; mS = jS + 1; cglen += dlen_u32(lenS, p10) + 1u; }
-                if (mS < mE) {
-                    const u32 o1 = minus ? no - mE : mS, o2 = minus ? no - 1 - mS : mE - 1;   // original index range [o1, o2]
-                    mid_a = o1 ? gm->opos[o1 - 1] + 1u : ca;
-                    mid_b = gm->opos[o2] + 1u;
-                    cglen += mid_b - mid_a;
-                }
-            }
-            cglen += dlen_u32(lenE, p10) + 1u;
-        }
-
-        // PAF columns (gaf2paf_main.cpp:214-217) and the line length
-        const i32 qlen = (i32)gm->hdr[H_QLEN], m_ = (i32)gm->hdr[H_M], b_ = (i32)gm->hdr[H_B], mapq = (i32)gm->hdr[H_MAPQ];
-        const u32 qn_b = gm->hdr[H_QN_B];
-        const u32 tp_a = gm->hdr[H_TP_A], tp_b = gm->hdr[H_TP_B], rc_a = gm->hdr[H_RC_A], rc_b = gm->hdr[H_RC_B];
-        u8 gi[8];
-        const u32 gi_n = gi_fast(m_, b_, gi);
-        if (gi_n == 0) { deleg = true; break; }   // uniform: same m, b in the whole group
-        const i32 so2 = rev ? eo : so, eo2 = rev ? so : eo;
-        const u32 q0 = (u32)qs + qex, q1 = q0 + q;
-        const u32 ts = (u32)(sa + so2), te = (u32)(se - eo2);
+        // PAF columns (gaf2paf_main.cpp:214-217).  Query consumed before step i == CQ at its start
+        // boundary (the per-step sums telescope), so no scan over steps is needed.
+        LineRec R;
+        R.qn_b = gm->hdr[H_QN_B];
+        R.qlen = (i32)gm->hdr[H_QLEN]; R.m = (i32)gm->hdr[H_M]; R.b = (i32)gm->hdr[H_B]; R.mapq = (i32)gm->hdr[H_MAPQ];
+        R.tp_a = gm->hdr[H_TP_A]; R.tp_b = gm->hdr[H_TP_B]; R.rc_a = gm->hdr[H_RC_A]; R.rc_b = gm->hdr[H_RC_B];
+        R.gi_n = gi_fast(R.m, R.b, R.gi);
+        if (R.gi_n == 0) { deleg = true; break; }   // uniform: same m, b in the whole group
+        LineStep L;
+        L.rev = rev;
+        L.q0 = (u32)qs + bCQ; L.q1 = L.q0 + q;
+        L.name_a = name_a; L.nl = nl; L.tlen = (u32)tlen;
+        L.ts = (u32)(sa + (rev ? eo : so)); L.te = (u32)(se - (rev ? so : eo));
+        L.nm = nm; L.nb = nb;
+        // pieces of the step: ops jS..jE (normalised order); first / last explicit, the rest verbatim
+        L.lenS = 0; L.codeS = 0; L.codeE = 0; L.mid_a = L.mid_b = 0;
+        L.mid_fwd = rev == minus;   // text order == output order
+        L.lenE = eB - (et > B ? et : B);
         u32 line = 0;
         if (emit_line) {
-            line = qn_b + dlen_i32(qlen, p10) + 12u + dlen_i32(mapq, p10) + (tp_b ? 4u + (tp_b - tp_a) : 0u) + (rc_b ? 4u + (rc_b - rc_a) : 0u) +
-                   6u + dlen_i32(m_, p10) + 6u + dlen_i32(b_, p10) + 6u + gi_n + 6u + 1u +
-                   nl + cglen + dlen_u32(q0, p10) + dlen_u32(q1, p10) + dlen_u32((u32)tlen, p10) + dlen_u32(ts, p10) + dlen_u32(te, p10) +
-                   dlen_u32(nm, p10) + dlen_u32(nb, p10);
+            const u32 jS = (B == 0) ? 0u : (bcut ? bj : bj + 1u);
+            const bool cutS = B != 0 && bcut;
+            const u32 jE = ej;
+            u32 mS = jS;   // verbatim middle tokens: [mS, jE)
+            if (jS < jE) {
+                if (cutS) { L.lenS = gm->w.pEnd[jS] - B; L.codeS = rt[gm->opos[minus ? no - 1 - jS : jS]]; mS = jS + 1; }
+                if (mS < jE) {
+                    const u32 o1 = minus ? no - jE : mS, o2 = minus ? no - 1 - mS : jE - 1;   // original index range [o1, o2]
+                    L.mid_a = o1 ? gm->opos[o1 - 1] + 1u : ca;
+                    L.mid_b = gm->opos[o2] + 1u;
+                }
+            }
+            L.codeE = rt[gm->opos[minus ? no - 1 - jE : jE]];
+            line = line_const_len(R, p10) + line_step_len(L, p10);
         }
         const u32 loff = g.excl_scan(line, size);
 
@@ -533,50 +610,7 @@ __global__ void __launch_bounds__(kSThreads, 4) k_short(const ShortArgs a) {
             const bool staged = size <= kSOutCap;
             const u32 pad = (u32)(o & 15u);
             g.sync();   // the staging buffer aliases tabs / prefix arrays: everyone is done reading them
-            if (emit_line) {
-                u8* p = staged ? gm->out + pad + loff : a.out + o + loff;
-                p = put_bytes(p, rt, qn_b); *p++ = '\t';
-                p = put_i32(p, qlen, p10); *p++ = '\t';
-                p = put_u32(p, q0, p10); *p++ = '\t';
-                p = put_u32(p, q1, p10); *p++ = '\t';
-                *p++ = rev ? '-' : '+'; *p++ = '\t';
-                p = put_bytes(p, rt + name_a, nl); *p++ = '\t';
-                p = put_u32(p, (u32)tlen, p10); *p++ = '\t';
-                p = put_u32(p, ts, p10); *p++ = '\t';
-                p = put_u32(p, te, p10); *p++ = '\t';
-                p = put_u32(p, nm, p10); *p++ = '\t';
-                p = put_u32(p, nb, p10); *p++ = '\t';
-                p = put_i32(p, mapq, p10);
-                if (tp_b) { p[0] = '\t'; p[1] = 't'; p[2] = 'p'; p[3] = ':'; p = put_bytes(p + 4, rt + tp_a, tp_b - tp_a); }
-                if (rc_b) { p[0] = '\t'; p[1] = 'r'; p[2] = 'c'; p[3] = ':'; p = put_bytes(p + 4, rt + rc_a, rc_b - rc_a); }
-                p = put_tag(p, 'g', 'm', 'i'); p = put_i32(p, m_, p10);
-                p = put_tag(p, 'g', 'l', 'i'); p = put_i32(p, b_, p10);
-                p = put_tag(p, 'g', 'i', 'f'); p = put_bytes(p, gi, gi_n);
-                p = put_tag(p, 'c', 'g', 'Z');
-                // pieces, reversed for '<' steps (gaf2paf_main.cpp:184-211)
-                const u8 codeE = rt[gm->opos[minus ? no - 1 - jE : jE]];
-                const u8 codeS = cutS && jS < jE ? rt[gm->opos[minus ? no - 1 - jS : jS]] : 0;
-                if (!rev) {
-                    if (codeS) { p = put_u32(p, lenS, p10); *p++ = codeS; }
-                } else {
-                    p = put_u32(p, lenE, p10); *p++ = codeE;
-                }
-                if (mid_b > mid_a) {
-                    if (rev == minus) p = put_bytes(p, rt + mid_a, mid_b - mid_a);   // text order == output order
-                    else {
-                        u32 t1 = mid_b;   // token by token, backwards
-                        while (t1 > mid_a) {
-                            u32 t0 = t1 - 1;
-                            while (t0 > mid_a && rt[t0 - 1] <= '9') --t0;
-                            p = put_bytes(p, rt + t0, t1 - t0);
-                            t1 = t0;
-                        }
-                    }
-                }
-                if (!rev) { p = put_u32(p, lenE, p10); *p++ = codeE; }
-                else if (codeS) { p = put_u32(p, lenS, p10); *p++ = codeS; }
-                *p++ = '\n';
-            }
+            if (emit_line) write_line(staged ? gm->out + pad + loff : a.out + o + loff, rt, R, L, p10);
             if (staged) {
                 g.sync();
                 const u32 total = pad + size;

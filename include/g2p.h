@@ -61,8 +61,8 @@ typedef struct g2p_result {
     float emit_ms;          /* CUDA-event time of the emit kernel alone */
     float size_ms;          /* CUDA-event time of the size kernel alone */
     float index_ms;         /* CUDA-event time of the line index kernels */
-    uint32_t n_delegated;   /* records converted by the general (slow) kernel instead of the short-record kernel */
-    uint32_t reserved;
+    uint32_t n_delegated;   /* records converted by the general per-record kernel (non-canonical or erroneous records) */
+    uint32_t n_long;        /* records converted by the streaming kernel k_long (incl. those it passed on) */
 } g2p_result;
 
 /* Context bound to one CUDA device. */

@@ -22,6 +22,7 @@ def _built():
         os.path.join(ROOT, "build", "libgafgen.so"),
         os.path.join(ROOT, "build", "g2p_hostsim"),
         os.path.join(ROOT, "build", "g2p_simt"),
+        os.path.join(ROOT, "build", "g2p_simt_long"),
     ]
     if not all(os.path.exists(p) for p in need):
         subprocess.check_call(["make", "-C", ROOT], stdout=subprocess.DEVNULL)

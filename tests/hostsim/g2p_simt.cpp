@@ -64,7 +64,7 @@ int main(int argc, char** argv) {
     if (ntiles) hs::launch(dim3(ntiles), dim3(kIdxThreads), 0, [&] { k_fill_lines(gaf, n, tiles.data(), rec.data(), &meta); });
     if (nrec == 0) return 0;
 
-    std::vector<u32> status(nrec), list(nrec);
+    std::vector<u32> status(nrec), list(nrec), list2(nrec);
     std::vector<u64> off(nrec + 1);
     const u32 nscan = (nrec + kScanTile - 1) / kScanTile;
     std::vector<u64> blocks(nscan);
@@ -72,21 +72,26 @@ int main(int argc, char** argv) {
     const u32 nlist = std::min<u32>((nrec + kListThreads - 1) / kListThreads, 8u);
     ShortArgs sa{gaf, n, rec.data(), nrec, T, off.data(), status.data(), nullptr, list.data(), &meta.n_deleg};
     hs::launch(dim3(ncta), dim3(kSThreads), kShortSmem, [&] { k_short<kSG, false>(sa); });
-    hs::launch(dim3(nlist), dim3(kListThreads), 0, [&] { k_convert_list<false>(gaf, rec.data(), T, off.data(), status.data(), nullptr, &meta, list.data()); });
+    LongArgs la{gaf, n, rec.data(), T, off.data(), status.data(), nullptr, list.data(), &meta.n_deleg, list2.data(), &meta.n_deleg2};
+    const u32 nlong = 2;
+    hs::launch(dim3(nlong), dim3(kLThreads), kLongSmem, [&] { k_long<false>(la); });
+    hs::launch(dim3(nlist), dim3(kListThreads), 0, [&] { k_convert_list<false>(gaf, rec.data(), T, off.data(), status.data(), nullptr, &meta, list2.data(), &meta.n_deleg2); });
     hs::launch(dim3(nscan), dim3(kScanThreads), 0, [&] { k_scan_reduce(off.data(), nrec, blocks.data()); });
     hs::launch(dim3(1), dim3(1024), 0, [&] { k_scan_blocks(blocks.data(), nscan, &meta); });
     hs::launch(dim3(nscan), dim3(kScanThreads), 0, [&] { k_scan_apply(off.data(), nrec, blocks.data(), &meta); });
     std::vector<u8> out(meta.out_total + 256, 0xEE);
     sa.out = out.data();
     hs::launch(dim3(ncta), dim3(kSThreads), kShortSmem, [&] { k_short<kSG, true>(sa); });
-    if (meta.n_deleg)
-        hs::launch(dim3(nlist), dim3(kListThreads), 0, [&] { k_convert_list<true>(gaf, rec.data(), T, off.data(), status.data(), out.data(), &meta, list.data()); });
+    la.out = out.data();
+    if (meta.n_deleg) hs::launch(dim3(nlong), dim3(kLThreads), kLongSmem, [&] { k_long<true>(la); });
+    if (meta.n_deleg2)
+        hs::launch(dim3(nlist), dim3(kListThreads), 0, [&] { k_convert_list<true>(gaf, rec.data(), T, off.data(), status.data(), out.data(), &meta, list2.data(), &meta.n_deleg2); });
     u64 out_bytes = meta.out_total;
     if (meta.first_err != 0xFFFFFFFFu) {
         hs::launch(dim3(1), dim3(1), 0, [&] { k_diagnose(gaf, rec.data(), T, off.data(), &meta); });
         out_bytes = meta.err_out_end;
     }
-    if (std::getenv("G2P_SIMT_STATS")) std::fprintf(stderr, "g2p_simt: %u records, %u delegated, %llu bytes out\n", nrec, meta.n_deleg, (unsigned long long)out_bytes);
+    if (std::getenv("G2P_SIMT_STATS")) std::fprintf(stderr, "g2p_simt: %u records, %u to k_long, %u to the general kernel, %llu bytes out\n", nrec, meta.n_deleg, meta.n_deleg2, (unsigned long long)out_bytes);
     std::fwrite(out.data(), 1, out_bytes, stdout);
     std::fflush(stdout);
     if (meta.first_err != 0xFFFFFFFFu) {

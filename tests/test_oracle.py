@@ -39,8 +39,9 @@ def test_device_code_on_host_matches_golden():
 
 
 def test_kernels_under_simt_emulator_match_golden():
-    """k_short / k_convert_list / scans / index kernels, executed warp-accurately on the CPU."""
+    """k_short / k_long / k_convert_list / scans / index kernels, executed warp-accurately on the CPU."""
     _run_vectors(SIMT)
+    _run_vectors(SIMT + "_long")   # variant built with the k_short length limit at 0: every record goes through k_long
 
 
 @pytest.mark.skipif(not os.path.exists(REF), reason="reference build (oracle/_ref) not present")
