@@ -7,7 +7,12 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
+#include <mutex>
+#include <thread>
+#include <vector>
 #include <cstring>
 #include <new>
 #include <string>
@@ -52,27 +57,49 @@ struct PinBuf {
 
 }  // namespace
 
+// One pipeline instance: a stream plus the grow-only work buffers of one in-flight chunk.
+struct Worker {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    DevBuf d_in, d_tiles, d_rec, d_status, d_off, d_blocks, d_out, d_meta, d_list, d_list2;
+    PinBuf h_meta;
+    bool init() {
+        if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) return false;
+        for (auto& e : ev) if (cudaEventCreate(&e) != cudaSuccess) return false;
+        return d_meta.ensure(sizeof(PipelineMeta)) == cudaSuccess && h_meta.ensure(sizeof(PipelineMeta)) == cudaSuccess;
+    }
+    void release() {
+        for (DevBuf* b : {&d_in, &d_tiles, &d_rec, &d_status, &d_off, &d_blocks, &d_out, &d_meta, &d_list, &d_list2}) b->release();
+        h_meta.release();
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+constexpr int kWorkers = 3;            // chunks in flight in g2p_convert_host: H2D / kernels / D2H overlap
+constexpr size_t kHostChunk = 96u << 20;   // bytes of GAF per chunk (cut at a newline)
+
 struct g2p_ctx {
     int device = 0;
+    int n_sm = 148;
     std::string err;
+    std::mutex err_mu;
     // table
     DevBuf d_slots, d_arena;
     LenTableView table{nullptr, nullptr, 0};
     uint64_t table_entries = 0;
     bool have_table = false;
-    // work buffers
-    DevBuf d_in, d_tiles, d_rec, d_status, d_off, d_blocks, d_out, d_meta, d_list, d_list2;
-    int n_sm = 148;
-    PinBuf h_out, h_meta;
-    cudaStream_t own_stream = nullptr;
-    cudaEvent_t ev[8] = {};
+    Worker w[kWorkers];
+    PinBuf h_out;
+    size_t host_chunk = kHostChunk;
+    void set_err(const std::string& m) { std::lock_guard<std::mutex> g(err_mu); err = m; }
 };
 
 #define G2P_CUDA(call)                                                                        \
     do {                                                                                      \
         cudaError_t e__ = (call);                                                             \
         if (e__ != cudaSuccess) {                                                             \
-            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                   \
+            ctx->set_err(std::string(#call) + ": " + cudaGetErrorString(e__));                \
             return G2P_E_CUDA;                                                                \
         }                                                                                     \
     } while (0)
@@ -89,16 +116,16 @@ int g2p_create(int device, g2p_ctx** out) {
     g2p_ctx* ctx = new (std::nothrow) g2p_ctx();
     if (!ctx) return G2P_E_ARG;
     ctx->device = device;
-    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return G2P_E_NO_DEVICE; }
-    for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    for (auto& w : ctx->w)
+        if (!w.init()) { g2p_destroy(ctx); return G2P_E_NO_DEVICE; }
     cudaFuncSetAttribute(k_short<kSG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShortSmem);
     cudaFuncSetAttribute(k_short<kSG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShortSmem);
     cudaFuncSetAttribute(k_long<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmem);
     cudaFuncSetAttribute(k_long<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmem);
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
-    if (ctx->d_meta.ensure(sizeof(PipelineMeta)) != cudaSuccess || ctx->h_meta.ensure(sizeof(PipelineMeta)) != cudaSuccess) {
-        delete ctx;
-        return G2P_E_NO_DEVICE;
+    if (const char* c = std::getenv("G2P_HOST_CHUNK_MB")) {
+        long v = std::atol(c);
+        if (v > 0) ctx->host_chunk = (size_t)v << 20;
     }
     *out = ctx;
     return G2P_OK;
@@ -108,13 +135,10 @@ void g2p_destroy(g2p_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (DevBuf* b : {&ctx->d_slots, &ctx->d_arena, &ctx->d_in, &ctx->d_tiles, &ctx->d_rec, &ctx->d_status, &ctx->d_off, &ctx->d_blocks,
-                      &ctx->d_out, &ctx->d_meta, &ctx->d_list, &ctx->d_list2})
-        b->release();
+    ctx->d_slots.release();
+    ctx->d_arena.release();
+    for (auto& w : ctx->w) w.release();
     ctx->h_out.release();
-    ctx->h_meta.release();
-    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
-    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
 
@@ -139,7 +163,8 @@ int g2p_load_lengths(g2p_ctx* ctx, const char* tsv, size_t n) {
     G2P_CUDA(cudaSetDevice(ctx->device));
     HostLenTable t;
     u32 st = build_len_table(tsv, n, t);
-    if (st != ST_OK) { ctx->err = "lengths table: std::stol would throw"; return G2P_E_TABLE; }
+    if (st != ST_OK) { ctx->set_err("lengths table: std::stol would throw"); return G2P_E_TABLE; }
+    G2P_CUDA(cudaDeviceSynchronize());
     G2P_CUDA(ctx->d_slots.ensure(t.slots.size() * sizeof(LenSlot)));
     G2P_CUDA(ctx->d_arena.ensure(t.arena.size()));
     G2P_CUDA(cudaMemcpy(ctx->d_slots.p, t.slots.data(), t.slots.size() * sizeof(LenSlot), cudaMemcpyHostToDevice));
@@ -154,21 +179,21 @@ int g2p_load_lengths(g2p_ctx* ctx, const char* tsv, size_t n) {
 
 uint64_t g2p_table_entries(const g2p_ctx* ctx) { return ctx ? ctx->table_entries : 0; }
 
-// Line index into ctx->d_rec; leaves meta (n_lines, n_records) in ctx->h_meta.
-static int run_index(g2p_ctx* ctx, const u8* d_text, size_t n, cudaStream_t st, uint32_t* launches) {
+// Line index into w.d_rec; leaves meta (n_lines, n_records) in w.h_meta.
+static int run_index(g2p_ctx* ctx, Worker& w, const u8* d_text, size_t n, cudaStream_t st, uint32_t* launches) {
     const u32 ntiles = (u32)((n + kIdxTile - 1) / kIdxTile);
-    G2P_CUDA(ctx->d_tiles.ensure(((size_t)ntiles + 1) * sizeof(u32)));
-    PipelineMeta* d_meta = static_cast<PipelineMeta*>(ctx->d_meta.p);
-    u32* d_tiles = static_cast<u32*>(ctx->d_tiles.p);
+    G2P_CUDA(w.d_tiles.ensure(((size_t)ntiles + 1) * sizeof(u32)));
+    PipelineMeta* d_meta = static_cast<PipelineMeta*>(w.d_meta.p);
+    u32* d_tiles = static_cast<u32*>(w.d_tiles.p);
     if (ntiles) { k_count_lines<<<ntiles, kIdxThreads, 0, st>>>(d_text, n, d_tiles); ++*launches; }
     k_scan_tiles<<<1, 1024, 0, st>>>(d_tiles, ntiles, d_text, n, d_meta);
     ++*launches;
-    G2P_CUDA(cudaMemcpyAsync(ctx->h_meta.p, d_meta, sizeof(PipelineMeta), cudaMemcpyDeviceToHost, st));
+    G2P_CUDA(cudaMemcpyAsync(w.h_meta.p, d_meta, sizeof(PipelineMeta), cudaMemcpyDeviceToHost, st));
     G2P_CUDA(cudaStreamSynchronize(st));
-    const PipelineMeta* hm = static_cast<const PipelineMeta*>(ctx->h_meta.p);
-    G2P_CUDA(ctx->d_rec.ensure(((size_t)hm->n_records + 2) * sizeof(u32)));
+    const PipelineMeta* hm = static_cast<const PipelineMeta*>(w.h_meta.p);
+    G2P_CUDA(w.d_rec.ensure(((size_t)hm->n_records + 2) * sizeof(u32)));
     if (ntiles) {
-        k_fill_lines<<<ntiles, kIdxThreads, 0, st>>>(d_text, n, d_tiles, static_cast<u32*>(ctx->d_rec.p), d_meta);
+        k_fill_lines<<<ntiles, kIdxThreads, 0, st>>>(d_text, n, d_tiles, static_cast<u32*>(w.d_rec.p), d_meta);
         ++*launches;
     }
     G2P_CUDA(cudaGetLastError());
@@ -179,55 +204,50 @@ int g2p_index_lines(g2p_ctx* ctx, const void* d_text, size_t n, const uint32_t**
     if (!ctx || !d_starts || !n_lines) return G2P_E_ARG;
     if (n >= 0xFFFFFFF0ULL) return G2P_E_TOOBIG;
     G2P_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->own_stream;
+    Worker& w = ctx->w[0];
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : w.stream;
     uint32_t launches = 0;
-    int rc = run_index(ctx, static_cast<const u8*>(d_text), n, st, &launches);
+    int rc = run_index(ctx, w, static_cast<const u8*>(d_text), n, st, &launches);
     if (rc) return rc;
     G2P_CUDA(cudaStreamSynchronize(st));
-    *d_starts = static_cast<const uint32_t*>(ctx->d_rec.p);
-    *n_lines = static_cast<const PipelineMeta*>(ctx->h_meta.p)->n_records;
+    *d_starts = static_cast<const uint32_t*>(w.d_rec.p);
+    *n_lines = static_cast<const PipelineMeta*>(w.h_meta.p)->n_records;
     return G2P_OK;
 }
 
-int g2p_convert_device(g2p_ctx* ctx, const void* d_gaf_v, size_t n, void** d_out, g2p_result* res, void* stream) {
-    if (!ctx || !res || !d_out) return G2P_E_ARG;
-    if (!ctx->have_table) return G2P_E_NOTABLE;
-    if (n >= 0xFFFFFFF0ULL) return G2P_E_TOOBIG;
-    if ((reinterpret_cast<uintptr_t>(d_gaf_v) & 15) != 0) { ctx->err = "d_gaf must be 16-byte aligned"; return G2P_E_ARG; }
+// The device pipeline on one worker: index, size pass, scan, emit pass.  Returns with the stream
+// synchronised; *d_out is the worker's output buffer.
+static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cudaStream_t st, g2p_result* res, u8** d_out) {
     std::memset(res, 0, sizeof *res);
     *d_out = nullptr;
-    G2P_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->own_stream;
-    const u8* d_gaf = static_cast<const u8*>(d_gaf_v);
     uint32_t launches = 0;
-
-    G2P_CUDA(cudaEventRecord(ctx->ev[0], st));
-    int rc = run_index(ctx, d_gaf, n, st, &launches);
+    G2P_CUDA(cudaEventRecord(w.ev[0], st));
+    int rc = run_index(ctx, w, d_gaf, n, st, &launches);
     if (rc) return rc;
-    G2P_CUDA(cudaEventRecord(ctx->ev[1], st));
-    PipelineMeta* hm = static_cast<PipelineMeta*>(ctx->h_meta.p);
-    PipelineMeta* d_meta = static_cast<PipelineMeta*>(ctx->d_meta.p);
+    G2P_CUDA(cudaEventRecord(w.ev[1], st));
+    PipelineMeta* hm = static_cast<PipelineMeta*>(w.h_meta.p);
+    PipelineMeta* d_meta = static_cast<PipelineMeta*>(w.d_meta.p);
     const u32 nrec = hm->n_records;
     res->n_records = nrec;
     if (nrec == 0) {
-        G2P_CUDA(ctx->d_out.ensure(256));
-        *d_out = ctx->d_out.p;
+        G2P_CUDA(w.d_out.ensure(256));
+        *d_out = static_cast<u8*>(w.d_out.p);
         G2P_CUDA(cudaStreamSynchronize(st));
         res->gpu_launches = launches;
         return G2P_OK;
     }
-    G2P_CUDA(ctx->d_status.ensure((size_t)nrec * sizeof(u32)));
-    G2P_CUDA(ctx->d_off.ensure(((size_t)nrec + 1) * sizeof(u64)));
+    G2P_CUDA(w.d_status.ensure((size_t)nrec * sizeof(u32)));
+    G2P_CUDA(w.d_off.ensure(((size_t)nrec + 1) * sizeof(u64)));
     const u32 nscan = (nrec + kScanTile - 1) / kScanTile;
-    G2P_CUDA(ctx->d_blocks.ensure((size_t)nscan * sizeof(u64)));
-    u32* d_rec = static_cast<u32*>(ctx->d_rec.p);
-    u32* d_status = static_cast<u32*>(ctx->d_status.p);
-    u64* d_off = static_cast<u64*>(ctx->d_off.p);
-    u64* d_blocks = static_cast<u64*>(ctx->d_blocks.p);
-    G2P_CUDA(ctx->d_list.ensure((size_t)nrec * sizeof(u32)));
-    G2P_CUDA(ctx->d_list2.ensure((size_t)nrec * sizeof(u32)));
-    u32* d_list = static_cast<u32*>(ctx->d_list.p);
-    u32* d_list2 = static_cast<u32*>(ctx->d_list2.p);
+    G2P_CUDA(w.d_blocks.ensure((size_t)nscan * sizeof(u64)));
+    G2P_CUDA(w.d_list.ensure((size_t)nrec * sizeof(u32)));
+    G2P_CUDA(w.d_list2.ensure((size_t)nrec * sizeof(u32)));
+    u32* d_rec = static_cast<u32*>(w.d_rec.p);
+    u32* d_status = static_cast<u32*>(w.d_status.p);
+    u64* d_off = static_cast<u64*>(w.d_off.p);
+    u64* d_blocks = static_cast<u64*>(w.d_blocks.p);
+    u32* d_list = static_cast<u32*>(w.d_list.p);
+    u32* d_list2 = static_cast<u32*>(w.d_list2.p);
     const u32 ncta = (nrec + kShortRecsPerCta - 1) / kShortRecsPerCta;
     const u32 nlong = (u32)ctx->n_sm * 4u;
     const u32 nlist = std::min<u32>((nrec + kListThreads - 1) / kListThreads, (u32)ctx->n_sm * 16u);
@@ -240,7 +260,7 @@ int g2p_convert_device(g2p_ctx* ctx, const void* d_gaf_v, size_t n, void** d_out
     k_long<false><<<nlong, kLThreads, kLongSmem, st>>>(la);
     k_convert_list<false><<<nlist, kListThreads, 0, st>>>(d_gaf, d_rec, ctx->table, d_off, d_status, nullptr, d_meta, d_list2, &d_meta->n_deleg2);
     launches += 3;
-    G2P_CUDA(cudaEventRecord(ctx->ev[2], st));
+    G2P_CUDA(cudaEventRecord(w.ev[2], st));
     // exclusive scan -> offsets
     k_scan_reduce<<<nscan, kScanThreads, 0, st>>>(d_off, nrec, d_blocks);
     k_scan_blocks<<<1, 1024, 0, st>>>(d_blocks, nscan, d_meta);
@@ -251,10 +271,10 @@ int g2p_convert_device(g2p_ctx* ctx, const void* d_gaf_v, size_t n, void** d_out
     const u64 out_total = hm->out_total;
     res->n_long = hm->n_deleg;
     res->n_delegated = hm->n_deleg2;
-    G2P_CUDA(ctx->d_out.ensure(out_total + 256));
-    u8* d_o = static_cast<u8*>(ctx->d_out.p);
+    G2P_CUDA(w.d_out.ensure(out_total + 256));
+    u8* d_o = static_cast<u8*>(w.d_out.p);
     // pass 2: emit
-    G2P_CUDA(cudaEventRecord(ctx->ev[3], st));
+    G2P_CUDA(cudaEventRecord(w.ev[3], st));
     sa.out = d_o;
     la.out = d_o;
     k_short<kSG, true><<<ncta, kSThreads, kShortSmem, st>>>(sa);
@@ -267,7 +287,7 @@ int g2p_convert_device(g2p_ctx* ctx, const void* d_gaf_v, size_t n, void** d_out
         k_convert_list<true><<<nlist, kListThreads, 0, st>>>(d_gaf, d_rec, ctx->table, d_off, d_status, d_o, d_meta, d_list2, &d_meta->n_deleg2);
         ++launches;
     }
-    G2P_CUDA(cudaEventRecord(ctx->ev[4], st));
+    G2P_CUDA(cudaEventRecord(w.ev[4], st));
     res->out_bytes = out_total;
     if (hm->first_err != 0xFFFFFFFFu) {
         k_diagnose<<<1, 1, 0, st>>>(d_gaf, d_rec, ctx->table, d_off, d_meta);
@@ -284,29 +304,152 @@ int g2p_convert_device(g2p_ctx* ctx, const void* d_gaf_v, size_t n, void** d_out
         res->err_name_len = hm->err_b - hm->err_a;
         res->out_bytes = hm->err_out_end;   // what the reference has written before it stops
     }
-    cudaEventElapsedTime(&res->index_ms, ctx->ev[0], ctx->ev[1]);
-    cudaEventElapsedTime(&res->size_ms, ctx->ev[1], ctx->ev[2]);
-    cudaEventElapsedTime(&res->emit_ms, ctx->ev[3], ctx->ev[4]);
-    cudaEventElapsedTime(&res->device_ms, ctx->ev[0], ctx->ev[4]);
+    cudaEventElapsedTime(&res->index_ms, w.ev[0], w.ev[1]);
+    cudaEventElapsedTime(&res->size_ms, w.ev[1], w.ev[2]);
+    cudaEventElapsedTime(&res->emit_ms, w.ev[3], w.ev[4]);
+    cudaEventElapsedTime(&res->device_ms, w.ev[0], w.ev[4]);
     res->gpu_launches = launches;
     *d_out = d_o;
     return G2P_OK;
 }
 
+int g2p_convert_device(g2p_ctx* ctx, const void* d_gaf_v, size_t n, void** d_out, g2p_result* res, void* stream) {
+    if (!ctx || !res || !d_out) return G2P_E_ARG;
+    if (!ctx->have_table) return G2P_E_NOTABLE;
+    if (n >= 0xFFFFFFF0ULL) return G2P_E_TOOBIG;
+    if ((reinterpret_cast<uintptr_t>(d_gaf_v) & 15) != 0) { ctx->set_err("d_gaf must be 16-byte aligned"); return G2P_E_ARG; }
+    G2P_CUDA(cudaSetDevice(ctx->device));
+    Worker& w = ctx->w[0];
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : w.stream;
+    u8* d_o = nullptr;
+    int rc = run_pipeline(ctx, w, static_cast<const u8*>(d_gaf_v), n, st, res, &d_o);
+    *d_out = d_o;
+    return rc;
+}
+
+// Host-buffer entry point.  The input is cut into newline-aligned chunks; kWorkers host threads
+// each drive one chunk at a time through its own stream (H2D, pipeline, D2H), so the copies of
+// one chunk overlap the kernels of another.  Output bytes land in one pinned buffer in input
+// order; everything after the first failing record is dropped, like the reference's exit.
 int g2p_convert_host(g2p_ctx* ctx, const char* gaf, size_t n, const char** out, g2p_result* res) {
     if (!ctx || !res || !out || (!gaf && n)) return G2P_E_ARG;
+    if (!ctx->have_table) return G2P_E_NOTABLE;
     if (n >= 0xFFFFFFF0ULL) return G2P_E_TOOBIG;
     *out = nullptr;
+    std::memset(res, 0, sizeof *res);
     G2P_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->own_stream;
-    G2P_CUDA(ctx->d_in.ensure(n + 256));
-    if (n) G2P_CUDA(cudaMemcpyAsync(ctx->d_in.p, gaf, n, cudaMemcpyHostToDevice, st));
-    void* d_o = nullptr;
-    int rc = g2p_convert_device(ctx, ctx->d_in.p, n, &d_o, res, st);
-    if (rc) return rc;
-    G2P_CUDA(ctx->h_out.ensure(res->out_bytes + 1));
-    if (res->out_bytes) G2P_CUDA(cudaMemcpyAsync(ctx->h_out.p, d_o, res->out_bytes, cudaMemcpyDeviceToHost, st));
-    G2P_CUDA(cudaStreamSynchronize(st));
+
+    // newline-aligned chunk boundaries
+    std::vector<size_t> cut{0};
+    while (cut.back() < n) {
+        size_t e = cut.back() + ctx->host_chunk;
+        if (e >= n) e = n;
+        else {
+            const void* nl = std::memchr(gaf + e - 1, '\n', n - (e - 1));
+            e = nl ? (size_t)(static_cast<const char*>(nl) - gaf) + 1 : n;
+        }
+        cut.push_back(e);
+    }
+    const size_t nchunks = cut.size() - 1;
+    if (nchunks == 0) {
+        G2P_CUDA(ctx->h_out.ensure(1));
+        *out = static_cast<const char*>(ctx->h_out.p);
+        return G2P_OK;
+    }
+
+    struct Shared {
+        std::mutex mu;
+        std::condition_variable cv;
+        size_t published = 0;        // chunks whose output offset is known (prefix valid up to here)
+        size_t copied = 0;           // chunks (in order) whose D2H has completed
+        std::vector<u64> off;        // output offset of chunk i
+        std::vector<u64> recs;       // records before chunk i
+        size_t stop_at;              // first chunk with an error (chunks after it are ignored)
+        int rc = G2P_OK;
+    } S;
+    S.off.assign(nchunks + 1, 0);
+    S.recs.assign(nchunks + 1, 0);
+    S.stop_at = nchunks;
+    std::vector<g2p_result> cres(nchunks);
+    std::vector<char> done(nchunks, 0);
+    // first guess of the output size: keep what earlier calls needed, else 3x the input
+    if (ctx->h_out.cap == 0) G2P_CUDA(ctx->h_out.ensure(n * 3 + (1 << 20)));
+
+    auto worker = [&](int wi) {
+        cudaSetDevice(ctx->device);
+        Worker& w = ctx->w[wi];
+        for (size_t i = wi; i < nchunks; i += kWorkers) {
+            {
+                std::lock_guard<std::mutex> g(S.mu);
+                if (i > S.stop_at || S.rc != G2P_OK) break;
+            }
+            const size_t a = cut[i], len = cut[i + 1] - cut[i];
+            int rc = G2P_OK;
+            u8* d_o = nullptr;
+            g2p_result r;
+            std::memset(&r, 0, sizeof r);
+            if (w.d_in.ensure(len + 256) != cudaSuccess) rc = G2P_E_CUDA;
+            if (rc == G2P_OK && cudaMemcpyAsync(w.d_in.p, gaf + a, len, cudaMemcpyHostToDevice, w.stream) != cudaSuccess) rc = G2P_E_CUDA;
+            if (rc == G2P_OK) rc = run_pipeline(ctx, w, static_cast<const u8*>(w.d_in.p), len, w.stream, &r, &d_o);
+            // publish this chunk's output offset (in chunk order)
+            std::unique_lock<std::mutex> lk(S.mu);
+            S.cv.wait(lk, [&] { return S.published == i || S.rc != G2P_OK || i > S.stop_at; });
+            if (S.rc != G2P_OK || i > S.stop_at) break;   // an earlier chunk failed: this one is never reached
+            if (rc != G2P_OK) { S.rc = rc; S.cv.notify_all(); break; }
+            cres[i] = r;
+            S.off[i + 1] = S.off[i] + r.out_bytes;
+            S.recs[i + 1] = S.recs[i] + r.n_records;
+            if (r.rec_status != G2P_REC_OK) S.stop_at = i;
+            if (S.off[i + 1] + 1 > ctx->h_out.cap) {
+                // grow the pinned output: wait for the copies of earlier chunks, then move what is there
+                S.cv.wait(lk, [&] { return S.copied == i || S.rc != G2P_OK; });
+                PinBuf nb;
+                if (S.rc == G2P_OK && nb.ensure(S.off[i + 1] + (n - cut[i + 1]) * 4 + (1 << 20)) != cudaSuccess) { S.rc = G2P_E_CUDA; ctx->set_err("pinned output allocation failed"); }
+                if (S.rc != G2P_OK) { S.cv.notify_all(); break; }
+                std::memcpy(nb.p, ctx->h_out.p, S.off[i]);
+                ctx->h_out.release();
+                ctx->h_out = nb;
+            }
+            char* dst = static_cast<char*>(ctx->h_out.p) + S.off[i];
+            S.published = i + 1;
+            S.cv.notify_all();
+            lk.unlock();
+            cudaError_t ce = cudaSuccess;
+            if (r.out_bytes) ce = cudaMemcpyAsync(dst, d_o, r.out_bytes, cudaMemcpyDeviceToHost, w.stream);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(w.stream);
+            lk.lock();
+            if (ce != cudaSuccess) { S.rc = G2P_E_CUDA; ctx->set_err(std::string("D2H: ") + cudaGetErrorString(ce)); S.cv.notify_all(); break; }
+            done[i] = 1;
+            while (S.copied < nchunks && done[S.copied]) ++S.copied;
+            S.cv.notify_all();
+        }
+    };
+    if (nchunks == 1) worker(0);
+    else {
+        std::vector<std::thread> th;
+        const int nw = (int)std::min<size_t>(kWorkers, nchunks);
+        for (int wi = 1; wi < nw; ++wi) th.emplace_back(worker, wi);
+        worker(0);
+        for (auto& t : th) t.join();
+    }
+    if (S.rc != G2P_OK) return S.rc;
+    // aggregate
+    const size_t last = std::min(S.stop_at, nchunks - 1);
+    for (size_t i = 0; i <= last; ++i) {
+        const g2p_result& r = cres[i];
+        res->n_records += r.n_records;
+        res->gpu_launches += r.gpu_launches;
+        res->device_ms += r.device_ms; res->emit_ms += r.emit_ms; res->size_ms += r.size_ms; res->index_ms += r.index_ms;
+        res->n_delegated += r.n_delegated; res->n_long += r.n_long;
+    }
+    res->out_bytes = S.off[last + 1];
+    if (S.stop_at < nchunks) {
+        const g2p_result& r = cres[S.stop_at];
+        res->rec_status = r.rec_status; res->rec_aux = r.rec_aux;
+        res->err_record = S.recs[S.stop_at] + r.err_record;
+        res->err_name_off = cut[S.stop_at] + r.err_name_off;
+        res->err_name_len = r.err_name_len;
+    }
     *out = static_cast<const char*>(ctx->h_out.p);
     return G2P_OK;
 }

@@ -220,3 +220,35 @@ def test_cli_end_to_end(g2p):
         rc, out, err = H.run_tool(exe, ["-", "-l", lp], bad)
         rrc, rout2, rerr = H.run_tool(binary, ["-", "-l", lp], bad)
         assert rc == rrc == 1 and out == rout2 and err == rerr
+
+
+def test_host_call_pipelines_chunks(g2p, monkeypatch):
+    """g2p_convert_host cuts large inputs into newline-aligned chunks driven by several host threads
+    (copy/compute overlap).  Force many small chunks and compare with the oracle, with and without
+    a failing record in a middle chunk."""
+    monkeypatch.setenv("G2P_HOST_CHUNK_MB", "1")
+    p = H.preset("short", seed=81, pct_star=1)
+    lengths = H.gen_lengths(p)
+    gaf = H.gen_records(p, 0, 70000)
+    pa = H.preset("asm", seed=81, n_nodes=200000, node_len_lo=20, node_len_hi=400, steps_lo=300, steps_hi=3000)
+    gaf = gaf[:len(gaf) // 2] + H.gen_records(pa, 0, 20) + gaf[len(gaf) // 2:]
+    cv = g2p.Converter(0)
+    try:
+        assert cv.load_lengths(lengths)
+        out, res = cv.convert_host(gaf)
+        rc, ref, err, kind = H.run_gaf2paf_cpu(gaf, lengths)
+        assert rc == 0 and g2p.exit_code(res) == 0
+        assert res.n_records == gaf.count(b"\n") and out == ref
+        # second call reuses the grown buffers
+        out2, _ = cv.convert_host(gaf)
+        assert out2 == ref
+        # failing record in a middle chunk: output up to it, same message, later chunks ignored
+        cutp = gaf.rfind(b"\n", 0, len(gaf) * 2 // 3) + 1
+        bad = gaf[:cutp] + b"q\t100\t0\t15\t+\t>zzz:0-15\t15\t0\t15\t15\t15\t60\tcg:Z:15M\n" + gaf[cutp:]
+        out, res = cv.convert_host(bad)
+        rc, ref, err, kind = H.run_gaf2paf_cpu(bad, lengths)
+        assert rc == 1 and g2p.exit_code(res) == 1
+        assert out == ref and g2p.Converter.format_error(res, bad) == err
+        assert res.err_record == gaf[:cutp].count(b"\n")
+    finally:
+        cv.close()
