@@ -14,7 +14,7 @@ CXXFLAGS  := -O2 -std=c++17 -Wall -fPIC
 LIB       := $(PKG)/lib/libg2p.so
 HDRS      := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.hpp include/*.h)
 
-all: $(LIB) $(PKG)/bin/gaf2paf $(BUILD)/libgafgen.so $(BUILD)/gafgen hostsim
+all: $(LIB) $(PKG)/bin/gaf2paf $(PKG)/bin/gaf2unstable $(BUILD)/libgafgen.so $(BUILD)/gafgen hostsim
 
 $(LIB): $(CSRC)/g2p_capi.cu $(HDRS)
 	@mkdir -p $(PKG)/lib
@@ -37,7 +37,10 @@ $(BUILD)/gafgen: tools/gafgen.cpp
 	@mkdir -p $(BUILD)
 	$(CXX) $(CXXFLAGS) -DGAFGEN_MAIN -pthread -o $@ $<
 
-hostsim: $(BUILD)/g2p_hostsim $(BUILD)/g2p_simt $(BUILD)/g2p_simt_long
+hostsim: $(BUILD)/g2p_hostsim $(BUILD)/g2p_simt $(BUILD)/g2p_simt_long $(BUILD)/g2u_hostsim
+$(BUILD)/g2u_hostsim: tests/hostsim/g2u_hostsim.cpp $(HDRS)
+	@mkdir -p $(BUILD)
+	$(CXX) $(CXXFLAGS) -ffp-contract=off -o $@ $<
 $(BUILD)/g2p_simt_long: tests/hostsim/g2p_simt.cpp tests/hostsim/cuda_shim.hpp $(HDRS)
 	@mkdir -p $(BUILD)
 	$(CXX) -O1 -g -std=c++17 -ffp-contract=off -Wall -Wno-unused-function -Wno-unknown-pragmas -DG2P_S_LIMIT=0 -Itests/hostsim -o $@ $<

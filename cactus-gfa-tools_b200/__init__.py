@@ -37,6 +37,7 @@ REC_ABORT = 16
 EXPORTED_SYMBOLS = (
     "g2p_create", "g2p_destroy", "g2p_last_error", "g2p_host_alloc", "g2p_host_free", "g2p_load_lengths",
     "g2p_table_entries", "g2p_copy_to_device", "g2p_copy_to_host", "g2p_convert_device", "g2p_convert_host", "g2p_index_lines", "g2p_format_error",
+    "g2p_load_rgfa", "g2p_rgfa_node_lengths", "g2p_unstable_device", "g2p_unstable_host", "g2p_unstable_warnings", "g2p_format_unstable_warning",
 )
 
 
@@ -62,6 +63,11 @@ class Result(ctypes.Structure):
         ("n_delegated", ctypes.c_uint32),
         ("n_long", ctypes.c_uint32),
     ]
+
+
+class Warn(ctypes.Structure):
+    """struct g2p_warn (include/g2p.h)."""
+    _fields_ = [("record", ctypes.c_uint64), ("out_off", ctypes.c_uint64), ("out_len", ctypes.c_uint64)]
 
 
 def _load():
@@ -96,6 +102,18 @@ def _load():
     lib.g2p_index_lines.restype = ctypes.c_int
     lib.g2p_format_error.argtypes = [ctypes.POINTER(Result), vp, sz, vp, sz]
     lib.g2p_format_error.restype = ctypes.c_int
+    lib.g2p_load_rgfa.argtypes = [vp, vp, sz, ctypes.POINTER(ctypes.c_int), vp, sz]
+    lib.g2p_load_rgfa.restype = ctypes.c_int
+    lib.g2p_rgfa_node_lengths.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(sz)]
+    lib.g2p_rgfa_node_lengths.restype = ctypes.c_int
+    lib.g2p_unstable_device.argtypes = [vp, vp, sz, ctypes.POINTER(vp), ctypes.POINTER(Result), vp]
+    lib.g2p_unstable_device.restype = ctypes.c_int
+    lib.g2p_unstable_host.argtypes = [vp, vp, sz, ctypes.POINTER(vp), ctypes.POINTER(Result)]
+    lib.g2p_unstable_host.restype = ctypes.c_int
+    lib.g2p_unstable_warnings.argtypes = [vp, ctypes.POINTER(ctypes.POINTER(Warn)), ctypes.POINTER(sz)]
+    lib.g2p_unstable_warnings.restype = ctypes.c_int
+    lib.g2p_format_unstable_warning.argtypes = [vp, vp, sz, vp, sz]
+    lib.g2p_format_unstable_warning.restype = ctypes.c_int
     return lib
 
 
@@ -179,6 +197,43 @@ class Converter:
         nl = ctypes.c_uint64()
         self._check(lib.g2p_index_lines(self._h, d_ptr, n, ctypes.byref(starts), ctypes.byref(nl), stream or None))
         return starts.value, nl.value
+
+    # ---- gaf2unstable
+    def load_rgfa(self, rgfa):
+        """get_unstable_mapping + rgfa2contig (reference gaf2unstable_main.cpp:34-68, rgfa-split.cpp:35-161).
+        Returns (ok, reference exit code, reference stderr text)."""
+        addr, n, keep = _buf_ptr(rgfa)
+        code = ctypes.c_int()
+        msg = ctypes.create_string_buffer(1 << 16)
+        rc = lib.g2p_load_rgfa(self._h, addr, n, ctypes.byref(code), msg, len(msg))
+        if rc == G2P_E_TABLE:
+            return False, code.value, msg.value.decode("latin-1")
+        self._check(rc)
+        return True, 0, ""
+
+    def node_lengths(self):
+        """Contents of the -o file of gaf2unstable."""
+        p, n = ctypes.c_void_p(), ctypes.c_size_t()
+        self._check(lib.g2p_rgfa_node_lengths(self._h, ctypes.byref(p), ctypes.byref(n)))
+        return ctypes.string_at(p.value, n.value) if n.value else b""
+
+    def unstable_host(self, gaf):
+        """Stable-coordinate GAF in host memory -> (node-coordinate GAF bytes, Result, warning texts)."""
+        addr, n, keep = _buf_ptr(gaf)
+        out = ctypes.c_void_p()
+        res = Result()
+        self._check(lib.g2p_unstable_host(self._h, addr, n, ctypes.byref(out), ctypes.byref(res)))
+        data = ctypes.string_at(out.value, res.out_bytes) if res.out_bytes else b""
+        wp, wn = ctypes.POINTER(Warn)(), ctypes.c_size_t()
+        self._check(lib.g2p_unstable_warnings(self._h, ctypes.byref(wp), ctypes.byref(wn)))
+        warns = []
+        for i in range(wn.value):
+            w = wp[i]
+            line = data[w.out_off:w.out_off + w.out_len]
+            buf = ctypes.create_string_buffer(len(line) + 4096)
+            lib.g2p_format_unstable_warning(self._h, line, len(line), buf, len(buf))
+            warns.append(buf.value.decode("latin-1"))
+        return data, res, warns
 
     @staticmethod
     def format_error(res, gaf):

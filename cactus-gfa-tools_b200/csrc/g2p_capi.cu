@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
+#include <set>
 #include <thread>
 #include <vector>
 #include <cstring>
@@ -20,6 +21,7 @@
 #include "../../include/g2p.h"
 #include "g2p_kernels.cuh"
 #include "g2p_table.hpp"
+#include "g2u_rgfa.hpp"
 
 using namespace g2p;
 
@@ -91,7 +93,15 @@ struct g2p_ctx {
     bool have_table = false;
     Worker w[kWorkers];
     PinBuf h_out;
+    // gaf2unstable tables
+    DevBuf u_slots, u_arena, u_begin, u_nodes, u_names, u_refoff, u_refnames;
+    UnstableView uview{};
+    bool have_rgfa = false;
+    RgfaTables* rgfa = nullptr;
+    std::string node_lengths;
+    std::vector<g2p_warn> warns;
     size_t host_chunk = kHostChunk;
+    bool host_chunk_fixed = false;   // G2P_HOST_CHUNK_MB given: no adaptation to the record length
     void set_err(const std::string& m) { std::lock_guard<std::mutex> g(err_mu); err = m; }
 };
 
@@ -125,7 +135,7 @@ int g2p_create(int device, g2p_ctx** out) {
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
     if (const char* c = std::getenv("G2P_HOST_CHUNK_MB")) {
         long v = std::atol(c);
-        if (v > 0) ctx->host_chunk = (size_t)v << 20;
+        if (v > 0) { ctx->host_chunk = (size_t)v << 20; ctx->host_chunk_fixed = true; }
     }
     *out = ctx;
     return G2P_OK;
@@ -137,6 +147,8 @@ void g2p_destroy(g2p_ctx* ctx) {
     cudaDeviceSynchronize();
     ctx->d_slots.release();
     ctx->d_arena.release();
+    for (DevBuf* b : {&ctx->u_slots, &ctx->u_arena, &ctx->u_begin, &ctx->u_nodes, &ctx->u_names, &ctx->u_refoff, &ctx->u_refnames}) b->release();
+    delete ctx->rgfa;
     for (auto& w : ctx->w) w.release();
     ctx->h_out.release();
     delete ctx;
@@ -339,10 +351,19 @@ int g2p_convert_host(g2p_ctx* ctx, const char* gaf, size_t n, const char** out, 
     std::memset(res, 0, sizeof *res);
     G2P_CUDA(cudaSetDevice(ctx->device));
 
-    // newline-aligned chunk boundaries
+    // newline-aligned chunk boundaries.  Chunks must hold enough records to fill the GPU: short
+    // reads do at 96 MB, chromosome-scale records (one warp each in k_long) need more.
+    size_t chunk = ctx->host_chunk;
+    if (!ctx->host_chunk_fixed && n > chunk) {
+        const size_t probe = std::min<size_t>(n, 4u << 20);
+        size_t nl = 1;
+        for (const char* q = gaf; (q = static_cast<const char*>(std::memchr(q, '\n', gaf + probe - q))) != nullptr; ++q) ++nl;
+        const size_t avg = probe / nl;
+        chunk = std::min<size_t>(std::max<size_t>(chunk, avg * 4096), 768u << 20);
+    }
     std::vector<size_t> cut{0};
     while (cut.back() < n) {
-        size_t e = cut.back() + ctx->host_chunk;
+        size_t e = cut.back() + chunk;
         if (e >= n) e = n;
         else {
             const void* nl = std::memchr(gaf + e - 1, '\n', n - (e - 1));
@@ -451,6 +472,250 @@ int g2p_convert_host(g2p_ctx* ctx, const char* gaf, size_t n, const char** out, 
         res->err_name_len = r.err_name_len;
     }
     *out = static_cast<const char*>(ctx->h_out.p);
+    return G2P_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// gaf2unstable
+// ---------------------------------------------------------------------------------------
+int g2p_load_rgfa(g2p_ctx* ctx, const char* rgfa, size_t n, int* ref_exit_code, char* msg, size_t msg_cap) {
+    if (!ctx || (!rgfa && n)) return G2P_E_ARG;
+    if (ref_exit_code) *ref_exit_code = 0;
+    if (msg && msg_cap) msg[0] = 0;
+    G2P_CUDA(cudaSetDevice(ctx->device));
+    delete ctx->rgfa;
+    ctx->rgfa = new RgfaTables();
+    RgfaTables& T = *ctx->rgfa;
+    build_rgfa_tables(rgfa, n, T);
+    if (T.exit_code) {
+        if (ref_exit_code) *ref_exit_code = T.exit_code;
+        if (msg && msg_cap) std::snprintf(msg, msg_cap, "%s", T.exit_code == 1 ? T.error.c_str() : "");
+        ctx->set_err("rGFA: " + T.error);
+        ctx->have_rgfa = false;
+        return G2P_E_TABLE;
+    }
+    // flatten: contig hash -> index, nodes per contig sorted by SO, names, node -> reference contig
+    HostLenTable ct;
+    ct.reserve_for(T.mapping.size());
+    std::vector<u32> begin;
+    std::vector<UNode> nodes;
+    std::vector<u8> names;
+    ctx->node_lengths.clear();
+    u32 ci = 0;
+    for (const auto& cs : T.mapping) {
+        ct.put(reinterpret_cast<const u8*>(cs.first.data()), (u32)cs.first.size(), (i64)ci++);
+        begin.push_back((u32)nodes.size());
+        i64 cum = 0;
+        for (const RgfaNode& nd : cs.second) {
+            UNode u;
+            u.offset = nd.offset; u.cum = cum; u.length = (u32)nd.length;
+            u.name_off = (u32)names.size(); u.name_len = (u32)nd.name.size();
+            names.insert(names.end(), nd.name.begin(), nd.name.end());
+            int64_t id;
+            u.ref = -1;
+            if (rgfa_detail::node_id_of(nd.name, id)) {
+                auto it = T.node_to_contig.find(id);
+                if (it != T.node_to_contig.end()) u.ref = (i32)it->second;
+            }
+            cum += nd.length;
+            nodes.push_back(u);
+            ctx->node_lengths += nd.name;
+            ctx->node_lengths += '\t';
+            ctx->node_lengths += std::to_string(nd.length);
+            ctx->node_lengths += '\n';
+        }
+    }
+    begin.push_back((u32)nodes.size());
+    if (ct.arena.empty()) ct.arena.push_back(0);
+    std::vector<u32> refoff{0};
+    std::vector<u8> refnames;
+    for (const std::string& c : T.ref_contigs) { refnames.insert(refnames.end(), c.begin(), c.end()); refoff.push_back((u32)refnames.size()); }
+    if (names.empty()) names.push_back(0);
+    if (refnames.empty()) refnames.push_back(0);
+    if (nodes.empty()) nodes.push_back(UNode{0, 0, 0, 0, 0, -1});
+    G2P_CUDA(cudaDeviceSynchronize());
+    auto up = [&](DevBuf& b, const void* src, size_t bytes) -> cudaError_t {
+        cudaError_t e = b.ensure(bytes ? bytes : 16);
+        if (e != cudaSuccess) return e;
+        return bytes ? cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice) : cudaSuccess;
+    };
+    G2P_CUDA(up(ctx->u_slots, ct.slots.data(), ct.slots.size() * sizeof(LenSlot)));
+    G2P_CUDA(up(ctx->u_arena, ct.arena.data(), ct.arena.size()));
+    G2P_CUDA(up(ctx->u_begin, begin.data(), begin.size() * sizeof(u32)));
+    G2P_CUDA(up(ctx->u_nodes, nodes.data(), nodes.size() * sizeof(UNode)));
+    G2P_CUDA(up(ctx->u_names, names.data(), names.size()));
+    G2P_CUDA(up(ctx->u_refoff, refoff.data(), refoff.size() * sizeof(u32)));
+    G2P_CUDA(up(ctx->u_refnames, refnames.data(), refnames.size()));
+    ctx->uview.contigs.slots = static_cast<const LenSlot*>(ctx->u_slots.p);
+    ctx->uview.contigs.arena = static_cast<const u8*>(ctx->u_arena.p);
+    ctx->uview.contigs.nslots = (u32)ct.slots.size();
+    ctx->uview.contig_begin = static_cast<const u32*>(ctx->u_begin.p);
+    ctx->uview.nodes = static_cast<const UNode*>(ctx->u_nodes.p);
+    ctx->uview.node_names = static_cast<const u8*>(ctx->u_names.p);
+    ctx->uview.ref_off = static_cast<const u32*>(ctx->u_refoff.p);
+    ctx->uview.ref_names = static_cast<const u8*>(ctx->u_refnames.p);
+    ctx->have_rgfa = true;
+    return G2P_OK;
+}
+
+int g2p_rgfa_node_lengths(g2p_ctx* ctx, const char** tsv, size_t* n) {
+    if (!ctx || !tsv || !n) return G2P_E_ARG;
+    if (!ctx->have_rgfa) return G2P_E_NOTABLE;
+    *tsv = ctx->node_lengths.data();
+    *n = ctx->node_lengths.size();
+    return G2P_OK;
+}
+
+static int run_unstable(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cudaStream_t st, g2p_result* res, u8** d_out) {
+    std::memset(res, 0, sizeof *res);
+    *d_out = nullptr;
+    ctx->warns.clear();
+    uint32_t launches = 0;
+    G2P_CUDA(cudaEventRecord(w.ev[0], st));
+    int rc = run_index(ctx, w, d_gaf, n, st, &launches);
+    if (rc) return rc;
+    G2P_CUDA(cudaEventRecord(w.ev[1], st));
+    PipelineMeta* hm = static_cast<PipelineMeta*>(w.h_meta.p);
+    PipelineMeta* d_meta = static_cast<PipelineMeta*>(w.d_meta.p);
+    const u32 nrec = hm->n_records;
+    res->n_records = nrec;
+    G2P_CUDA(w.d_out.ensure(256));
+    *d_out = static_cast<u8*>(w.d_out.p);
+    if (nrec == 0) { G2P_CUDA(cudaStreamSynchronize(st)); res->gpu_launches = launches; return G2P_OK; }
+    G2P_CUDA(w.d_status.ensure((size_t)nrec * sizeof(u32)));
+    G2P_CUDA(w.d_off.ensure(((size_t)nrec + 1) * sizeof(u64)));
+    const u32 nscan = (nrec + kScanTile - 1) / kScanTile;
+    G2P_CUDA(w.d_blocks.ensure((size_t)nscan * sizeof(u64)));
+    G2P_CUDA(w.d_list.ensure((size_t)nrec * sizeof(u32)));
+    u32* d_rec = static_cast<u32*>(w.d_rec.p);
+    u32* d_status = static_cast<u32*>(w.d_status.p);
+    u64* d_off = static_cast<u64*>(w.d_off.p);
+    u64* d_blocks = static_cast<u64*>(w.d_blocks.p);
+    u32* d_list = static_cast<u32*>(w.d_list.p);
+    const u32 ncta = std::min<u32>((nrec + kListThreads - 1) / kListThreads, (u32)ctx->n_sm * 32u);
+    k_unstable<false><<<ncta, kListThreads, 0, st>>>(d_gaf, d_rec, nrec, ctx->uview, d_off, d_status, nullptr, d_meta, d_list);
+    ++launches;
+    G2P_CUDA(cudaEventRecord(w.ev[2], st));
+    k_scan_reduce<<<nscan, kScanThreads, 0, st>>>(d_off, nrec, d_blocks);
+    k_scan_blocks<<<1, 1024, 0, st>>>(d_blocks, nscan, d_meta);
+    k_scan_apply<<<nscan, kScanThreads, 0, st>>>(d_off, nrec, d_blocks, d_meta);
+    launches += 3;
+    G2P_CUDA(cudaMemcpyAsync(hm, d_meta, sizeof(PipelineMeta), cudaMemcpyDeviceToHost, st));
+    G2P_CUDA(cudaStreamSynchronize(st));
+    const u64 out_total = hm->out_total;
+    G2P_CUDA(w.d_out.ensure(out_total + 256));
+    u8* d_o = static_cast<u8*>(w.d_out.p);
+    G2P_CUDA(cudaEventRecord(w.ev[3], st));
+    k_unstable<true><<<ncta, kListThreads, 0, st>>>(d_gaf, d_rec, nrec, ctx->uview, d_off, d_status, d_o, d_meta, d_list);
+    ++launches;
+    G2P_CUDA(cudaEventRecord(w.ev[4], st));
+    G2P_CUDA(cudaStreamSynchronize(st));
+    G2P_CUDA(cudaGetLastError());
+    res->out_bytes = out_total;
+    const u32 first_err = hm->first_err;
+    std::vector<u64> off;
+    if (first_err != 0xFFFFFFFFu || hm->n_deleg) {
+        off.resize((size_t)nrec + 1);
+        G2P_CUDA(cudaMemcpy(off.data(), d_off, off.size() * sizeof(u64), cudaMemcpyDeviceToHost));
+    }
+    if (first_err != 0xFFFFFFFFu) {
+        u32 stv = 0;
+        G2P_CUDA(cudaMemcpy(&stv, d_status + first_err, sizeof(u32), cudaMemcpyDeviceToHost));
+        res->rec_status = stv & 0xff;
+        res->rec_aux = (stv >> 8) & 0xff;
+        res->err_record = first_err;
+        res->out_bytes = off[first_err];
+    }
+    if (hm->n_deleg) {
+        std::vector<u32> wl(hm->n_deleg);
+        G2P_CUDA(cudaMemcpy(wl.data(), d_list, wl.size() * sizeof(u32), cudaMemcpyDeviceToHost));
+        std::sort(wl.begin(), wl.end());
+        for (u32 r : wl) {
+            if (first_err != 0xFFFFFFFFu && r >= first_err) break;
+            ctx->warns.push_back(g2p_warn{r, off[r], off[r + 1] - off[r]});
+        }
+    }
+    cudaEventElapsedTime(&res->index_ms, w.ev[0], w.ev[1]);
+    cudaEventElapsedTime(&res->size_ms, w.ev[1], w.ev[2]);
+    cudaEventElapsedTime(&res->emit_ms, w.ev[3], w.ev[4]);
+    cudaEventElapsedTime(&res->device_ms, w.ev[0], w.ev[4]);
+    res->gpu_launches = launches;
+    *d_out = d_o;
+    return G2P_OK;
+}
+
+int g2p_unstable_device(g2p_ctx* ctx, const void* d_gaf_v, size_t n, void** d_out, g2p_result* res, void* stream) {
+    if (!ctx || !res || !d_out) return G2P_E_ARG;
+    if (!ctx->have_rgfa) return G2P_E_NOTABLE;
+    if (n >= 0xFFFFFFF0ULL) return G2P_E_TOOBIG;
+    if ((reinterpret_cast<uintptr_t>(d_gaf_v) & 15) != 0) { ctx->set_err("d_gaf must be 16-byte aligned"); return G2P_E_ARG; }
+    G2P_CUDA(cudaSetDevice(ctx->device));
+    Worker& w = ctx->w[0];
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : w.stream;
+    u8* d_o = nullptr;
+    int rc = run_unstable(ctx, w, static_cast<const u8*>(d_gaf_v), n, st, res, &d_o);
+    *d_out = d_o;
+    return rc;
+}
+
+int g2p_unstable_host(g2p_ctx* ctx, const char* gaf, size_t n, const char** out, g2p_result* res) {
+    if (!ctx || !res || !out || (!gaf && n)) return G2P_E_ARG;
+    if (!ctx->have_rgfa) return G2P_E_NOTABLE;
+    if (n >= 0xFFFFFFF0ULL) return G2P_E_TOOBIG;
+    *out = nullptr;
+    G2P_CUDA(cudaSetDevice(ctx->device));
+    Worker& w = ctx->w[0];
+    G2P_CUDA(w.d_in.ensure(n + 256));
+    if (n) G2P_CUDA(cudaMemcpyAsync(w.d_in.p, gaf, n, cudaMemcpyHostToDevice, w.stream));
+    u8* d_o = nullptr;
+    int rc = run_unstable(ctx, w, static_cast<const u8*>(w.d_in.p), n, w.stream, res, &d_o);
+    if (rc) return rc;
+    G2P_CUDA(ctx->h_out.ensure(res->out_bytes + 1));
+    if (res->out_bytes) G2P_CUDA(cudaMemcpyAsync(ctx->h_out.p, d_o, res->out_bytes, cudaMemcpyDeviceToHost, w.stream));
+    G2P_CUDA(cudaStreamSynchronize(w.stream));
+    *out = static_cast<const char*>(ctx->h_out.p);
+    return G2P_OK;
+}
+
+int g2p_unstable_warnings(g2p_ctx* ctx, const g2p_warn** warns, size_t* n) {
+    if (!ctx || !warns || !n) return G2P_E_ARG;
+    *warns = ctx->warns.data();
+    *n = ctx->warns.size();
+    return G2P_OK;
+}
+
+// "[gaf2unstable] warning: Target path spans multiple reference contigs a, b, \nthe (unstable) record is\n<line>\n"
+// (gaf2unstable_main.cpp:165-171): contig names in ascending contig-id order; the record printed
+// there does not carry an rc tag of its own making, which is what the output line holds as well.
+int g2p_format_unstable_warning(g2p_ctx* ctx, const char* line, size_t len, char* buf, size_t cap) {
+    if (!ctx || !line || !buf || cap == 0 || !ctx->rgfa) return G2P_E_ARG;
+    buf[0] = 0;
+    const RgfaTables& T = *ctx->rgfa;
+    // column 6 = the path
+    size_t a = 0;
+    for (int c = 0; c < 5 && a < len; ++c) { const void* t = std::memchr(line + a, '\t', len - a); if (!t) return G2P_E_ARG; a = static_cast<const char*>(t) - line + 1; }
+    const void* te = std::memchr(line + a, '\t', len - a);
+    const size_t b = te ? static_cast<const char*>(te) - line : len;
+    std::set<int64_t> ids;
+    size_t p = a;
+    while (p < b) {
+        size_t q = p + 1;
+        while (q < b && line[q] != '>' && line[q] != '<') ++q;
+        int64_t id;
+        if (rgfa_detail::node_id_of(std::string(line + p + 1, q - p - 1), id)) {
+            auto it = T.node_to_contig.find(id);
+            if (it != T.node_to_contig.end()) ids.insert(it->second);
+        }
+        p = q;
+    }
+    std::string m = "[gaf2unstable] warning: Target path spans multiple reference contigs ";
+    for (int64_t id : ids) { m += T.ref_contigs[(size_t)id]; m += ", "; }
+    m += "\nthe (unstable) record is\n";
+    size_t ll = len;
+    while (ll > 0 && line[ll - 1] == '\n') --ll;
+    m.append(line, ll);
+    m += "\n";
+    std::snprintf(buf, cap, "%s", m.c_str());
     return G2P_OK;
 }
 

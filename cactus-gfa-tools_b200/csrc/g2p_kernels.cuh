@@ -20,6 +20,7 @@
 #include "g2p_core.cuh"
 #include "g2p_short.cuh"
 #include "g2p_long.cuh"
+#include "g2u_core.cuh"
 
 namespace g2p {
 
@@ -260,6 +261,42 @@ __global__ void __launch_bounds__(kListThreads) k_convert_list(const u8* __restr
             if (st_is_abort(st) || (st & 0xff) == ST_SKIP) continue;
             StoreSink ss(out + out_off[r]);
             convert_record_global(gaf + s, len, T, ss, ea, eb);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------
+// gaf2unstable: one thread rewrites one record with
+// unstable_record (g2u_core.cuh): per step a hash probe for the stable contig and two
+// binary searches in its node array, then the record is re-serialised with its tags in
+// name order.  Same two passes as gaf2paf (size -> scan -> emit).  Records whose path
+// spans several reference contigs are listed for the host, which prints the reference's
+// warning for them.
+// ------------------------------------------------------------------------------
+template <class Sink>
+__device__ G2P_NOINLINE u32 unstable_record_global(const u8* r, u32 len, const UnstableView& V, Sink& S, u32& ea, u32& eb) {
+    return unstable_record(r, len, V, S, ea, eb);
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(kListThreads) k_unstable(const u8* __restrict__ gaf, const u32* __restrict__ rec_start, u32 nrec, UnstableView V,
+                                                           u64* __restrict__ out_off, u32* __restrict__ status, u8* __restrict__ out,
+                                                           PipelineMeta* __restrict__ meta, u32* __restrict__ warn_list) {
+    for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < nrec; r += gridDim.x * blockDim.x) {
+        const u32 s = rec_start[r], len = rec_start[r + 1] - s - 1;
+        u32 ea = 0, eb = 0;
+        if (!EMIT) {
+            CountSink cs;
+            const u32 st = unstable_record_global(gaf + s, len, V, cs, ea, eb);
+            out_off[r] = (st_is_abort(st) || (st & 0xff) == ST_SKIP) ? 0 : cs.n;
+            status[r] = st;
+            if (st_is_error(st)) atomicMin(&meta->first_err, r);
+            else if ((st & 0xff) == ST_WARN_MULTIREF) warn_list[atomicAdd(&meta->n_deleg, 1u)] = r;
+        } else {
+            const u32 st = status[r];
+            if (st_is_abort(st) || (st & 0xff) == ST_SKIP) continue;
+            StoreSink ss(out + out_off[r]);
+            unstable_record_global(gaf + s, len, V, ss, ea, eb);
         }
     }
 }

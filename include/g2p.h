@@ -105,6 +105,39 @@ int g2p_convert_host(g2p_ctx* ctx, const char* gaf, size_t n, const char** out, 
  * n_lines+1 uint32 offsets (last = n, or n+1 when the final line lacks '\n'). */
 int g2p_index_lines(g2p_ctx* ctx, const void* d_text, size_t n, const uint32_t** d_starts, uint64_t* n_lines, void* stream);
 
+/* ---- gaf2unstable (config 2: stable -> unstable node coordinates) ---------------------- */
+
+/* Replaces get_unstable_mapping (gaf2unstable_main.cpp:34-68) and rgfa2contig
+ * (rgfa-split.cpp:35-161): scans the S and L lines of a minigraph rGFA held in host memory
+ * (gfakluge.hpp:757-967 semantics), builds stable contig -> nodes sorted by SO and node ->
+ * reference contig on the host, and uploads them as flat arrays.  When the reference would
+ * die on this rGFA, returns G2P_E_TABLE with *ref_exit_code = 1 or 134 and its stderr text
+ * (exit 1 cases) in msg. */
+int g2p_load_rgfa(g2p_ctx* ctx, const char* rgfa, size_t n, int* ref_exit_code, char* msg, size_t msg_cap);
+
+/* Contents of the -o node-lengths file (gaf2unstable_main.cpp:274-285), rows in the
+ * reference's order.  Library-owned, valid until the next g2p_load_rgfa / g2p_destroy. */
+int g2p_rgfa_node_lengths(g2p_ctx* ctx, const char** tsv, size_t* n);
+
+/* Replaces the record loop of gaf2unstable main() (gaf2unstable_main.cpp:288-297) with
+ * parse_gaf_record / gaf2unstable / operator<<(GafRecord) (gafkluge.hpp:84-204, :288-323,
+ * gaf2unstable_main.cpp:70-175) for a newline-delimited block of GAF text.  On a record the
+ * reference would abort on, res->rec_status >= G2P_REC_ABORT, res->err_record names it and
+ * out_bytes covers the records before it. */
+int g2p_unstable_device(g2p_ctx* ctx, const void* d_gaf, size_t n, void** d_out, g2p_result* res, void* stream);
+int g2p_unstable_host(g2p_ctx* ctx, const char* gaf, size_t n, const char** out, g2p_result* res);
+
+/* Records of the last g2p_unstable_* call whose path spans several reference contigs
+ * (gaf2unstable_main.cpp:165-171), in record order: their output line is out + out_off. */
+typedef struct g2p_warn {
+    uint64_t record;
+    uint64_t out_off;
+    uint64_t out_len;   /* including the trailing newline */
+} g2p_warn;
+int g2p_unstable_warnings(g2p_ctx* ctx, const g2p_warn** warns, size_t* n);
+/* The reference's stderr text for one such output line. */
+int g2p_format_unstable_warning(g2p_ctx* ctx, const char* out_line, size_t len, char* buf, size_t cap);
+
 /* Formats the stderr line the reference prints for a failed record (empty for aborts,
  * whose text comes from the C++ runtime).  `gaf` is the host copy of the input. */
 int g2p_format_error(const g2p_result* res, const char* gaf, size_t n, char* buf, size_t cap);

@@ -127,3 +127,113 @@ def run_gaf2paf_cpu(gaf, lengths, kind="auto"):
 def golden(name):
     with open(os.path.join(GOLDEN, name)) as f:
         return json.load(f)
+
+
+# ---- gaf2unstable: synthetic rGFA + stable-coordinate GAF (BASELINE config 2 shape) -------------
+def gen_rgfa_case(seed, n_contigs=4, n_records=500, aligned=False, multi_ref_pct=3):
+    """Returns (rgfa bytes, gaf bytes).  Rank-0 chains over `n_contigs` reference contigs (one with an
+    "id=..|" SN prefix), rank-1 bubble nodes on non-reference contigs, and minigraph-like GAF records
+    whose path steps are stable intervals (`aligned`: intervals coincide with node boundaries, as
+    minigraph emits them, so that the output is valid input for gaf2paf), whole-contig paths,
+    unmapped records and '*' lines."""
+    import random
+    rnd = random.Random(seed)
+    lines, contigs = [], []          # contigs: (sn, [(name, off, len)])
+    nid = 1
+    links = []
+    for c in range(n_contigs):
+        sn = ("id=HG%d|chr%d" % (c, c + 1)) if c == 1 else "chr%d" % (c + 1)
+        nodes, off = [], 0
+        for _ in range(rnd.randrange(8, 40)):
+            ln = rnd.randrange(20, 300)
+            nodes.append(("s%d" % nid, off, ln)); nid += 1
+            off += ln
+        contigs.append((sn, nodes))
+    bubbles = []
+    for c, (sn, nodes) in enumerate(contigs):
+        for k in range(rnd.randrange(1, 4)):
+            i = rnd.randrange(0, len(nodes) - 2)
+            ln = rnd.randrange(20, 200)
+            bsn = "HG00%d#1#ctg%d_%d" % (c, c, k)
+            boff = rnd.randrange(0, 5000)
+            bubbles.append((bsn, [("s%d" % nid, boff, ln)], nodes[i][0], nodes[i + 2][0]))
+            nid += 1
+    def seq(n):
+        return "".join(rnd.choice("ACGT") for _ in range(n))
+    for sn, nodes in contigs:
+        for j, (name, off, ln) in enumerate(nodes):
+            lines.append("S\t%s\t%s\tLN:i:%d\tSN:Z:%s\tSO:i:%d\tSR:i:0" % (name, seq(ln), ln, sn, off))
+            if j:
+                links.append("L\t%s\t+\t%s\t+\t0M\tSR:i:0\tL1:i:%d\tL2:i:%d" % (nodes[j - 1][0], name, nodes[j - 1][2], ln))
+    for bsn, bn, left, right in bubbles:
+        name, off, ln = bn[0]
+        lines.append("S\t%s\t%s\tLN:i:%d\tSN:Z:%s\tSO:i:%d\tSR:i:1" % (name, seq(ln), ln, bsn, off))
+        links.append("L\t%s\t+\t%s\t+\t0M\tSR:i:1\tL1:i:1\tL2:i:%d" % (left, name, ln))
+        links.append("L\t%s\t+\t%s\t+\t0M\tSR:i:1\tL1:i:%d\tL2:i:1" % (name, right, ln))
+    rgfa = ("\n".join(lines + links) + "\n").encode()
+    allc = contigs + [(b[0], b[1]) for b in bubbles]
+
+    def interval(sn, nodes):
+        lo, hi = nodes[0][1], nodes[-1][1] + nodes[-1][2]
+        if aligned:
+            i = rnd.randrange(len(nodes))   # minigraph's stable steps are exactly one node each
+            return nodes[i][1], nodes[i][1] + nodes[i][2]
+        s = rnd.randrange(lo, hi - 1)
+        return s, rnd.randrange(s + 1, min(hi, s + 900) + 1)
+
+    recs = []
+    for r in range(n_records):
+        x = rnd.random()
+        tags = rnd.sample(["tp:A:P", "cm:i:%d" % rnd.randrange(100), "s1:i:%d" % rnd.randrange(500), "dv:f:0.0123", "rc:Z:old", "zd:i:3"],
+                          rnd.randrange(0, 5))
+        mapq = rnd.choice([0, 1, 60, 255, 300])
+        strand = rnd.choice("+-")
+        if x < 0.02:
+            recs.append("*\t>s43\t97\t12\t0\t6\t92")
+            continue
+        if x < 0.05 and not aligned:   # unmapped record: no cg tag, gaf2paf would stop on it
+            recs.append("\t".join(["q%d" % r, "200", "0", "60", "+", "*", "*", "*", "*", "*", "*", "255"] + tags))
+            continue
+        if x < 0.20:   # whole-contig path
+            sn, nodes = rnd.choice(contigs)
+            s, e = interval(sn, nodes)
+            plen = nodes[-1][1] + nodes[-1][2]
+            W = e - s
+            cg = "cg:Z:%dM" % W
+            cols = ["q%d" % r, str(W + 20), "5", str(5 + W), strand, sn, str(plen), str(s), str(e), str(W), str(W), str(mapq)]
+        else:
+            ci = rnd.randrange(len(contigs))
+            steps, total, lens = [], 0, []
+            for k in range(rnd.randrange(1, 7)):
+                pool = contigs[ci:ci + 1] + [(b[0], b[1]) for b in bubbles if b[0].startswith("HG00%d#" % ci)]
+                if rnd.random() * 100 < multi_ref_pct:
+                    pool = allc
+                sn, nodes = rnd.choice(pool)
+                s, e = interval(sn, nodes)
+                steps.append("%s%s:%d-%d" % (rnd.choice("><"), sn, s, e))
+                lens.append(e - s); total += e - s
+            ps = rnd.randrange(0, lens[0])
+            pe = total - rnd.randrange(0, lens[-1]) if len(lens) > 1 else rnd.randrange(ps + 1, total + 1)
+            if pe <= ps:
+                ps, pe = 0, total
+            W = pe - ps
+            a = rnd.randrange(1, W) if W > 3 else W
+            cg = "cg:Z:%dM" % W if a == W else "cg:Z:%dM2I%dM" % (a, W - a)
+            q = W + (0 if a == W else 2)
+            cols = ["q%d" % r, str(q + 20), "5", str(5 + q), strand, "".join(steps), str(total), str(ps), str(pe), str(W), str(q), str(mapq)]
+        pos = rnd.randrange(0, len(tags) + 1)
+        recs.append("\t".join(cols + tags[:pos] + [cg] + tags[pos:]))
+    return rgfa, ("\n".join(recs) + "\n").encode()
+
+
+def run_gaf2unstable_ref(gaf, rgfa, want_lengths=False):
+    """The reference gaf2unstable (oracle/_ref) on in-memory inputs -> (rc, stdout, stderr[, node-lengths])."""
+    binary = os.path.join(REF_BIN, "gaf2unstable")
+    with tempfile.TemporaryDirectory() as td:
+        gp, lp = os.path.join(td, "g.gfa"), os.path.join(td, "nl.tsv")
+        with open(gp, "wb") as f:
+            f.write(rgfa)
+        rc, out, err = run_tool(binary, ["-", "-g", gp] + (["-o", lp] if want_lengths else []), gaf)
+        if want_lengths:
+            return rc, out, err, open(lp, "rb").read() if os.path.exists(lp) else b""
+    return rc, out, err

@@ -231,7 +231,8 @@ def test_host_call_pipelines_chunks(g2p, monkeypatch):
     lengths = H.gen_lengths(p)
     gaf = H.gen_records(p, 0, 70000)
     pa = H.preset("asm", seed=81, n_nodes=200000, node_len_lo=20, node_len_hi=400, steps_lo=300, steps_hi=3000)
-    gaf = gaf[:len(gaf) // 2] + H.gen_records(pa, 0, 20) + gaf[len(gaf) // 2:]
+    mid = gaf.rfind(b"\n", 0, len(gaf) // 2) + 1
+    gaf = gaf[:mid] + H.gen_records(pa, 0, 20) + gaf[mid:]
     cv = g2p.Converter(0)
     try:
         assert cv.load_lengths(lengths)
@@ -252,3 +253,72 @@ def test_host_call_pipelines_chunks(g2p, monkeypatch):
         assert res.err_record == gaf[:cutp].count(b"\n")
     finally:
         cv.close()
+
+
+# ---- gaf2unstable (BASELINE config 2) ------------------------------------------------------
+def test_gaf2unstable_golden(g2p):
+    d = H.golden("gaf2unstable_kat.json")
+    cv = g2p.Converter(0)
+    try:
+        ok, code, msg = cv.load_rgfa(d["rgfa"].encode())
+        assert ok
+        assert cv.node_lengths().decode() == d["node_lengths"]
+        for v in d["vectors"]:
+            out, res, warns = cv.unstable_host((v["in"] + "\n").encode())
+            assert g2p.exit_code(res) == v["rc"] and out.decode() == v["out"], v["in"]
+        out, res, warns = cv.unstable_host(("\n".join(d["stream"]["in"]) + "\n").encode())
+        assert out.decode() == d["stream"]["out"] and res.gpu_launches >= 5
+        # second stage on the same context: gaf2paf -l node-lengths
+        assert cv.load_lengths(cv.node_lengths())
+        paf, res2 = cv.convert_host(out)
+        assert paf.decode() == d["paf"]["out"] and g2p.exit_code(res2) == d["paf"]["rc"]
+    finally:
+        cv.close()
+
+
+@pytest.mark.parametrize("seed,aligned", [(11, False), (12, True)])
+def test_gaf2unstable_synthetic_and_two_stage(g2p, seed, aligned):
+    """gaf2unstable on a synthetic rGFA == reference (stdout, -o file, warnings); for node-aligned
+    input the two-stage pipeline gaf2unstable | gaf2paf == the reference's (README.md:55-58)."""
+    rgfa, gaf = H.gen_rgfa_case(seed, n_records=4000, aligned=aligned)
+    rc, ref, err, nl = H.run_gaf2unstable_ref(gaf, rgfa, True)
+    assert rc == 0
+    cv = g2p.Converter(0)
+    try:
+        ok, code, msg = cv.load_rgfa(rgfa)
+        assert ok and cv.node_lengths() == nl
+        out, res, warns = cv.unstable_host(gaf)
+        assert g2p.exit_code(res) == 0 and out == ref
+        assert "".join(warns) == err
+        if aligned:
+            rc2, paf_ref, err2, kind = H.run_gaf2paf_cpu(ref, nl)
+            assert cv.load_lengths(nl)
+            paf, res2 = cv.convert_host(out)
+            assert rc2 == 0 and g2p.exit_code(res2) == 0 and paf == paf_ref
+    finally:
+        cv.close()
+
+
+def test_gaf2unstable_abort_and_cli(g2p):
+    rgfa, gaf = H.gen_rgfa_case(21, n_records=1500, aligned=True)
+    bad = gaf + b"q\t100\t0\t15\t+\t>nosuchcontig:0-15\t15\t0\t15\t15\t15\t60\tcg:Z:15M\n" + gaf[:2000]
+    exe = os.path.join(g2p.BIN_DIR, "gaf2unstable")
+    ref_exe = os.path.join(H.REF_BIN, "gaf2unstable")
+    with tempfile.TemporaryDirectory() as td:
+        gp, a = os.path.join(td, "g.gfa"), os.path.join(td, "a.gaf")
+        open(gp, "wb").write(rgfa)
+        open(a, "wb").write(gaf)
+        l1, l2 = os.path.join(td, "l1.tsv"), os.path.join(td, "l2.tsv")
+        rc, out, err = H.run_tool(exe, [a, "-g", gp, "-o", l1])
+        rrc, rout, rerr = H.run_tool(ref_exe, [a, "-g", gp, "-o", l2])
+        assert rc == rrc == 0 and out == rout and err == rerr
+        assert open(l1, "rb").read() == open(l2, "rb").read()
+        rc, out, err = H.run_tool(exe, ["-", "--rgfa", gp], bad)
+        rrc, rout, rerr = H.run_tool(ref_exe, ["-", "--rgfa", gp], bad)
+        assert rc == rrc == 134
+        assert out == rout[:len(out)] and out.count(b"\n") == gaf.count(b"\n")   # records before the failing one
+        # usage errors
+        for args in ([], [a], [a, "b", "c", "-g", gp]):
+            rc, out, err = H.run_tool(exe, args)
+            rrc, rout, rerr = H.run_tool(ref_exe, args)
+            assert rc == rrc and err.replace(exe, "X") == rerr.replace(ref_exe, "X")

@@ -89,3 +89,36 @@ def test_unterminated_last_line_and_two_files():
         for binary in (PORT, HOSTSIM):
             rc, out, err = H.run_tool(binary, [a, b, "-l", lp])
             assert rc == 0 and out.decode("latin-1") == d["stream"]["out"], binary
+
+
+# ---- gaf2unstable (config 2) ---------------------------------------------------------------
+G2U_HOSTSIM = os.path.join(H.BUILD, "g2u_hostsim")
+G2U_REF = os.path.join(H.REF_BIN, "gaf2unstable")
+
+
+def test_gaf2unstable_host_code_matches_golden():
+    d = H.golden("gaf2unstable_kat.json")
+    with tempfile.TemporaryDirectory() as td:
+        gp, lp = os.path.join(td, "g.gfa"), os.path.join(td, "nl.tsv")
+        open(gp, "w").write(d["rgfa"])
+        for v in d["vectors"]:
+            rc, out, err = H.run_tool(G2U_HOSTSIM, ["-g", gp, "-"], (v["in"] + "\n").encode())
+            assert rc == v["rc"] and out.decode() == v["out"], v["in"]
+        rc, out, err = H.run_tool(G2U_HOSTSIM, ["-g", gp, "-o", lp, "-"], ("\n".join(d["stream"]["in"]) + "\n").encode())
+        assert rc == 0 and out.decode() == d["stream"]["out"]
+        assert open(lp).read() == d["node_lengths"]
+
+
+@pytest.mark.skipif(not os.path.exists(G2U_REF), reason="reference build (oracle/_ref) not present")
+@pytest.mark.parametrize("seed,aligned", [(1, False), (2, True), (3, False)])
+def test_gaf2unstable_differential(seed, aligned):
+    """device code on the host == reference binary on a synthetic rGFA + stable GAF, incl. the -o file."""
+    rgfa, gaf = H.gen_rgfa_case(seed, n_records=600, aligned=aligned)
+    rc, ref, err, nl = H.run_gaf2unstable_ref(gaf, rgfa, True)
+    assert rc == 0
+    with tempfile.TemporaryDirectory() as td:
+        gp, lp = os.path.join(td, "g.gfa"), os.path.join(td, "nl.tsv")
+        open(gp, "wb").write(rgfa)
+        rc, out, serr = H.run_tool(G2U_HOSTSIM, ["-g", gp, "-o", lp, "-"], gaf)
+        assert rc == 0 and out == ref and open(lp, "rb").read() == nl
+        assert serr.count("warning") == err.count("[gaf2unstable] warning")
