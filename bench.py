@@ -7,7 +7,7 @@ vs the HBM roofline), one JSON line on stdout.
     python bench.py --impl reference ...      # the reference's CPU gaf2paf on the host cores
 
 A step is one pass of the whole device pipeline (line index -> size pass -> scan -> emit
-pass) over one synthetic batch.  `value` is measured with the batch already resident in HBM
+pass; kernels k_short / k_long / k_convert_list) over one synthetic batch.  `value` is measured with the batch already resident in HBM
 (CUDA events around exactly K steps, max over ranks); `e2e` is the same metric through the
 host-buffer C-ABI call (pinned host input -> H2D -> pipeline -> D2H), i.e. what the
 `gaf2paf` executable does per chunk.  Multi-GPU runs shard by records: every rank converts
@@ -255,12 +255,25 @@ def main():
 
     peak, peak_src = peaks()
     value = n_records * world * a.steps / (t_ms / 1000.0)
-    # dominant kernel: the emit pass (reads the GAF, writes the PAF) or the size pass (reads the GAF)
+    # dominant kernel: the emit pass (reads the GAF, writes the PAF) or the size pass (reads the GAF);
+    # k_short converts short records, k_long the ones it delegates (res.n_long)
     em, sz = statistics.mean(emit_ms), statistics.mean(size_ms)
+    kname = "k_long" if res.n_long * 2 > n_records else "k_short<8>"
     if em >= sz:
-        dom, dom_ms, dom_bytes = "k_convert<true> (emit pass)", em, nbytes + out_bytes
+        dom, dom_ms, dom_bytes, dom_key = kname + " EMIT=true (emit pass)", em, nbytes + out_bytes, kname.split("<")[0] + "_emit"
     else:
-        dom, dom_ms, dom_bytes = "k_convert<false> (size pass)", sz, nbytes
+        dom, dom_ms, dom_bytes, dom_key = kname + " EMIT=false (size pass)", sz, nbytes, kname.split("<")[0] + "_size"
+    # DRAM traffic of that kernel from the committed ncu --set full capture (bytes per record of the
+    # captured launch, scaled to this launch's record count); null when no capture is committed
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        per_rec = tj.get(a.workload, {}).get(dom_key)
+        if per_rec:
+            traffic = per_rec * n_records
+    except Exception:
+        pass
     achieved = dom_bytes / (dom_ms / 1000.0) / 1e9
     line = {
         "metric": "gaf2paf_records_per_s", "value": value, "unit": "records/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -274,7 +287,8 @@ def main():
         "pipeline_frac_of_hbm_peak": (nbytes + out_bytes) * a.steps / (t_ms / 1000.0) / 1e9 / peak,
         "kernel_ms": {"index": statistics.mean(index_ms), "size": sz, "emit": em, "device_pipeline": statistics.mean(dev_ms)},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "algorithmic_bytes_per_launch": dom_bytes, "peak_source": peak_src},
+                     "traffic": traffic, "algorithmic_bytes_per_launch": dom_bytes, "peak_source": peak_src},
+        "records_by_kernel": {"k_short": int(n_records - res.n_long), "k_long": int(res.n_long - res.n_delegated), "general": int(res.n_delegated)},
         "gpu_launches": launches,
         "clocks": clocks,
     }
