@@ -63,7 +63,7 @@ struct PinBuf {
 struct Worker {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
-    DevBuf d_in, d_tiles, d_rec, d_status, d_off, d_blocks, d_out, d_meta, d_list, d_list2;
+    DevBuf d_in, d_tiles, d_rec, d_status, d_off, d_blocks, d_out, d_meta, d_list, d_list2, d_desc, d_rdesc;
     PinBuf h_meta;
     bool init() {
         if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) return false;
@@ -71,7 +71,7 @@ struct Worker {
         return d_meta.ensure(sizeof(PipelineMeta)) == cudaSuccess && h_meta.ensure(sizeof(PipelineMeta)) == cudaSuccess;
     }
     void release() {
-        for (DevBuf* b : {&d_in, &d_tiles, &d_rec, &d_status, &d_off, &d_blocks, &d_out, &d_meta, &d_list, &d_list2}) b->release();
+        for (DevBuf* b : {&d_in, &d_tiles, &d_rec, &d_status, &d_off, &d_blocks, &d_out, &d_meta, &d_list, &d_list2, &d_desc, &d_rdesc}) b->release();
         h_meta.release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
@@ -130,6 +130,7 @@ int g2p_create(int device, g2p_ctx** out) {
         if (!w.init()) { g2p_destroy(ctx); return G2P_E_NO_DEVICE; }
     cudaFuncSetAttribute(k_short<kSG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShortSmem);
     cudaFuncSetAttribute(k_short<kSG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShortSmem);
+    cudaFuncSetAttribute(k_emit_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmitSmem);
     cudaFuncSetAttribute(k_long<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmem);
     cudaFuncSetAttribute(k_long<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmem);
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
@@ -263,7 +264,15 @@ static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
     const u32 ncta = (nrec + kShortRecsPerCta - 1) / kShortRecsPerCta;
     const u32 nlong = (u32)ctx->n_sm * 4u;
     const u32 nlist = std::min<u32>((nrec + kListThreads - 1) / kListThreads, (u32)ctx->n_sm * 16u);
-    ShortArgs sa{d_gaf, (u64)n, d_rec, nrec, ctx->table, d_off, d_status, nullptr, d_list, &d_meta->n_deleg};
+    // line descriptors: 6 slots per record on average are plenty for short reads (2.3 lines + padding);
+    // CTAs that find the array full fall back to k_short<EMIT=true> for their records
+    const u64 desc_cap64 = std::min<u64>((u64)nrec * 6 + 1024, 0xFFFFFF00ULL);
+    const u32 desc_cap = (u32)desc_cap64;
+    G2P_CUDA(w.d_desc.ensure((size_t)desc_cap * sizeof(LineDesc)));
+    G2P_CUDA(w.d_rdesc.ensure((size_t)nrec * sizeof(RecDesc)));
+    LineDesc* d_desc = static_cast<LineDesc*>(w.d_desc.p);
+    RecDesc* d_rdesc = static_cast<RecDesc*>(w.d_rdesc.p);
+    ShortArgs sa{d_gaf, (u64)n, d_rec, nrec, ctx->table, d_off, d_status, nullptr, d_list, &d_meta->n_deleg, d_desc, d_rdesc, &d_meta->n_desc, desc_cap};
     LongArgs la{d_gaf, (u64)n, d_rec, ctx->table, d_off, d_status, nullptr, d_list, &d_meta->n_deleg, d_list2, &d_meta->n_deleg2};
 
     // pass 1: sizes + status.  k_short takes the short canonical records, k_long what it left,
@@ -289,8 +298,16 @@ static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
     G2P_CUDA(cudaEventRecord(w.ev[3], st));
     sa.out = d_o;
     la.out = d_o;
-    k_short<kSG, true><<<ncta, kSThreads, kShortSmem, st>>>(sa);
-    ++launches;
+    const u32 n_slots = std::min<u32>(hm->n_desc, desc_cap);
+    if (n_slots) {
+        EmitArgs ea{d_gaf, d_rec, d_off, d_desc, d_rdesc, n_slots, d_o};
+        k_emit_lines<<<(n_slots + kEThreads - 1) / kEThreads, kEThreads, kEmitSmem, st>>>(ea);
+        ++launches;
+    }
+    if (hm->n_desc > desc_cap) {   // descriptor array overflowed: some records take the re-parsing emit
+        k_short<kSG, true><<<ncta, kSThreads, kShortSmem, st>>>(sa);
+        ++launches;
+    }
     if (hm->n_deleg) {
         k_long<true><<<nlong, kLThreads, kLongSmem, st>>>(la);
         ++launches;

@@ -29,7 +29,8 @@
 namespace g2p {
 
 enum : u32 {
-    ST_F_FAST = 0x10000u   // status flag: record was converted by k_short (else by the general kernel)
+    ST_F_FAST = 0x10000u,  // status flag: record was converted by k_short (else by k_long / the general kernel)
+    ST_F_DESC = 0x40000u   // its PAF lines are described in the line-descriptor array (emitted by k_emit_lines)
 };
 
 constexpr int kSG = 8;                 // lanes per record
@@ -74,6 +75,7 @@ struct Grp {
         gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << gbase);
     }
     __device__ __forceinline__ bool any(bool p) const { return __any_sync(gmask, p) != 0; }
+    __device__ __forceinline__ u32 ballot(bool p) const { return (__ballot_sync(gmask, p) >> gbase) & ((G == 32) ? 0xffffffffu : ((1u << (G & 31)) - 1u)); }
     template <class T> __device__ __forceinline__ T shfl(T v, int src) const { return __shfl_sync(gmask, v, src, G); }
     template <class T> __device__ __forceinline__ T up(T v, int d) const { return __shfl_up_sync(gmask, v, d, G); }
     template <class T> __device__ __forceinline__ T down(T v, int d) const { return __shfl_down_sync(gmask, v, d, G); }
@@ -289,6 +291,30 @@ __device__ __forceinline__ u8* write_line(u8* p, const u8* rt, const LineRec& R,
     return p;
 }
 
+// ---- line descriptors: what the size pass hands to k_emit_lines ---------------------------
+// One 64-byte descriptor per PAF line and one 32-byte header per record; k_emit_lines formats
+// one line per thread from them without parsing the record again.
+struct __align__(16) LineDesc {
+    u32 rec;              // record index (0xFFFFFFFF: padding slot)
+    u32 loff;             // byte offset of the line inside the record's output
+    u32 q0, q1;
+    u32 tlen, ts, te, nm;
+    u32 nb, lenS, lenE;
+    u16 name_a, mid_a;
+    u16 mid_b, len;       // len: bytes of the whole line
+    u8 nl, codeS, codeE, flags;   // flags: bit0 rev, bit1 mid_fwd
+    u32 pad[2];
+};
+static_assert(sizeof(LineDesc) == 64, "LineDesc is four 16-byte vectors");
+struct __align__(16) RecDesc {
+    i32 qlen, m, b;
+    i32 mapq;
+    u16 qn_b, tp_a, tp_b, rc_a, rc_b;
+    u8 gi_n, gi[5];
+};
+static_assert(sizeof(RecDesc) == 32, "RecDesc is two 16-byte vectors");
+constexpr u32 kDescInvalid = 0xFFFFFFFFu;
+
 __device__ __forceinline__ uint4 ldg_vec_guarded(const u8* base, u64 off, u64 n) {
     if (off + 16 <= n) return __ldg(reinterpret_cast<const uint4*>(base + off));
     u32 w[4] = {0, 0, 0, 0};
@@ -314,6 +340,10 @@ struct ShortArgs {
     u8* out;
     u32* deleg_list;     // size pass: indices of records left to the general kernel
     u32* n_deleg;
+    LineDesc* desc;      // size pass: line descriptors (dense, CTA reservations padded to 32)
+    RecDesc* rdesc;      // size pass: per-record constants of the lines
+    u32* n_desc;         // slots reserved so far
+    u32 desc_cap;
 };
 
 // One record per G-lane group.  EMIT=false: size + status (or delegate).  EMIT=true: write PAF.
@@ -332,13 +362,15 @@ __global__ void __launch_bounds__(kSThreads, 4) k_short(const ShortArgs a) {
     const u32 gid = threadIdx.x / G;
     SGroupMem* gm = reinterpret_cast<SGroupMem*>(smem) + gid;
     const u32 r = blockIdx.x * (kSThreads / G) + gid;
-    if (r >= a.nrec) return;
-    const u32 s = a.rec_start[r], e = a.rec_start[r + 1];
+    const bool valid = r < a.nrec;
+    if (EMIT && !valid) return;
+    const u32 s = valid ? a.rec_start[r] : 0u, e = valid ? a.rec_start[r + 1] : 1u;
     const u32 len = e - s - 1;
     u64 o = 0;
     u32 osize = 0;
-    if (EMIT) {
-        if (!(a.status[r] & ST_F_FAST)) return;
+    if (EMIT) {   // legacy emit: only records whose descriptors did not fit the descriptor array
+        const u32 st0 = a.status[r];
+        if (!(st0 & ST_F_FAST) || (st0 & ST_F_DESC)) return;
         o = a.out_off[r];
         osize = (u32)(a.out_off[r + 1] - o);
         if (osize == 0) return;
@@ -347,6 +379,11 @@ __global__ void __launch_bounds__(kSThreads, 4) k_short(const ShortArgs a) {
     bool deleg = false;      // group-uniform
     u32 size = 0;
     u32 status = ST_OK | ST_F_FAST;
+    LineRec R;
+    LineStep L;
+    bool emit_line = false;
+    u32 line = 0, loff = 0;
+    if (valid)
     do {
         if (len == 0 || len > kSLimit) { deleg = true; break; }
         // ---------------- phase 0: stage + classify
@@ -566,17 +603,15 @@ __global__ void __launch_bounds__(kSThreads, 4) k_short(const ShortArgs a) {
         if (live && eexh) lbad = 1;   // :80 assert(cur_len > target_len): CIGAR shorter than the path
         if (g.any(lbad != 0)) { deleg = true; break; }
         const u32 q = live ? eCQ - bCQ : 0u, nm = live ? eCM - bCM : 0u, nb = live ? eCB - bCB : 0u;
-        const bool emit_line = live && nm > 0;   // :225
+        emit_line = live && nm > 0;   // :225
 
         // PAF columns (gaf2paf_main.cpp:214-217).  Query consumed before step i == CQ at its start
         // boundary (the per-step sums telescope), so no scan over steps is needed.
-        LineRec R;
         R.qn_b = gm->hdr[H_QN_B];
         R.qlen = (i32)gm->hdr[H_QLEN]; R.m = (i32)gm->hdr[H_M]; R.b = (i32)gm->hdr[H_B]; R.mapq = (i32)gm->hdr[H_MAPQ];
         R.tp_a = gm->hdr[H_TP_A]; R.tp_b = gm->hdr[H_TP_B]; R.rc_a = gm->hdr[H_RC_A]; R.rc_b = gm->hdr[H_RC_B];
         R.gi_n = gi_fast(R.m, R.b, R.gi);
         if (R.gi_n == 0) { deleg = true; break; }   // uniform: same m, b in the whole group
-        LineStep L;
         L.rev = rev;
         L.q0 = (u32)qs + bCQ; L.q1 = L.q0 + q;
         L.name_a = name_a; L.nl = nl; L.tlen = (u32)tlen;
@@ -586,7 +621,7 @@ __global__ void __launch_bounds__(kSThreads, 4) k_short(const ShortArgs a) {
         L.lenS = 0; L.codeS = 0; L.codeE = 0; L.mid_a = L.mid_b = 0;
         L.mid_fwd = rev == minus;   // text order == output order
         L.lenE = eB - (et > B ? et : B);
-        u32 line = 0;
+        line = 0;
         if (emit_line) {
             const u32 jS = (B == 0) ? 0u : (bcut ? bj : bj + 1u);
             const bool cutS = B != 0 && bcut;
@@ -603,7 +638,7 @@ __global__ void __launch_bounds__(kSThreads, 4) k_short(const ShortArgs a) {
             L.codeE = rt[gm->opos[minus ? no - 1 - jE : jE]];
             line = line_const_len(R, p10) + line_step_len(L, p10);
         }
-        const u32 loff = g.excl_scan(line, size);
+        loff = g.excl_scan(line, size);
 
         if (EMIT) {
             if (size != osize) break;   // cannot happen: both passes run the same code
@@ -626,15 +661,157 @@ __global__ void __launch_bounds__(kSThreads, 4) k_short(const ShortArgs a) {
         }
     } while (0);
 
-    if (!EMIT && g.gl == 0) {
-        if (deleg) {
-            a.status[r] = ST_OK;   // overwritten by the general kernel
-            a.out_off[r] = 0;
-            a.deleg_list[atomicAdd(a.n_deleg, 1u)] = r;
-        } else {
-            a.status[r] = status;
-            a.out_off[r] = size;
+    if (!EMIT) {
+        // ---------------- line descriptors: one dense reservation per CTA, padded to whole warps
+        __shared__ u32 s_cnt[kSThreads / G + 1];
+        __shared__ u32 s_base, s_total, s_ok;
+        const bool fast = valid && !deleg && size != 0;
+        const u32 lmask = g.ballot(fast && emit_line);
+        if (g.gl == 0) s_cnt[gid] = fast ? (u32)__popc(lmask) : 0u;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            constexpr u32 NG = kSThreads / G;
+            const u32 lane = threadIdx.x;
+            u32 v = 0;
+            for (u32 k = lane; k < NG; k += 32) v += s_cnt[k];   // NG <= 32 for G >= 8
+            u32 incl = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (u32)d) incl += t; }
+            if (lane < NG) s_cnt[lane] = incl - v;
+            if (lane == 31) {
+                const u32 total = incl, rsv = (total + 31u) & ~31u;
+                u32 base = 0, ok = 0;
+                if (total) { base = atomicAdd(a.n_desc, rsv); ok = (base <= a.desc_cap && rsv <= a.desc_cap - base) ? 1u : 0u; }
+                s_base = base; s_total = total; s_ok = ok;
+            }
         }
+        __syncthreads();
+        const bool desc_ok = s_ok != 0;
+        if (desc_ok) {
+            if (fast && emit_line) {
+                const u32 slot = s_base + s_cnt[gid] + (u32)__popc(lmask & ((1u << g.gl) - 1u));
+                LineDesc d;
+                d.rec = r; d.loff = loff; d.q0 = L.q0; d.q1 = L.q1; d.tlen = L.tlen; d.ts = L.ts; d.te = L.te; d.nm = L.nm;
+                d.nb = L.nb; d.lenS = L.lenS; d.lenE = L.lenE;
+                d.name_a = (u16)L.name_a; d.mid_a = (u16)L.mid_a; d.mid_b = (u16)L.mid_b; d.len = (u16)line;
+                d.nl = (u8)L.nl; d.codeS = L.codeS; d.codeE = L.codeE; d.flags = (u8)((L.rev ? 1u : 0u) | (L.mid_fwd ? 2u : 0u));
+                d.pad[0] = d.pad[1] = 0;
+                const uint4* src = reinterpret_cast<const uint4*>(&d);
+                uint4* dst = reinterpret_cast<uint4*>(a.desc + slot);
+                dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+            }
+            if (fast && g.gl == 0) {
+                RecDesc rd;
+                rd.qlen = R.qlen; rd.m = R.m; rd.b = R.b; rd.mapq = R.mapq;
+                rd.qn_b = (u16)R.qn_b; rd.tp_a = (u16)R.tp_a; rd.tp_b = (u16)R.tp_b; rd.rc_a = (u16)R.rc_a; rd.rc_b = (u16)R.rc_b;
+                rd.gi_n = (u8)R.gi_n;
+                for (int k = 0; k < 5; ++k) rd.gi[k] = R.gi[k];
+                const uint4* src = reinterpret_cast<const uint4*>(&rd);
+                uint4* dst = reinterpret_cast<uint4*>(a.rdesc + r);
+                dst[0] = src[0]; dst[1] = src[1];
+            }
+            const u32 npad = ((s_total + 31u) & ~31u) - s_total;
+            if (threadIdx.x < npad) a.desc[s_base + s_total + threadIdx.x].rec = kDescInvalid;
+        } else if (s_total && s_base < a.desc_cap) {
+            // reservation rejected (array full): blank the slots it owns below the capacity; the
+            // records keep ST_F_DESC clear and are emitted by k_short<EMIT=true>
+            const u32 rsv = (s_total + 31u) & ~31u;
+            const u32 hi = rsv < a.desc_cap - s_base ? s_base + rsv : a.desc_cap;
+            for (u32 k = s_base + threadIdx.x; k < hi; k += kSThreads) a.desc[k].rec = kDescInvalid;
+        }
+        if (valid && g.gl == 0) {
+            if (deleg) {
+                a.status[r] = ST_OK;   // overwritten by k_long / the general kernel
+                a.out_off[r] = 0;
+                a.deleg_list[atomicAdd(a.n_deleg, 1u)] = r;
+            } else {
+                a.status[r] = status | ((fast && desc_ok) ? (u32)ST_F_DESC : 0u);
+                a.out_off[r] = size;
+            }
+        }
+    }
+}
+
+// One PAF line per thread from its descriptor (dense: CTA reservations of the size pass are
+// padded to 32 slots, so the lines of a warp belong to consecutive records and are contiguous in
+// the output unless a delegated record lies between them).  Lines are formatted into a per-warp
+// staging buffer and flushed with 128-bit stores.
+constexpr int kEThreads = 256;
+constexpr u32 kEOutCap = 6144;     // staged bytes per warp
+constexpr size_t kEmitSmem = (size_t)(kEThreads / 32) * (kEOutCap + 16);
+
+struct EmitArgs {
+    const u8* gaf;
+    const u32* rec_start;
+    const u64* out_off;
+    const LineDesc* desc;
+    const RecDesc* rdesc;
+    u32 n_slots;
+    u8* out;
+};
+
+__global__ void __launch_bounds__(kEThreads) k_emit_lines(const EmitArgs a) {
+    G2P_DYN_SMEM(smem);
+    __shared__ u32 p10[10];
+    if (threadIdx.x < 10) {
+        u32 v = 1;
+        for (u32 i = 0; i < threadIdx.x; ++i) v *= 10u;
+        p10[threadIdx.x] = v;
+    }
+    __syncthreads();
+    const u32 FULL = 0xffffffffu;
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    u8* sm = smem + (size_t)warp * (kEOutCap + 16);
+    const u32 slot = blockIdx.x * kEThreads + threadIdx.x;
+    LineDesc d;
+    d.rec = kDescInvalid; d.len = 0; d.loff = 0;
+    if (slot < a.n_slots) {
+        const uint4* src = reinterpret_cast<const uint4*>(a.desc + slot);
+        uint4* dst = reinterpret_cast<uint4*>(&d);
+        dst[0] = __ldg(src); dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2); dst[3] = __ldg(src + 3);
+    }
+    const bool valid = d.rec != kDescInvalid;
+    if (!__any_sync(FULL, valid)) return;
+    u64 o = 0;
+    LineRec R;
+    LineStep L;
+    const u8* rt = a.gaf;
+    if (valid) {
+        RecDesc rd;
+        const uint4* src = reinterpret_cast<const uint4*>(a.rdesc + d.rec);
+        uint4* dst = reinterpret_cast<uint4*>(&rd);
+        dst[0] = __ldg(src); dst[1] = __ldg(src + 1);
+        rt = a.gaf + a.rec_start[d.rec];
+        o = a.out_off[d.rec] + d.loff;
+        R.qn_b = rd.qn_b; R.qlen = rd.qlen; R.mapq = rd.mapq; R.m = rd.m; R.b = rd.b;
+        R.tp_a = rd.tp_a; R.tp_b = rd.tp_b; R.rc_a = rd.rc_a; R.rc_b = rd.rc_b; R.gi_n = rd.gi_n;
+        for (int k = 0; k < 5; ++k) R.gi[k] = rd.gi[k];
+        L.q0 = d.q0; L.q1 = d.q1; L.name_a = d.name_a; L.nl = d.nl; L.tlen = d.tlen; L.ts = d.ts; L.te = d.te; L.nm = d.nm; L.nb = d.nb;
+        L.lenS = d.lenS; L.lenE = d.lenE; L.mid_a = d.mid_a; L.mid_b = d.mid_b; L.codeS = d.codeS; L.codeE = d.codeE;
+        L.rev = (d.flags & 1u) != 0; L.mid_fwd = (d.flags & 2u) != 0;
+    }
+    // contiguity of the warp's lines in the output
+    const u64 end = o + d.len;
+    const u64 onext = __shfl_down_sync(FULL, o, 1);
+    const bool vnext = __shfl_down_sync(FULL, (u32)valid, 1) != 0 && lane < 31;
+    const bool gap = valid && vnext && onext != end;
+    const u32 vmask = __ballot_sync(FULL, valid);
+    const int first = __ffs((int)vmask) - 1, last = 31 - __clz((int)vmask);
+    const u64 o0 = __shfl_sync(FULL, o, first), o1 = __shfl_sync(FULL, end, last);
+    const bool holes = (vmask >> first) != (0xffffffffu >> (31 - (last - first)));
+    const bool staged = !__any_sync(FULL, gap) && !holes && (o1 - o0) <= kEOutCap;
+    const u32 pad = (u32)(o0 & 15u);
+    if (valid) write_line(staged ? sm + pad + (u32)(o - o0) : a.out + o, rt, R, L, p10);
+    if (staged) {
+        __syncwarp();
+        const u32 total = pad + (u32)(o1 - o0);
+        u8* gb = a.out + (o0 - pad);
+        const u32 full_b = total >> 4;
+        for (u32 u = (pad ? 1u : 0u) + lane; u < full_b; u += 32) reinterpret_cast<uint4*>(gb)[u] = reinterpret_cast<const uint4*>(sm)[u];
+        const u32 head_end = pad ? (total < 16u ? total : 16u) : 0u;
+        for (u32 b = pad + lane; b < head_end; b += 32) gb[b] = sm[b];
+        const u32 tail_a = full_b * 16u > head_end ? full_b * 16u : head_end;
+        for (u32 b = tail_a + lane; b < total; b += 32) gb[b] = sm[b];
     }
 }
 

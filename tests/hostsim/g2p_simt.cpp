@@ -70,7 +70,11 @@ int main(int argc, char** argv) {
     std::vector<u64> blocks(nscan);
     const u32 ncta = (nrec + kShortRecsPerCta - 1) / kShortRecsPerCta;
     const u32 nlist = std::min<u32>((nrec + kListThreads - 1) / kListThreads, 8u);
-    ShortArgs sa{gaf, n, rec.data(), nrec, T, off.data(), status.data(), nullptr, list.data(), &meta.n_deleg};
+    // G2P_SIMT_DESC_CAP=<slots> shrinks the descriptor array to exercise the overflow fallback
+    const u32 desc_cap = std::getenv("G2P_SIMT_DESC_CAP") ? (u32)std::atol(std::getenv("G2P_SIMT_DESC_CAP")) : nrec * 4 + 1024;
+    std::vector<LineDesc> desc(desc_cap + 1);
+    std::vector<RecDesc> rdesc(nrec);
+    ShortArgs sa{gaf, n, rec.data(), nrec, T, off.data(), status.data(), nullptr, list.data(), &meta.n_deleg, desc.data(), rdesc.data(), &meta.n_desc, desc_cap};
     hs::launch(dim3(ncta), dim3(kSThreads), kShortSmem, [&] { k_short<kSG, false>(sa); });
     LongArgs la{gaf, n, rec.data(), T, off.data(), status.data(), nullptr, list.data(), &meta.n_deleg, list2.data(), &meta.n_deleg2};
     const u32 nlong = 2;
@@ -81,7 +85,12 @@ int main(int argc, char** argv) {
     hs::launch(dim3(nscan), dim3(kScanThreads), 0, [&] { k_scan_apply(off.data(), nrec, blocks.data(), &meta); });
     std::vector<u8> out(meta.out_total + 256, 0xEE);
     sa.out = out.data();
-    hs::launch(dim3(ncta), dim3(kSThreads), kShortSmem, [&] { k_short<kSG, true>(sa); });
+    const u32 n_slots = std::min<u32>(meta.n_desc, desc_cap);
+    if (n_slots) {
+        EmitArgs ea{gaf, rec.data(), off.data(), desc.data(), rdesc.data(), n_slots, out.data()};
+        hs::launch(dim3((n_slots + kEThreads - 1) / kEThreads), dim3(kEThreads), kEmitSmem, [&] { k_emit_lines(ea); });
+    }
+    if (meta.n_desc > desc_cap) hs::launch(dim3(ncta), dim3(kSThreads), kShortSmem, [&] { k_short<kSG, true>(sa); });
     la.out = out.data();
     if (meta.n_deleg) hs::launch(dim3(nlong), dim3(kLThreads), kLongSmem, [&] { k_long<true>(la); });
     if (meta.n_deleg2)
@@ -91,7 +100,7 @@ int main(int argc, char** argv) {
         hs::launch(dim3(1), dim3(1), 0, [&] { k_diagnose(gaf, rec.data(), T, off.data(), &meta); });
         out_bytes = meta.err_out_end;
     }
-    if (std::getenv("G2P_SIMT_STATS")) std::fprintf(stderr, "g2p_simt: %u records, %u to k_long, %u to the general kernel, %llu bytes out\n", nrec, meta.n_deleg, meta.n_deleg2, (unsigned long long)out_bytes);
+    if (std::getenv("G2P_SIMT_STATS")) std::fprintf(stderr, "g2p_simt: %u records, %u to k_long, %u to the general kernel, %u line slots (cap %u), %llu bytes out\n", nrec, meta.n_deleg, meta.n_deleg2, meta.n_desc, desc_cap, (unsigned long long)out_bytes);
     std::fwrite(out.data(), 1, out_bytes, stdout);
     std::fflush(stdout);
     if (meta.first_err != 0xFFFFFFFFu) {
