@@ -9,7 +9,7 @@ CXX       ?= g++
 PKG       := cactus-gfa-tools_b200
 CSRC      := $(PKG)/csrc
 BUILD     := build
-NVFLAGS   := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function
+NVFLAGS   := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function $(EXTRA_NVFLAGS)
 CXXFLAGS  := -O2 -std=c++17 -Wall -fPIC
 LIB       := $(PKG)/lib/libg2p.so
 HDRS      := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.hpp include/*.h)

@@ -128,8 +128,8 @@ int g2p_create(int device, g2p_ctx** out) {
     ctx->device = device;
     for (auto& w : ctx->w)
         if (!w.init()) { g2p_destroy(ctx); return G2P_E_NO_DEVICE; }
-    cudaFuncSetAttribute(k_short<kSG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShortSmem);
-    cudaFuncSetAttribute(k_short<kSG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShortSmem);
+    cudaFuncSetAttribute(k_short<kSG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)short_smem<true>());
+    cudaFuncSetAttribute(k_short<kSG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)short_smem<false>());
     cudaFuncSetAttribute(k_emit_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmitSmem);
     cudaFuncSetAttribute(k_long<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmem);
     cudaFuncSetAttribute(k_long<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmem);
@@ -277,7 +277,7 @@ static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
 
     // pass 1: sizes + status.  k_short takes the short canonical records, k_long what it left,
     // the general kernel what neither converts (non-canonical or erroneous records).
-    k_short<kSG, false><<<ncta, kSThreads, kShortSmem, st>>>(sa);
+    k_short<kSG, false><<<ncta, kSThreads, short_smem<false>(), st>>>(sa);
     k_long<false><<<nlong, kLThreads, kLongSmem, st>>>(la);
     k_convert_list<false><<<nlist, kListThreads, 0, st>>>(d_gaf, d_rec, ctx->table, d_off, d_status, nullptr, d_meta, d_list2, &d_meta->n_deleg2);
     launches += 3;
@@ -300,12 +300,12 @@ static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
     la.out = d_o;
     const u32 n_slots = std::min<u32>(hm->n_desc, desc_cap);
     if (n_slots) {
-        EmitArgs ea{d_gaf, d_rec, d_off, d_desc, d_rdesc, n_slots, d_o};
+        EmitArgs ea{d_gaf, (u64)n, d_rec, d_off, d_desc, d_rdesc, n_slots, d_o};
         k_emit_lines<<<(n_slots + kEThreads - 1) / kEThreads, kEThreads, kEmitSmem, st>>>(ea);
         ++launches;
     }
     if (hm->n_desc > desc_cap) {   // descriptor array overflowed: some records take the re-parsing emit
-        k_short<kSG, true><<<ncta, kSThreads, kShortSmem, st>>>(sa);
+        k_short<kSG, true><<<ncta, kSThreads, short_smem<true>(), st>>>(sa);
         ++launches;
     }
     if (hm->n_deleg) {

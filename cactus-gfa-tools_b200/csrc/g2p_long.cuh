@@ -455,7 +455,7 @@ __device__ __forceinline__ void long_record(const LongArgs& a, LWarpMem* wm, con
                 const u64 ob = o + run;
                 const bool staged = btot <= kLOutCap;
                 const u32 pad = (u32)(ob & 15u);
-                if (emit_line) write_line(staged ? wm->out + pad + (lincl - line) : a.out + ob + (lincl - line), rt, R, Ls, p10);
+                if (emit_line) write_line((staged ? wm->out + pad + (lincl - line) : a.out + ob + (lincl - line)) + line, rt, R, Ls);
                 if (staged) {
                     __syncwarp();
                     const u32 total = pad + btot;

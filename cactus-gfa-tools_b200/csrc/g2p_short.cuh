@@ -33,6 +33,9 @@ enum : u32 {
     ST_F_DESC = 0x40000u   // its PAF lines are described in the line-descriptor array (emitted by k_emit_lines)
 };
 
+#ifndef G2P_SHORT_CTAS
+#define G2P_SHORT_CTAS 6   /* resident CTAs per SM the size pass is compiled for (register budget) */
+#endif
 constexpr int kSG = 8;                 // lanes per record
 constexpr int kSThreads = 256;         // 32 records per CTA
 #ifndef G2P_S_LIMIT
@@ -48,7 +51,8 @@ constexpr u32 kSOutCap = 1024;         // staged PAF bytes per record; larger ou
 enum { H_QN_B = 0, H_QLEN = 1, H_QS = 2, H_QE = 3, H_MINUS = 4, H_PATH_A = 5, H_PLEN = 6, H_PS = 7, H_PE = 8, H_M = 9, H_B = 10,
        H_MAPQ = 11, H_CG_A = 12, H_CG_B = 13, H_TP_A = 14, H_TP_B = 15, H_RC_A = 16, H_RC_B = 17, H_PATH_B = 18, H_N = 20 };
 
-struct __align__(16) SGroupMem {
+template <bool WITH_OUT>
+struct __align__(16) SGroupMemT {
     u8 text[288];                  // the record, staged at its global 16-byte phase
     u16 spos[16];                  // path-step marker positions (+ end); tag keys alias spos..opos
     u16 opos[kSMaxOps];            // positions of the CIGAR op letters
@@ -58,12 +62,12 @@ struct __align__(16) SGroupMem {
             u16 tabs[32];
             u32 pEnd[kSMaxOps], pQ[kSMaxOps], pNM[kSMaxOps], pNB[kSMaxOps];   // inclusive prefix sums, normalised op order
         } w;
-        u8 out[kSOutCap + 16];
+        u8 out[WITH_OUT ? kSOutCap + 16 : 16];   // staging of the re-parsing emit (fallback path only)
     };
 };
 constexpr u32 kShortRecsPerCta = kSThreads / kSG;
-constexpr size_t kShortSmem = sizeof(SGroupMem) * kShortRecsPerCta;
-static_assert(sizeof(SGroupMem) % 16 == 0, "group slices must keep 16-byte alignment");
+template <bool EMIT> constexpr size_t short_smem() { return sizeof(SGroupMemT<EMIT>) * kShortRecsPerCta; }
+static_assert(sizeof(SGroupMemT<true>) % 16 == 0 && sizeof(SGroupMemT<false>) % 16 == 0, "group slices must keep 16-byte alignment");
 
 template <int G>
 struct Grp {
@@ -125,24 +129,6 @@ __device__ __forceinline__ u32 dlen_u32(u32 v, const u32* p10) {
     return t + 1u - (u32)((v | 1u) < p10[t]);
 }
 __device__ __forceinline__ u32 dlen_i32(i32 v, const u32* p10) { return v < 0 ? 1u + dlen_u32(0u - (u32)v, p10) : dlen_u32((u32)v, p10); }
-__device__ __forceinline__ u8* put_u32(u8* p, u32 v, const u32* p10) {
-    const u32 n = dlen_u32(v, p10);
-    for (u32 k = n; k-- > 0;) { const u32 q = v / 10u; p[k] = (u8)('0' + (v - q * 10u)); v = q; }
-    return p + n;
-}
-__device__ __forceinline__ u8* put_i32(u8* p, i32 v, const u32* p10) {
-    if (v < 0) { *p++ = '-'; return put_u32(p, 0u - (u32)v, p10); }
-    return put_u32(p, (u32)v, p10);
-}
-__device__ __forceinline__ u8* put_bytes(u8* p, const u8* s, u32 n) {
-    for (u32 i = 0; i < n; ++i) p[i] = s[i];
-    return p + n;
-}
-__device__ __forceinline__ u8* put_tag(u8* p, u8 a, u8 b, u8 t) {   // "\tab:t:"
-    p[0] = '\t'; p[1] = a; p[2] = b; p[3] = ':'; p[4] = t; p[5] = ':';
-    return p + 6;
-}
-
 // gi:f: text for 0 <= floor(m/b*1000+0.5) <= 1000 (gaf2paf_main.cpp:248-253); returns 0 if outside.
 __device__ __forceinline__ u32 gi_fast(i32 m, i32 b, u8* out) {
     if (b <= 0) { out[0] = '0'; return 1; }
@@ -248,46 +234,65 @@ __device__ __forceinline__ u32 line_step_len(const LineStep& L, const u32* p10) 
     if (L.mid_b > L.mid_a) n += L.mid_b - L.mid_a;
     return n;
 }
-__device__ __forceinline__ u8* write_line(u8* p, const u8* rt, const LineRec& R, const LineStep& L, const u32* p10) {
-    p = put_bytes(p, rt, R.qn_b); *p++ = '\t';
-    p = put_i32(p, R.qlen, p10); *p++ = '\t';
-    p = put_u32(p, L.q0, p10); *p++ = '\t';
-    p = put_u32(p, L.q1, p10); *p++ = '\t';
-    *p++ = L.rev ? '-' : '+'; *p++ = '\t';
-    p = put_bytes(p, rt + L.name_a, L.nl); *p++ = '\t';
-    p = put_u32(p, L.tlen, p10); *p++ = '\t';
-    p = put_u32(p, L.ts, p10); *p++ = '\t';
-    p = put_u32(p, L.te, p10); *p++ = '\t';
-    p = put_u32(p, L.nm, p10); *p++ = '\t';
-    p = put_u32(p, L.nb, p10); *p++ = '\t';
-    p = put_i32(p, R.mapq, p10);
-    if (R.tp_b) { p[0] = '\t'; p[1] = 't'; p[2] = 'p'; p[3] = ':'; p = put_bytes(p + 4, rt + R.tp_a, R.tp_b - R.tp_a); }
-    if (R.rc_b) { p[0] = '\t'; p[1] = 'r'; p[2] = 'c'; p[3] = ':'; p = put_bytes(p + 4, rt + R.rc_a, R.rc_b - R.rc_a); }
-    p = put_tag(p, 'g', 'm', 'i'); p = put_i32(p, R.m, p10);
-    p = put_tag(p, 'g', 'l', 'i'); p = put_i32(p, R.b, p10);
-    p = put_tag(p, 'g', 'i', 'f'); p = put_bytes(p, R.gi, R.gi_n);
-    p = put_tag(p, 'c', 'g', 'Z');
-    // pieces, reversed for '<' steps (gaf2paf_main.cpp:184-211)
-    if (!L.rev) {
-        if (L.codeS) { p = put_u32(p, L.lenS, p10); *p++ = L.codeS; }
-    } else {
-        p = put_u32(p, L.lenE, p10); *p++ = L.codeE;
-    }
+// Right-to-left writers: the line's length is known from the size pass, so the line is written
+// from its last byte backwards -- decimal digits come out in the order they are produced and no
+// digit-count pass is needed.
+__device__ __forceinline__ u8* rput_u32(u8* p, u32 v) {
+    do { const u32 q = v / 10u; *--p = (u8)('0' + (v - q * 10u)); v = q; } while (v);
+    return p;
+}
+__device__ __forceinline__ u8* rput_i32(u8* p, i32 v) {
+    if (v < 0) { p = rput_u32(p, 0u - (u32)v); *--p = '-'; return p; }
+    return rput_u32(p, (u32)v);
+}
+__device__ __forceinline__ u8* rput_bytes(u8* p, const u8* s, u32 n) {
+    for (u32 i = n; i-- > 0;) *--p = s[i];
+    return p;
+}
+__device__ __forceinline__ u8* rput_tag(u8* p, u8 a, u8 b, u8 t) {   // "\tab:t:"
+    p -= 6;
+    p[0] = '\t'; p[1] = a; p[2] = b; p[3] = ':'; p[4] = t; p[5] = ':';
+    return p;
+}
+// Writes the line that ends at `pend` (exclusive); returns its first byte.
+__device__ __forceinline__ u8* write_line(u8* pend, const u8* rt, const LineRec& R, const LineStep& L) {
+    u8* p = pend;
+    *--p = '\n';
+    // pieces, reversed for '<' steps (gaf2paf_main.cpp:184-211); here in reverse output order
+    if (!L.rev) { *--p = L.codeE; p = rput_u32(p, L.lenE); }
+    else if (L.codeS) { *--p = L.codeS; p = rput_u32(p, L.lenS); }
     if (L.mid_b > L.mid_a) {
-        if (L.mid_fwd) p = put_bytes(p, rt + L.mid_a, L.mid_b - L.mid_a);
+        if (L.mid_fwd) p = rput_bytes(p, rt + L.mid_a, L.mid_b - L.mid_a);
         else {
-            u32 t1 = L.mid_b;   // token by token, backwards
-            while (t1 > L.mid_a) {
-                u32 t0 = t1 - 1;
-                while (t0 > L.mid_a && rt[t0 - 1] <= '9') --t0;
-                p = put_bytes(p, rt + t0, t1 - t0);
-                t1 = t0;
+            u32 t = L.mid_a;   // output order is the reverse token order: first text token is written last
+            while (t < L.mid_b) {
+                u32 e = t;
+                while (rt[e] <= '9') ++e;   // the op letter ends the token
+                for (u32 k = e + 1; k-- > t;) *--p = rt[k];
+                t = e + 1;
             }
         }
     }
-    if (!L.rev) { p = put_u32(p, L.lenE, p10); *p++ = L.codeE; }
-    else if (L.codeS) { p = put_u32(p, L.lenS, p10); *p++ = L.codeS; }
-    *p++ = '\n';
+    if (!L.rev) { if (L.codeS) { *--p = L.codeS; p = rput_u32(p, L.lenS); } }
+    else { *--p = L.codeE; p = rput_u32(p, L.lenE); }
+    p = rput_tag(p, 'c', 'g', 'Z');
+    p = rput_bytes(p, R.gi, R.gi_n); p = rput_tag(p, 'g', 'i', 'f');
+    p = rput_i32(p, R.b); p = rput_tag(p, 'g', 'l', 'i');
+    p = rput_i32(p, R.m); p = rput_tag(p, 'g', 'm', 'i');
+    if (R.rc_b) { p = rput_bytes(p, rt + R.rc_a, R.rc_b - R.rc_a); p -= 4; p[0] = '\t'; p[1] = 'r'; p[2] = 'c'; p[3] = ':'; }
+    if (R.tp_b) { p = rput_bytes(p, rt + R.tp_a, R.tp_b - R.tp_a); p -= 4; p[0] = '\t'; p[1] = 't'; p[2] = 'p'; p[3] = ':'; }
+    p = rput_i32(p, R.mapq); *--p = '\t';
+    p = rput_u32(p, L.nb); *--p = '\t';
+    p = rput_u32(p, L.nm); *--p = '\t';
+    p = rput_u32(p, L.te); *--p = '\t';
+    p = rput_u32(p, L.ts); *--p = '\t';
+    p = rput_u32(p, L.tlen); *--p = '\t';
+    p = rput_bytes(p, rt + L.name_a, L.nl); *--p = '\t';
+    *--p = L.rev ? '-' : '+'; *--p = '\t';
+    p = rput_u32(p, L.q1); *--p = '\t';
+    p = rput_u32(p, L.q0); *--p = '\t';
+    p = rput_i32(p, R.qlen); *--p = '\t';
+    p = rput_bytes(p, rt, R.qn_b);
     return p;
 }
 
@@ -348,7 +353,7 @@ struct ShortArgs {
 
 // One record per G-lane group.  EMIT=false: size + status (or delegate).  EMIT=true: write PAF.
 template <int G, bool EMIT>
-__global__ void __launch_bounds__(kSThreads, 4) k_short(const ShortArgs a) {
+__global__ void __launch_bounds__(kSThreads, EMIT ? 4 : G2P_SHORT_CTAS) k_short(const ShortArgs a) {
     G2P_DYN_SMEM(smem);
     __shared__ u32 p10[10];
     if (threadIdx.x < 10) {
@@ -360,6 +365,7 @@ __global__ void __launch_bounds__(kSThreads, 4) k_short(const ShortArgs a) {
 
     const Grp<G> g;
     const u32 gid = threadIdx.x / G;
+    typedef SGroupMemT<EMIT> SGroupMem;
     SGroupMem* gm = reinterpret_cast<SGroupMem*>(smem) + gid;
     const u32 r = blockIdx.x * (kSThreads / G) + gid;
     const bool valid = r < a.nrec;
@@ -645,7 +651,7 @@ __global__ void __launch_bounds__(kSThreads, 4) k_short(const ShortArgs a) {
             const bool staged = size <= kSOutCap;
             const u32 pad = (u32)(o & 15u);
             g.sync();   // the staging buffer aliases tabs / prefix arrays: everyone is done reading them
-            if (emit_line) write_line(staged ? gm->out + pad + loff : a.out + o + loff, rt, R, L, p10);
+            if (emit_line) write_line((staged ? gm->out + pad + loff : a.out + o + loff) + line, rt, R, L);
             if (staged) {
                 g.sync();
                 const u32 total = pad + size;
@@ -737,11 +743,13 @@ __global__ void __launch_bounds__(kSThreads, 4) k_short(const ShortArgs a) {
 // the output unless a delegated record lies between them).  Lines are formatted into a per-warp
 // staging buffer and flushed with 128-bit stores.
 constexpr int kEThreads = 256;
-constexpr u32 kEOutCap = 6144;     // staged bytes per warp
-constexpr size_t kEmitSmem = (size_t)(kEThreads / 32) * (kEOutCap + 16);
+constexpr u32 kEOutCap = 5120;     // staged PAF bytes per warp
+constexpr u32 kETextCap = 4096;    // staged GAF bytes per warp (the records its 32 lines come from)
+constexpr size_t kEmitSmem = (size_t)(kEThreads / 32) * (kEOutCap + 16 + kETextCap + 32);
 
 struct EmitArgs {
     const u8* gaf;
+    u64 n;
     const u32* rec_start;
     const u64* out_off;
     const LineDesc* desc;
@@ -752,16 +760,10 @@ struct EmitArgs {
 
 __global__ void __launch_bounds__(kEThreads) k_emit_lines(const EmitArgs a) {
     G2P_DYN_SMEM(smem);
-    __shared__ u32 p10[10];
-    if (threadIdx.x < 10) {
-        u32 v = 1;
-        for (u32 i = 0; i < threadIdx.x; ++i) v *= 10u;
-        p10[threadIdx.x] = v;
-    }
-    __syncthreads();
     const u32 FULL = 0xffffffffu;
     const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    u8* sm = smem + (size_t)warp * (kEOutCap + 16);
+    u8* sm = smem + (size_t)warp * (kEOutCap + 16 + kETextCap + 32);
+    u8* sm_text = sm + kEOutCap + 16;
     const u32 slot = blockIdx.x * kEThreads + threadIdx.x;
     LineDesc d;
     d.rec = kDescInvalid; d.len = 0; d.loff = 0;
@@ -771,17 +773,19 @@ __global__ void __launch_bounds__(kEThreads) k_emit_lines(const EmitArgs a) {
         dst[0] = __ldg(src); dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2); dst[3] = __ldg(src + 3);
     }
     const bool valid = d.rec != kDescInvalid;
-    if (!__any_sync(FULL, valid)) return;
+    const u32 vmask = __ballot_sync(FULL, valid);
+    if (vmask == 0) return;
+    const int first = __ffs((int)vmask) - 1, last = 31 - __clz((int)vmask);
     u64 o = 0;
     LineRec R;
     LineStep L;
-    const u8* rt = a.gaf;
+    u32 rs = 0, re = 0;   // text span of this lane's record
     if (valid) {
         RecDesc rd;
         const uint4* src = reinterpret_cast<const uint4*>(a.rdesc + d.rec);
         uint4* dst = reinterpret_cast<uint4*>(&rd);
         dst[0] = __ldg(src); dst[1] = __ldg(src + 1);
-        rt = a.gaf + a.rec_start[d.rec];
+        rs = a.rec_start[d.rec]; re = a.rec_start[d.rec + 1];
         o = a.out_off[d.rec] + d.loff;
         R.qn_b = rd.qn_b; R.qlen = rd.qlen; R.mapq = rd.mapq; R.m = rd.m; R.b = rd.b;
         R.tp_a = rd.tp_a; R.tp_b = rd.tp_b; R.rc_a = rd.rc_a; R.rc_b = rd.rc_b; R.gi_n = rd.gi_n;
@@ -790,18 +794,26 @@ __global__ void __launch_bounds__(kEThreads) k_emit_lines(const EmitArgs a) {
         L.lenS = d.lenS; L.lenE = d.lenE; L.mid_a = d.mid_a; L.mid_b = d.mid_b; L.codeS = d.codeS; L.codeE = d.codeE;
         L.rev = (d.flags & 1u) != 0; L.mid_fwd = (d.flags & 2u) != 0;
     }
+    // stage the text of the warp's records (one contiguous span) with 128-bit coalesced loads
+    const u32 t0 = __shfl_sync(FULL, rs, first), t1 = __shfl_sync(FULL, re, last);
+    const u32 A = t0 & ~15u;
+    const bool text_staged = t1 > t0 && t1 - A <= kETextCap;
+    if (text_staged) {
+        const u32 nvec = (t1 - A + 15u) >> 4;
+        for (u32 v = lane; v < nvec; v += 32) reinterpret_cast<uint4*>(sm_text)[v] = ldg_vec_guarded(a.gaf, (u64)A + 16u * v, a.n);
+        __syncwarp();
+    }
+    const u8* rt = text_staged ? sm_text + (rs - A) : a.gaf + rs;
     // contiguity of the warp's lines in the output
     const u64 end = o + d.len;
     const u64 onext = __shfl_down_sync(FULL, o, 1);
     const bool vnext = __shfl_down_sync(FULL, (u32)valid, 1) != 0 && lane < 31;
     const bool gap = valid && vnext && onext != end;
-    const u32 vmask = __ballot_sync(FULL, valid);
-    const int first = __ffs((int)vmask) - 1, last = 31 - __clz((int)vmask);
     const u64 o0 = __shfl_sync(FULL, o, first), o1 = __shfl_sync(FULL, end, last);
     const bool holes = (vmask >> first) != (0xffffffffu >> (31 - (last - first)));
     const bool staged = !__any_sync(FULL, gap) && !holes && (o1 - o0) <= kEOutCap;
     const u32 pad = (u32)(o0 & 15u);
-    if (valid) write_line(staged ? sm + pad + (u32)(o - o0) : a.out + o, rt, R, L, p10);
+    if (valid) write_line((staged ? sm + pad + (u32)(o - o0) : a.out + o) + d.len, rt, R, L);
     if (staged) {
         __syncwarp();
         const u32 total = pad + (u32)(o1 - o0);

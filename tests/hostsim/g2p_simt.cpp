@@ -75,7 +75,7 @@ int main(int argc, char** argv) {
     std::vector<LineDesc> desc(desc_cap + 1);
     std::vector<RecDesc> rdesc(nrec);
     ShortArgs sa{gaf, n, rec.data(), nrec, T, off.data(), status.data(), nullptr, list.data(), &meta.n_deleg, desc.data(), rdesc.data(), &meta.n_desc, desc_cap};
-    hs::launch(dim3(ncta), dim3(kSThreads), kShortSmem, [&] { k_short<kSG, false>(sa); });
+    hs::launch(dim3(ncta), dim3(kSThreads), short_smem<false>(), [&] { k_short<kSG, false>(sa); });
     LongArgs la{gaf, n, rec.data(), T, off.data(), status.data(), nullptr, list.data(), &meta.n_deleg, list2.data(), &meta.n_deleg2};
     const u32 nlong = 2;
     hs::launch(dim3(nlong), dim3(kLThreads), kLongSmem, [&] { k_long<false>(la); });
@@ -87,10 +87,10 @@ int main(int argc, char** argv) {
     sa.out = out.data();
     const u32 n_slots = std::min<u32>(meta.n_desc, desc_cap);
     if (n_slots) {
-        EmitArgs ea{gaf, rec.data(), off.data(), desc.data(), rdesc.data(), n_slots, out.data()};
+        EmitArgs ea{gaf, n, rec.data(), off.data(), desc.data(), rdesc.data(), n_slots, out.data()};
         hs::launch(dim3((n_slots + kEThreads - 1) / kEThreads), dim3(kEThreads), kEmitSmem, [&] { k_emit_lines(ea); });
     }
-    if (meta.n_desc > desc_cap) hs::launch(dim3(ncta), dim3(kSThreads), kShortSmem, [&] { k_short<kSG, true>(sa); });
+    if (meta.n_desc > desc_cap) hs::launch(dim3(ncta), dim3(kSThreads), short_smem<true>(), [&] { k_short<kSG, true>(sa); });
     la.out = out.data();
     if (meta.n_deleg) hs::launch(dim3(nlong), dim3(kLThreads), kLongSmem, [&] { k_long<true>(la); });
     if (meta.n_deleg2)
