@@ -32,11 +32,16 @@ constexpr int kLThreads = kLWarps * 32;
 constexpr u32 kLRing = 512;      // ring entries (power of two, >= 33 + 256)
 constexpr u32 kLChunk = 512;     // bytes classified per refill
 constexpr u32 kLBatch = 31;      // steps per batch; the next lane holds the batch's end boundary
-constexpr u32 kLOutCap = 8192;   // staged PAF bytes per batch
+constexpr u32 kLOutCap = 6144;   // staged PAF bytes per batch
+constexpr u32 kLText = 4096;     // bytes of text each stream keeps in shared memory (power of two, multiple of kLChunk)
+constexpr u32 kLHead = 64;       // cached query name / tp / rc text
 
 struct __align__(16) LWarpMem {
     u32 sring[kLRing];
     u32 oring[kLRing];
+    u8 stext[kLText];            // last chunks of the path column, addressed by (offset & (kLText-1))
+    u8 otext[kLText];            // last chunks of the cg value
+    u8 qname[kLHead], tp[kLHead], rc[kLHead];
     u32 tabs[32];
     u32 hdr[H_N];
     u32 tkeys[kSMaxTags];
@@ -61,11 +66,11 @@ __device__ __forceinline__ u64 wscan64(u64 v, u32 lane) {
     return v;
 }
 
-// 16 bytes of global text from an arbitrary offset (gaf itself is 16-byte aligned).
-__device__ __forceinline__ void ldg16_unaligned(const u8* gaf, u32 off, u32& w0, u32& w1, u32& w2, u32& w3) {
-    const u32* q = reinterpret_cast<const u32*>(gaf + (off & ~3u));
-    const u32 sh = (off & 3u) * 8u;
-    const u32 x0 = __ldg(q), x1 = __ldg(q + 1), x2 = __ldg(q + 2), x3 = __ldg(q + 3), x4 = __ldg(q + 4);
+// 16 bytes from base[off..], base 4-byte aligned for off == 0 (global text or a shared text window).
+__device__ __forceinline__ void ld16_unaligned(const u8* base4, u32 sh_bytes, u32& w0, u32& w1, u32& w2, u32& w3) {
+    const u32* q = reinterpret_cast<const u32*>(base4);
+    const u32 sh = sh_bytes * 8u;
+    const u32 x0 = q[0], x1 = q[1], x2 = q[2], x3 = q[3], x4 = q[4];
     w0 = __funnelshift_r(x0, x1, sh); w1 = __funnelshift_r(x1, x2, sh);
     w2 = __funnelshift_r(x2, x3, sh); w3 = __funnelshift_r(x3, x4, sh);
 }
@@ -75,22 +80,39 @@ __device__ __forceinline__ void ldg16_unaligned(const u8* gaf, u32 off, u32& w0,
 template <bool MARKERS>
 struct TokStream {
     u32* ring;
+    u8* text;          // shared copy of the most recent chunks
+    const u8* gaf;
     u32 lo, hi;        // span [lo, hi)
     u32 cur;           // base of the next chunk (multiple of kLChunk)
     u32 head, count;
+    u32 tlo, thi;      // offsets currently held in `text`: [tlo, thi)
     bool bwd, done;
 
-    __device__ __forceinline__ void init(u32* ring_, u32 lo_, u32 hi_, bool bwd_) {
-        ring = ring_; lo = lo_; hi = hi_; bwd = bwd_;
+    __device__ __forceinline__ void init(u32* ring_, u8* text_, const u8* gaf_, u32 lo_, u32 hi_, bool bwd_) {
+        ring = ring_; text = text_; gaf = gaf_; lo = lo_; hi = hi_; bwd = bwd_;
         head = count = 0;
+        tlo = thi = 0;
         done = hi_ <= lo_;
         cur = done ? 0u : (bwd_ ? ((hi_ - 1u) & ~(kLChunk - 1u)) : (lo_ & ~(kLChunk - 1u)));
     }
-    __device__ __forceinline__ void refill(const u8* gaf, u64 n, u32 lane) {
+    // Pointer to the n bytes at offset x: the shared copy when it holds all of them without
+    // wrapping, else global memory.
+    __device__ __forceinline__ const u8* src(u32 x, u32 n) const {
+        const u32 k = x & (kLText - 1u);
+        return (x >= tlo && x + n <= thi && k + n <= kLText) ? text + k : gaf + x;
+    }
+    __device__ __forceinline__ void refill(const u8* /*gaf*/, u64 n, u32 lane) {
         const u32 off = cur + 16u * lane;
         u32 m = 0;
+        {   // the chunk replaces the oldest one in the shared text window
+            const uint4 v0 = ldg_vec_guarded(gaf, off, n);
+            *reinterpret_cast<uint4*>(text + (off & (kLText - 1u))) = v0;
+            if (thi == tlo) { tlo = cur; thi = cur + kLChunk; }
+            else if (!bwd) { thi = cur + kLChunk; if (thi - tlo > kLText) tlo = thi - kLText; }
+            else { tlo = cur; if (thi - tlo > kLText) thi = tlo + kLText; }
+        }
         if (off < hi && off + 16u > lo) {
-            const uint4 v = ldg_vec_guarded(gaf, off, n);
+            const uint4 v = *reinterpret_cast<const uint4*>(text + (off & (kLText - 1u)));
             const u32 w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -125,14 +147,15 @@ struct StepTok2 {
 };
 
 // One path step token [p, q) (p = its marker, or pa-1 for an unprefixed path): name, optional
-// ":start-end", table probe.  Returns the lane's "not canonical" flag.
-__device__ __forceinline__ u32 parse_step_global(const u8* gaf, u64 n, const LenTableView& T, u32 p, u32 q, bool prefixed, StepTok2& t) {
+// ":start-end", table probe.  Text comes from the step stream's shared window when it holds the
+// token.  Returns the lane's "not canonical" flag.
+__device__ __forceinline__ u32 parse_step_global(const TokStream<true>& ss, u64 n, const LenTableView& T, u32 p, u32 q, bool prefixed, StepTok2& t) {
     t.name_a = p + 1;
     const u32 tl = q - t.name_a;
     t.nl = tl; t.tlen = 0; t.sa = 0; t.se = 0;
     if ((u64)t.name_a + 24 > n) return 1;
     u32 w0, w1, w2, w3;
-    ldg16_unaligned(gaf, t.name_a, w0, w1, w2, w3);
+    ld16_unaligned(ss.src(t.name_a & ~3u, 24), t.name_a & 3u, w0, w1, w2, w3);
     bool interval = false;
     if (prefixed) {
         u32 cm = movemask4(zero_bytes(w0 ^ 0x3A3A3A3Au)) | (movemask4(zero_bytes(w1 ^ 0x3A3A3A3Au)) << 4) |
@@ -149,13 +172,15 @@ __device__ __forceinline__ u32 parse_step_global(const u8* gaf, u64 n, const Len
     t.tlen = (i32)tl64;
     t.se = t.tlen;
     if (interval) {
-        u32 k = t.name_a + t.nl + 1, x = 0, nd = 0;
-        while (k < q && nd < 10) { const u32 d = (u32)gaf[k] - '0'; if (d > 9) break; x = x * 10u + d; ++nd; ++k; }
-        if (nd == 0 || nd > 9 || k >= q || gaf[k] != '-') return 1;
+        const u32 i0 = t.name_a + t.nl + 1, il = q - i0;   // "start-end"
+        const u8* tx = ss.src(i0, il);
+        u32 k = 0, x = 0, nd = 0;
+        while (k < il && nd < 10) { const u32 d = (u32)tx[k] - '0'; if (d > 9) break; x = x * 10u + d; ++nd; ++k; }
+        if (nd == 0 || nd > 9 || k >= il || tx[k] != '-') return 1;
         t.sa = (i32)x;
         ++k; x = 0; nd = 0;
-        while (k < q && nd < 10) { const u32 d = (u32)gaf[k] - '0'; if (d > 9) break; x = x * 10u + d; ++nd; ++k; }
-        if (nd == 0 || nd > 9 || k != q) return 1;
+        while (k < il && nd < 10) { const u32 d = (u32)tx[k] - '0'; if (d > 9) break; x = x * 10u + d; ++nd; ++k; }
+        if (nd == 0 || nd > 9 || k != il) return 1;
         t.se = (i32)x;
     }
     return t.se < t.sa ? 1u : 0u;
@@ -239,6 +264,14 @@ __device__ __forceinline__ void long_record(const LongArgs& a, LWarpMem* wm, con
         R.gi_n = gi_fast(R.m, R.b, R.gi);
         if (R.gi_n == 0) { deleg = true; break; }
         const u32 const_len = line_const_len(R, p10);
+        // query name and tp / rc text are the same for every line of the record: cache them
+        const bool head_cached = R.qn_b <= kLHead && R.tp_b - R.tp_a <= kLHead && R.rc_b - R.rc_a <= kLHead;
+        if (head_cached) {
+            for (u32 k = lane; k < R.qn_b; k += 32) wm->qname[k] = rt[k];
+            for (u32 k = lane; k < R.tp_b - R.tp_a; k += 32) wm->tp[k] = rt[R.tp_a + k];
+            for (u32 k = lane; k < R.rc_b - R.rc_a; k += 32) wm->rc[k] = rt[R.rc_a + k];
+            __syncwarp();
+        }
 
         TokStream<true> ss;
         TokStream<false> os;
@@ -247,7 +280,7 @@ __device__ __forceinline__ void long_record(const LongArgs& a, LWarpMem* wm, con
         if (minus) {
             u64 L = 0;
             if (prefixed) {
-                ss.init(wm->sring, pA, pB, false);
+                ss.init(wm->sring, wm->stext, gaf, pA, pB, false);
                 for (;;) {
                     ss.ensure(33, gaf, a.n, lane);
                     const u32 nb_ = ss.count < 32u ? ss.count : 32u;
@@ -256,7 +289,7 @@ __device__ __forceinline__ void long_record(const LongArgs& a, LWarpMem* wm, con
                     if (lane < nb_) {
                         const u32 p = ss.at(lane), q = lane + 1 < ss.count ? ss.at(lane + 1) : pB;
                         StepTok2 t;
-                        lbad |= parse_step_global(gaf, a.n, a.T, p, q, true, t);
+                        lbad |= parse_step_global(ss, a.n, a.T, p, q, true, t);
                         v = (u64)(u32)(t.se - t.sa);
                     }
                     v = wscan64(v, lane);
@@ -266,7 +299,8 @@ __device__ __forceinline__ void long_record(const LongArgs& a, LWarpMem* wm, con
                 }
             } else if (!empty_path) {
                 StepTok2 t;
-                lbad |= parse_step_global(gaf, a.n, a.T, pA - 1, pB, false, t);
+                ss.init(wm->sring, wm->stext, gaf, 0u, 0u, false);
+                lbad |= parse_step_global(ss, a.n, a.T, pA - 1, pB, false, t);
                 L = (u64)(u32)(t.se - t.sa);
             }
             if (__any_sync(FULL, lbad != 0) || L > 0x7fffffffULL) { deleg = true; break; }
@@ -276,8 +310,8 @@ __device__ __forceinline__ void long_record(const LongArgs& a, LWarpMem* wm, con
         if (ps2 < 0 || W < 0) { deleg = true; break; }
 
         // ---------------- streams
-        ss.init(wm->sring, prefixed ? pA : 0u, prefixed ? pB : 0u, minus);
-        os.init(wm->oring, cA, cB, minus);
+        ss.init(wm->sring, wm->stext, gaf, prefixed ? pA : 0u, prefixed ? pB : 0u, minus);
+        os.init(wm->oring, wm->otext, gaf, cA, cB, minus);
         // op window (one op per lane, inclusive prefixes carried across windows)
         u64 wEND = 0, wQ = 0, wM = 0, wNB = 0, cE = 0, cQ = 0, cM = 0, cNB = 0;
         u32 wlen = 0, wlp = 0, wds = 0, wk = 0, nwin = 0;
@@ -299,11 +333,12 @@ __device__ __forceinline__ void long_record(const LongArgs& a, LWarpMem* wm, con
                 if (!minus) wds = prev + 1u;
                 else wds = lane + 1 < os.count ? os.at(lane + 1) + 1u : cA;
                 const u32 nd = wlp - wds;
-                wk = (u32)gaf[wlp] - '=';
-                if (wk >= 28 || !((kOpMask >> wk) & 1u) || nd == 0 || nd > 9 || (nd > 1 && gaf[wds] == '0')) lbad = 1;
+                const u8* tx = os.src(wds, nd + 1);   // digits + op letter
+                wk = (u32)tx[nd] - '=';
+                if (wk >= 28 || !((kOpMask >> wk) & 1u) || nd == 0 || nd > 9 || (nd > 1 && tx[0] == '0')) lbad = 1;
                 else {
                     u32 x = 0;
-                    for (u32 t = wds; t < wlp; ++t) x = x * 10u + ((u32)gaf[t] - '0');
+                    for (u32 t = 0; t < nd; ++t) x = x * 10u + ((u32)tx[t] - '0');
                     if (x == 0) lbad = 1;
                     wlen = x;
                     vB = x;
@@ -355,8 +390,8 @@ __device__ __forceinline__ void long_record(const LongArgs& a, LWarpMem* wm, con
                     prev_p = __shfl_sync(FULL, myp, (int)nsb - 1);
                 } else { p = pA - 1; q = pB; }
                 if (is_step) {
-                    rev = (prefixed && gaf[p] == '<') != minus;
-                    lbad |= parse_step_global(gaf, a.n, a.T, p, q, prefixed, t);
+                    rev = (prefixed && *ss.src(p, 1) == '<') != minus;
+                    lbad |= parse_step_global(ss, a.n, a.T, p, q, prefixed, t);
                 }
             }
             __syncwarp();
@@ -455,7 +490,15 @@ __device__ __forceinline__ void long_record(const LongArgs& a, LWarpMem* wm, con
                 const u64 ob = o + run;
                 const bool staged = btot <= kLOutCap;
                 const u32 pad = (u32)(ob & 15u);
-                if (emit_line) write_line((staged ? wm->out + pad + (lincl - line) : a.out + ob + (lincl - line)) + line, rt, R, Ls);
+                if (emit_line) {
+                    LineSrc S;
+                    S.qname = head_cached ? wm->qname : rt;
+                    S.tp = head_cached ? wm->tp : rt + R.tp_a;
+                    S.rc = head_cached ? wm->rc : rt + R.rc_a;
+                    S.name = ss.src(t.name_a, t.nl);
+                    S.mid = os.src(s + Ls.mid_a, Ls.mid_b - Ls.mid_a);
+                    write_line((staged ? wm->out + pad + (lincl - line) : a.out + ob + (lincl - line)) + line, S, R, Ls);
+                }
                 if (staged) {
                     __syncwarp();
                     const u32 total = pad + btot;

@@ -254,21 +254,35 @@ __device__ __forceinline__ u8* rput_tag(u8* p, u8 a, u8 b, u8 t) {   // "\tab:t:
     p[0] = '\t'; p[1] = a; p[2] = b; p[3] = ':'; p[4] = t; p[5] = ':';
     return p;
 }
+// Where the variable-length pieces of a line are read from (any address space).
+struct LineSrc {
+    const u8* qname;   // R.qn_b bytes
+    const u8* name;    // L.nl bytes
+    const u8* tp;      // R.tp_b - R.tp_a bytes ("type:value")
+    const u8* rc;
+    const u8* mid;     // L.mid_b - L.mid_a bytes of CIGAR text copied verbatim
+};
+__device__ __forceinline__ LineSrc line_src(const u8* rt, const LineRec& R, const LineStep& L) {   // everything inside one record buffer
+    LineSrc S;
+    S.qname = rt; S.name = rt + L.name_a; S.tp = rt + R.tp_a; S.rc = rt + R.rc_a; S.mid = rt + L.mid_a;
+    return S;
+}
 // Writes the line that ends at `pend` (exclusive); returns its first byte.
-__device__ __forceinline__ u8* write_line(u8* pend, const u8* rt, const LineRec& R, const LineStep& L) {
+__device__ __forceinline__ u8* write_line(u8* pend, const LineSrc& S, const LineRec& R, const LineStep& L) {
     u8* p = pend;
     *--p = '\n';
     // pieces, reversed for '<' steps (gaf2paf_main.cpp:184-211); here in reverse output order
     if (!L.rev) { *--p = L.codeE; p = rput_u32(p, L.lenE); }
     else if (L.codeS) { *--p = L.codeS; p = rput_u32(p, L.lenS); }
     if (L.mid_b > L.mid_a) {
-        if (L.mid_fwd) p = rput_bytes(p, rt + L.mid_a, L.mid_b - L.mid_a);
+        const u32 mlen = L.mid_b - L.mid_a;
+        if (L.mid_fwd) p = rput_bytes(p, S.mid, mlen);
         else {
-            u32 t = L.mid_a;   // output order is the reverse token order: first text token is written last
-            while (t < L.mid_b) {
+            u32 t = 0;   // output order is the reverse token order: first text token is written last
+            while (t < mlen) {
                 u32 e = t;
-                while (rt[e] <= '9') ++e;   // the op letter ends the token
-                for (u32 k = e + 1; k-- > t;) *--p = rt[k];
+                while (S.mid[e] <= '9') ++e;   // the op letter ends the token
+                for (u32 k = e + 1; k-- > t;) *--p = S.mid[k];
                 t = e + 1;
             }
         }
@@ -279,20 +293,20 @@ __device__ __forceinline__ u8* write_line(u8* pend, const u8* rt, const LineRec&
     p = rput_bytes(p, R.gi, R.gi_n); p = rput_tag(p, 'g', 'i', 'f');
     p = rput_i32(p, R.b); p = rput_tag(p, 'g', 'l', 'i');
     p = rput_i32(p, R.m); p = rput_tag(p, 'g', 'm', 'i');
-    if (R.rc_b) { p = rput_bytes(p, rt + R.rc_a, R.rc_b - R.rc_a); p -= 4; p[0] = '\t'; p[1] = 'r'; p[2] = 'c'; p[3] = ':'; }
-    if (R.tp_b) { p = rput_bytes(p, rt + R.tp_a, R.tp_b - R.tp_a); p -= 4; p[0] = '\t'; p[1] = 't'; p[2] = 'p'; p[3] = ':'; }
+    if (R.rc_b) { p = rput_bytes(p, S.rc, R.rc_b - R.rc_a); p -= 4; p[0] = '\t'; p[1] = 'r'; p[2] = 'c'; p[3] = ':'; }
+    if (R.tp_b) { p = rput_bytes(p, S.tp, R.tp_b - R.tp_a); p -= 4; p[0] = '\t'; p[1] = 't'; p[2] = 'p'; p[3] = ':'; }
     p = rput_i32(p, R.mapq); *--p = '\t';
     p = rput_u32(p, L.nb); *--p = '\t';
     p = rput_u32(p, L.nm); *--p = '\t';
     p = rput_u32(p, L.te); *--p = '\t';
     p = rput_u32(p, L.ts); *--p = '\t';
     p = rput_u32(p, L.tlen); *--p = '\t';
-    p = rput_bytes(p, rt + L.name_a, L.nl); *--p = '\t';
+    p = rput_bytes(p, S.name, L.nl); *--p = '\t';
     *--p = L.rev ? '-' : '+'; *--p = '\t';
     p = rput_u32(p, L.q1); *--p = '\t';
     p = rput_u32(p, L.q0); *--p = '\t';
     p = rput_i32(p, R.qlen); *--p = '\t';
-    p = rput_bytes(p, rt, R.qn_b);
+    p = rput_bytes(p, S.qname, R.qn_b);
     return p;
 }
 
@@ -651,7 +665,7 @@ __global__ void __launch_bounds__(kSThreads, EMIT ? 4 : G2P_SHORT_CTAS) k_short(
             const bool staged = size <= kSOutCap;
             const u32 pad = (u32)(o & 15u);
             g.sync();   // the staging buffer aliases tabs / prefix arrays: everyone is done reading them
-            if (emit_line) write_line((staged ? gm->out + pad + loff : a.out + o + loff) + line, rt, R, L);
+            if (emit_line) write_line((staged ? gm->out + pad + loff : a.out + o + loff) + line, line_src(rt, R, L), R, L);
             if (staged) {
                 g.sync();
                 const u32 total = pad + size;
@@ -813,7 +827,7 @@ __global__ void __launch_bounds__(kEThreads) k_emit_lines(const EmitArgs a) {
     const bool holes = (vmask >> first) != (0xffffffffu >> (31 - (last - first)));
     const bool staged = !__any_sync(FULL, gap) && !holes && (o1 - o0) <= kEOutCap;
     const u32 pad = (u32)(o0 & 15u);
-    if (valid) write_line((staged ? sm + pad + (u32)(o - o0) : a.out + o) + d.len, rt, R, L);
+    if (valid) write_line((staged ? sm + pad + (u32)(o - o0) : a.out + o) + d.len, line_src(rt, R, L), R, L);
     if (staged) {
         __syncwarp();
         const u32 total = pad + (u32)(o1 - o0);
