@@ -266,14 +266,15 @@ static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
     const u32 nlist = std::min<u32>((nrec + kListThreads - 1) / kListThreads, (u32)ctx->n_sm * 16u);
     // line descriptors: 6 slots per record on average are plenty for short reads (2.3 lines + padding);
     // CTAs that find the array full fall back to k_short<EMIT=true> for their records
-    const u64 desc_cap64 = std::min<u64>((u64)nrec * 6 + 1024, 0xFFFFFF00ULL);
+    const u64 desc_cap64 = std::min<u64>((u64)nrec * 6 + (u64)n / 16 + 1024, 0xFFFFFF00ULL);   // long records: ~1 line per 40 bytes
     const u32 desc_cap = (u32)desc_cap64;
     G2P_CUDA(w.d_desc.ensure((size_t)desc_cap * sizeof(LineDesc)));
     G2P_CUDA(w.d_rdesc.ensure((size_t)nrec * sizeof(RecDesc)));
     LineDesc* d_desc = static_cast<LineDesc*>(w.d_desc.p);
     RecDesc* d_rdesc = static_cast<RecDesc*>(w.d_rdesc.p);
     ShortArgs sa{d_gaf, (u64)n, d_rec, nrec, ctx->table, d_off, d_status, nullptr, d_list, &d_meta->n_deleg, d_desc, d_rdesc, &d_meta->n_desc, desc_cap};
-    LongArgs la{d_gaf, (u64)n, d_rec, ctx->table, d_off, d_status, nullptr, d_list, &d_meta->n_deleg, d_list2, &d_meta->n_deleg2};
+    LongArgs la{d_gaf, (u64)n, d_rec, ctx->table, d_off, d_status, nullptr, d_list, &d_meta->n_deleg, d_list2, &d_meta->n_deleg2,
+                d_desc, d_rdesc, &d_meta->n_desc, desc_cap, &d_meta->legacy_long};
 
     // pass 1: sizes + status.  k_short takes the short canonical records, k_long what it left,
     // the general kernel what neither converts (non-canonical or erroneous records).
@@ -308,7 +309,7 @@ static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
         k_short<kSG, true><<<ncta, kSThreads, short_smem<true>(), st>>>(sa);
         ++launches;
     }
-    if (hm->n_deleg) {
+    if (hm->legacy_long) {   // records k_long could not describe (descriptor array full)
         k_long<true><<<nlong, kLThreads, kLongSmem, st>>>(la);
         ++launches;
     }

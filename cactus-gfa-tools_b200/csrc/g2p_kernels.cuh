@@ -37,8 +37,8 @@ struct PipelineMeta {
     u64 err_out_end;   // output offset just after the failing record's (partial) output
     u32 n_deleg;       // records k_short left to k_long
     u32 n_deleg2;      // records k_long left to the general kernel
-    u32 n_desc;        // line-descriptor slots reserved by k_short
-    u32 pad3;
+    u32 n_desc;        // line-descriptor slots reserved by k_short / k_long
+    u32 legacy_long;   // some k_long record is not described: run k_long<true>
 };
 
 // ------------------------------------------------------------------------------
@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(u32* __restrict__ tile_coun
         meta->n_deleg = 0;
         meta->n_deleg2 = 0;
         meta->n_desc = 0;
+        meta->legacy_long = 0;
     }
 }
 

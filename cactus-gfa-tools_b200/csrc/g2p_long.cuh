@@ -32,8 +32,8 @@ constexpr int kLThreads = kLWarps * 32;
 constexpr u32 kLRing = 512;      // ring entries (power of two, >= 33 + 256)
 constexpr u32 kLChunk = 512;     // bytes classified per refill
 constexpr u32 kLBatch = 31;      // steps per batch; the next lane holds the batch's end boundary
-constexpr u32 kLOutCap = 6144;   // staged PAF bytes per batch
-constexpr u32 kLText = 4096;     // bytes of text each stream keeps in shared memory (power of two, multiple of kLChunk)
+constexpr u32 kLOutCap = 5120;   // staged PAF bytes per batch
+constexpr u32 kLText = 2048;     // bytes of text each stream keeps in shared memory (power of two, multiple of kLChunk)
 constexpr u32 kLHead = 64;       // cached query name / tp / rc text
 
 struct __align__(16) LWarpMem {
@@ -198,6 +198,11 @@ struct LongArgs {
     const u32* n_list;
     u32* deleg_list;       // size pass: records left to the general kernel
     u32* n_deleg;
+    LineDesc* desc;        // size pass: line descriptors for k_emit_lines (one padded 32-slot block per batch)
+    RecDesc* rdesc;
+    u32* n_desc;
+    u32 desc_cap;
+    u32* need_legacy;      // set when a record could not be described (array full): k_long<true> emits it
 };
 
 template <bool EMIT>
@@ -208,13 +213,15 @@ __device__ __forceinline__ void long_record(const LongArgs& a, LWarpMem* wm, con
     const u32 s = a.rec_start[r], len = a.rec_start[r + 1] - s - 1;
     const u8* rt = gaf + s;
     u64 o = 0, osize = 0;
-    if (EMIT) {
-        if (!(a.status[r] & ST_F_LONG)) return;
+    if (EMIT) {   // legacy emit: only records whose lines are not in the descriptor array
+        const u32 st0 = a.status[r];
+        if (!(st0 & ST_F_LONG) || (st0 & ST_F_DESC)) return;
         o = a.out_off[r];
         osize = a.out_off[r + 1] - o;
         if (osize == 0) return;
     }
     bool deleg = false;
+    bool desc_fail = false;   // (size pass) some line of the record is not in the descriptor array
     u64 size = 0;
     u32 status = ST_OK | ST_F_LONG;
     do {
@@ -264,6 +271,10 @@ __device__ __forceinline__ void long_record(const LongArgs& a, LWarpMem* wm, con
         R.gi_n = gi_fast(R.m, R.b, R.gi);
         if (R.gi_n == 0) { deleg = true; break; }
         const u32 const_len = line_const_len(R, p10);
+        if (!EMIT) {
+            desc_fail = !rec_desc_fits(R);
+            if (!desc_fail && lane == 0) store_rec_desc(a.rdesc + r, R);
+        }
         // query name and tp / rc text are the same for every line of the record: cache them
         const bool head_cached = R.qn_b <= kLHead && R.tp_b - R.tp_a <= kLHead && R.rc_b - R.rc_a <= kLHead;
         if (head_cached) {
@@ -323,7 +334,7 @@ __device__ __forceinline__ void long_record(const LongArgs& a, LWarpMem* wm, con
             os.ensure(33, gaf, a.n, lane);
             nwin = os.count < 32u ? os.count : 32u;
             if (nwin == 0) { win_valid = false; ops_done = true; return; }
-            u64 vE = 0, vQ = 0, vM = 0, vB = 0;
+            u32 vE = 0, vQ = 0, vM = 0, vB = 0;   // op lengths < 10^8: a window's sums fit 32 bits
             wlen = 0; wlp = 0; wds = 0; wk = 0;
             const u32 mylp = lane < nwin ? os.at(lane) : 0u;
             u32 prev = __shfl_up_sync(FULL, mylp, 1);
@@ -335,7 +346,7 @@ __device__ __forceinline__ void long_record(const LongArgs& a, LWarpMem* wm, con
                 const u32 nd = wlp - wds;
                 const u8* tx = os.src(wds, nd + 1);   // digits + op letter
                 wk = (u32)tx[nd] - '=';
-                if (wk >= 28 || !((kOpMask >> wk) & 1u) || nd == 0 || nd > 9 || (nd > 1 && tx[0] == '0')) lbad = 1;
+                if (wk >= 28 || !((kOpMask >> wk) & 1u) || nd == 0 || nd > 8 || (nd > 1 && tx[0] == '0')) lbad = 1;
                 else {
                     u32 x = 0;
                     for (u32 t = 0; t < nd; ++t) x = x * 10u + ((u32)tx[t] - '0');
@@ -347,7 +358,7 @@ __device__ __forceinline__ void long_record(const LongArgs& a, LWarpMem* wm, con
                     vM = ((kMatchMask >> wk) & 1u) ? x : 0u;
                 }
             }
-            wEND = wscan64(vE, lane) + cE; wQ = wscan64(vQ, lane) + cQ; wM = wscan64(vM, lane) + cM; wNB = wscan64(vB, lane) + cNB;
+            wEND = (u64)wscan32(vE, lane) + cE; wQ = (u64)wscan32(vQ, lane) + cQ; wM = (u64)wscan32(vM, lane) + cM; wNB = (u64)wscan32(vB, lane) + cNB;
             cE = __shfl_sync(FULL, wEND, nwin - 1); cQ = __shfl_sync(FULL, wQ, nwin - 1);
             cM = __shfl_sync(FULL, wM, nwin - 1); cNB = __shfl_sync(FULL, wNB, nwin - 1);
             win_last = cE;
@@ -486,6 +497,22 @@ __device__ __forceinline__ void long_record(const LongArgs& a, LWarpMem* wm, con
             }
             const u32 lincl = wscan32(line, lane);
             const u32 btot = __shfl_sync(FULL, lincl, 31);
+            if (!EMIT && btot && !desc_fail) {
+                // describe the batch's lines for k_emit_lines: one 32-slot block, lines first
+                u32 base = 0;
+                if (lane == 0) base = atomicAdd(a.n_desc, 32u);
+                base = __shfl_sync(FULL, base, 0);
+                const u64 lo64 = run + (lincl - line);
+                if (base > a.desc_cap || a.desc_cap - base < 32u || run + btot > 0xffffffffULL) {
+                    desc_fail = true;
+                    if (base < a.desc_cap) { const u32 k = base + lane; if (k < a.desc_cap) a.desc[k].rec = kDescInvalid; }
+                } else {
+                    const u32 em = __ballot_sync(FULL, emit_line);
+                    const u32 rank = (u32)__popc(em & ((1u << lane) - 1u));
+                    if (emit_line) store_line_desc(a.desc + base + rank, r, (u32)lo64, line, Ls);
+                    if (lane >= (u32)__popc(em)) a.desc[base + lane].rec = kDescInvalid;
+                }
+            }
             if (EMIT && btot) {
                 const u64 ob = o + run;
                 const bool staged = btot <= kLOutCap;
@@ -532,8 +559,10 @@ __device__ __forceinline__ void long_record(const LongArgs& a, LWarpMem* wm, con
             a.out_off[r] = 0;
             a.deleg_list[atomicAdd(a.n_deleg, 1u)] = r;
         } else {
-            a.status[r] = status;
+            const bool described = !desc_fail && size != 0;
+            a.status[r] = status | (described ? (u32)ST_F_DESC : 0u);
             a.out_off[r] = size;
+            if (!described && size != 0) *a.need_legacy = 1u;
         }
     }
     (void)osize;

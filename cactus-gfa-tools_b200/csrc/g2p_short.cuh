@@ -319,19 +319,46 @@ struct __align__(16) LineDesc {
     u32 q0, q1;
     u32 tlen, ts, te, nm;
     u32 nb, lenS, lenE;
-    u16 name_a, mid_a;
-    u16 mid_b, len;       // len: bytes of the whole line
+    u32 name_a;           // record-relative offsets of the name and of the verbatim CIGAR span
+    u32 mid_a, mid_len;
+    u32 len;              // bytes of the whole line
     u8 nl, codeS, codeE, flags;   // flags: bit0 rev, bit1 mid_fwd
-    u32 pad[2];
 };
 static_assert(sizeof(LineDesc) == 64, "LineDesc is four 16-byte vectors");
 struct __align__(16) RecDesc {
     i32 qlen, m, b;
     i32 mapq;
-    u16 qn_b, tp_a, tp_b, rc_a, rc_b;
-    u8 gi_n, gi[5];
+    u32 tp_a, rc_a;       // record-relative offsets of the "type:value" text of tp / rc
+    u16 qn_b, tp_len, rc_len;
+    u8 gi_n, pad0;
+    u8 gi[5];
+    u8 pad1[11];
 };
-static_assert(sizeof(RecDesc) == 32, "RecDesc is two 16-byte vectors");
+static_assert(sizeof(RecDesc) == 48, "RecDesc is three 16-byte vectors");
+__device__ __forceinline__ void store_line_desc(LineDesc* dst, u32 rec, u32 loff, u32 line, const LineStep& L) {
+    LineDesc d;
+    d.rec = rec; d.loff = loff; d.q0 = L.q0; d.q1 = L.q1; d.tlen = L.tlen; d.ts = L.ts; d.te = L.te; d.nm = L.nm;
+    d.nb = L.nb; d.lenS = L.lenS; d.lenE = L.lenE; d.name_a = L.name_a;
+    d.mid_a = L.mid_a; d.mid_len = L.mid_b > L.mid_a ? L.mid_b - L.mid_a : 0u; d.len = line;
+    d.nl = (u8)L.nl; d.codeS = L.codeS; d.codeE = L.codeE; d.flags = (u8)((L.rev ? 1u : 0u) | (L.mid_fwd ? 2u : 0u));
+    const uint4* src = reinterpret_cast<const uint4*>(&d);
+    uint4* out = reinterpret_cast<uint4*>(dst);
+    out[0] = src[0]; out[1] = src[1]; out[2] = src[2]; out[3] = src[3];
+}
+// false when the record's constants do not fit the descriptor (very long name / tag text)
+__device__ __forceinline__ bool rec_desc_fits(const LineRec& R) { return R.qn_b <= 0xffffu && R.tp_b - R.tp_a <= 0xffffu && R.rc_b - R.rc_a <= 0xffffu; }
+__device__ __forceinline__ void store_rec_desc(RecDesc* dst, const LineRec& R) {
+    RecDesc rd;
+    rd.qlen = R.qlen; rd.m = R.m; rd.b = R.b; rd.mapq = R.mapq;
+    rd.tp_a = R.tp_a; rd.rc_a = R.rc_a;
+    rd.qn_b = (u16)R.qn_b; rd.tp_len = (u16)(R.tp_b - R.tp_a); rd.rc_len = (u16)(R.rc_b - R.rc_a);
+    rd.gi_n = (u8)R.gi_n; rd.pad0 = 0;
+    for (int k = 0; k < 5; ++k) rd.gi[k] = R.gi[k];
+    for (int k = 0; k < 11; ++k) rd.pad1[k] = 0;
+    const uint4* src = reinterpret_cast<const uint4*>(&rd);
+    uint4* out = reinterpret_cast<uint4*>(dst);
+    out[0] = src[0]; out[1] = src[1]; out[2] = src[2];
+}
 constexpr u32 kDescInvalid = 0xFFFFFFFFu;
 
 __device__ __forceinline__ uint4 ldg_vec_guarded(const u8* base, u64 off, u64 n) {
@@ -685,7 +712,7 @@ __global__ void __launch_bounds__(kSThreads, EMIT ? 4 : G2P_SHORT_CTAS) k_short(
         // ---------------- line descriptors: one dense reservation per CTA, padded to whole warps
         __shared__ u32 s_cnt[kSThreads / G + 1];
         __shared__ u32 s_base, s_total, s_ok;
-        const bool fast = valid && !deleg && size != 0;
+        const bool fast = valid && !deleg && size != 0 && rec_desc_fits(R);
         const u32 lmask = g.ballot(fast && emit_line);
         if (g.gl == 0) s_cnt[gid] = fast ? (u32)__popc(lmask) : 0u;
         __syncthreads();
@@ -710,26 +737,9 @@ __global__ void __launch_bounds__(kSThreads, EMIT ? 4 : G2P_SHORT_CTAS) k_short(
         if (desc_ok) {
             if (fast && emit_line) {
                 const u32 slot = s_base + s_cnt[gid] + (u32)__popc(lmask & ((1u << g.gl) - 1u));
-                LineDesc d;
-                d.rec = r; d.loff = loff; d.q0 = L.q0; d.q1 = L.q1; d.tlen = L.tlen; d.ts = L.ts; d.te = L.te; d.nm = L.nm;
-                d.nb = L.nb; d.lenS = L.lenS; d.lenE = L.lenE;
-                d.name_a = (u16)L.name_a; d.mid_a = (u16)L.mid_a; d.mid_b = (u16)L.mid_b; d.len = (u16)line;
-                d.nl = (u8)L.nl; d.codeS = L.codeS; d.codeE = L.codeE; d.flags = (u8)((L.rev ? 1u : 0u) | (L.mid_fwd ? 2u : 0u));
-                d.pad[0] = d.pad[1] = 0;
-                const uint4* src = reinterpret_cast<const uint4*>(&d);
-                uint4* dst = reinterpret_cast<uint4*>(a.desc + slot);
-                dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+                store_line_desc(a.desc + slot, r, loff, line, L);
             }
-            if (fast && g.gl == 0) {
-                RecDesc rd;
-                rd.qlen = R.qlen; rd.m = R.m; rd.b = R.b; rd.mapq = R.mapq;
-                rd.qn_b = (u16)R.qn_b; rd.tp_a = (u16)R.tp_a; rd.tp_b = (u16)R.tp_b; rd.rc_a = (u16)R.rc_a; rd.rc_b = (u16)R.rc_b;
-                rd.gi_n = (u8)R.gi_n;
-                for (int k = 0; k < 5; ++k) rd.gi[k] = R.gi[k];
-                const uint4* src = reinterpret_cast<const uint4*>(&rd);
-                uint4* dst = reinterpret_cast<uint4*>(a.rdesc + r);
-                dst[0] = src[0]; dst[1] = src[1];
-            }
+            if (fast && g.gl == 0) store_rec_desc(a.rdesc + r, R);
             const u32 npad = ((s_total + 31u) & ~31u) - s_total;
             if (threadIdx.x < npad) a.desc[s_base + s_total + threadIdx.x].rec = kDescInvalid;
         } else if (s_total && s_base < a.desc_cap) {
@@ -798,14 +808,16 @@ __global__ void __launch_bounds__(kEThreads) k_emit_lines(const EmitArgs a) {
         RecDesc rd;
         const uint4* src = reinterpret_cast<const uint4*>(a.rdesc + d.rec);
         uint4* dst = reinterpret_cast<uint4*>(&rd);
-        dst[0] = __ldg(src); dst[1] = __ldg(src + 1);
+        dst[0] = __ldg(src); dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2);
         rs = a.rec_start[d.rec]; re = a.rec_start[d.rec + 1];
         o = a.out_off[d.rec] + d.loff;
         R.qn_b = rd.qn_b; R.qlen = rd.qlen; R.mapq = rd.mapq; R.m = rd.m; R.b = rd.b;
-        R.tp_a = rd.tp_a; R.tp_b = rd.tp_b; R.rc_a = rd.rc_a; R.rc_b = rd.rc_b; R.gi_n = rd.gi_n;
+        R.tp_a = rd.tp_a; R.tp_b = rd.tp_a + rd.tp_len; R.rc_a = rd.rc_a; R.rc_b = rd.rc_a + rd.rc_len; R.gi_n = rd.gi_n;
+        if (!rd.tp_len) R.tp_b = 0;
+        if (!rd.rc_len) R.rc_b = 0;
         for (int k = 0; k < 5; ++k) R.gi[k] = rd.gi[k];
         L.q0 = d.q0; L.q1 = d.q1; L.name_a = d.name_a; L.nl = d.nl; L.tlen = d.tlen; L.ts = d.ts; L.te = d.te; L.nm = d.nm; L.nb = d.nb;
-        L.lenS = d.lenS; L.lenE = d.lenE; L.mid_a = d.mid_a; L.mid_b = d.mid_b; L.codeS = d.codeS; L.codeE = d.codeE;
+        L.lenS = d.lenS; L.lenE = d.lenE; L.mid_a = d.mid_a; L.mid_b = d.mid_a + d.mid_len; L.codeS = d.codeS; L.codeE = d.codeE;
         L.rev = (d.flags & 1u) != 0; L.mid_fwd = (d.flags & 2u) != 0;
     }
     // stage the text of the warp's records (one contiguous span) with 128-bit coalesced loads

@@ -71,12 +71,13 @@ int main(int argc, char** argv) {
     const u32 ncta = (nrec + kShortRecsPerCta - 1) / kShortRecsPerCta;
     const u32 nlist = std::min<u32>((nrec + kListThreads - 1) / kListThreads, 8u);
     // G2P_SIMT_DESC_CAP=<slots> shrinks the descriptor array to exercise the overflow fallback
-    const u32 desc_cap = std::getenv("G2P_SIMT_DESC_CAP") ? (u32)std::atol(std::getenv("G2P_SIMT_DESC_CAP")) : nrec * 4 + 1024;
+    const u32 desc_cap = std::getenv("G2P_SIMT_DESC_CAP") ? (u32)std::atol(std::getenv("G2P_SIMT_DESC_CAP")) : nrec * 6 + (u32)(n / 16) + 1024;
     std::vector<LineDesc> desc(desc_cap + 1);
     std::vector<RecDesc> rdesc(nrec);
     ShortArgs sa{gaf, n, rec.data(), nrec, T, off.data(), status.data(), nullptr, list.data(), &meta.n_deleg, desc.data(), rdesc.data(), &meta.n_desc, desc_cap};
     hs::launch(dim3(ncta), dim3(kSThreads), short_smem<false>(), [&] { k_short<kSG, false>(sa); });
-    LongArgs la{gaf, n, rec.data(), T, off.data(), status.data(), nullptr, list.data(), &meta.n_deleg, list2.data(), &meta.n_deleg2};
+    LongArgs la{gaf, n, rec.data(), T, off.data(), status.data(), nullptr, list.data(), &meta.n_deleg, list2.data(), &meta.n_deleg2,
+                desc.data(), rdesc.data(), &meta.n_desc, desc_cap, &meta.legacy_long};
     const u32 nlong = 2;
     hs::launch(dim3(nlong), dim3(kLThreads), kLongSmem, [&] { k_long<false>(la); });
     hs::launch(dim3(nlist), dim3(kListThreads), 0, [&] { k_convert_list<false>(gaf, rec.data(), T, off.data(), status.data(), nullptr, &meta, list2.data(), &meta.n_deleg2); });
@@ -92,7 +93,7 @@ int main(int argc, char** argv) {
     }
     if (meta.n_desc > desc_cap) hs::launch(dim3(ncta), dim3(kSThreads), short_smem<true>(), [&] { k_short<kSG, true>(sa); });
     la.out = out.data();
-    if (meta.n_deleg) hs::launch(dim3(nlong), dim3(kLThreads), kLongSmem, [&] { k_long<true>(la); });
+    if (meta.legacy_long) hs::launch(dim3(nlong), dim3(kLThreads), kLongSmem, [&] { k_long<true>(la); });
     if (meta.n_deleg2)
         hs::launch(dim3(nlist), dim3(kListThreads), 0, [&] { k_convert_list<true>(gaf, rec.data(), T, off.data(), status.data(), out.data(), &meta, list2.data(), &meta.n_deleg2); });
     u64 out_bytes = meta.out_total;
