@@ -131,8 +131,8 @@ int g2p_create(int device, g2p_ctx** out) {
     cudaFuncSetAttribute(k_short<kSG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)short_smem<true>());
     cudaFuncSetAttribute(k_short<kSG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)short_smem<false>());
     cudaFuncSetAttribute(k_emit_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmitSmem);
-    cudaFuncSetAttribute(k_long<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmem);
-    cudaFuncSetAttribute(k_long<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmem);
+    cudaFuncSetAttribute(k_long<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)long_smem<true>());
+    cudaFuncSetAttribute(k_long<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)long_smem<false>());
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
     if (const char* c = std::getenv("G2P_HOST_CHUNK_MB")) {
         long v = std::atol(c);
@@ -262,7 +262,7 @@ static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
     u32* d_list = static_cast<u32*>(w.d_list.p);
     u32* d_list2 = static_cast<u32*>(w.d_list2.p);
     const u32 ncta = (nrec + kShortRecsPerCta - 1) / kShortRecsPerCta;
-    const u32 nlong = (u32)ctx->n_sm * 4u;
+    const u32 nlong = (u32)ctx->n_sm * 6u;
     const u32 nlist = std::min<u32>((nrec + kListThreads - 1) / kListThreads, (u32)ctx->n_sm * 16u);
     // line descriptors: 6 slots per record on average are plenty for short reads (2.3 lines + padding);
     // CTAs that find the array full fall back to k_short<EMIT=true> for their records
@@ -279,7 +279,7 @@ static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
     // pass 1: sizes + status.  k_short takes the short canonical records, k_long what it left,
     // the general kernel what neither converts (non-canonical or erroneous records).
     k_short<kSG, false><<<ncta, kSThreads, short_smem<false>(), st>>>(sa);
-    k_long<false><<<nlong, kLThreads, kLongSmem, st>>>(la);
+    k_long<false><<<nlong, kLThreads, long_smem<false>(), st>>>(la);
     k_convert_list<false><<<nlist, kListThreads, 0, st>>>(d_gaf, d_rec, ctx->table, d_off, d_status, nullptr, d_meta, d_list2, &d_meta->n_deleg2);
     launches += 3;
     G2P_CUDA(cudaEventRecord(w.ev[2], st));
@@ -310,7 +310,7 @@ static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
         ++launches;
     }
     if (hm->legacy_long) {   // records k_long could not describe (descriptor array full)
-        k_long<true><<<nlong, kLThreads, kLongSmem, st>>>(la);
+        k_long<true><<<nlong, kLThreads, long_smem<true>(), st>>>(la);
         ++launches;
     }
     if (hm->n_deleg2) {

@@ -36,7 +36,8 @@ constexpr u32 kLOutCap = 5120;   // staged PAF bytes per batch
 constexpr u32 kLText = 2048;     // bytes of text each stream keeps in shared memory (power of two, multiple of kLChunk)
 constexpr u32 kLHead = 64;       // cached query name / tp / rc text
 
-struct __align__(16) LWarpMem {
+template <bool WITH_OUT>
+struct __align__(16) LWarpMemT {
     u32 sring[kLRing];
     u32 oring[kLRing];
     u8 stext[kLText];            // last chunks of the path column, addressed by (offset & (kLText-1))
@@ -45,10 +46,13 @@ struct __align__(16) LWarpMem {
     u32 tabs[32];
     u32 hdr[H_N];
     u32 tkeys[kSMaxTags];
-    u8 out[kLOutCap + 16];
+    u8 out[WITH_OUT ? kLOutCap + 16 : 16];   // line staging of the streaming emit (fallback path only)
 };
-static_assert(sizeof(LWarpMem) % 16 == 0, "warp slices must keep 16-byte alignment");
-constexpr size_t kLongSmem = sizeof(LWarpMem) * kLWarps;
+static_assert(sizeof(LWarpMemT<true>) % 16 == 0 && sizeof(LWarpMemT<false>) % 16 == 0, "warp slices must keep 16-byte alignment");
+template <bool EMIT> constexpr size_t long_smem() { return sizeof(LWarpMemT<EMIT>) * kLWarps; }
+#ifndef G2P_LONG_CTAS
+#define G2P_LONG_CTAS 6   /* resident CTAs per SM the size pass of k_long is compiled for */
+#endif
 
 __device__ __forceinline__ u32 range16u(u32 lo, u32 hi) {   // bits [lo, hi), both clamped to 16
     lo = lo > 16u ? 16u : lo;
@@ -206,7 +210,7 @@ struct LongArgs {
 };
 
 template <bool EMIT>
-__device__ __forceinline__ void long_record(const LongArgs& a, LWarpMem* wm, const u32 r, const u32 lane, const u32* p10) {
+__device__ __forceinline__ void long_record(const LongArgs& a, LWarpMemT<EMIT>* wm, const u32 r, const u32 lane, const u32* p10) {
     const u32 FULL = 0xffffffffu;
     const Grp<32> g;
     const u8* gaf = a.gaf;
@@ -569,7 +573,7 @@ __device__ __forceinline__ void long_record(const LongArgs& a, LWarpMem* wm, con
 }
 
 template <bool EMIT>
-__global__ void __launch_bounds__(kLThreads) k_long(const LongArgs a) {
+__global__ void __launch_bounds__(kLThreads, EMIT ? 4 : G2P_LONG_CTAS) k_long(const LongArgs a) {
     G2P_DYN_SMEM(smem);
     __shared__ u32 p10[10];
     if (threadIdx.x < 10) {
@@ -579,7 +583,7 @@ __global__ void __launch_bounds__(kLThreads) k_long(const LongArgs a) {
     }
     __syncthreads();
     const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    LWarpMem* wm = reinterpret_cast<LWarpMem*>(smem) + warp;
+    LWarpMemT<EMIT>* wm = reinterpret_cast<LWarpMemT<EMIT>*>(smem) + warp;
     const u32 nl = *a.n_list;
     for (u32 k = blockIdx.x * kLWarps + warp; k < nl; k += gridDim.x * kLWarps) {
         long_record<EMIT>(a, wm, a.list[k], lane, p10);

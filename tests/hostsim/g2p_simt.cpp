@@ -79,7 +79,7 @@ int main(int argc, char** argv) {
     LongArgs la{gaf, n, rec.data(), T, off.data(), status.data(), nullptr, list.data(), &meta.n_deleg, list2.data(), &meta.n_deleg2,
                 desc.data(), rdesc.data(), &meta.n_desc, desc_cap, &meta.legacy_long};
     const u32 nlong = 2;
-    hs::launch(dim3(nlong), dim3(kLThreads), kLongSmem, [&] { k_long<false>(la); });
+    hs::launch(dim3(nlong), dim3(kLThreads), long_smem<false>(), [&] { k_long<false>(la); });
     hs::launch(dim3(nlist), dim3(kListThreads), 0, [&] { k_convert_list<false>(gaf, rec.data(), T, off.data(), status.data(), nullptr, &meta, list2.data(), &meta.n_deleg2); });
     hs::launch(dim3(nscan), dim3(kScanThreads), 0, [&] { k_scan_reduce(off.data(), nrec, blocks.data()); });
     hs::launch(dim3(1), dim3(1024), 0, [&] { k_scan_blocks(blocks.data(), nscan, &meta); });
@@ -93,7 +93,7 @@ int main(int argc, char** argv) {
     }
     if (meta.n_desc > desc_cap) hs::launch(dim3(ncta), dim3(kSThreads), short_smem<true>(), [&] { k_short<kSG, true>(sa); });
     la.out = out.data();
-    if (meta.legacy_long) hs::launch(dim3(nlong), dim3(kLThreads), kLongSmem, [&] { k_long<true>(la); });
+    if (meta.legacy_long) hs::launch(dim3(nlong), dim3(kLThreads), long_smem<true>(), [&] { k_long<true>(la); });
     if (meta.n_deleg2)
         hs::launch(dim3(nlist), dim3(kListThreads), 0, [&] { k_convert_list<true>(gaf, rec.data(), T, off.data(), status.data(), out.data(), &meta, list2.data(), &meta.n_deleg2); });
     u64 out_bytes = meta.out_total;
