@@ -51,7 +51,7 @@ struct __align__(16) LWarpMemT {
 static_assert(sizeof(LWarpMemT<true>) % 16 == 0 && sizeof(LWarpMemT<false>) % 16 == 0, "warp slices must keep 16-byte alignment");
 template <bool EMIT> constexpr size_t long_smem() { return sizeof(LWarpMemT<EMIT>) * kLWarps; }
 #ifndef G2P_LONG_CTAS
-#define G2P_LONG_CTAS 6   /* resident CTAs per SM the size pass of k_long is compiled for */
+#define G2P_LONG_CTAS 4   /* resident CTAs per SM the size pass of k_long is compiled for */
 #endif
 
 __device__ __forceinline__ u32 range16u(u32 lo, u32 hi) {   // bits [lo, hi), both clamped to 16

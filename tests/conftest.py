@@ -23,10 +23,11 @@ def _built():
         os.path.join(ROOT, "build", "g2p_hostsim"),
         os.path.join(ROOT, "build", "g2p_simt"),
         os.path.join(ROOT, "build", "g2p_simt_long"),
+        os.path.join(ROOT, "build", "g2u_hostsim"),
     ]
     if not all(os.path.exists(p) for p in need):
         subprocess.check_call(["make", "-C", ROOT], stdout=subprocess.DEVNULL)
-    if not os.path.exists(os.path.join(ROOT, "oracle", "bin", "gaf2paf_oracle")):
+    if not all(os.path.exists(os.path.join(ROOT, "oracle", "bin", b)) for b in ("gaf2paf_oracle", "gaf2unstable_oracle")):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
     yield
 

@@ -228,7 +228,7 @@ def gen_rgfa_case(seed, n_contigs=4, n_records=500, aligned=False, multi_ref_pct
 
 def run_gaf2unstable_ref(gaf, rgfa, want_lengths=False):
     """The reference gaf2unstable (oracle/_ref) on in-memory inputs -> (rc, stdout, stderr[, node-lengths])."""
-    binary = os.path.join(REF_BIN, "gaf2unstable")
+    binary, _kind = oracle_path("auto", "gaf2unstable")   # reference build when present, else the restatement
     with tempfile.TemporaryDirectory() as td:
         gp, lp = os.path.join(td, "g.gfa"), os.path.join(td, "nl.tsv")
         with open(gp, "wb") as f:

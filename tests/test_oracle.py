@@ -94,17 +94,20 @@ def test_unterminated_last_line_and_two_files():
 # ---- gaf2unstable (config 2) ---------------------------------------------------------------
 G2U_HOSTSIM = os.path.join(H.BUILD, "g2u_hostsim")
 G2U_REF = os.path.join(H.REF_BIN, "gaf2unstable")
+G2U_PORT = os.path.join(H.ORACLE_BIN, "gaf2unstable_oracle")
 
 
-def test_gaf2unstable_host_code_matches_golden():
+@pytest.mark.parametrize("binary", [G2U_HOSTSIM, G2U_PORT])
+def test_gaf2unstable_host_code_matches_golden(binary):
+    """the device code on the host, and the independent oracle restatement, against the golden vectors"""
     d = H.golden("gaf2unstable_kat.json")
     with tempfile.TemporaryDirectory() as td:
         gp, lp = os.path.join(td, "g.gfa"), os.path.join(td, "nl.tsv")
         open(gp, "w").write(d["rgfa"])
         for v in d["vectors"]:
-            rc, out, err = H.run_tool(G2U_HOSTSIM, ["-g", gp, "-"], (v["in"] + "\n").encode())
+            rc, out, err = H.run_tool(binary, ["-g", gp, "-"], (v["in"] + "\n").encode())
             assert rc == v["rc"] and out.decode() == v["out"], v["in"]
-        rc, out, err = H.run_tool(G2U_HOSTSIM, ["-g", gp, "-o", lp, "-"], ("\n".join(d["stream"]["in"]) + "\n").encode())
+        rc, out, err = H.run_tool(binary, ["-g", gp, "-o", lp, "-"], ("\n".join(d["stream"]["in"]) + "\n").encode())
         assert rc == 0 and out.decode() == d["stream"]["out"]
         assert open(lp).read() == d["node_lengths"]
 
@@ -122,3 +125,5 @@ def test_gaf2unstable_differential(seed, aligned):
         rc, out, serr = H.run_tool(G2U_HOSTSIM, ["-g", gp, "-o", lp, "-"], gaf)
         assert rc == 0 and out == ref and open(lp, "rb").read() == nl
         assert serr.count("warning") == err.count("[gaf2unstable] warning")
+        rc, out, serr = H.run_tool(G2U_PORT, ["-g", gp, "-o", lp, "-"], gaf)   # oracle restatement: stderr verbatim too
+        assert rc == 0 and out == ref and open(lp, "rb").read() == nl and serr == err
