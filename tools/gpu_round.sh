@@ -9,7 +9,7 @@ nproc > gpurun_out/nproc.txt; free -g >> gpurun_out/nproc.txt
 echo "== pytest"; timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest.log
 echo "== smoke"; timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/smoke.log
 echo "== bench short"; timeout 1200 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_short.json 2> gpurun_out/bench_short.err; echo "rc=$?"; cat gpurun_out/bench_short.json; tail -3 gpurun_out/bench_short.err
-echo "== bench asm"; timeout 1200 python bench.py --workload asm --records ${ASM_RECORDS:-2000} --steps 3 --warmup 3 > gpurun_out/bench_asm.json 2> gpurun_out/bench_asm.err; echo "rc=$?"; cat gpurun_out/bench_asm.json; tail -3 gpurun_out/bench_asm.err
+echo "== bench asm"; timeout 1200 python bench.py --workload asm --steps 3 --warmup 3 > gpurun_out/bench_asm.json 2> gpurun_out/bench_asm.err; echo "rc=$?"; cat gpurun_out/bench_asm.json; tail -3 gpurun_out/bench_asm.err
 if [ "${SKIP_NCU:-0}" != "1" ]; then
   CMD="python bench.py --records 1000000 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e"
   echo "== ncu launch list"
