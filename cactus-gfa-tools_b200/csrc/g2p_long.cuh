@@ -70,6 +70,15 @@ __device__ __forceinline__ u64 wscan64(u64 v, u32 lane) {
     return v;
 }
 
+// L2 prefetch of the line holding p (no register is tied up by the request).
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+#if !defined(G2P_HOSTSIM)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 // 16 bytes from base[off..], base 4-byte aligned for off == 0 (global text or a shared text window).
 __device__ __forceinline__ void ld16_unaligned(const u8* base4, u32 sh_bytes, u32& w0, u32& w1, u32& w2, u32& w3) {
     const u32* q = reinterpret_cast<const u32*>(base4);
@@ -136,6 +145,7 @@ struct TokStream {
         count += total;
         if (!bwd) { if (hi - cur <= kLChunk) done = true; else cur += kLChunk; }
         else { if (cur <= lo) done = true; else cur -= kLChunk; }
+        if (!done && (lane & 7u) == 0) prefetch_l2(gaf + cur + 16u * lane);   // the chunk the next refill reads
         __syncwarp();
     }
     __device__ __forceinline__ void ensure(u32 need, const u8* gaf, u64 n, u32 lane) {
@@ -188,6 +198,23 @@ __device__ __forceinline__ u32 parse_step_global(const TokStream<true>& ss, u64 
         t.se = (i32)x;
     }
     return t.se < t.sa ? 1u : 0u;
+}
+
+// Requests the table slot the step token [p, q) will probe, one batch ahead of its use: the probe
+// is a dependent random access (DRAM or far L2) and was the largest single stall of the kernel.
+__device__ __forceinline__ void prefetch_step_slot(const TokStream<true>& ss, u64 n, const LenTableView& T, u32 p, u32 q) {
+    const u32 name_a = p + 1, tl = q - name_a;
+    if ((u64)name_a + 24 > n || T.nslots == 0) return;
+    u32 w0, w1, w2, w3;
+    ld16_unaligned(ss.src(name_a & ~3u, 24), name_a & 3u, w0, w1, w2, w3);
+    u32 cm = movemask4(zero_bytes(w0 ^ 0x3A3A3A3Au)) | (movemask4(zero_bytes(w1 ^ 0x3A3A3A3Au)) << 4) |
+             (movemask4(zero_bytes(w2 ^ 0x3A3A3A3Au)) << 8) | (movemask4(zero_bytes(w3 ^ 0x3A3A3A3Au)) << 12);
+    cm &= tl >= 16 ? 0xffffu : ((1u << tl) - 1u);
+    const u32 nl = cm ? (u32)__ffs((int)cm) - 1u : tl;
+    if (nl == 0 || nl > 16) return;
+    const int k = (int)nl;
+    w0 = keep_bytes(w0, k); w1 = keep_bytes(w1, k - 4); w2 = keep_bytes(w2, k - 8); w3 = keep_bytes(w3, k - 12);
+    prefetch_l2(T.slots + slot_index((u64)w0 | ((u64)w1 << 32), (u64)w2 | ((u64)w3 << 32), nl, T.nslots));
 }
 
 struct LongArgs {
@@ -411,6 +438,15 @@ __device__ __forceinline__ void long_record(const LongArgs& a, LWarpMemT<EMIT>* 
             }
             __syncwarp();
             if (prefixed) ss.pop(nsb);
+            if (prefixed && !has_last) {   // next batch: bring its markers in and request its table slots now
+                ss.ensure(kLBatch + 1, gaf, a.n, lane);
+                const u32 nn = ss.count < kLBatch ? ss.count : kLBatch;
+                const u32 np = lane < nn ? ss.at(lane) : 0u;
+                u32 nq;
+                if (!minus) nq = lane + 1 < ss.count ? ss.at(lane + 1) : pB;
+                else { nq = __shfl_up_sync(FULL, np, 1); if (lane == 0) nq = prev_p; }
+                if (lane < nn) prefetch_step_slot(ss, a.n, a.T, np, nq);
+            }
             const i32 slen = t.se - t.sa;
             const i32 so = (first_batch && lane == 0) ? ps2 : 0;
             const bool is_last = has_last && lane + 1 == nsb;
