@@ -102,6 +102,7 @@ struct g2p_ctx {
     std::vector<g2p_warn> warns;
     size_t host_chunk = kHostChunk;
     bool host_chunk_fixed = false;   // G2P_HOST_CHUNK_MB given: no adaptation to the record length
+    uint64_t desc_cap_override = 0;  // G2P_DESC_CAP (tests): line-descriptor slots, to exercise the overflow fallback
     void set_err(const std::string& m) { std::lock_guard<std::mutex> g(err_mu); err = m; }
 };
 
@@ -134,6 +135,7 @@ int g2p_create(int device, g2p_ctx** out) {
     cudaFuncSetAttribute(k_long<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)long_smem<true>());
     cudaFuncSetAttribute(k_long<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)long_smem<false>());
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
+    if (const char* c = std::getenv("G2P_DESC_CAP")) ctx->desc_cap_override = std::strtoull(c, nullptr, 10);
     if (const char* c = std::getenv("G2P_HOST_CHUNK_MB")) {
         long v = std::atol(c);
         if (v > 0) { ctx->host_chunk = (size_t)v << 20; ctx->host_chunk_fixed = true; }
@@ -267,7 +269,7 @@ static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
     // line descriptors: 6 slots per record on average are plenty for short reads (2.3 lines + padding);
     // CTAs that find the array full fall back to k_short<EMIT=true> for their records
     const u64 desc_cap64 = std::min<u64>((u64)nrec * 6 + (u64)n / 16 + 1024, 0xFFFFFF00ULL);   // long records: ~1 line per 40 bytes
-    const u32 desc_cap = (u32)desc_cap64;
+    const u32 desc_cap = ctx->desc_cap_override ? (u32)std::min<u64>(ctx->desc_cap_override, desc_cap64) : (u32)desc_cap64;
     G2P_CUDA(w.d_desc.ensure((size_t)desc_cap * sizeof(LineDesc)));
     G2P_CUDA(w.d_rdesc.ensure((size_t)nrec * sizeof(RecDesc)));
     LineDesc* d_desc = static_cast<LineDesc*>(w.d_desc.p);

@@ -323,3 +323,21 @@ def test_gaf2unstable_abort_and_cli(g2p):
             rc, out, err = H.run_tool(exe, args)
             rrc, rout, rerr = H.run_tool(ref_exe, args)
             assert rc == rrc and err.replace(exe, "X") == rerr.replace(ref_exe, "X")
+
+
+def test_descriptor_overflow_falls_back_to_reparsing_emit(g2p, monkeypatch):
+    """A descriptor array that is too small must only cost speed: the records whose lines do not fit
+    are emitted by the re-parsing kernels (k_short<true>, k_long<true>)."""
+    monkeypatch.setenv("G2P_DESC_CAP", "4096")
+    ps = H.preset("short", seed=91)
+    pm = H.preset("medium", seed=91)
+    lengths = H.gen_lengths(ps)
+    gaf = H.gen_records(ps, 0, 20000) + H.gen_records(pm, 0, 300) + H.gen_records(ps, 20000, 5000)
+    cv = g2p.Converter(0)
+    try:
+        assert cv.load_lengths(lengths)
+        out, res = cv.convert_host(gaf)
+    finally:
+        cv.close()
+    rc, ref, err, kind = H.run_gaf2paf_cpu(gaf, lengths)
+    assert rc == 0 and g2p.exit_code(res) == 0 and out == ref
