@@ -63,7 +63,7 @@ struct PinBuf {
 struct Worker {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
-    DevBuf d_in, d_tiles, d_rec, d_status, d_off, d_blocks, d_out, d_meta, d_list, d_list2, d_desc, d_rdesc;
+    DevBuf d_in, d_tiles, d_rec, d_status, d_off, d_blocks, d_out, d_meta, d_list, d_list2, d_desc, d_rdesc, d_sdesc, d_loff, d_map;
     PinBuf h_meta;
     bool init() {
         if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) return false;
@@ -71,7 +71,7 @@ struct Worker {
         return d_meta.ensure(sizeof(PipelineMeta)) == cudaSuccess && h_meta.ensure(sizeof(PipelineMeta)) == cudaSuccess;
     }
     void release() {
-        for (DevBuf* b : {&d_in, &d_tiles, &d_rec, &d_status, &d_off, &d_blocks, &d_out, &d_meta, &d_list, &d_list2, &d_desc, &d_rdesc}) b->release();
+        for (DevBuf* b : {&d_in, &d_tiles, &d_rec, &d_status, &d_off, &d_blocks, &d_out, &d_meta, &d_list, &d_list2, &d_desc, &d_rdesc, &d_sdesc, &d_loff, &d_map}) b->release();
         h_meta.release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
@@ -129,8 +129,7 @@ int g2p_create(int device, g2p_ctx** out) {
     ctx->device = device;
     for (auto& w : ctx->w)
         if (!w.init()) { g2p_destroy(ctx); return G2P_E_NO_DEVICE; }
-    cudaFuncSetAttribute(k_short<kSG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)short_smem<true>());
-    cudaFuncSetAttribute(k_short<kSG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)short_smem<false>());
+    cudaFuncSetAttribute(k_short<kSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShortSmem);
     cudaFuncSetAttribute(k_emit_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmitSmem);
     cudaFuncSetAttribute(k_long<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)long_smem<true>());
     cudaFuncSetAttribute(k_long<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)long_smem<false>());
@@ -266,30 +265,38 @@ static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
     const u32 ncta = (nrec + kShortRecsPerCta - 1) / kShortRecsPerCta;
     const u32 nlong = (u32)ctx->n_sm * 6u;
     const u32 nlist = std::min<u32>((nrec + kListThreads - 1) / kListThreads, (u32)ctx->n_sm * 16u);
-    // line descriptors: 6 slots per record on average are plenty for short reads (2.3 lines + padding);
-    // CTAs that find the array full fall back to k_short<EMIT=true> for their records
-    const u64 desc_cap64 = std::min<u64>((u64)nrec * 6 + (u64)n / 16 + 1024, 0xFFFFFF00ULL);   // long records: ~1 line per 40 bytes
+    // line descriptors: k_short's records own kSMaxLines slots each (sparse, addressed through the
+    // line map); k_long reserves 32-slot blocks in a dense array (~1 line per 40 bytes of text) and
+    // falls back to its streaming emit when that array is full
+    const u64 desc_cap64 = std::min<u64>((u64)n / 16 + 1024, 0xFFFFFF00ULL);
     const u32 desc_cap = ctx->desc_cap_override ? (u32)std::min<u64>(ctx->desc_cap_override, desc_cap64) : (u32)desc_cap64;
     G2P_CUDA(w.d_desc.ensure((size_t)desc_cap * sizeof(LineDesc)));
+    G2P_CUDA(w.d_sdesc.ensure((size_t)nrec * kSMaxLines * sizeof(LineDesc)));
     G2P_CUDA(w.d_rdesc.ensure((size_t)nrec * sizeof(RecDesc)));
+    G2P_CUDA(w.d_loff.ensure(((size_t)nrec + 1) * sizeof(u64)));
     LineDesc* d_desc = static_cast<LineDesc*>(w.d_desc.p);
+    LineDesc* d_sdesc = static_cast<LineDesc*>(w.d_sdesc.p);
     RecDesc* d_rdesc = static_cast<RecDesc*>(w.d_rdesc.p);
-    ShortArgs sa{d_gaf, (u64)n, d_rec, nrec, ctx->table, d_off, d_status, nullptr, d_list, &d_meta->n_deleg, d_desc, d_rdesc, &d_meta->n_desc, desc_cap};
+    u64* d_loff = static_cast<u64*>(w.d_loff.p);
+    ShortArgs sa{d_gaf, (u64)n, d_rec, nrec, ctx->table, d_off, d_loff, d_status, d_list, &d_meta->n_deleg, d_sdesc, d_rdesc};
     LongArgs la{d_gaf, (u64)n, d_rec, ctx->table, d_off, d_status, nullptr, d_list, &d_meta->n_deleg, d_list2, &d_meta->n_deleg2,
                 d_desc, d_rdesc, &d_meta->n_desc, desc_cap, &d_meta->legacy_long};
 
-    // pass 1: sizes + status.  k_short takes the short canonical records, k_long what it left,
-    // the general kernel what neither converts (non-canonical or erroneous records).
-    k_short<kSG, false><<<ncta, kSThreads, short_smem<false>(), st>>>(sa);
+    // pass 1: sizes, status, line descriptors.  k_short takes the short canonical records, k_long
+    // what it left, the general kernel what neither converts (non-canonical or erroneous records).
+    k_short<kSG><<<ncta, kSThreads, kShortSmem, st>>>(sa);
     k_long<false><<<nlong, kLThreads, long_smem<false>(), st>>>(la);
     k_convert_list<false><<<nlist, kListThreads, 0, st>>>(d_gaf, d_rec, ctx->table, d_off, d_status, nullptr, d_meta, d_list2, &d_meta->n_deleg2);
     launches += 3;
     G2P_CUDA(cudaEventRecord(w.ev[2], st));
-    // exclusive scan -> offsets
+    // exclusive scans: byte counts -> output offsets, line counts -> line slots
     k_scan_reduce<<<nscan, kScanThreads, 0, st>>>(d_off, nrec, d_blocks);
-    k_scan_blocks<<<1, 1024, 0, st>>>(d_blocks, nscan, d_meta);
-    k_scan_apply<<<nscan, kScanThreads, 0, st>>>(d_off, nrec, d_blocks, d_meta);
-    launches += 3;
+    k_scan_blocks<<<1, 1024, 0, st>>>(d_blocks, nscan, &d_meta->out_total);
+    k_scan_apply<<<nscan, kScanThreads, 0, st>>>(d_off, nrec, d_blocks, &d_meta->out_total);
+    k_scan_reduce<<<nscan, kScanThreads, 0, st>>>(d_loff, nrec, d_blocks);
+    k_scan_blocks<<<1, 1024, 0, st>>>(d_blocks, nscan, &d_meta->lines_total);
+    k_scan_apply<<<nscan, kScanThreads, 0, st>>>(d_loff, nrec, d_blocks, &d_meta->lines_total);
+    launches += 6;
     G2P_CUDA(cudaMemcpyAsync(hm, d_meta, sizeof(PipelineMeta), cudaMemcpyDeviceToHost, st));
     G2P_CUDA(cudaStreamSynchronize(st));
     const u64 out_total = hm->out_total;
@@ -299,16 +306,21 @@ static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
     u8* d_o = static_cast<u8*>(w.d_out.p);
     // pass 2: emit
     G2P_CUDA(cudaEventRecord(w.ev[3], st));
-    sa.out = d_o;
     la.out = d_o;
-    const u32 n_slots = std::min<u32>(hm->n_desc, desc_cap);
-    if (n_slots) {
-        EmitArgs ea{d_gaf, (u64)n, d_rec, d_off, d_desc, d_rdesc, n_slots, d_o};
-        k_emit_lines<<<(n_slots + kEThreads - 1) / kEThreads, kEThreads, kEmitSmem, st>>>(ea);
-        ++launches;
+    if (hm->lines_total) {   // k_short's records: line slot -> descriptor through the map
+        if (hm->lines_total > 0xFFFFFF00ULL) { ctx->set_err("too many PAF lines in one call: split the input"); return G2P_E_TOOBIG; }
+        const u32 nl = (u32)hm->lines_total;
+        G2P_CUDA(w.d_map.ensure((size_t)nl * sizeof(u32)));
+        u32* d_map = static_cast<u32*>(w.d_map.p);
+        k_line_map<<<(nrec + 255) / 256, 256, 0, st>>>(d_loff, nrec, d_map);
+        EmitArgs ea{d_gaf, (u64)n, d_rec, d_off, d_sdesc, d_map, d_rdesc, nl, d_o};
+        k_emit_lines<<<(nl + kEThreads - 1) / kEThreads, kEThreads, kEmitSmem, st>>>(ea);
+        launches += 2;
     }
-    if (hm->n_desc > desc_cap) {   // descriptor array overflowed: some records take the re-parsing emit
-        k_short<kSG, true><<<ncta, kSThreads, short_smem<true>(), st>>>(sa);
+    const u32 n_slots = std::min<u32>(hm->n_desc, desc_cap);
+    if (n_slots) {           // k_long's records: dense 32-slot blocks
+        EmitArgs ea{d_gaf, (u64)n, d_rec, d_off, d_desc, nullptr, d_rdesc, n_slots, d_o};
+        k_emit_lines<<<(n_slots + kEThreads - 1) / kEThreads, kEThreads, kEmitSmem, st>>>(ea);
         ++launches;
     }
     if (hm->legacy_long) {   // records k_long could not describe (descriptor array full)
@@ -617,8 +629,8 @@ static int run_unstable(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
     ++launches;
     G2P_CUDA(cudaEventRecord(w.ev[2], st));
     k_scan_reduce<<<nscan, kScanThreads, 0, st>>>(d_off, nrec, d_blocks);
-    k_scan_blocks<<<1, 1024, 0, st>>>(d_blocks, nscan, d_meta);
-    k_scan_apply<<<nscan, kScanThreads, 0, st>>>(d_off, nrec, d_blocks, d_meta);
+    k_scan_blocks<<<1, 1024, 0, st>>>(d_blocks, nscan, &d_meta->out_total);
+    k_scan_apply<<<nscan, kScanThreads, 0, st>>>(d_off, nrec, d_blocks, &d_meta->out_total);
     launches += 3;
     G2P_CUDA(cudaMemcpyAsync(hm, d_meta, sizeof(PipelineMeta), cudaMemcpyDeviceToHost, st));
     G2P_CUDA(cudaStreamSynchronize(st));

@@ -1,9 +1,10 @@
 // g2p_kernels.cuh — sm_100a kernels of the GAF -> PAF pipeline.
 //
 //   k_count_lines / k_scan_tiles / k_fill_lines   newline index (record start offsets)
-//   k_short / k_long / k_convert_list <false>      pass 1: per-record PAF byte length + status
-//   k_scan_*                                       exclusive scan of the lengths -> output offsets
-//   k_short / k_long / k_convert_list <true>       pass 2: write the PAF bytes
+//   k_short / k_long<false> / k_convert_list<false>  pass 1: per-record PAF byte length, status, line descriptors
+//   k_scan_*                                       exclusive scans: byte lengths -> output offsets, line counts -> line slots
+//   k_line_map + k_emit_lines                      pass 2: one thread per PAF line writes the bytes
+//   k_long<true> / k_convert_list<true>            pass 2 for records without descriptors
 //   k_diagnose                                     details of the first failing record
 //
 // All work is byte / integer; the pipeline is bound by HBM traffic and by the
@@ -37,8 +38,9 @@ struct PipelineMeta {
     u64 err_out_end;   // output offset just after the failing record's (partial) output
     u32 n_deleg;       // records k_short left to k_long
     u32 n_deleg2;      // records k_long left to the general kernel
-    u32 n_desc;        // line-descriptor slots reserved by k_short / k_long
+    u32 n_desc;        // line-descriptor slots reserved by k_long (32 per batch)
     u32 legacy_long;   // some k_long record is not described: run k_long<true>
+    u64 lines_total;   // PAF lines of the records k_short converted
 };
 
 // ------------------------------------------------------------------------------
@@ -108,6 +110,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(u32* __restrict__ tile_coun
         meta->n_deleg2 = 0;
         meta->n_desc = 0;
         meta->legacy_long = 0;
+        meta->lines_total = 0;
     }
 }
 
@@ -196,7 +199,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_reduce(const u64* __restr
     if (threadIdx.x == 0) block_sum[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(1024) k_scan_blocks(u64* __restrict__ block_sum, u32 nblocks, PipelineMeta* __restrict__ meta) {
+__global__ void __launch_bounds__(1024) k_scan_blocks(u64* __restrict__ block_sum, u32 nblocks, u64* __restrict__ total_out) {
     __shared__ u64 part[1024];
     const u32 per = (nblocks + 1023) / 1024;
     const u32 a = threadIdx.x * per, b = min(a + per, nblocks);
@@ -212,12 +215,12 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(u64* __restrict__ block_su
     }
     u64 run = threadIdx.x ? part[threadIdx.x - 1] : 0;
     for (u32 i = a; i < b; ++i) { u64 c = block_sum[i]; block_sum[i] = run; run += c; }
-    if (threadIdx.x == 1023) meta->out_total = part[1023];
+    if (threadIdx.x == 1023) *total_out = part[1023];
 }
 
 // x[0..n) lengths -> exclusive offsets; x[n] = total
 __global__ void __launch_bounds__(kScanThreads) k_scan_apply(u64* __restrict__ x, u32 n, const u64* __restrict__ block_off,
-                                                             const PipelineMeta* __restrict__ meta) {
+                                                             const u64* __restrict__ total_in) {
     const u32 base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
     u64 v[kScanItems];
     u64 s = 0;
@@ -230,7 +233,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_apply(u64* __restrict__ x
         if (base + i < n) x[base + i] = run;
         run += v[i];
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) x[n] = meta->out_total;
+    if (blockIdx.x == 0 && threadIdx.x == 0) x[n] = *total_in;
 }
 
 // ------------------------------------------------------------------------------

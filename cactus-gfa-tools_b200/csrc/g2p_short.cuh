@@ -45,29 +45,23 @@ constexpr u32 kSLimit = G2P_S_LIMIT;   // longest record (bytes, without '\n') t
 constexpr u32 kSMaxTabs = 31;          // 12 columns + up to 20 tags
 constexpr u32 kSMaxTags = 20;
 constexpr u32 kSMaxOps = 24;
-constexpr u32 kSOutCap = 1024;         // staged PAF bytes per record; larger outputs are written directly
 
 // header slots (u32 / i32) in shared memory
 enum { H_QN_B = 0, H_QLEN = 1, H_QS = 2, H_QE = 3, H_MINUS = 4, H_PATH_A = 5, H_PLEN = 6, H_PS = 7, H_PE = 8, H_M = 9, H_B = 10,
        H_MAPQ = 11, H_CG_A = 12, H_CG_B = 13, H_TP_A = 14, H_TP_B = 15, H_RC_A = 16, H_RC_B = 17, H_PATH_B = 18, H_N = 20 };
 
-template <bool WITH_OUT>
-struct __align__(16) SGroupMemT {
+struct __align__(16) SGroupMem {
     u8 text[288];                  // the record, staged at its global 16-byte phase
     u16 spos[16];                  // path-step marker positions (+ end); tag keys alias spos..opos
     u16 opos[kSMaxOps];            // positions of the CIGAR op letters
     u32 hdr[H_N];
-    union {
-        struct {
-            u16 tabs[32];
-            u32 pEnd[kSMaxOps], pQ[kSMaxOps], pNM[kSMaxOps], pNB[kSMaxOps];   // inclusive prefix sums, normalised op order
-        } w;
-        u8 out[WITH_OUT ? kSOutCap + 16 : 16];   // staging of the re-parsing emit (fallback path only)
-    };
+    u16 tabs[32];
+    u32 pEnd[kSMaxOps], pQ[kSMaxOps], pNM[kSMaxOps], pNB[kSMaxOps];   // inclusive prefix sums, normalised op order
 };
 constexpr u32 kShortRecsPerCta = kSThreads / kSG;
-template <bool EMIT> constexpr size_t short_smem() { return sizeof(SGroupMemT<EMIT>) * kShortRecsPerCta; }
-static_assert(sizeof(SGroupMemT<true>) % 16 == 0 && sizeof(SGroupMemT<false>) % 16 == 0, "group slices must keep 16-byte alignment");
+constexpr u32 kSMaxLines = 8;          // line-descriptor slots per record (a record has <= G-1 lines)
+constexpr size_t kShortSmem = sizeof(SGroupMem) * kShortRecsPerCta;
+static_assert(sizeof(SGroupMem) % 16 == 0, "group slices must keep 16-byte alignment");
 
 template <int G>
 struct Grp {
@@ -381,20 +375,19 @@ struct ShortArgs {
     const u32* rec_start;
     u32 nrec;
     LenTableView T;
-    u64* out_off;        // size pass: per-record byte count; emit pass: exclusive offsets
+    u64* out_off;        // per-record PAF byte count (scanned into offsets afterwards)
+    u64* line_off;       // per-record PAF line count (scanned into line offsets afterwards)
     u32* status;
-    u8* out;
-    u32* deleg_list;     // size pass: indices of records left to the general kernel
+    u32* deleg_list;     // indices of records left to k_long / the general kernel
     u32* n_deleg;
-    LineDesc* desc;      // size pass: line descriptors (dense, CTA reservations padded to 32)
-    RecDesc* rdesc;      // size pass: per-record constants of the lines
-    u32* n_desc;         // slots reserved so far
-    u32 desc_cap;
+    LineDesc* sdesc;     // line descriptors: record r owns slots [r * kSMaxLines, (r + 1) * kSMaxLines)
+    RecDesc* rdesc;      // per-record constants of the lines
 };
 
-// One record per G-lane group.  EMIT=false: size + status (or delegate).  EMIT=true: write PAF.
-template <int G, bool EMIT>
-__global__ void __launch_bounds__(kSThreads, EMIT ? 4 : G2P_SHORT_CTAS) k_short(const ShortArgs a) {
+// One record per G-lane group: PAF size, status and one line descriptor per PAF line -- or the
+// record is delegated.
+template <int G>
+__global__ void __launch_bounds__(kSThreads, G2P_SHORT_CTAS) k_short(const ShortArgs a) {
     G2P_DYN_SMEM(smem);
     __shared__ u32 p10[10];
     if (threadIdx.x < 10) {
@@ -406,22 +399,11 @@ __global__ void __launch_bounds__(kSThreads, EMIT ? 4 : G2P_SHORT_CTAS) k_short(
 
     const Grp<G> g;
     const u32 gid = threadIdx.x / G;
-    typedef SGroupMemT<EMIT> SGroupMem;
     SGroupMem* gm = reinterpret_cast<SGroupMem*>(smem) + gid;
     const u32 r = blockIdx.x * (kSThreads / G) + gid;
-    const bool valid = r < a.nrec;
-    if (EMIT && !valid) return;
-    const u32 s = valid ? a.rec_start[r] : 0u, e = valid ? a.rec_start[r + 1] : 1u;
+    if (r >= a.nrec) return;
+    const u32 s = a.rec_start[r], e = a.rec_start[r + 1];
     const u32 len = e - s - 1;
-    u64 o = 0;
-    u32 osize = 0;
-    if (EMIT) {   // legacy emit: only records whose descriptors did not fit the descriptor array
-        const u32 st0 = a.status[r];
-        if (!(st0 & ST_F_FAST) || (st0 & ST_F_DESC)) return;
-        o = a.out_off[r];
-        osize = (u32)(a.out_off[r + 1] - o);
-        if (osize == 0) return;
-    }
 
     bool deleg = false;      // group-uniform
     u32 size = 0;
@@ -430,7 +412,6 @@ __global__ void __launch_bounds__(kSThreads, EMIT ? 4 : G2P_SHORT_CTAS) k_short(
     LineStep L;
     bool emit_line = false;
     u32 line = 0, loff = 0;
-    if (valid)
     do {
         if (len == 0 || len > kSLimit) { deleg = true; break; }
         // ---------------- phase 0: stage + classify
@@ -469,7 +450,7 @@ __global__ void __launch_bounds__(kSThreads, EMIT ? 4 : G2P_SHORT_CTAS) k_short(
             while (m) {
                 const u32 b = (u32)__ffs((int)m) - 1u;
                 m &= m - 1u;
-                if (k < 32) gm->w.tabs[k] = (u16)(base + b);
+                if (k < 32) gm->tabs[k] = (u16)(base + b);
                 ++k;
             }
             nt += tot;
@@ -478,7 +459,7 @@ __global__ void __launch_bounds__(kSThreads, EMIT ? 4 : G2P_SHORT_CTAS) k_short(
         if (rt[0] == '*') { status = ST_SKIP | ST_F_FAST; break; }   // gaf2paf_main.cpp:360
         if (nt < 11 || nt > kSMaxTabs) { deleg = true; break; }
         // ---------------- phase 1: columns 1..12 and tags, one lane per field
-        u32 lbad = parse_fields<G>(g, rt, gm->w.tabs, nt, len, gm->hdr, reinterpret_cast<u32*>(gm->spos));
+        u32 lbad = parse_fields<G>(g, rt, gm->tabs, nt, len, gm->hdr, reinterpret_cast<u32*>(gm->spos));
         if (g.any(lbad != 0)) { deleg = true; break; }   // also orders the tkeys reads before the scatter below
 
         const bool minus = gm->hdr[H_MINUS] != 0;
@@ -617,7 +598,7 @@ __global__ void __launch_bounds__(kSThreads, EMIT ? 4 : G2P_SHORT_CTAS) k_short(
                     }
                 }
                 vE = g.incl_scan(vE) + cE; vQ = g.incl_scan(vQ) + cQ; vM = g.incl_scan(vM) + cM; vB = g.incl_scan(vB) + cB;
-                if (j < no) { gm->w.pEnd[j] = vE; gm->w.pQ[j] = vQ; gm->w.pNM[j] = vM; gm->w.pNB[j] = vB; }
+                if (j < no) { gm->pEnd[j] = vE; gm->pQ[j] = vQ; gm->pNM[j] = vM; gm->pNB[j] = vB; }
                 cE = g.shfl(vE, G - 1); cQ = g.shfl(vQ, G - 1); cM = g.shfl(vM, G - 1); cB = g.shfl(vB, G - 1);
             }
         }
@@ -628,17 +609,17 @@ __global__ void __launch_bounds__(kSThreads, EMIT ? 4 : G2P_SHORT_CTAS) k_short(
         bool bcut = false, bexh = false;
         if (i <= ns && B != 0) {
             u32 lo = 0, hi = no;
-            while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (gm->w.pEnd[mid] >= B) hi = mid; else lo = mid + 1; }
+            while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (gm->pEnd[mid] >= B) hi = mid; else lo = mid + 1; }
             bj = lo;
             if (bj == no) bexh = true;
             else {
-                const u32 Ej = gm->w.pEnd[bj];
-                bt = bj ? gm->w.pEnd[bj - 1] : 0u;
+                const u32 Ej = gm->pEnd[bj];
+                bt = bj ? gm->pEnd[bj - 1] : 0u;
                 const u32 off = B - bt;
                 const u32 k = (u32)rt[gm->opos[minus ? no - 1 - bj : bj]] - '=';
-                bCQ = (bj ? gm->w.pQ[bj - 1] : 0u) + (((kQueryMask >> k) & 1u) ? off : 0u);
-                bCM = (bj ? gm->w.pNM[bj - 1] : 0u) + (((kMatchMask >> k) & 1u) ? off : 0u);
-                bCB = (bj ? gm->w.pNB[bj - 1] : 0u) + off;
+                bCQ = (bj ? gm->pQ[bj - 1] : 0u) + (((kQueryMask >> k) & 1u) ? off : 0u);
+                bCM = (bj ? gm->pNM[bj - 1] : 0u) + (((kMatchMask >> k) & 1u) ? off : 0u);
+                bCB = (bj ? gm->pNB[bj - 1] : 0u) + off;
                 bcut = Ej > B;
             }
         }
@@ -658,7 +639,7 @@ __global__ void __launch_bounds__(kSThreads, EMIT ? 4 : G2P_SHORT_CTAS) k_short(
         R.qlen = (i32)gm->hdr[H_QLEN]; R.m = (i32)gm->hdr[H_M]; R.b = (i32)gm->hdr[H_B]; R.mapq = (i32)gm->hdr[H_MAPQ];
         R.tp_a = gm->hdr[H_TP_A]; R.tp_b = gm->hdr[H_TP_B]; R.rc_a = gm->hdr[H_RC_A]; R.rc_b = gm->hdr[H_RC_B];
         R.gi_n = gi_fast(R.m, R.b, R.gi);
-        if (R.gi_n == 0) { deleg = true; break; }   // uniform: same m, b in the whole group
+        if (R.gi_n == 0 || !rec_desc_fits(R)) { deleg = true; break; }   // uniform: same m, b in the whole group
         L.rev = rev;
         L.q0 = (u32)qs + bCQ; L.q1 = L.q0 + q;
         L.name_a = name_a; L.nl = nl; L.tlen = (u32)tlen;
@@ -675,7 +656,7 @@ __global__ void __launch_bounds__(kSThreads, EMIT ? 4 : G2P_SHORT_CTAS) k_short(
             const u32 jE = ej;
             u32 mS = jS;   // verbatim middle tokens: [mS, jE)
             if (jS < jE) {
-                if (cutS) { L.lenS = gm->w.pEnd[jS] - B; L.codeS = rt[gm->opos[minus ? no - 1 - jS : jS]]; mS = jS + 1; }
+                if (cutS) { L.lenS = gm->pEnd[jS] - B; L.codeS = rt[gm->opos[minus ? no - 1 - jS : jS]]; mS = jS + 1; }
                 if (mS < jE) {
                     const u32 o1 = minus ? no - jE : mS, o2 = minus ? no - 1 - mS : jE - 1;   // original index range [o1, o2]
                     L.mid_a = o1 ? gm->opos[o1 - 1] + 1u : ca;
@@ -687,84 +668,31 @@ __global__ void __launch_bounds__(kSThreads, EMIT ? 4 : G2P_SHORT_CTAS) k_short(
         }
         loff = g.excl_scan(line, size);
 
-        if (EMIT) {
-            if (size != osize) break;   // cannot happen: both passes run the same code
-            const bool staged = size <= kSOutCap;
-            const u32 pad = (u32)(o & 15u);
-            g.sync();   // the staging buffer aliases tabs / prefix arrays: everyone is done reading them
-            if (emit_line) write_line((staged ? gm->out + pad + loff : a.out + o + loff) + line, line_src(rt, R, L), R, L);
-            if (staged) {
-                g.sync();
-                const u32 total = pad + size;
-                u8* gbase = a.out + (o - pad);
-                const u32 full_b = total >> 4;
-                for (u32 u = (pad ? 1u : 0u) + g.gl; u < full_b; u += G)
-                    reinterpret_cast<uint4*>(gbase)[u] = reinterpret_cast<const uint4*>(gm->out)[u];
-                const u32 head_end = pad ? (total < 16u ? total : 16u) : 0u;
-                for (u32 b = pad + g.gl; b < head_end; b += G) gbase[b] = gm->out[b];
-                const u32 tail_a = full_b * 16u > head_end ? full_b * 16u : head_end;
-                for (u32 b = tail_a + g.gl; b < total; b += G) gbase[b] = gm->out[b];
-            }
-        }
     } while (0);
 
-    if (!EMIT) {
-        // ---------------- line descriptors: one dense reservation per CTA, padded to whole warps
-        __shared__ u32 s_cnt[kSThreads / G + 1];
-        __shared__ u32 s_base, s_total, s_ok;
-        const bool fast = valid && !deleg && size != 0 && rec_desc_fits(R);
-        const u32 lmask = g.ballot(fast && emit_line);
-        if (g.gl == 0) s_cnt[gid] = fast ? (u32)__popc(lmask) : 0u;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            constexpr u32 NG = kSThreads / G;
-            const u32 lane = threadIdx.x;
-            u32 v = 0;
-            for (u32 k = lane; k < NG; k += 32) v += s_cnt[k];   // NG <= 32 for G >= 8
-            u32 incl = v;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (u32)d) incl += t; }
-            if (lane < NG) s_cnt[lane] = incl - v;
-            if (lane == 31) {
-                const u32 total = incl, rsv = (total + 31u) & ~31u;
-                u32 base = 0, ok = 0;
-                if (total) { base = atomicAdd(a.n_desc, rsv); ok = (base <= a.desc_cap && rsv <= a.desc_cap - base) ? 1u : 0u; }
-                s_base = base; s_total = total; s_ok = ok;
-            }
-        }
-        __syncthreads();
-        const bool desc_ok = s_ok != 0;
-        if (desc_ok) {
-            if (fast && emit_line) {
-                const u32 slot = s_base + s_cnt[gid] + (u32)__popc(lmask & ((1u << g.gl) - 1u));
-                store_line_desc(a.desc + slot, r, loff, line, L);
-            }
-            if (fast && g.gl == 0) store_rec_desc(a.rdesc + r, R);
-            const u32 npad = ((s_total + 31u) & ~31u) - s_total;
-            if (threadIdx.x < npad) a.desc[s_base + s_total + threadIdx.x].rec = kDescInvalid;
-        } else if (s_total && s_base < a.desc_cap) {
-            // reservation rejected (array full): blank the slots it owns below the capacity; the
-            // records keep ST_F_DESC clear and are emitted by k_short<EMIT=true>
-            const u32 rsv = (s_total + 31u) & ~31u;
-            const u32 hi = rsv < a.desc_cap - s_base ? s_base + rsv : a.desc_cap;
-            for (u32 k = s_base + threadIdx.x; k < hi; k += kSThreads) a.desc[k].rec = kDescInvalid;
-        }
-        if (valid && g.gl == 0) {
-            if (deleg) {
-                a.status[r] = ST_OK;   // overwritten by k_long / the general kernel
-                a.out_off[r] = 0;
-                a.deleg_list[atomicAdd(a.n_deleg, 1u)] = r;
-            } else {
-                a.status[r] = status | ((fast && desc_ok) ? (u32)ST_F_DESC : 0u);
-                a.out_off[r] = size;
-            }
+    // ---------------- results: sizes, status, descriptors (record r owns kSMaxLines slots)
+    const bool fast = !deleg && size != 0;
+    const u32 lmask = g.ballot(fast && emit_line);
+    if (fast && emit_line)
+        store_line_desc(a.sdesc + (size_t)r * kSMaxLines + (u32)__popc(lmask & ((1u << g.gl) - 1u)), r, loff, line, L);
+    if (g.gl == 0) {
+        if (deleg) {
+            a.status[r] = ST_OK;   // overwritten by k_long / the general kernel
+            a.out_off[r] = 0;
+            a.line_off[r] = 0;
+            a.deleg_list[atomicAdd(a.n_deleg, 1u)] = r;
+        } else {
+            a.status[r] = status | (fast ? (u32)ST_F_DESC : 0u);
+            a.out_off[r] = size;
+            a.line_off[r] = (u32)__popc(lmask);
+            if (fast) store_rec_desc(a.rdesc + r, R);
         }
     }
 }
 
-// One PAF line per thread from its descriptor (dense: CTA reservations of the size pass are
-// padded to 32 slots, so the lines of a warp belong to consecutive records and are contiguous in
-// the output unless a delegated record lies between them).  Lines are formatted into a per-warp
+// One PAF line per thread from its descriptor.  Line slots are dense and in output order (k_short's
+// records through the line map, k_long's batches as 32-slot blocks), so the lines of a warp are
+// contiguous in the output unless a record converted by another kernel lies between them.  Lines are formatted into a per-warp
 // staging buffer and flushed with 128-bit stores.
 constexpr int kEThreads = 256;
 constexpr u32 kEOutCap = 5120;     // staged PAF bytes per warp
@@ -777,10 +705,20 @@ struct EmitArgs {
     const u32* rec_start;
     const u64* out_off;
     const LineDesc* desc;
+    const u32* map;        // line slot -> descriptor index (k_short's per-record slots), or null: identity
     const RecDesc* rdesc;
     u32 n_slots;
     u8* out;
 };
+
+// line slot -> descriptor index for k_short's records: record r's lines are descriptors
+// r * kSMaxLines + j, its first line slot is line_off[r] (after the scan)
+__global__ void __launch_bounds__(256) k_line_map(const u64* __restrict__ line_off, u32 nrec, u32* __restrict__ map) {
+    const u32 r = blockIdx.x * 256u + threadIdx.x;
+    if (r >= nrec) return;
+    const u64 b = line_off[r], e = line_off[r + 1];
+    for (u64 k = b; k < e; ++k) map[k] = r * kSMaxLines + (u32)(k - b);
+}
 
 __global__ void __launch_bounds__(kEThreads) k_emit_lines(const EmitArgs a) {
     G2P_DYN_SMEM(smem);
@@ -792,7 +730,7 @@ __global__ void __launch_bounds__(kEThreads) k_emit_lines(const EmitArgs a) {
     LineDesc d;
     d.rec = kDescInvalid; d.len = 0; d.loff = 0;
     if (slot < a.n_slots) {
-        const uint4* src = reinterpret_cast<const uint4*>(a.desc + slot);
+        const uint4* src = reinterpret_cast<const uint4*>(a.desc + (a.map ? a.map[slot] : slot));
         uint4* dst = reinterpret_cast<uint4*>(&d);
         dst[0] = __ldg(src); dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2); dst[3] = __ldg(src + 3);
     }

@@ -70,29 +70,38 @@ int main(int argc, char** argv) {
     std::vector<u64> blocks(nscan);
     const u32 ncta = (nrec + kShortRecsPerCta - 1) / kShortRecsPerCta;
     const u32 nlist = std::min<u32>((nrec + kListThreads - 1) / kListThreads, 8u);
-    // G2P_SIMT_DESC_CAP=<slots> shrinks the descriptor array to exercise the overflow fallback
-    const u32 desc_cap = std::getenv("G2P_SIMT_DESC_CAP") ? (u32)std::atol(std::getenv("G2P_SIMT_DESC_CAP")) : nrec * 6 + (u32)(n / 16) + 1024;
-    std::vector<LineDesc> desc(desc_cap + 1);
+    // G2P_SIMT_DESC_CAP=<slots> shrinks k_long's descriptor array to exercise the overflow fallback
+    const u32 desc_cap = std::getenv("G2P_SIMT_DESC_CAP") ? (u32)std::atol(std::getenv("G2P_SIMT_DESC_CAP")) : (u32)(n / 16) + 1024;
+    std::vector<LineDesc> desc(desc_cap + 1), sdesc((size_t)nrec * kSMaxLines);
     std::vector<RecDesc> rdesc(nrec);
-    ShortArgs sa{gaf, n, rec.data(), nrec, T, off.data(), status.data(), nullptr, list.data(), &meta.n_deleg, desc.data(), rdesc.data(), &meta.n_desc, desc_cap};
-    hs::launch(dim3(ncta), dim3(kSThreads), short_smem<false>(), [&] { k_short<kSG, false>(sa); });
+    std::vector<u64> loff(nrec + 1);
+    ShortArgs sa{gaf, n, rec.data(), nrec, T, off.data(), loff.data(), status.data(), list.data(), &meta.n_deleg, sdesc.data(), rdesc.data()};
+    hs::launch(dim3(ncta), dim3(kSThreads), kShortSmem, [&] { k_short<kSG>(sa); });
     LongArgs la{gaf, n, rec.data(), T, off.data(), status.data(), nullptr, list.data(), &meta.n_deleg, list2.data(), &meta.n_deleg2,
                 desc.data(), rdesc.data(), &meta.n_desc, desc_cap, &meta.legacy_long};
     const u32 nlong = 2;
     hs::launch(dim3(nlong), dim3(kLThreads), long_smem<false>(), [&] { k_long<false>(la); });
     hs::launch(dim3(nlist), dim3(kListThreads), 0, [&] { k_convert_list<false>(gaf, rec.data(), T, off.data(), status.data(), nullptr, &meta, list2.data(), &meta.n_deleg2); });
     hs::launch(dim3(nscan), dim3(kScanThreads), 0, [&] { k_scan_reduce(off.data(), nrec, blocks.data()); });
-    hs::launch(dim3(1), dim3(1024), 0, [&] { k_scan_blocks(blocks.data(), nscan, &meta); });
-    hs::launch(dim3(nscan), dim3(kScanThreads), 0, [&] { k_scan_apply(off.data(), nrec, blocks.data(), &meta); });
+    hs::launch(dim3(1), dim3(1024), 0, [&] { k_scan_blocks(blocks.data(), nscan, &meta.out_total); });
+    hs::launch(dim3(nscan), dim3(kScanThreads), 0, [&] { k_scan_apply(off.data(), nrec, blocks.data(), &meta.out_total); });
+    hs::launch(dim3(nscan), dim3(kScanThreads), 0, [&] { k_scan_reduce(loff.data(), nrec, blocks.data()); });
+    hs::launch(dim3(1), dim3(1024), 0, [&] { k_scan_blocks(blocks.data(), nscan, &meta.lines_total); });
+    hs::launch(dim3(nscan), dim3(kScanThreads), 0, [&] { k_scan_apply(loff.data(), nrec, blocks.data(), &meta.lines_total); });
     std::vector<u8> out(meta.out_total + 256, 0xEE);
-    sa.out = out.data();
+    la.out = out.data();
+    if (meta.lines_total) {
+        const u32 nl = (u32)meta.lines_total;
+        std::vector<u32> map(nl);
+        hs::launch(dim3((nrec + 255) / 256), dim3(256), 0, [&] { k_line_map(loff.data(), nrec, map.data()); });
+        EmitArgs ea{gaf, n, rec.data(), off.data(), sdesc.data(), map.data(), rdesc.data(), nl, out.data()};
+        hs::launch(dim3((nl + kEThreads - 1) / kEThreads), dim3(kEThreads), kEmitSmem, [&] { k_emit_lines(ea); });
+    }
     const u32 n_slots = std::min<u32>(meta.n_desc, desc_cap);
     if (n_slots) {
-        EmitArgs ea{gaf, n, rec.data(), off.data(), desc.data(), rdesc.data(), n_slots, out.data()};
+        EmitArgs ea{gaf, n, rec.data(), off.data(), desc.data(), nullptr, rdesc.data(), n_slots, out.data()};
         hs::launch(dim3((n_slots + kEThreads - 1) / kEThreads), dim3(kEThreads), kEmitSmem, [&] { k_emit_lines(ea); });
     }
-    if (meta.n_desc > desc_cap) hs::launch(dim3(ncta), dim3(kSThreads), short_smem<true>(), [&] { k_short<kSG, true>(sa); });
-    la.out = out.data();
     if (meta.legacy_long) hs::launch(dim3(nlong), dim3(kLThreads), long_smem<true>(), [&] { k_long<true>(la); });
     if (meta.n_deleg2)
         hs::launch(dim3(nlist), dim3(kListThreads), 0, [&] { k_convert_list<true>(gaf, rec.data(), T, off.data(), status.data(), out.data(), &meta, list2.data(), &meta.n_deleg2); });
@@ -101,7 +110,7 @@ int main(int argc, char** argv) {
         hs::launch(dim3(1), dim3(1), 0, [&] { k_diagnose(gaf, rec.data(), T, off.data(), &meta); });
         out_bytes = meta.err_out_end;
     }
-    if (std::getenv("G2P_SIMT_STATS")) std::fprintf(stderr, "g2p_simt: %u records, %u to k_long, %u to the general kernel, %u line slots (cap %u), %llu bytes out\n", nrec, meta.n_deleg, meta.n_deleg2, meta.n_desc, desc_cap, (unsigned long long)out_bytes);
+    if (std::getenv("G2P_SIMT_STATS")) std::fprintf(stderr, "g2p_simt: %u records, %u to k_long, %u to the general kernel, %llu short lines, %u long line slots (cap %u), %llu bytes out\n", nrec, meta.n_deleg, meta.n_deleg2, (unsigned long long)meta.lines_total, meta.n_desc, desc_cap, (unsigned long long)out_bytes);
     std::fwrite(out.data(), 1, out_bytes, stdout);
     std::fflush(stdout);
     if (meta.first_err != 0xFFFFFFFFu) {
