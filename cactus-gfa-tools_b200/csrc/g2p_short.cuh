@@ -694,6 +694,36 @@ __global__ void __launch_bounds__(kSThreads, G2P_SHORT_CTAS) k_short(const Short
 // records through the line map, k_long's batches as 32-slot blocks), so the lines of a warp are
 // contiguous in the output unless a record converted by another kernel lies between them.  Lines are formatted into a per-warp
 // staging buffer and flushed with 128-bit stores.
+// ---- TMA 1-D bulk copies (cp.async.bulk, SASS UBLKCP): shared <-> global without passing through
+// registers, completion through an mbarrier (loads) or a bulk async-group (stores).  The emulator
+// build (G2P_HOSTSIM) takes the plain load/store loops instead.
+#if !defined(G2P_HOSTSIM)
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, u32 bytes, u64* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(u64* bar, u32 parity) {
+    u32 ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, u32 bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+#endif
+
 constexpr int kEThreads = 256;
 constexpr u32 kEOutCap = 5120;     // staged PAF bytes per warp
 constexpr u32 kETextCap = 4096;    // staged GAF bytes per warp (the records its 32 lines come from)
@@ -726,6 +756,11 @@ __global__ void __launch_bounds__(kEThreads) k_emit_lines(const EmitArgs a) {
     const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     u8* sm = smem + (size_t)warp * (kEOutCap + 16 + kETextCap + 32);
     u8* sm_text = sm + kEOutCap + 16;
+#if !defined(G2P_HOSTSIM)
+    __shared__ __align__(8) u64 s_bar[kEThreads / 32];   // one mbarrier per warp (used once: parity 0)
+    if (lane == 0) { mbar_init(&s_bar[warp], 1); fence_mbar_init(); }
+    __syncwarp();
+#endif
     const u32 slot = blockIdx.x * kEThreads + threadIdx.x;
     LineDesc d;
     d.rec = kDescInvalid; d.len = 0; d.loff = 0;
@@ -764,8 +799,17 @@ __global__ void __launch_bounds__(kEThreads) k_emit_lines(const EmitArgs a) {
     const bool text_staged = t1 > t0 && t1 - A <= kETextCap;
     if (text_staged) {
         const u32 nvec = (t1 - A + 15u) >> 4;
-        for (u32 v = lane; v < nvec; v += 32) reinterpret_cast<uint4*>(sm_text)[v] = ldg_vec_guarded(a.gaf, (u64)A + 16u * v, a.n);
-        __syncwarp();
+#if !defined(G2P_HOSTSIM)
+        if ((u64)A + 16ull * nvec <= a.n) {   // whole vectors inside the buffer: one TMA bulk copy
+            if (lane == 0) { mbar_expect_tx(&s_bar[warp], nvec * 16u); bulk_g2s(sm_text, a.gaf + A, nvec * 16u, &s_bar[warp]); }
+            u32 spins = 0;
+            while (!mbar_try_wait(&s_bar[warp], 0)) { if (++spins > (1u << 24)) __trap(); }
+        } else
+#endif
+        {
+            for (u32 v = lane; v < nvec; v += 32) reinterpret_cast<uint4*>(sm_text)[v] = ldg_vec_guarded(a.gaf, (u64)A + 16u * v, a.n);
+            __syncwarp();
+        }
     }
     const u8* rt = text_staged ? sm_text + (rs - A) : a.gaf + rs;
     // contiguity of the warp's lines in the output
@@ -779,15 +823,26 @@ __global__ void __launch_bounds__(kEThreads) k_emit_lines(const EmitArgs a) {
     const u32 pad = (u32)(o0 & 15u);
     if (valid) write_line((staged ? sm + pad + (u32)(o - o0) : a.out + o) + d.len, line_src(rt, R, L), R, L);
     if (staged) {
-        __syncwarp();
         const u32 total = pad + (u32)(o1 - o0);
         u8* gb = a.out + (o0 - pad);
         const u32 full_b = total >> 4;
+#if !defined(G2P_HOSTSIM)
+        // the 16-byte aligned middle of the run leaves as one TMA bulk store
+        fence_async_smem();
+        __syncwarp();
+        const u32 first_b = pad ? 1u : 0u;
+        if (lane == 0 && full_b > first_b) { bulk_s2g(gb + 16u * first_b, sm + 16u * first_b, 16u * (full_b - first_b)); bulk_commit(); }
+#else
+        __syncwarp();
         for (u32 u = (pad ? 1u : 0u) + lane; u < full_b; u += 32) reinterpret_cast<uint4*>(gb)[u] = reinterpret_cast<const uint4*>(sm)[u];
+#endif
         const u32 head_end = pad ? (total < 16u ? total : 16u) : 0u;
         for (u32 b = pad + lane; b < head_end; b += 32) gb[b] = sm[b];
         const u32 tail_a = full_b * 16u > head_end ? full_b * 16u : head_end;
         for (u32 b = tail_a + lane; b < total; b += 32) gb[b] = sm[b];
+#if !defined(G2P_HOSTSIM)
+        if (lane == 0) bulk_wait_read0();   // the staging buffer must outlive the copy's reads
+#endif
     }
 }
 
