@@ -419,11 +419,11 @@ __global__ void __launch_bounds__(kSThreads, G2P_SHORT_CTAS) k_short(const Short
         const u32 nchunks = (sh + len + 15) >> 4;   // <= 16
         const u8* rt = gm->text + sh;
         constexpr int NIT = (16 + G - 1) / G;
-        static_assert(NIT <= 2, "two 16-bit chunk masks are packed per register");
-        u32 tabm = 0, mrkm = 0, ndgm = 0;   // chunk masks of iteration `it` in bits [16*it, 16*it+16)
-#pragma unroll 1
-        for (int it = 0; it < NIT; ++it) {   // kept rolled: the kernel is instruction-cache sensitive
+        u32 tabm[NIT], mrkm[NIT], ndgm[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
             const u32 c = it * G + g.gl;
+            tabm[it] = mrkm[it] = ndgm[it] = 0;
             if (c < nchunks) {
                 const uint4 v = ldg_vec_guarded(a.gaf, (u64)A + 16u * c, a.n);
                 reinterpret_cast<uint4*>(gm->text)[c] = v;
@@ -436,16 +436,16 @@ __global__ void __launch_bounds__(kSThreads, G2P_SHORT_CTAS) k_short(const Short
                     d |= movemask4(nondigit_bytes(w[k])) << (4 * k);
                 }
                 const u32 vm = range16((int)sh - 16 * (int)c, (int)(sh + len) - 16 * (int)c);
-                tabm |= (t & vm) << (16 * it); mrkm |= (m & vm) << (16 * it); ndgm |= (d & vm) << (16 * it);
+                tabm[it] = t & vm; mrkm[it] = m & vm; ndgm[it] = d & vm;
             }
         }
         if (g.gl < 6) gm->hdr[H_CG_A + g.gl] = 0;
         u32 nt = 0;
-#pragma unroll 1
+#pragma unroll
         for (int it = 0; it < NIT; ++it) {
             u32 tot;
-            u32 m = (tabm >> (16 * it)) & 0xffffu;
-            u32 k = nt + g.excl_scan((u32)__popc(m), tot);
+            u32 k = nt + g.excl_scan((u32)__popc(tabm[it]), tot);
+            u32 m = tabm[it];
             const u32 base = 16u * (it * G + g.gl) - sh;
             while (m) {
                 const u32 b = (u32)__ffs((int)m) - 1u;
@@ -473,11 +473,11 @@ __global__ void __launch_bounds__(kSThreads, G2P_SHORT_CTAS) k_short(const Short
 
         // ---------------- phase 2: step markers and op letters -> positions
         u32 ns = 0, no = 0;
-#pragma unroll 1
+#pragma unroll
         for (int it = 0; it < NIT; ++it) {
             const int base = 16 * (it * G + (int)g.gl) - (int)sh;
-            u32 mm = prefixed ? (((mrkm >> (16 * it)) & 0xffffu) & range16((int)pa - base, (int)pb - base)) : 0u;
-            u32 dm = ((ndgm >> (16 * it)) & 0xffffu) & range16((int)ca - base, (int)cb - base);
+            u32 mm = prefixed ? (mrkm[it] & range16((int)pa - base, (int)pb - base)) : 0u;
+            u32 dm = ndgm[it] & range16((int)ca - base, (int)cb - base);
             u32 tot;
             const u32 ex = g.excl_scan((u32)__popc(mm) | ((u32)__popc(dm) << 16), tot);
             u32 k = ns + (ex & 0xffffu);
