@@ -578,22 +578,20 @@ G2P_HD u32 parse_header(const u8* r, u32 len, const LenTableView& T, RecHdr& h, 
 
     if (!h.has_cg) return ST_ERR_NOCG;
 
-    // cg syntax: the reference materialises the whole CIGAR before any output
-    // (for_each_cg, gafkluge.hpp:226-239).  Strict SAM grammar ([0-9]+[MIDNSHPX=])+ ;
-    // anything else is reported as an abort.  Lengths of more than 18 significant
-    // digits are rejected too.
+    // cg tokens: the reference materialises the whole CIGAR before any output (for_each_cg,
+    // gafkluge.hpp:226-239): each token runs up to the next of "MIDNSHPX=" and its length is
+    // std::stol of what precedes the letter -- leading blanks, a sign and trailing junk are
+    // accepted, no digits or > int64 is an uncaught exception, a missing letter an assert.
     {
         u32 i = h.cg_a;
         while (i < h.cg_b) {
-            u32 nd = 0, nsig = 0;
-            while (i < h.cg_b) {
-                u32 d = (u32)r[i] - '0';
-                if (d > 9) break;
-                if (nsig > 0 || d != 0) ++nsig;
-                ++nd; ++i;
-            }
-            if (nd == 0 || nsig > 18 || i >= h.cg_b || !op_in(kOpMask, r[i])) return ST_ABORT_CIGAR;
-            ++i;
+            u32 j = i;
+            while (j < h.cg_b && !op_in(kOpMask, r[j])) ++j;
+            if (j >= h.cg_b) return ST_ABORT_CIGAR;
+            i64 v;
+            const u32 cst = stol_general(r, i, j, v);
+            if (cst) return cst;
+            i = j + 1;
         }
     }
 
@@ -619,23 +617,23 @@ struct OpCur {
 };
 
 template <bool BWD>
-G2P_HD void op_read(const u8* r, u32 lo, u32& pos, i64& l, u8& c) {
+G2P_HD void op_read(const u8* r, u32 lo, u32 hi, u32& pos, i64& l, u8& c) {
+    // token = text up to (forwards) / back to (backwards) the neighbouring op letter; the CIGAR
+    // has been validated by parse_header, so every token ends in a letter and std::stol succeeds
     if (!BWD) {
-        u64 v = 0;
-        u8 ch;
-        while ((ch = r[pos++]) <= '9') v = v * 10 + (u32)(ch - '0');
-        l = (i64)v; c = ch;
+        u32 j = pos;
+        while (j < hi && !op_in(kOpMask, r[j])) ++j;
+        l = 0;
+        stol_span(r, pos, j, l);
+        c = r[j];
+        pos = j + 1;
     } else {
         c = r[--pos];
-        u64 v = 0, mul = 1;
-        while (pos > lo) {
-            u8 ch = r[pos - 1];
-            if (ch > '9') break;
-            v += (u64)(u32)(ch - '0') * mul;
-            mul *= 10;
-            --pos;
-        }
-        l = (i64)v;
+        u32 j = pos;
+        while (j > lo && !op_in(kOpMask, r[j - 1])) --j;
+        l = 0;
+        stol_span(r, j, pos, l);
+        pos = j;
     }
 }
 
@@ -665,7 +663,7 @@ G2P_HD u32 consume_step(const u8* r, u32 cg_a, u32 cg_b, OpCur& c, i64 quota, St
             s.had_pending = 1; s.first_code = code;
         } else {
             if (BWD ? (c.pos <= cg_a) : (c.pos >= cg_b)) return ST_ABORT_ASSERT;   // :80 assert(cur_len > target_len)
-            op_read<BWD>(r, cg_a, c.pos, l, code);
+            op_read<BWD>(r, cg_a, cg_b, c.pos, l, code);
             ++s.n_new;
         }
         const u32 k = (u32)code - '=';
@@ -684,7 +682,7 @@ G2P_HD u32 consume_step(const u8* r, u32 cg_a, u32 cg_b, OpCur& c, i64 quota, St
         if ((kQueryMask >> k) & 1u) s.q += l;
         if ((kMatchMask >> k) & 1u) s.nm += l;
         s.nb += l;
-        s.cglen += dec_len_u64((u64)l) + 1;
+        s.cglen += dec_len_i64(l) + 1;
     }
     return ST_OK;
 }
@@ -728,12 +726,12 @@ G2P_HD void emit_pieces(const u8* r, u32 cg_a, u32 cg_b, const OpCur& c0, const 
             i64 l;
             u8 code;
             if (c.rem > 0) { l = c.rem; code = c.code; c.rem = 0; }
-            else op_read<BWD>(r, cg_a, c.pos, l, code);
+            else op_read<BWD>(r, cg_a, cg_b, c.pos, l, code);
             if (op_in(kTargetMask, code)) {
                 if (l > quota - cur) l = quota - cur;
                 cur += l;
             }
-            S.udec((u64)l);
+            S.dec(l);
             S.ch(code);
         }
     } else {
@@ -741,14 +739,13 @@ G2P_HD void emit_pieces(const u8* r, u32 cg_a, u32 cg_b, const OpCur& c0, const 
         for (u32 i = 0; i < s.n_new; ++i) {
             i64 l;
             u8 code;
-            op_read<!BWD>(r, cg_a, pos, l, code);
+            op_read<!BWD>(r, cg_a, cg_b, pos, l, code);
             if (i == 0 && s.cut) l = s.last_len;
-            S.udec((u64)l);
+            S.dec(l);
             S.ch(code);
         }
-        if (s.had_pending) { S.udec((u64)s.first_len); S.ch(s.first_code); }
+        if (s.had_pending) { S.dec(s.first_len); S.ch(s.first_code); }
     }
-    (void)cg_b;
 }
 
 // ---------------------------------------------------------------------------------

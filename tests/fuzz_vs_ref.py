@@ -4,9 +4,9 @@ or unusual records.  Compares exit code and stdout (and stderr text for rc 1).
 
     python tests/fuzz_vs_ref.py [--n 2000] [--seed 1] [--bin build/g2p_hostsim]
 
-Development tool (needs oracle/_ref, i.e. the build container).  Known, documented
-deviation classes are filtered by `tolerated()`: inputs whose CIGAR is outside the
-SAM grammar but that std::stol happens to accept (DESIGN.md, "strictness").
+Development tool (needs oracle/_ref, i.e. the build container).  CIGAR text outside the SAM
+grammar that std::stol accepts is handled like the reference does; the only tolerated class is
+int64 overflow (undefined behaviour in the reference), see `tolerated()`.
 """
 import argparse
 import os
@@ -40,7 +40,8 @@ WEIRD = ["*", "", "-5", " 12", "+7", "12x", "x12", "99999999999999999999", "0", 
 WEIRD_STEP = [">a", "<b", ">c:0-5", ">c:5", ">:0-5", ">>", "<", ">a:", ">a:-", ">a:1-", ">a:-3", ">a:1--3", ">nope",
               ">chrA:10-20", "chrB", "*", ">a:2-8x", ">a: 2-8", ">n2:0-20:9"]
 WEIRD_CG = ["", "M", "5", "5M", "0M", "5Q", "5M3", "-5M", "+5M", " 5M", "5 M", "05M", "5m", "10=", "3X", "2I", "2D", "99999999999M",
-            "5M\r", "1M1M1M1M", "20M", "3S", "4H", "2N", "1P"]
+            "5M\r", "1M1M1M1M", "20M", "3S", "4H", "2N", "1P", "-3M", "-2I", "5Q3M", "5.5M", "0005M", "00M", "9223372036854775807M",
+            "9223372036854775808M", "-9223372036854775808D", "\t", "5 5M", "+0M", "x", "3=-1X", "7MM", "\x0b4M", "4M-", "--4M"]
 TAGS = ["tp:A:P", "tp:A:S", "rc:Z:x", "rc:Z:", "cm:i:5", "ab:1", "abc", "a:b:c", "xx:Z:y:z", "tp:ZZ:hello", "cg:Z:5M", "", "tpp:A:P", ":::::", "cg:i:5M"]
 
 
@@ -119,15 +120,12 @@ CG_STRICT = re.compile(rb"^(\d+[MIDNSHPX=])*$")
 
 
 def tolerated(line, ref, got):
-    """Documented strictness deviations: CIGAR text outside the SAM grammar
-    that std::stol still accepts (sign, whitespace, junk before the op letter), and op
-    lengths of 19+ significant digits.  We abort (rc 134) where the reference continues."""
+    """The one tolerated class: CIGAR lengths of 19 digits (|v| >= 10^18).  Their sums overflow
+    int64, which is undefined behaviour in the reference (its outcome depends on how the compiler
+    happened to arrange the arithmetic), so there is nothing to be identical to.  Everything else
+    -- sign, blanks, trailing junk, negative or zero lengths -- must match exactly."""
     m = re.search(rb"\tcg:[^\t:]*:([^\t]*)", line)
-    if m and not CG_STRICT.match(m.group(1)) and got[0] == 134:
-        return True
-    if m and re.search(rb"[1-9]\d{18,}[MIDNSHPX=]", m.group(1)) and got[0] == 134:
-        return True
-    return False
+    return bool(m and re.search(rb"\d{19,}", m.group(1)))
 
 
 def main():
@@ -160,7 +158,7 @@ def main():
                     print("MISMATCH #%d: %r" % (it, data))
                     print("   ref rc=%d out=%r err=%r" % (ref[0], ref[1][:200], ref[2][-160:]))
                     print("   got rc=%d out=%r err=%r" % (got[0], got[1][:200], got[2][-160:]))
-    print("fuzz: %d cases, %d mismatches, %d tolerated strictness deviations" % (a.n, bad, tol))
+    print("fuzz: %d cases, %d mismatches, %d tolerated (int64-overflow UB in the reference)" % (a.n, bad, tol))
     return 1 if bad else 0
 
 
