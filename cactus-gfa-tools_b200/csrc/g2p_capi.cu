@@ -310,9 +310,9 @@ static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
     if (hm->lines_total) {   // k_short's records: line slot -> descriptor through the map
         if (hm->lines_total > 0xFFFFFF00ULL) { ctx->set_err("too many PAF lines in one call: split the input"); return G2P_E_TOOBIG; }
         const u32 nl = (u32)hm->lines_total;
-        G2P_CUDA(w.d_map.ensure((size_t)nl * sizeof(u32)));
-        u32* d_map = static_cast<u32*>(w.d_map.p);
-        k_line_map<<<(nrec + 255) / 256, 256, 0, st>>>(d_loff, nrec, d_map);
+        G2P_CUDA(w.d_map.ensure((size_t)nl * sizeof(LineMapEnt)));
+        LineMapEnt* d_map = static_cast<LineMapEnt*>(w.d_map.p);
+        k_line_map<<<(nrec + 255) / 256, 256, 0, st>>>(d_loff, d_rec, d_off, nrec, d_map);
         EmitArgs ea{d_gaf, (u64)n, d_rec, d_off, d_sdesc, d_map, d_rdesc, nl, d_o};
         k_emit_lines<<<(nl + kEThreads - 1) / kEThreads, kEThreads, kEmitSmem, st>>>(ea);
         launches += 2;

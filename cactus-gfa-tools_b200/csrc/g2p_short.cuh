@@ -729,25 +729,37 @@ constexpr u32 kEOutCap = 5120;     // staged PAF bytes per warp
 constexpr u32 kETextCap = 4096;    // staged GAF bytes per warp (the records its 32 lines come from)
 constexpr size_t kEmitSmem = (size_t)(kEThreads / 32) * (kEOutCap + 16 + kETextCap + 32);
 
+// What k_emit_lines needs to start all its loads at once for a line of a k_short record.
+struct __align__(16) LineMapEnt {
+    u32 desc_idx;     // r * kSMaxLines + j
+    u32 rec_start;    // text offset of the record
+    u64 out_off;      // output offset of the record
+};
+
 struct EmitArgs {
     const u8* gaf;
     u64 n;
     const u32* rec_start;
     const u64* out_off;
     const LineDesc* desc;
-    const u32* map;        // line slot -> descriptor index (k_short's per-record slots), or null: identity
+    const LineMapEnt* map;   // line slot -> descriptor + record offsets (k_short's records), or null: slot == descriptor index
     const RecDesc* rdesc;
     u32 n_slots;
     u8* out;
 };
 
-// line slot -> descriptor index for k_short's records: record r's lines are descriptors
-// r * kSMaxLines + j, its first line slot is line_off[r] (after the scan)
-__global__ void __launch_bounds__(256) k_line_map(const u64* __restrict__ line_off, u32 nrec, u32* __restrict__ map) {
+// Line map of k_short's records (after the scans): record r's lines are descriptors
+// r * kSMaxLines + j, its first line slot is line_off[r].
+__global__ void __launch_bounds__(256) k_line_map(const u64* __restrict__ line_off, const u32* __restrict__ rec_start,
+                                                  const u64* __restrict__ out_off, u32 nrec, LineMapEnt* __restrict__ map) {
     const u32 r = blockIdx.x * 256u + threadIdx.x;
     if (r >= nrec) return;
     const u64 b = line_off[r], e = line_off[r + 1];
-    for (u64 k = b; k < e; ++k) map[k] = r * kSMaxLines + (u32)(k - b);
+    if (b == e) return;
+    LineMapEnt m;
+    m.rec_start = rec_start[r];
+    m.out_off = out_off[r];
+    for (u64 k = b; k < e; ++k) { m.desc_idx = r * kSMaxLines + (u32)(k - b); map[k] = m; }
 }
 
 __global__ void __launch_bounds__(kEThreads) k_emit_lines(const EmitArgs a) {
@@ -762,28 +774,60 @@ __global__ void __launch_bounds__(kEThreads) k_emit_lines(const EmitArgs a) {
     __syncwarp();
 #endif
     const u32 slot = blockIdx.x * kEThreads + threadIdx.x;
-    LineDesc d;
-    d.rec = kDescInvalid; d.len = 0; d.loff = 0;
-    if (slot < a.n_slots) {
-        const uint4* src = reinterpret_cast<const uint4*>(a.desc + (a.map ? a.map[slot] : slot));
+    const bool in_range = slot < a.n_slots;
+    LineDesc d{};
+    d.rec = kDescInvalid;
+    u32 rs = 0, re = 0;   // text span of this lane's record
+    u64 obase = 0;
+    const LineDesc* dp = a.desc + slot;
+    if (a.map && in_range) {   // k_short's lines: one 16-byte entry tells where everything is
+        const uint4 m = __ldg(reinterpret_cast<const uint4*>(a.map + slot));
+        dp = a.desc + m.x;
+        rs = m.y;
+        re = rs + kSLimit + 1;   // upper bound of the record's end (its length is not needed exactly)
+        obase = (u64)m.z | ((u64)m.w << 32);
+    }
+    if (in_range) {
+        const uint4* src = reinterpret_cast<const uint4*>(dp);
         uint4* dst = reinterpret_cast<uint4*>(&d);
         dst[0] = __ldg(src); dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2); dst[3] = __ldg(src + 3);
     }
-    const bool valid = d.rec != kDescInvalid;
+    const bool valid = a.map ? in_range : d.rec != kDescInvalid;
     const u32 vmask = __ballot_sync(FULL, valid);
     if (vmask == 0) return;
     const int first = __ffs((int)vmask) - 1, last = 31 - __clz((int)vmask);
     u64 o = 0;
     LineRec R;
     LineStep L;
-    u32 rs = 0, re = 0;   // text span of this lane's record
+    // text staging can start before the descriptors arrive when the map gave the offsets
+    bool text_staged = false, text_tma = false;
+    u32 A = 0;
+    if (a.map) {
+        const u32 t0 = __shfl_sync(FULL, rs, first);
+        u32 t1 = __shfl_sync(FULL, re, last);
+        if ((u64)t1 > a.n) t1 = (u32)a.n;
+        A = t0 & ~15u;
+        text_staged = t1 > t0 && t1 - A <= kETextCap;
+        if (text_staged) {
+            const u32 nvec = (t1 - A + 15u) >> 4;
+#if !defined(G2P_HOSTSIM)
+            if ((u64)A + 16ull * nvec <= a.n) {   // whole vectors inside the buffer: one TMA bulk copy
+                if (lane == 0) { mbar_expect_tx(&s_bar[warp], nvec * 16u); bulk_g2s(sm_text, a.gaf + A, nvec * 16u, &s_bar[warp]); }
+                text_tma = true;
+            } else
+#endif
+            {
+                for (u32 v = lane; v < nvec; v += 32) reinterpret_cast<uint4*>(sm_text)[v] = ldg_vec_guarded(a.gaf, (u64)A + 16u * v, a.n);
+            }
+        }
+    }
     if (valid) {
         RecDesc rd;
         const uint4* src = reinterpret_cast<const uint4*>(a.rdesc + d.rec);
         uint4* dst = reinterpret_cast<uint4*>(&rd);
         dst[0] = __ldg(src); dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2);
-        rs = a.rec_start[d.rec]; re = a.rec_start[d.rec + 1];
-        o = a.out_off[d.rec] + d.loff;
+        if (!a.map) { rs = a.rec_start[d.rec]; obase = a.out_off[d.rec]; }
+        o = obase + d.loff;
         R.qn_b = rd.qn_b; R.qlen = rd.qlen; R.mapq = rd.mapq; R.m = rd.m; R.b = rd.b;
         R.tp_a = rd.tp_a; R.tp_b = rd.tp_a + rd.tp_len; R.rc_a = rd.rc_a; R.rc_b = rd.rc_a + rd.rc_len; R.gi_n = rd.gi_n;
         if (!rd.tp_len) R.tp_b = 0;
@@ -793,24 +837,16 @@ __global__ void __launch_bounds__(kEThreads) k_emit_lines(const EmitArgs a) {
         L.lenS = d.lenS; L.lenE = d.lenE; L.mid_a = d.mid_a; L.mid_b = d.mid_a + d.mid_len; L.codeS = d.codeS; L.codeE = d.codeE;
         L.rev = (d.flags & 1u) != 0; L.mid_fwd = (d.flags & 2u) != 0;
     }
-    // stage the text of the warp's records (one contiguous span) with 128-bit coalesced loads
-    const u32 t0 = __shfl_sync(FULL, rs, first), t1 = __shfl_sync(FULL, re, last);
-    const u32 A = t0 & ~15u;
-    const bool text_staged = t1 > t0 && t1 - A <= kETextCap;
     if (text_staged) {
-        const u32 nvec = (t1 - A + 15u) >> 4;
 #if !defined(G2P_HOSTSIM)
-        if ((u64)A + 16ull * nvec <= a.n) {   // whole vectors inside the buffer: one TMA bulk copy
-            if (lane == 0) { mbar_expect_tx(&s_bar[warp], nvec * 16u); bulk_g2s(sm_text, a.gaf + A, nvec * 16u, &s_bar[warp]); }
+        if (text_tma) {
             u32 spins = 0;
             while (!mbar_try_wait(&s_bar[warp], 0)) { if (++spins > (1u << 24)) __trap(); }
         } else
 #endif
-        {
-            for (u32 v = lane; v < nvec; v += 32) reinterpret_cast<uint4*>(sm_text)[v] = ldg_vec_guarded(a.gaf, (u64)A + 16u * v, a.n);
             __syncwarp();
-        }
     }
+    (void)text_tma;
     const u8* rt = text_staged ? sm_text + (rs - A) : a.gaf + rs;
     // contiguity of the warp's lines in the output
     const u64 end = o + d.len;

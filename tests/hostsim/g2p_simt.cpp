@@ -92,8 +92,8 @@ int main(int argc, char** argv) {
     la.out = out.data();
     if (meta.lines_total) {
         const u32 nl = (u32)meta.lines_total;
-        std::vector<u32> map(nl);
-        hs::launch(dim3((nrec + 255) / 256), dim3(256), 0, [&] { k_line_map(loff.data(), nrec, map.data()); });
+        std::vector<LineMapEnt> map(nl);
+        hs::launch(dim3((nrec + 255) / 256), dim3(256), 0, [&] { k_line_map(loff.data(), rec.data(), off.data(), nrec, map.data()); });
         EmitArgs ea{gaf, n, rec.data(), off.data(), sdesc.data(), map.data(), rdesc.data(), nl, out.data()};
         hs::launch(dim3((nl + kEThreads - 1) / kEThreads), dim3(kEThreads), kEmitSmem, [&] { k_emit_lines(ea); });
     }
