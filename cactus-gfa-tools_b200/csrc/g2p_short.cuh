@@ -857,7 +857,12 @@ __global__ void __launch_bounds__(kEThreads) k_emit_lines(const EmitArgs a) {
     const bool holes = (vmask >> first) != (0xffffffffu >> (31 - (last - first)));
     const bool staged = !__any_sync(FULL, gap) && !holes && (o1 - o0) <= kEOutCap;
     const u32 pad = (u32)(o0 & 15u);
-    if (valid) write_line((staged ? sm + pad + (u32)(o - o0) : a.out + o) + d.len, line_src(rt, R, L), R, L);
+    if (valid) {
+        // two instantiations so that the common one (staged lines, staged text) works on pointers the
+        // compiler can prove to be shared memory: LDS / STS instead of generic 64-bit LD / ST
+        if (staged && text_staged) write_line(sm + pad + (u32)(o - o0) + d.len, line_src(sm_text + (rs - A), R, L), R, L);
+        else write_line((staged ? sm + pad + (u32)(o - o0) : a.out + o) + d.len, line_src(rt, R, L), R, L);
+    }
     if (staged) {
         const u32 total = pad + (u32)(o1 - o0);
         u8* gb = a.out + (o0 - pad);
