@@ -861,7 +861,8 @@ __global__ void __launch_bounds__(kEThreads) k_emit_lines(const EmitArgs a) {
         // two instantiations so that the common one (staged lines, staged text) works on pointers the
         // compiler can prove to be shared memory: LDS / STS instead of generic 64-bit LD / ST
         if (staged && text_staged) write_line(sm + pad + (u32)(o - o0) + d.len, line_src(sm_text + (rs - A), R, L), R, L);
-        else write_line((staged ? sm + pad + (u32)(o - o0) : a.out + o) + d.len, line_src(rt, R, L), R, L);
+        else if (staged) write_line(sm + pad + (u32)(o - o0) + d.len, line_src(a.gaf + rs, R, L), R, L);   // long records: text from global
+        else write_line(a.out + o + d.len, line_src(rt, R, L), R, L);
     }
     if (staged) {
         const u32 total = pad + (u32)(o1 - o0);
