@@ -375,10 +375,11 @@ __device__ __forceinline__ void long_record(const LongArgs& a, LWarpMemT<EMIT>* 
                 if (!minus) wds = prev + 1u;
                 else wds = lane + 1 < os.count ? os.at(lane + 1) + 1u : cA;
                 const u32 nd = wlp - wds;
-                const u8* tx = os.src(wds, nd + 1);   // digits + op letter
-                wk = (u32)tx[nd] - '=';
-                if (wk >= 28 || !((kOpMask >> wk) & 1u) || nd == 0 || nd > 8 || (nd > 1 && tx[0] == '0')) lbad = 1;
-                else {
+                // digits + op letter: two call sites so that the common one works on a pointer the
+                // compiler can prove to be shared memory (LDS instead of generic loads)
+                auto parse_op = [&](const u8* tx) {
+                    wk = (u32)tx[nd] - '=';
+                    if (wk >= 28 || !((kOpMask >> wk) & 1u) || nd == 0 || nd > 8 || (nd > 1 && tx[0] == '0')) { lbad = 1; return; }
                     u32 x = 0;
                     for (u32 t = 0; t < nd; ++t) x = x * 10u + ((u32)tx[t] - '0');
                     if (x == 0) lbad = 1;
@@ -387,7 +388,10 @@ __device__ __forceinline__ void long_record(const LongArgs& a, LWarpMemT<EMIT>* 
                     vE = ((kTargetMask >> wk) & 1u) ? x : 0u;
                     vQ = ((kQueryMask >> wk) & 1u) ? x : 0u;
                     vM = ((kMatchMask >> wk) & 1u) ? x : 0u;
-                }
+                };
+                const u32 tk = wds & (kLText - 1u);
+                if (wds >= os.tlo && wlp + 1u <= os.thi && tk + nd + 1u <= kLText) parse_op(wm->otext + tk);
+                else parse_op(gaf + wds);
             }
             wEND = (u64)wscan32(vE, lane) + cE; wQ = (u64)wscan32(vQ, lane) + cQ; wM = (u64)wscan32(vM, lane) + cM; wNB = (u64)wscan32(vB, lane) + cNB;
             cE = __shfl_sync(FULL, wEND, nwin - 1); cQ = __shfl_sync(FULL, wQ, nwin - 1);
