@@ -124,17 +124,19 @@ __device__ __forceinline__ u32 dlen_u32(u32 v, const u32* p10) {
 }
 __device__ __forceinline__ u32 dlen_i32(i32 v, const u32* p10) { return v < 0 ? 1u + dlen_u32(0u - (u32)v, p10) : dlen_u32((u32)v, p10); }
 // gi:f: text for 0 <= floor(m/b*1000+0.5) <= 1000 (gaf2paf_main.cpp:248-253); returns 0 if outside.
-__device__ __forceinline__ u32 gi_fast(i32 m, i32 b, u8* out) {
-    if (b <= 0) { out[0] = '0'; return 1; }
+// The text is returned packed (byte k of the text in bits [8k, 8k+8) of `pack`) so that it lives
+// in registers and never forces a local-memory array.
+__device__ __forceinline__ u32 gi_fast(i32 m, i32 b, u64& pack) {
+    pack = '0';
+    if (b <= 0) return 1;
     const double x = __ddiv_rn((double)m, (double)b);
     const double k = floor(__dadd_rn(__dmul_rn(x, 1000.0), 0.5));
     if (!(k >= 0.0 && k <= 1000.0)) return 0;
     const u32 ki = (u32)k;
-    if (ki == 0) { out[0] = '0'; return 1; }
-    if (ki == 1000) { out[0] = '1'; return 1; }
+    if (ki == 0) return 1;
+    if (ki == 1000) { pack = '1'; return 1; }
     const u32 d0 = ki / 100, d1 = (ki / 10) % 10, d2 = ki % 10;
-    out[0] = '0'; out[1] = '.';
-    out[2] = (u8)('0' + d0); out[3] = (u8)('0' + d1); out[4] = (u8)('0' + d2);
+    pack = (u64)'0' | ((u64)'.' << 8) | ((u64)('0' + d0) << 16) | ((u64)('0' + d1) << 24) | ((u64)('0' + d2) << 32);
     return d2 ? 5 : (d1 ? 4 : 3);
 }
 
@@ -208,7 +210,7 @@ struct LineRec {    // constant over the lines of one record
     i32 qlen, mapq, m, b;
     u32 tp_a, tp_b, rc_a, rc_b;   // "type:value" spans of the tp / rc tags (b == 0: absent)
     u32 gi_n;
-    u8 gi[8];
+    u64 gi;               // gi:f: value text, byte k in bits [8k, 8k+8)
 };
 struct LineStep {
     u32 q0, q1, name_a, nl, tlen, ts, te, nm, nb;
@@ -284,7 +286,8 @@ __device__ __forceinline__ u8* write_line(u8* pend, const LineSrc& S, const Line
     if (!L.rev) { if (L.codeS) { *--p = L.codeS; p = rput_u32(p, L.lenS); } }
     else { *--p = L.codeE; p = rput_u32(p, L.lenE); }
     p = rput_tag(p, 'c', 'g', 'Z');
-    p = rput_bytes(p, R.gi, R.gi_n); p = rput_tag(p, 'g', 'i', 'f');
+    for (u32 i = R.gi_n; i-- > 0;) *--p = (u8)(R.gi >> (8 * i));
+    p = rput_tag(p, 'g', 'i', 'f');
     p = rput_i32(p, R.b); p = rput_tag(p, 'g', 'l', 'i');
     p = rput_i32(p, R.m); p = rput_tag(p, 'g', 'm', 'i');
     if (R.rc_b) { p = rput_bytes(p, S.rc, R.rc_b - R.rc_a); p -= 4; p[0] = '\t'; p[1] = 'r'; p[2] = 'c'; p[3] = ':'; }
@@ -329,29 +332,41 @@ struct __align__(16) RecDesc {
     u8 pad1[11];
 };
 static_assert(sizeof(RecDesc) == 48, "RecDesc is three 16-byte vectors");
+// Descriptors are packed to / unpacked from four (three) 16-byte vectors in registers: no struct
+// whose address is taken, hence no local-memory traffic on either side.
 __device__ __forceinline__ void store_line_desc(LineDesc* dst, u32 rec, u32 loff, u32 line, const LineStep& L) {
-    LineDesc d;
-    d.rec = rec; d.loff = loff; d.q0 = L.q0; d.q1 = L.q1; d.tlen = L.tlen; d.ts = L.ts; d.te = L.te; d.nm = L.nm;
-    d.nb = L.nb; d.lenS = L.lenS; d.lenE = L.lenE; d.name_a = L.name_a;
-    d.mid_a = L.mid_a; d.mid_len = L.mid_b > L.mid_a ? L.mid_b - L.mid_a : 0u; d.len = line;
-    d.nl = (u8)L.nl; d.codeS = L.codeS; d.codeE = L.codeE; d.flags = (u8)((L.rev ? 1u : 0u) | (L.mid_fwd ? 2u : 0u));
-    const uint4* src = reinterpret_cast<const uint4*>(&d);
     uint4* out = reinterpret_cast<uint4*>(dst);
-    out[0] = src[0]; out[1] = src[1]; out[2] = src[2]; out[3] = src[3];
+    out[0] = make_uint4(rec, loff, L.q0, L.q1);
+    out[1] = make_uint4(L.tlen, L.ts, L.te, L.nm);
+    out[2] = make_uint4(L.nb, L.lenS, L.lenE, L.name_a);
+    out[3] = make_uint4(L.mid_a, L.mid_b > L.mid_a ? L.mid_b - L.mid_a : 0u, line,
+                        (L.nl & 0xffu) | ((u32)L.codeS << 8) | ((u32)L.codeE << 16) | ((L.rev ? 1u : 0u) << 24) | ((L.mid_fwd ? 2u : 0u) << 24));
+}
+__device__ __forceinline__ void unpack_line_desc(const uint4& v0, const uint4& v1, const uint4& v2, const uint4& v3, u32& rec, u32& loff, u32& line,
+                                                 LineStep& L) {
+    rec = v0.x; loff = v0.y; L.q0 = v0.z; L.q1 = v0.w;
+    L.tlen = v1.x; L.ts = v1.y; L.te = v1.z; L.nm = v1.w;
+    L.nb = v2.x; L.lenS = v2.y; L.lenE = v2.z; L.name_a = v2.w;
+    L.mid_a = v3.x; L.mid_b = v3.x + v3.y; line = v3.z;
+    L.nl = v3.w & 0xffu; L.codeS = (u8)(v3.w >> 8); L.codeE = (u8)(v3.w >> 16);
+    L.rev = ((v3.w >> 24) & 1u) != 0; L.mid_fwd = ((v3.w >> 24) & 2u) != 0;
 }
 // false when the record's constants do not fit the descriptor (very long name / tag text)
 __device__ __forceinline__ bool rec_desc_fits(const LineRec& R) { return R.qn_b <= 0xffffu && R.tp_b - R.tp_a <= 0xffffu && R.rc_b - R.rc_a <= 0xffffu; }
 __device__ __forceinline__ void store_rec_desc(RecDesc* dst, const LineRec& R) {
-    RecDesc rd;
-    rd.qlen = R.qlen; rd.m = R.m; rd.b = R.b; rd.mapq = R.mapq;
-    rd.tp_a = R.tp_a; rd.rc_a = R.rc_a;
-    rd.qn_b = (u16)R.qn_b; rd.tp_len = (u16)(R.tp_b - R.tp_a); rd.rc_len = (u16)(R.rc_b - R.rc_a);
-    rd.gi_n = (u8)R.gi_n; rd.pad0 = 0;
-    for (int k = 0; k < 5; ++k) rd.gi[k] = R.gi[k];
-    for (int k = 0; k < 11; ++k) rd.pad1[k] = 0;
-    const uint4* src = reinterpret_cast<const uint4*>(&rd);
     uint4* out = reinterpret_cast<uint4*>(dst);
-    out[0] = src[0]; out[1] = src[1]; out[2] = src[2];
+    out[0] = make_uint4((u32)R.qlen, (u32)R.m, (u32)R.b, (u32)R.mapq);
+    out[1] = make_uint4(R.tp_a, R.rc_a, (R.qn_b & 0xffffu) | ((R.tp_b - R.tp_a) << 16), ((R.rc_b - R.rc_a) & 0xffffu) | (R.gi_n << 16));
+    out[2] = make_uint4((u32)R.gi, (u32)(R.gi >> 32), 0u, 0u);
+}
+__device__ __forceinline__ void unpack_rec_desc(const uint4& v0, const uint4& v1, const uint4& v2, LineRec& R) {
+    R.qlen = (i32)v0.x; R.m = (i32)v0.y; R.b = (i32)v0.z; R.mapq = (i32)v0.w;
+    const u32 tp_len = v1.z >> 16, rc_len = v1.w & 0xffffu;
+    R.qn_b = v1.z & 0xffffu;
+    R.tp_a = v1.x; R.tp_b = tp_len ? v1.x + tp_len : 0u;
+    R.rc_a = v1.y; R.rc_b = rc_len ? v1.y + rc_len : 0u;
+    R.gi_n = (v1.w >> 16) & 0xffu;
+    R.gi = (u64)v2.x | ((u64)v2.y << 32);
 }
 constexpr u32 kDescInvalid = 0xFFFFFFFFu;
 
@@ -775,8 +790,7 @@ __global__ void __launch_bounds__(kEThreads) k_emit_lines(const EmitArgs a) {
 #endif
     const u32 slot = blockIdx.x * kEThreads + threadIdx.x;
     const bool in_range = slot < a.n_slots;
-    LineDesc d{};
-    d.rec = kDescInvalid;
+    uint4 v0 = make_uint4(kDescInvalid, 0u, 0u, 0u), v1 = make_uint4(0u, 0u, 0u, 0u), v2 = v1, v3 = v1;
     u32 rs = 0, re = 0;   // text span of this lane's record
     u64 obase = 0;
     const LineDesc* dp = a.desc + slot;
@@ -789,16 +803,18 @@ __global__ void __launch_bounds__(kEThreads) k_emit_lines(const EmitArgs a) {
     }
     if (in_range) {
         const uint4* src = reinterpret_cast<const uint4*>(dp);
-        uint4* dst = reinterpret_cast<uint4*>(&d);
-        dst[0] = __ldg(src); dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2); dst[3] = __ldg(src + 3);
+        v0 = __ldg(src); v1 = __ldg(src + 1); v2 = __ldg(src + 2); v3 = __ldg(src + 3);
     }
+    struct { u32 rec, loff, len; } d;
+    LineRec R;
+    LineStep L;
+    unpack_line_desc(v0, v1, v2, v3, d.rec, d.loff, d.len, L);
+    if (!in_range) d.len = 0;
     const bool valid = a.map ? in_range : d.rec != kDescInvalid;
     const u32 vmask = __ballot_sync(FULL, valid);
     if (vmask == 0) return;
     const int first = __ffs((int)vmask) - 1, last = 31 - __clz((int)vmask);
     u64 o = 0;
-    LineRec R;
-    LineStep L;
     // text staging can start before the descriptors arrive when the map gave the offsets
     bool text_staged = false, text_tma = false;
     u32 A = 0;
@@ -822,20 +838,11 @@ __global__ void __launch_bounds__(kEThreads) k_emit_lines(const EmitArgs a) {
         }
     }
     if (valid) {
-        RecDesc rd;
         const uint4* src = reinterpret_cast<const uint4*>(a.rdesc + d.rec);
-        uint4* dst = reinterpret_cast<uint4*>(&rd);
-        dst[0] = __ldg(src); dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2);
+        const uint4 r0 = __ldg(src), r1 = __ldg(src + 1), r2 = __ldg(src + 2);
         if (!a.map) { rs = a.rec_start[d.rec]; obase = a.out_off[d.rec]; }
         o = obase + d.loff;
-        R.qn_b = rd.qn_b; R.qlen = rd.qlen; R.mapq = rd.mapq; R.m = rd.m; R.b = rd.b;
-        R.tp_a = rd.tp_a; R.tp_b = rd.tp_a + rd.tp_len; R.rc_a = rd.rc_a; R.rc_b = rd.rc_a + rd.rc_len; R.gi_n = rd.gi_n;
-        if (!rd.tp_len) R.tp_b = 0;
-        if (!rd.rc_len) R.rc_b = 0;
-        for (int k = 0; k < 5; ++k) R.gi[k] = rd.gi[k];
-        L.q0 = d.q0; L.q1 = d.q1; L.name_a = d.name_a; L.nl = d.nl; L.tlen = d.tlen; L.ts = d.ts; L.te = d.te; L.nm = d.nm; L.nb = d.nb;
-        L.lenS = d.lenS; L.lenE = d.lenE; L.mid_a = d.mid_a; L.mid_b = d.mid_a + d.mid_len; L.codeS = d.codeS; L.codeE = d.codeE;
-        L.rev = (d.flags & 1u) != 0; L.mid_fwd = (d.flags & 2u) != 0;
+        unpack_rec_desc(r0, r1, r2, R);
     }
     if (text_staged) {
 #if !defined(G2P_HOSTSIM)
