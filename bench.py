@@ -262,7 +262,7 @@ def main():
     if em >= sz:   # k_emit_lines: reads descriptors + GAF text, writes the PAF
         dom, dom_ms, dom_bytes, dom_key = "k_emit_lines (emit pass)", em, nbytes + out_bytes, "k_emit_lines"
     else:          # size pass: parses the GAF, writes sizes + line descriptors
-        dom, dom_ms, dom_bytes, dom_key = kname + " EMIT=false (size pass)", sz, nbytes, kname.split("<")[0] + "_size"
+        dom, dom_ms, dom_bytes, dom_key = kname + " (size pass)", sz, nbytes, kname.split("<")[0] + "_size"
     # DRAM traffic of that kernel from the committed ncu --set full capture (bytes per record of the
     # captured launch, scaled to this launch's record count); null when no capture is committed
     traffic = None

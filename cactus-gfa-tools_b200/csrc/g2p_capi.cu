@@ -253,7 +253,7 @@ static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
     G2P_CUDA(w.d_status.ensure((size_t)nrec * sizeof(u32)));
     G2P_CUDA(w.d_off.ensure(((size_t)nrec + 1) * sizeof(u64)));
     const u32 nscan = (nrec + kScanTile - 1) / kScanTile;
-    G2P_CUDA(w.d_blocks.ensure((size_t)nscan * sizeof(u64)));
+    G2P_CUDA(w.d_blocks.ensure((size_t)nscan * 2 * sizeof(u64)));
     G2P_CUDA(w.d_list.ensure((size_t)nrec * sizeof(u32)));
     G2P_CUDA(w.d_list2.ensure((size_t)nrec * sizeof(u32)));
     u32* d_rec = static_cast<u32*>(w.d_rec.p);
@@ -289,14 +289,13 @@ static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
     k_convert_list<false><<<nlist, kListThreads, 0, st>>>(d_gaf, d_rec, ctx->table, d_off, d_status, nullptr, d_meta, d_list2, &d_meta->n_deleg2);
     launches += 3;
     G2P_CUDA(cudaEventRecord(w.ev[2], st));
-    // exclusive scans: byte counts -> output offsets, line counts -> line slots
-    k_scan_reduce<<<nscan, kScanThreads, 0, st>>>(d_off, nrec, d_blocks);
-    k_scan_blocks<<<1, 1024, 0, st>>>(d_blocks, nscan, &d_meta->out_total);
-    k_scan_apply<<<nscan, kScanThreads, 0, st>>>(d_off, nrec, d_blocks, &d_meta->out_total);
-    k_scan_reduce<<<nscan, kScanThreads, 0, st>>>(d_loff, nrec, d_blocks);
-    k_scan_blocks<<<1, 1024, 0, st>>>(d_blocks, nscan, &d_meta->lines_total);
-    k_scan_apply<<<nscan, kScanThreads, 0, st>>>(d_loff, nrec, d_blocks, &d_meta->lines_total);
-    launches += 6;
+    // exclusive scans: byte counts -> output offsets, line counts -> line slots (+ the line map)
+    G2P_CUDA(w.d_map.ensure((size_t)nrec * kSMaxLines * sizeof(LineMapEnt)));
+    LineMapEnt* d_map = static_cast<LineMapEnt*>(w.d_map.p);
+    k_scan_reduce2<<<nscan, kScanThreads, 0, st>>>(d_off, d_loff, nrec, d_blocks, d_blocks + nscan);
+    k_scan_blocks2<<<1, 1024, 0, st>>>(d_blocks, d_blocks + nscan, nscan, &d_meta->out_total, &d_meta->lines_total);
+    k_scan_apply2<<<nscan, kScanThreads, 0, st>>>(d_off, d_loff, nrec, d_blocks, d_blocks + nscan, &d_meta->out_total, &d_meta->lines_total, d_rec, d_map);
+    launches += 3;
     G2P_CUDA(cudaMemcpyAsync(hm, d_meta, sizeof(PipelineMeta), cudaMemcpyDeviceToHost, st));
     G2P_CUDA(cudaStreamSynchronize(st));
     const u64 out_total = hm->out_total;
@@ -310,12 +309,9 @@ static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
     if (hm->lines_total) {   // k_short's records: line slot -> descriptor through the map
         if (hm->lines_total > 0xFFFFFF00ULL) { ctx->set_err("too many PAF lines in one call: split the input"); return G2P_E_TOOBIG; }
         const u32 nl = (u32)hm->lines_total;
-        G2P_CUDA(w.d_map.ensure((size_t)nl * sizeof(LineMapEnt)));
-        LineMapEnt* d_map = static_cast<LineMapEnt*>(w.d_map.p);
-        k_line_map<<<(nrec + 255) / 256, 256, 0, st>>>(d_loff, d_rec, d_off, nrec, d_map);
         EmitArgs ea{d_gaf, (u64)n, d_rec, d_off, d_sdesc, d_map, d_rdesc, nl, d_o};
         k_emit_lines<<<(nl + kEThreads - 1) / kEThreads, kEThreads, kEmitSmem, st>>>(ea);
-        launches += 2;
+        ++launches;
     }
     const u32 n_slots = std::min<u32>(hm->n_desc, desc_cap);
     if (n_slots) {           // k_long's records: dense 32-slot blocks

@@ -236,6 +236,78 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_apply(u64* __restrict__ x
     if (blockIdx.x == 0 && threadIdx.x == 0) x[n] = *total_in;
 }
 
+// The two per-record arrays of gaf2paf (PAF bytes -> output offsets, PAF lines -> line slots) share
+// the three launches; the apply pass also writes the line map k_emit_lines reads (it has the
+// record's output offset, its first line slot and its line count in registers at that point).
+__global__ void __launch_bounds__(kScanThreads) k_scan_reduce2(const u64* __restrict__ x, const u64* __restrict__ y, u32 n,
+                                                               u64* __restrict__ bsx, u64* __restrict__ bsy) {
+    const u32 base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    u64 sx = 0, sy = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) if (base + i < n) { sx += x[base + i]; sy += y[base + i]; }
+    u64 tx, ty;
+    block_excl_scan_u64(sx, tx);
+    block_excl_scan_u64(sy, ty);
+    if (threadIdx.x == 0) { bsx[blockIdx.x] = tx; bsy[blockIdx.x] = ty; }
+}
+
+__global__ void __launch_bounds__(1024) k_scan_blocks2(u64* __restrict__ bsx, u64* __restrict__ bsy, u32 nblocks, u64* __restrict__ total_x,
+                                                       u64* __restrict__ total_y) {
+    __shared__ u64 part[1024];
+    const u32 per = (nblocks + 1023) / 1024;
+    const u32 a = threadIdx.x * per, b = min(a + per, nblocks);
+    for (int which = 0; which < 2; ++which) {
+        u64* bs = which ? bsy : bsx;
+        u64 s = 0;
+        for (u32 i = a; i < b; ++i) s += bs[i];
+        __syncthreads();
+        part[threadIdx.x] = s;
+        __syncthreads();
+        for (u32 o = 1; o < 1024; o <<= 1) {
+            u64 v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+            __syncthreads();
+            part[threadIdx.x] += v;
+            __syncthreads();
+        }
+        u64 run = threadIdx.x ? part[threadIdx.x - 1] : 0;
+        for (u32 i = a; i < b; ++i) { u64 c = bs[i]; bs[i] = run; run += c; }
+        if (threadIdx.x == 1023) *(which ? total_y : total_x) = part[1023];
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_apply2(u64* __restrict__ x, u64* __restrict__ y, u32 n, const u64* __restrict__ bsx,
+                                                              const u64* __restrict__ bsy, const u64* __restrict__ total_x,
+                                                              const u64* __restrict__ total_y, const u32* __restrict__ rec_start,
+                                                              LineMapEnt* __restrict__ map) {
+    const u32 base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    u64 vx[kScanItems], vy[kScanItems];
+    u64 sx = 0, sy = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        vx[i] = base + i < n ? x[base + i] : 0; sx += vx[i];
+        vy[i] = base + i < n ? y[base + i] : 0; sy += vy[i];
+    }
+    u64 tx, ty;
+    u64 runx = bsx[blockIdx.x] + block_excl_scan_u64(sx, tx);
+    u64 runy = bsy[blockIdx.x] + block_excl_scan_u64(sy, ty);
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        if (base + i < n) {
+            x[base + i] = runx;
+            y[base + i] = runy;
+            if (vy[i]) {   // lines of a k_short record: descriptors (base+i) * kSMaxLines + j
+                LineMapEnt m;
+                m.rec_start = rec_start[base + i];
+                m.out_off = runx;
+                for (u32 j = 0; j < (u32)vy[i]; ++j) { m.desc_idx = (base + i) * kSMaxLines + j; map[runy + j] = m; }
+            }
+        }
+        runx += vx[i];
+        runy += vy[i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { x[n] = *total_x; y[n] = *total_y; }
+}
+
 // ------------------------------------------------------------------------------
 // General per-record conversion: one thread walks one record with the streaming state
 // machine of g2p_core.cuh (any record length, every error path of the reference).  It

@@ -82,18 +82,17 @@ int main(int argc, char** argv) {
     const u32 nlong = 2;
     hs::launch(dim3(nlong), dim3(kLThreads), long_smem<false>(), [&] { k_long<false>(la); });
     hs::launch(dim3(nlist), dim3(kListThreads), 0, [&] { k_convert_list<false>(gaf, rec.data(), T, off.data(), status.data(), nullptr, &meta, list2.data(), &meta.n_deleg2); });
-    hs::launch(dim3(nscan), dim3(kScanThreads), 0, [&] { k_scan_reduce(off.data(), nrec, blocks.data()); });
-    hs::launch(dim3(1), dim3(1024), 0, [&] { k_scan_blocks(blocks.data(), nscan, &meta.out_total); });
-    hs::launch(dim3(nscan), dim3(kScanThreads), 0, [&] { k_scan_apply(off.data(), nrec, blocks.data(), &meta.out_total); });
-    hs::launch(dim3(nscan), dim3(kScanThreads), 0, [&] { k_scan_reduce(loff.data(), nrec, blocks.data()); });
-    hs::launch(dim3(1), dim3(1024), 0, [&] { k_scan_blocks(blocks.data(), nscan, &meta.lines_total); });
-    hs::launch(dim3(nscan), dim3(kScanThreads), 0, [&] { k_scan_apply(loff.data(), nrec, blocks.data(), &meta.lines_total); });
+    std::vector<u64> blocks2(nscan);
+    std::vector<LineMapEnt> map((size_t)nrec * kSMaxLines);
+    hs::launch(dim3(nscan), dim3(kScanThreads), 0, [&] { k_scan_reduce2(off.data(), loff.data(), nrec, blocks.data(), blocks2.data()); });
+    hs::launch(dim3(1), dim3(1024), 0, [&] { k_scan_blocks2(blocks.data(), blocks2.data(), nscan, &meta.out_total, &meta.lines_total); });
+    hs::launch(dim3(nscan), dim3(kScanThreads), 0, [&] {
+        k_scan_apply2(off.data(), loff.data(), nrec, blocks.data(), blocks2.data(), &meta.out_total, &meta.lines_total, rec.data(), map.data());
+    });
     std::vector<u8> out(meta.out_total + 256, 0xEE);
     la.out = out.data();
     if (meta.lines_total) {
         const u32 nl = (u32)meta.lines_total;
-        std::vector<LineMapEnt> map(nl);
-        hs::launch(dim3((nrec + 255) / 256), dim3(256), 0, [&] { k_line_map(loff.data(), rec.data(), off.data(), nrec, map.data()); });
         EmitArgs ea{gaf, n, rec.data(), off.data(), sdesc.data(), map.data(), rdesc.data(), nl, out.data()};
         hs::launch(dim3((nl + kEThreads - 1) / kEThreads), dim3(kEThreads), kEmitSmem, [&] { k_emit_lines(ea); });
     }
