@@ -102,6 +102,7 @@ struct g2p_ctx {
     std::vector<g2p_warn> warns;
     size_t host_chunk = kHostChunk;
     bool host_chunk_fixed = false;   // G2P_HOST_CHUNK_MB given: no adaptation to the record length
+    bool two_pass_index = false;     // G2P_TWO_PASS_INDEX=1 (tests): use the counting index kernels
     uint64_t desc_cap_override = 0;  // G2P_DESC_CAP (tests): line-descriptor slots, to exercise the overflow fallback
     void set_err(const std::string& m) { std::lock_guard<std::mutex> g(err_mu); err = m; }
 };
@@ -134,6 +135,7 @@ int g2p_create(int device, g2p_ctx** out) {
     cudaFuncSetAttribute(k_long<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)long_smem<true>());
     cudaFuncSetAttribute(k_long<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)long_smem<false>());
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
+    if (const char* c = std::getenv("G2P_TWO_PASS_INDEX")) ctx->two_pass_index = std::atoi(c) != 0;
     if (const char* c = std::getenv("G2P_DESC_CAP")) ctx->desc_cap_override = std::strtoull(c, nullptr, 10);
     if (const char* c = std::getenv("G2P_HOST_CHUNK_MB")) {
         long v = std::atol(c);
@@ -193,18 +195,34 @@ int g2p_load_lengths(g2p_ctx* ctx, const char* tsv, size_t n) {
 
 uint64_t g2p_table_entries(const g2p_ctx* ctx) { return ctx ? ctx->table_entries : 0; }
 
-// Line index into w.d_rec; leaves meta (n_lines, n_records) in w.h_meta.
+// Line index into w.d_rec; leaves meta (n_lines, n_records) in w.h_meta.  One pass over the text
+// (k_index1) with an index capacity of one record per 32 bytes; texts with more lines than that
+// take the counting kernels.
 static int run_index(g2p_ctx* ctx, Worker& w, const u8* d_text, size_t n, cudaStream_t st, uint32_t* launches) {
     const u32 ntiles = (u32)((n + kIdxTile - 1) / kIdxTile);
-    G2P_CUDA(w.d_tiles.ensure(((size_t)ntiles + 1) * sizeof(u32)));
+    G2P_CUDA(w.d_tiles.ensure(((size_t)ntiles + 2) * sizeof(u64)));
     PipelineMeta* d_meta = static_cast<PipelineMeta*>(w.d_meta.p);
+    const PipelineMeta* hm = static_cast<const PipelineMeta*>(w.h_meta.p);
+    if (ntiles && !ctx->two_pass_index) {
+        const u64 cap64 = std::min<u64>((u64)n / 32 + 1024, 0xFFFFFFF0ULL);
+        G2P_CUDA(w.d_rec.ensure((size_t)cap64 * sizeof(u32)));
+        u64* d_status = static_cast<u64*>(w.d_tiles.p);
+        u32* d_ticket = reinterpret_cast<u32*>(d_status + ntiles);
+        G2P_CUDA(cudaMemsetAsync(d_status, 0, ((size_t)ntiles + 1) * sizeof(u64), st));
+        k_index1<<<ntiles, kIdxThreads, 0, st>>>(d_text, n, ntiles, d_status, d_ticket, static_cast<u32*>(w.d_rec.p), (u32)cap64, d_meta);
+        ++*launches;
+        G2P_CUDA(cudaMemcpyAsync(w.h_meta.p, d_meta, sizeof(PipelineMeta), cudaMemcpyDeviceToHost, st));
+        G2P_CUDA(cudaStreamSynchronize(st));
+        G2P_CUDA(cudaGetLastError());
+        if ((u64)hm->n_records + 2 <= cap64) return G2P_OK;
+        // more lines than the capacity guess: count first
+    }
     u32* d_tiles = static_cast<u32*>(w.d_tiles.p);
     if (ntiles) { k_count_lines<<<ntiles, kIdxThreads, 0, st>>>(d_text, n, d_tiles); ++*launches; }
     k_scan_tiles<<<1, 1024, 0, st>>>(d_tiles, ntiles, d_text, n, d_meta);
     ++*launches;
     G2P_CUDA(cudaMemcpyAsync(w.h_meta.p, d_meta, sizeof(PipelineMeta), cudaMemcpyDeviceToHost, st));
     G2P_CUDA(cudaStreamSynchronize(st));
-    const PipelineMeta* hm = static_cast<const PipelineMeta*>(w.h_meta.p);
     G2P_CUDA(w.d_rec.ensure(((size_t)hm->n_records + 2) * sizeof(u32)));
     if (ntiles) {
         k_fill_lines<<<ntiles, kIdxThreads, 0, st>>>(d_text, n, d_tiles, static_cast<u32*>(w.d_rec.p), d_meta);

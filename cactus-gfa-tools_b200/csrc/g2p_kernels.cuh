@@ -1,6 +1,7 @@
 // g2p_kernels.cuh — sm_100a kernels of the GAF -> PAF pipeline.
 //
-//   k_count_lines / k_scan_tiles / k_fill_lines   newline index (record start offsets)
+//   k_index1                                       newline index in one pass (TMA tiles + decoupled look-back)
+//   k_count_lines / k_scan_tiles / k_fill_lines   two-pass newline index (fallback when the index capacity guess is too small)
 //   k_short / k_long<false> / k_convert_list<false>  pass 1: per-record PAF byte length, status, line descriptors
 //   k_scan_*                                       exclusive scans: byte lengths -> output offsets, line counts -> line slots
 //   k_line_map + k_emit_lines                      pass 2: one thread per PAF line writes the bytes
@@ -158,6 +159,135 @@ __global__ void __launch_bounds__(kIdxThreads) k_fill_lines(const u8* __restrict
                 m &= m - 1;
                 u64 p = off + j * 4 + (bit >> 3);
                 rec_start[rank + 1] = (u32)(p + 1);
+                ++rank;
+            }
+        }
+        kbase += (u32)((total >> (16 * k)) & 0xffff);
+    }
+}
+
+// ------------------------------------------------------------------------------
+// Single-pass line index.  Each CTA takes the next 16 KiB tile (ticket counter), brings it into
+// shared memory with one TMA bulk copy (cp.async.bulk + mbarrier), counts its newlines with SWAR
+// compares, ranks them with a block scan, obtains the number of newlines before the tile with a
+// decoupled look-back over the per-tile status words (flag in the top two bits, value below:
+// 1 = the tile's own count, 2 = inclusive prefix), and writes the record starts.  The text is
+// read from HBM once.  rec_start has room for `cap` entries; when the text holds more lines than
+// that (blank-line floods), nothing past the capacity is written and the caller falls back to
+// the counting kernels above.
+// ------------------------------------------------------------------------------
+constexpr u64 kIdxFlagAgg = 1ull << 62, kIdxFlagPre = 2ull << 62, kIdxValMask = (1ull << 62) - 1;
+
+__global__ void __launch_bounds__(kIdxThreads) k_index1(const u8* __restrict__ text, u64 n, u32 ntiles, u64* tile_status, u32* ticket,
+                                                        u32* __restrict__ rec_start, u32 cap, PipelineMeta* __restrict__ meta) {
+    __shared__ __align__(16) u8 s_text[kIdxTile];
+    __shared__ u64 wtot[kIdxThreads / 32];
+    __shared__ u32 s_tile, s_prefix;
+#if !defined(G2P_HOSTSIM)
+    __shared__ __align__(8) u64 s_bar;
+    if (threadIdx.x == 0) { s_tile = atomicAdd(ticket, 1u); mbar_init(&s_bar, 1); fence_mbar_init(); }
+#else
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+#endif
+    __syncthreads();
+    const u32 tile = s_tile;
+    const u64 base = (u64)tile * kIdxTile;
+    const u32 bytes = (u32)(n - base < (u64)kIdxTile ? n - base : (u64)kIdxTile);
+    const u32 full = bytes & ~15u;
+#if !defined(G2P_HOSTSIM)
+    if (threadIdx.x == 0 && full) { mbar_expect_tx(&s_bar, full); bulk_g2s(s_text, text + base, full, &s_bar); }
+    if (threadIdx.x < bytes - full) s_text[full + threadIdx.x] = text[base + full + threadIdx.x];   // last partial vector
+    if (full) { u32 spins = 0; while (!mbar_try_wait(&s_bar, 0)) { if (++spins > (1u << 24)) __trap(); } }
+#else
+    (void)full;
+    for (u32 i = threadIdx.x; i < bytes; i += kIdxThreads) s_text[i] = text[base + i];
+#endif
+    __syncthreads();
+    uint4 v[kIdxVec];
+    u64 packed = 0;   // four 16-bit counters, one per k
+#pragma unroll
+    for (int k = 0; k < kIdxVec; ++k) {
+        const u32 off = ((u32)k * kIdxThreads + threadIdx.x) * 16;
+        v[k] = make_uint4(0, 0, 0, 0);
+        if (off < bytes) {
+            v[k] = *reinterpret_cast<const uint4*>(s_text + off);
+            if (off + 16 > bytes) {   // bytes past the end of the text are not part of it
+                u32 w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+                for (u32 i = bytes - off; i < 16; ++i) w[i >> 2] &= ~(0xffu << (8 * (i & 3)));
+                v[k] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+        const u32 c = __popc(nl_bits(v[k].x)) + __popc(nl_bits(v[k].y)) + __popc(nl_bits(v[k].z)) + __popc(nl_bits(v[k].w));
+        packed |= (u64)c << (16 * k);
+    }
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u64 incl = packed;
+    for (int o = 1; o < 32; o <<= 1) {
+        const u64 up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (u32)o) incl += up;
+    }
+    if (lane == 31) wtot[warp] = incl;
+    __syncthreads();
+    u64 wpre = 0, total = 0;
+    for (int i = 0; i < kIdxThreads / 32; ++i) { if (i < (int)warp) wpre += wtot[i]; total += wtot[i]; }
+    const u64 excl = wpre + incl - packed;
+    const u32 tile_count = (u32)((total & 0xffff) + ((total >> 16) & 0xffff) + ((total >> 32) & 0xffff) + ((total >> 48) & 0xffff));
+    // ---- decoupled look-back (warp 0)
+    if (warp == 0) {
+        volatile u64* st = tile_status;
+        u64 prefix = 0;
+        if (tile > 0) {
+            if (lane == 0) { st[tile] = kIdxFlagAgg | tile_count; }
+            __syncwarp();
+            int j = (int)tile - 1;
+            for (;;) {
+                const int idx = j - (int)lane;
+                u64 w = kIdxFlagPre;   // tiles before the first: prefix 0
+                if (idx >= 0) {
+                    u32 spins = 0;
+                    while (((w = st[idx]) >> 62) == 0) { if (++spins > (1u << 26)) __trap(); }
+                }
+                const u32 pre = __ballot_sync(0xffffffffu, (w >> 62) == 2);
+                const u32 upto = pre ? (u32)__ffs((int)pre) - 1u : 31u;   // lanes 0..upto contribute
+                u64 val = lane <= upto ? (w & kIdxValMask) : 0;
+                for (int o = 16; o > 0; o >>= 1) val += __shfl_down_sync(0xffffffffu, val, o);
+                prefix += __shfl_sync(0xffffffffu, val, 0);
+                if (pre) break;
+                j -= 32;
+            }
+        }
+        if (lane == 0) {
+            st[tile] = kIdxFlagPre | (prefix + tile_count);
+            s_prefix = (u32)prefix;
+            if (tile == ntiles - 1) {   // totals + the fields the later kernels expect initialised
+                const u32 lines = (u32)prefix + tile_count;
+                const u32 recs = lines + ((n > 0 && text[n - 1] != '\n') ? 1u : 0u);
+                meta->n_lines = lines;
+                meta->n_records = recs;
+                meta->first_err = 0xFFFFFFFFu;
+                meta->out_total = 0;
+                meta->err_status = 0;
+                meta->n_deleg = 0; meta->n_deleg2 = 0; meta->n_desc = 0; meta->legacy_long = 0; meta->lines_total = 0;
+                if (recs != lines && recs < cap) rec_start[recs] = (u32)n + 1;   // unterminated last line
+            }
+            if (tile == 0 && cap) rec_start[0] = 0;
+        }
+    }
+    __syncthreads();
+    u32 kbase = s_prefix;
+#pragma unroll
+    for (int k = 0; k < kIdxVec; ++k) {
+        u32 rank = kbase + (u32)((excl >> (16 * k)) & 0xffff);
+        const u64 off = base + ((u64)k * kIdxThreads + threadIdx.x) * 16;
+        const u32 w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            u32 m = nl_bits(w[j]);
+            while (m) {
+                const u32 bit = __ffs(m) - 1;
+                m &= m - 1;
+                const u64 p = off + j * 4 + (bit >> 3);
+                if (rank + 1 < cap) rec_start[rank + 1] = (u32)(p + 1);
                 ++rank;
             }
         }

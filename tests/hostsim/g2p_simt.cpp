@@ -56,12 +56,26 @@ int main(int argc, char** argv) {
     PipelineMeta meta;
     std::memset(&meta, 0, sizeof meta);
     const u32 ntiles = (u32)((n + kIdxTile - 1) / kIdxTile);
-    std::vector<u32> tiles(ntiles + 1);
-    if (ntiles) hs::launch(dim3(ntiles), dim3(kIdxThreads), 0, [&] { k_count_lines(gaf, n, tiles.data()); });
-    hs::launch(dim3(1), dim3(1024), 0, [&] { k_scan_tiles(tiles.data(), ntiles, gaf, n, &meta); });
-    const u32 nrec = meta.n_records;
-    std::vector<u32> rec(nrec + 2);
-    if (ntiles) hs::launch(dim3(ntiles), dim3(kIdxThreads), 0, [&] { k_fill_lines(gaf, n, tiles.data(), rec.data(), &meta); });
+    std::vector<u32> rec;
+    u32 nrec = 0;
+    bool indexed = false;
+    if (ntiles && !std::getenv("G2P_TWO_PASS_INDEX")) {   // single-pass index, capacity like run_index (g2p_capi.cu)
+        const u64 cap = std::getenv("G2P_SIMT_INDEX_CAP") ? (u64)std::atol(std::getenv("G2P_SIMT_INDEX_CAP")) : n / 32 + 1024;
+        rec.assign(cap + 2, 0xDEADBEEFu);
+        std::vector<u64> tstat(ntiles + 1, 0);
+        u32* ticket = reinterpret_cast<u32*>(&tstat[ntiles]);
+        hs::launch(dim3(ntiles), dim3(kIdxThreads), 0, [&] { k_index1(gaf, n, ntiles, tstat.data(), ticket, rec.data(), (u32)cap, &meta); });
+        nrec = meta.n_records;
+        indexed = (u64)nrec + 2 <= cap;
+    }
+    if (!indexed) {
+        std::vector<u32> tiles(ntiles + 1);
+        if (ntiles) hs::launch(dim3(ntiles), dim3(kIdxThreads), 0, [&] { k_count_lines(gaf, n, tiles.data()); });
+        hs::launch(dim3(1), dim3(1024), 0, [&] { k_scan_tiles(tiles.data(), ntiles, gaf, n, &meta); });
+        nrec = meta.n_records;
+        rec.assign(nrec + 2, 0);
+        if (ntiles) hs::launch(dim3(ntiles), dim3(kIdxThreads), 0, [&] { k_fill_lines(gaf, n, tiles.data(), rec.data(), &meta); });
+    }
     if (nrec == 0) return 0;
 
     std::vector<u32> status(nrec), list(nrec), list2(nrec);

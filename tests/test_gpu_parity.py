@@ -341,3 +341,34 @@ def test_descriptor_overflow_falls_back_to_reparsing_emit(g2p, monkeypatch):
         cv.close()
     rc, ref, err, kind = H.run_gaf2paf_cpu(gaf, lengths)
     assert rc == 0 and g2p.exit_code(res) == 0 and out == ref
+
+
+def test_two_pass_index_fallback(g2p, monkeypatch):
+    """The counting index kernels (used when a text has more lines than the single-pass index's
+    capacity guess) give the same result; a blank-line flood exercises the automatic fallback."""
+    p = H.preset("short", seed=111, pct_star=1)
+    lengths = H.gen_lengths(p)
+    gaf = H.gen_records(p, 0, 30000)
+    monkeypatch.setenv("G2P_TWO_PASS_INDEX", "1")
+    cv = g2p.Converter(0)
+    try:
+        assert cv.load_lengths(lengths)
+        out, res = cv.convert_host(gaf)
+        out_nonl, _ = cv.convert_host(gaf[:-1])          # unterminated last line
+    finally:
+        cv.close()
+    monkeypatch.delenv("G2P_TWO_PASS_INDEX")
+    rc, ref, err, kind = H.run_gaf2paf_cpu(gaf, lengths)
+    assert rc == 0 and out == ref and out_nonl == ref
+    cv = g2p.Converter(0)
+    try:
+        assert cv.load_lengths(lengths)
+        out1, _ = cv.convert_host(gaf[:-1])
+        assert out1 == ref
+        flood = gaf[:5000].rsplit(b"\n", 1)[0] + b"\n" * 200000   # far more lines than bytes / 32: reference aborts on the first blank line
+        o2, r2 = cv.convert_host(flood)
+        rc2, ref2, err2, _ = H.run_gaf2paf_cpu(flood, lengths)
+        assert rc2 == 134 and g2p.exit_code(r2) == 134 and r2.n_records == flood.count(b"\n")
+        assert o2 == ref2[:len(o2)]
+    finally:
+        cv.close()
