@@ -102,7 +102,7 @@ struct g2p_ctx {
     std::vector<g2p_warn> warns;
     size_t host_chunk = kHostChunk;
     bool host_chunk_fixed = false;   // G2P_HOST_CHUNK_MB given: no adaptation to the record length
-    bool two_pass_index = false;     // G2P_TWO_PASS_INDEX=1 (tests): use the counting index kernels
+    bool two_pass_index = true;      // default: counting index (count, scan, fill); G2P_ONE_PASS_INDEX=1 selects k_index1 (measured slower, see profiles/r01_summary.md)
     uint64_t desc_cap_override = 0;  // G2P_DESC_CAP (tests): line-descriptor slots, to exercise the overflow fallback
     void set_err(const std::string& m) { std::lock_guard<std::mutex> g(err_mu); err = m; }
 };
@@ -135,7 +135,7 @@ int g2p_create(int device, g2p_ctx** out) {
     cudaFuncSetAttribute(k_long<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)long_smem<true>());
     cudaFuncSetAttribute(k_long<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)long_smem<false>());
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
-    if (const char* c = std::getenv("G2P_TWO_PASS_INDEX")) ctx->two_pass_index = std::atoi(c) != 0;
+    if (const char* c = std::getenv("G2P_ONE_PASS_INDEX")) ctx->two_pass_index = std::atoi(c) == 0;
     if (const char* c = std::getenv("G2P_DESC_CAP")) ctx->desc_cap_override = std::strtoull(c, nullptr, 10);
     if (const char* c = std::getenv("G2P_HOST_CHUNK_MB")) {
         long v = std::atol(c);
@@ -195,9 +195,11 @@ int g2p_load_lengths(g2p_ctx* ctx, const char* tsv, size_t n) {
 
 uint64_t g2p_table_entries(const g2p_ctx* ctx) { return ctx ? ctx->table_entries : 0; }
 
-// Line index into w.d_rec; leaves meta (n_lines, n_records) in w.h_meta.  One pass over the text
-// (k_index1) with an index capacity of one record per 32 bytes; texts with more lines than that
-// take the counting kernels.
+// Line index into w.d_rec; leaves meta (n_lines, n_records) in w.h_meta.  Default: the counting
+// kernels (count, scan, fill: two reads of the text, no inter-CTA dependency).  The one-pass
+// variant (k_index1: TMA tiles + decoupled look-back, index capacity of one record per 32 bytes with
+// the counting kernels as its overflow fallback) is selectable but measured slower on B200: its
+// 16 KiB tiles are too small to amortise the ticket / TMA / look-back latency chain.
 static int run_index(g2p_ctx* ctx, Worker& w, const u8* d_text, size_t n, cudaStream_t st, uint32_t* launches) {
     const u32 ntiles = (u32)((n + kIdxTile - 1) / kIdxTile);
     G2P_CUDA(w.d_tiles.ensure(((size_t)ntiles + 2) * sizeof(u64)));

@@ -59,7 +59,7 @@ int main(int argc, char** argv) {
     std::vector<u32> rec;
     u32 nrec = 0;
     bool indexed = false;
-    if (ntiles && !std::getenv("G2P_TWO_PASS_INDEX")) {   // single-pass index, capacity like run_index (g2p_capi.cu)
+    if (ntiles && !std::getenv("G2P_TWO_PASS_INDEX")) {   // the emulator exercises the single-pass index by default (the library defaults to the counting kernels)
         const u64 cap = std::getenv("G2P_SIMT_INDEX_CAP") ? (u64)std::atol(std::getenv("G2P_SIMT_INDEX_CAP")) : n / 32 + 1024;
         rec.assign(cap + 2, 0xDEADBEEFu);
         std::vector<u64> tstat(ntiles + 1, 0);

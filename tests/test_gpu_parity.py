@@ -343,13 +343,13 @@ def test_descriptor_overflow_falls_back_to_reparsing_emit(g2p, monkeypatch):
     assert rc == 0 and g2p.exit_code(res) == 0 and out == ref
 
 
-def test_two_pass_index_fallback(g2p, monkeypatch):
-    """The counting index kernels (used when a text has more lines than the single-pass index's
-    capacity guess) give the same result; a blank-line flood exercises the automatic fallback."""
+def test_one_pass_index_variant(g2p, monkeypatch):
+    """The optional single-pass index (k_index1: TMA tiles + decoupled look-back) gives the same
+    result as the default counting kernels; a blank-line flood exercises its capacity fallback."""
     p = H.preset("short", seed=111, pct_star=1)
     lengths = H.gen_lengths(p)
     gaf = H.gen_records(p, 0, 30000)
-    monkeypatch.setenv("G2P_TWO_PASS_INDEX", "1")
+    monkeypatch.setenv("G2P_ONE_PASS_INDEX", "0")
     cv = g2p.Converter(0)
     try:
         assert cv.load_lengths(lengths)
@@ -357,7 +357,7 @@ def test_two_pass_index_fallback(g2p, monkeypatch):
         out_nonl, _ = cv.convert_host(gaf[:-1])          # unterminated last line
     finally:
         cv.close()
-    monkeypatch.delenv("G2P_TWO_PASS_INDEX")
+    monkeypatch.setenv("G2P_ONE_PASS_INDEX", "1")
     rc, ref, err, kind = H.run_gaf2paf_cpu(gaf, lengths)
     assert rc == 0 and out == ref and out_nonl == ref
     cv = g2p.Converter(0)
