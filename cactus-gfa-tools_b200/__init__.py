@@ -120,6 +120,11 @@ def _load():
 lib = _load()
 
 
+def _bytes_at(addr, n):
+    """bytes of n bytes at a raw address (ctypes.string_at takes an int-sized length: not enough for > 2 GiB)."""
+    return bytes((ctypes.c_char * n).from_address(addr)) if n else b""
+
+
 def _buf_ptr(b):
     """(address, length, keepalive) of a bytes / bytearray / memoryview / (addr, n) pair."""
     if isinstance(b, tuple):
@@ -175,7 +180,7 @@ class Converter:
         out = ctypes.c_void_p()
         res = Result()
         self._check(lib.g2p_convert_host(self._h, addr, n, ctypes.byref(out), ctypes.byref(res)))
-        return ctypes.string_at(out.value, res.out_bytes) if res.out_bytes else b"", res
+        return _bytes_at(out.value, res.out_bytes), res
 
     def convert_host_raw(self, addr, n):
         """Like convert_host for a raw (pinned) host address; returns (out address, Result) without copying."""
@@ -223,7 +228,7 @@ class Converter:
         out = ctypes.c_void_p()
         res = Result()
         self._check(lib.g2p_unstable_host(self._h, addr, n, ctypes.byref(out), ctypes.byref(res)))
-        data = ctypes.string_at(out.value, res.out_bytes) if res.out_bytes else b""
+        data = _bytes_at(out.value, res.out_bytes)
         wp, wn = ctypes.POINTER(Warn)(), ctypes.c_size_t()
         self._check(lib.g2p_unstable_warnings(self._h, ctypes.byref(wp), ctypes.byref(wn)))
         warns = []
