@@ -29,7 +29,10 @@ enum : u32 { ST_F_LONG = 0x20000u };   // status flag: record was converted by k
 
 constexpr int kLWarps = 4;
 constexpr int kLThreads = kLWarps * 32;
-constexpr u32 kLRing = 512;      // ring entries (power of two, >= 33 + 256)
+#ifndef G2P_LONG_RING
+#define G2P_LONG_RING 256
+#endif
+constexpr u32 kLRing = G2P_LONG_RING;   // ring entries (power of two); a refill that would not fit flags the stream (record delegated)
 constexpr u32 kLChunk = 512;     // bytes classified per refill
 constexpr u32 kLBatch = 31;      // steps per batch; the next lane holds the batch's end boundary
 constexpr u32 kLOutCap = 5120;   // staged PAF bytes per batch
@@ -99,10 +102,11 @@ struct TokStream {
     u32 cur;           // base of the next chunk (multiple of kLChunk)
     u32 head, count;
     u32 tlo, thi;      // offsets currently held in `text`: [tlo, thi)
-    bool bwd, done;
+    bool bwd, done, overflow;
 
     __device__ __forceinline__ void init(u32* ring_, u8* text_, const u8* gaf_, u32 lo_, u32 hi_, bool bwd_) {
         ring = ring_; text = text_; gaf = gaf_; lo = lo_; hi = hi_; bwd = bwd_;
+        overflow = false;
         head = count = 0;
         tlo = thi = 0;
         done = hi_ <= lo_;
@@ -135,6 +139,7 @@ struct TokStream {
         const u32 cnt = (u32)__popc(m);
         const u32 incl = wscan32(cnt, lane);
         const u32 total = __shfl_sync(0xffffffffu, incl, 31);
+        if (count + total > kLRing) { overflow = true; done = true; __syncwarp(); return; }   // pathologically dense tokens
         if (!bwd) {
             u32 k = head + count + incl - cnt;
             while (m) { const u32 b = (u32)__ffs((int)m) - 1u; m &= m - 1u; ring[k & (kLRing - 1u)] = off + b; ++k; }
@@ -593,7 +598,7 @@ __device__ __forceinline__ void long_record(const LongArgs& a, LWarpMemT<EMIT>* 
             load_window();
             if (__any_sync(FULL, lbad != 0)) break;
         }
-        if (__any_sync(FULL, lbad != 0) || top_lp != cB - 1) { deleg = true; break; }
+        if (__any_sync(FULL, lbad != 0) || top_lp != cB - 1 || ss.overflow || os.overflow) { deleg = true; break; }
         size = run;
     } while (0);
     __syncwarp();

@@ -759,6 +759,8 @@ struct EmitArgs {
     const LineDesc* desc;
     const LineMapEnt* map;   // line slot -> descriptor + record offsets (k_short's records), or null: slot == descriptor index
     const RecDesc* rdesc;
+    const u32* status;       // dense mode: a line is emitted only if its record kept ST_F_DESC (k_long may describe the first
+                             // batches of a record and delegate it later)
     u32 n_slots;
     u8* out;
 };
@@ -810,7 +812,7 @@ __global__ void __launch_bounds__(kEThreads) k_emit_lines(const EmitArgs a) {
     LineStep L;
     unpack_line_desc(v0, v1, v2, v3, d.rec, d.loff, d.len, L);
     if (!in_range) d.len = 0;
-    const bool valid = a.map ? in_range : d.rec != kDescInvalid;
+    const bool valid = a.map ? in_range : (d.rec != kDescInvalid && (__ldg(a.status + d.rec) & ST_F_DESC) != 0);
     const u32 vmask = __ballot_sync(FULL, valid);
     if (vmask == 0) return;
     const int first = __ffs((int)vmask) - 1, last = 31 - __clz((int)vmask);

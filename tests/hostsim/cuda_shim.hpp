@@ -263,9 +263,13 @@ void launch(dim3 grid, dim3 block, size_t dyn_smem, const std::function<void()>&
     for (int i = 0; i < nt; ++i) th[i].stack = stacks + (size_t)i * kStack;
     g_bdim = block; g_gdim = grid; g_body = &body;
     g_dyn_smem = (unsigned char*)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
+    // G2P_SIMT_REVERSE=1 runs the CTAs of every launch in reverse order: kernels must not depend on
+    // the order their CTAs happen to execute in (tickets / look-back excepted, which do not use blockIdx)
+    static const bool reverse = std::getenv("G2P_SIMT_REVERSE") != nullptr;
     for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
-    for (unsigned bx = 0; bx < grid.x; ++bx) {
+    for (unsigned bi = 0; bi < grid.x; ++bi) {
+        const unsigned bx = reverse ? grid.x - 1 - bi : bi;
         g_block = uint3{bx, by, bz};
         std::memset(g_dyn_smem, 0xCD, dyn_smem);
         for (int i = 0; i < nt; ++i) {

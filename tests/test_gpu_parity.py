@@ -372,3 +372,21 @@ def test_one_pass_index_variant(g2p, monkeypatch):
         assert o2 == ref2[:len(o2)]
     finally:
         cv.close()
+
+
+def test_late_delegation(g2p):
+    """Long records that k_long delegates after having described some of their lines (non-canonical
+    or invalid last CIGAR op), in the middle and at the very end of the buffer."""
+    import test_oracle
+    lengths, cases = test_oracle._late_cases()
+    cv = g2p.Converter(0)
+    try:
+        assert cv.load_lengths(lengths)
+        for name, lines in cases.items():
+            data = b"\n".join(lines) + b"\n"
+            out, res = cv.convert_host(data)
+            rc, ref, err, kind = H.run_gaf2paf_cpu(data, lengths)
+            assert g2p.exit_code(res) == rc, name
+            assert (out == ref) if rc != 134 else ref.startswith(out), name
+    finally:
+        cv.close()

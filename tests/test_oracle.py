@@ -127,3 +127,50 @@ def test_gaf2unstable_differential(seed, aligned):
         assert serr.count("warning") == err.count("[gaf2unstable] warning")
         rc, out, serr = H.run_tool(G2U_PORT, ["-g", gp, "-o", lp, "-"], gaf)   # oracle restatement: stderr verbatim too
         assert rc == 0 and out == ref and open(lp, "rb").read() == nl and serr == err
+
+
+# ---- records delegated late (after k_long has already described some of their lines) ---------
+def _late_cases():
+    import re
+    pm, ps = H.preset("medium", seed=5), H.preset("short", seed=5)
+    lengths = H.gen_lengths(ps)
+    med = H.gen_records(pm, 0, 6, threads=1).split(b"\n")[:-1]
+    short = H.gen_records(ps, 0, 400, threads=1).split(b"\n")[:-1]
+
+    def last_op(line, f):
+        i = line.rfind(b"cg:Z:")
+        j = line.find(b"\t", i)
+        cg = line[i: j if j > 0 else len(line)]
+        ops = re.findall(rb"\d+[A-Z=]", cg[5:])
+        ops[-1] = f(ops[-1])
+        return line[:i] + b"cg:Z:" + b"".join(ops) + (line[j:] if j > 0 else b"")
+
+    noncanon = last_op(med[4], lambda o: b"0" + o)        # leading zero in the last op: valid, not canonical
+    abort = last_op(med[2], lambda o: o[:-1] + b"Q")      # invalid letter at the very end: the reference aborts
+    return lengths, {
+        "late-noncanonical": med[:2] + short[:150] + [noncanon] + short[150:300] + [med[5]] + short[300:],
+        "late-abort-last": med[:2] + short[:150] + [noncanon] + short[150:] + [abort],
+        "late-abort-middle": med[:2] + short[:150] + [abort] + short[150:],
+    }
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference build (oracle/_ref) not present")
+@pytest.mark.parametrize("reverse", [False, True])
+def test_late_delegation_under_emulator(reverse):
+    """k_long describes a long record batch by batch; when the record turns out non-canonical near
+    its end it is delegated, and the lines already described must not be emitted from the
+    descriptors.  Run with the emulator's CTAs in both orders."""
+    lengths, cases = _late_cases()
+    env = dict(os.environ, G2P_SIMT_REVERSE="1") if reverse else dict(os.environ)
+    import subprocess
+    with tempfile.TemporaryDirectory() as td:
+        lp = os.path.join(td, "l.tsv")
+        open(lp, "wb").write(lengths)
+        for name, lines in cases.items():
+            data = b"\n".join(lines) + b"\n"
+            rc, ref, err = H.run_tool(REF, ["-", "-l", lp], data)
+            for binary in (SIMT, SIMT + "_long"):
+                p = subprocess.run([binary, "-l", lp, "-"], input=data, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+                got_rc = p.returncode if p.returncode >= 0 else 128 - p.returncode
+                assert got_rc == rc, name
+                assert (p.stdout == ref) if rc != 134 else ref.startswith(p.stdout), name
