@@ -103,6 +103,8 @@ struct g2p_ctx {
     size_t host_chunk = kHostChunk;
     bool host_chunk_fixed = false;   // G2P_HOST_CHUNK_MB given: no adaptation to the record length
     bool two_pass_index = true;      // default: counting index (count, scan, fill); G2P_ONE_PASS_INDEX=1 selects k_index1 (measured slower, see profiles/r01_summary.md)
+    bool size_kernel_short = false;  // G2P_SIZE_KERNEL=short: k_short (8 lanes per record) instead of k_rec (thread per record)
+    uint32_t rec_chunks_override = 0; // G2P_REC_CHUNKS: k_rec slot capacity in 16-byte chunks
     uint64_t desc_cap_override = 0;  // G2P_DESC_CAP (tests): line-descriptor slots, to exercise the overflow fallback
     void set_err(const std::string& m) { std::lock_guard<std::mutex> g(err_mu); err = m; }
 };
@@ -131,6 +133,9 @@ int g2p_create(int device, g2p_ctx** out) {
     for (auto& w : ctx->w)
         if (!w.init()) { g2p_destroy(ctx); return G2P_E_NO_DEVICE; }
     cudaFuncSetAttribute(k_short<kSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShortSmem);
+    cudaFuncSetAttribute(k_rec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rec_smem(kRMaxChunks));
+    if (const char* c = std::getenv("G2P_SIZE_KERNEL")) ctx->size_kernel_short = std::strcmp(c, "short") == 0;
+    if (const char* c = std::getenv("G2P_REC_CHUNKS")) ctx->rec_chunks_override = (u32)std::min(std::max(std::atoi(c), (int)kRMinChunks), (int)kRMaxChunks);
     cudaFuncSetAttribute(k_emit_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmitSmem);
     cudaFuncSetAttribute(k_long<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)long_smem<true>());
     cudaFuncSetAttribute(k_long<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)long_smem<false>());
@@ -304,7 +309,12 @@ static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
 
     // pass 1: sizes, status, line descriptors.  k_short takes the short canonical records, k_long
     // what it left, the general kernel what neither converts (non-canonical or erroneous records).
-    k_short<kSG><<<ncta, kSThreads, kShortSmem, st>>>(sa);
+    if (ctx->size_kernel_short) k_short<kSG><<<ncta, kSThreads, kShortSmem, st>>>(sa);
+    else {
+        const u32 chunks = ctx->rec_chunks_override ? ctx->rec_chunks_override : rec_chunks_for((u64)n, nrec);
+        RecArgs ra{sa, chunks};
+        k_rec<<<(nrec + kRThreads - 1) / kRThreads, kRThreads, rec_smem(chunks), st>>>(ra);
+    }
     k_long<false><<<nlong, kLThreads, long_smem<false>(), st>>>(la);
     k_convert_list<false><<<nlist, kListThreads, 0, st>>>(d_gaf, d_rec, ctx->table, d_off, d_status, nullptr, d_meta, d_list2, &d_meta->n_deleg2);
     launches += 3;

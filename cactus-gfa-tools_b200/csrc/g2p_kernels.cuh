@@ -2,7 +2,7 @@
 //
 //   k_index1                                       newline index in one pass (TMA tiles + decoupled look-back)
 //   k_count_lines / k_scan_tiles / k_fill_lines   two-pass newline index (fallback when the index capacity guess is too small)
-//   k_short / k_long<false> / k_convert_list<false>  pass 1: per-record PAF byte length, status, line descriptors
+//   k_rec (or k_short) / k_long<false> / k_convert_list<false>  pass 1: per-record PAF byte length, status, line descriptors
 //   k_scan_*                                       exclusive scans: byte lengths -> output offsets, line counts -> line slots
 //   k_line_map + k_emit_lines                      pass 2: one thread per PAF line writes the bytes
 //   k_long<true> / k_convert_list<true>            pass 2 for records without descriptors
@@ -21,6 +21,7 @@
 
 #include "g2p_core.cuh"
 #include "g2p_short.cuh"
+#include "g2p_rec.cuh"
 #include "g2p_long.cuh"
 #include "g2u_core.cuh"
 

@@ -1,0 +1,390 @@
+// g2p_rec.cuh — size pass for short records, one thread per record.
+//
+// k_rec replaces k_short's size pass on the throughput path.  k_short spends ~690 warp
+// instructions per record on coordination (SWAR classification of every byte into three masks,
+// shuffle scans, scatter of token positions, five group votes) with 18 of 32 lanes active.  Here a
+// record is parsed by ONE thread with a plain scalar walk over its text, and the kernel is built
+// so that the 32 lanes of a warp stay in the same loop at the same time:
+//
+//   * staging: the CTA's 256 records are copied from global memory with 128-bit coalesced loads
+//     (8 lanes per record) into per-record shared-memory slots of an ODD number of 32-bit words, so
+//     that lane i's record starts in bank (i * stride) mod 32: byte loads of the 32 lanes at equal
+//     progress hit 32 different banks;
+//   * the walk is a fixed sequence of short loops (one per column, one per tag, one per path step,
+//     one per CIGAR op), never a state machine: lanes re-converge after every loop, the trip count
+//     of a loop is the maximum over the warp of a field length, not of a record length;
+//   * '+' records walk the path and the CIGAR forwards, '-' records backwards (flip_gaf,
+//     gaf2paf_main.cpp:92-131, is index arithmetic); a '-' record first sums its step lengths;
+//   * the CIGAR is cut at step boundaries by streaming (cigar_next_by_target, gaf2paf_main.cpp:71-90):
+//     ops are taken until the step's target quota is reached, the op that crosses the boundary is
+//     split and its remainder starts the next step.
+//
+// Outputs are exactly k_short's: per record the PAF byte count, line count, status and a RecDesc,
+// per PAF line a LineDesc in the record's own kSMaxLines slots; k_line_map / k_emit_lines are
+// unchanged.  Only canonical records are converted (same definition as k_short, see g2p_short.cuh);
+// anything else is appended to the delegate list for k_long / the general kernel.
+#pragma once
+#include "g2p_short.cuh"
+
+namespace g2p {
+
+constexpr int kRThreads = 256;          // records per CTA
+constexpr u32 kRStage = 8;              // lanes per record in the staging copy
+constexpr u32 kRMaxTags = 8;
+constexpr u32 kRMinChunks = 6, kRMaxChunks = 16;   // 16-byte chunks per record slot (host picks from the mean record length)
+#ifndef G2P_REC_CTAS
+#define G2P_REC_CTAS 4
+#endif
+
+__host__ __device__ __forceinline__ u32 rec_slot_words(u32 chunks) { return 4u * chunks + 1u; }   // odd: conflict-free lane stride
+static inline size_t rec_smem(u32 chunks) { return (size_t)kRThreads * rec_slot_words(chunks) * 4u + 32u; }
+
+// Slot capacity for an input of n bytes in nrec records: ~1.4x the mean record, so that the bulk of a
+// short-read file fits while four CTAs stay resident per SM; longer records go to k_long.
+static inline u32 rec_chunks_for(u64 n, u32 nrec) {
+    const u64 mean = nrec ? n / nrec : 0;
+    u64 c = (mean * 7 / 5 + 15) / 16 + 1;
+    if (c < kRMinChunks) c = kRMinChunks;
+    if (c > kRMaxChunks) c = kRMaxChunks;
+    return (u32)c;
+}
+
+struct RecArgs {
+    ShortArgs s;
+    u32 chunks;   // slot capacity in 16-byte chunks: a record is taken if its staged span (phase + bytes + '\n') fits
+};
+
+__device__ __forceinline__ u32 haszero16(u32 x) { return (x - 0x00010001u) & ~x & 0x80008000u; }
+
+// One path-step token "[><]name[:start-end]" at rt[mp .. te) (mp = its marker, or pa - 1 for a bare
+// stable name).  Returns false if not canonical.  The name key is left in (k0, k1).
+struct RStep {
+    u32 name_a, nl;
+    i32 sa, se;      // interval (valid after the probe for whole-contig steps)
+    bool interval;
+};
+__device__ __forceinline__ bool rec_parse_step(const u8* rt, u32 mp, u32 te, bool prefixed, RStep& S, u64& k0, u64& k1) {
+    S.name_a = mp + 1;
+    S.interval = false;
+    S.sa = 0; S.se = 0;
+    u32 k = S.name_a;
+    if (prefixed) {
+        while (k < te && rt[k] != ':') ++k;
+    } else k = te;
+    S.nl = k - S.name_a;
+    if (S.nl == 0 || S.nl > 16) return false;
+    u32 w0, w1, w2, w3;
+    lds16_unaligned(rt + S.name_a, w0, w1, w2, w3);
+    w0 = keep_bytes(w0, (int)S.nl); w1 = keep_bytes(w1, (int)S.nl - 4);
+    w2 = keep_bytes(w2, (int)S.nl - 8); w3 = keep_bytes(w3, (int)S.nl - 12);
+    k0 = (u64)w0 | ((u64)w1 << 32); k1 = (u64)w2 | ((u64)w3 << 32);
+    if (k < te) {   // ":start-end" (gafkluge.hpp:131-146), plain digits only
+        S.interval = true;
+        ++k;
+        u32 x = 0, nd = 0, d;
+        while ((d = (u32)rt[k] - '0') <= 9u) { x = x * 10u + d; ++nd; ++k; }
+        if (nd == 0 || nd > 9 || k >= te || rt[k] != '-') return false;
+        S.sa = (i32)x;
+        ++k; x = 0; nd = 0;
+        while ((d = (u32)rt[k] - '0') <= 9u) { x = x * 10u + d; ++nd; ++k; }
+        if (nd == 0 || nd > 9 || k != te) return false;
+        S.se = (i32)x;
+        if (S.se < S.sa) return false;
+    }
+    return true;
+}
+
+// One CIGAR token in walk direction.  Forward (dir = +1): "digits letter" starts at cp, cp advances
+// past the letter.  Backward (dir = -1): the token ends at cp (exclusive), cp retreats to its first
+// digit.  One digit loop serves both directions so that '+' and '-' records of a warp stay
+// converged.  [ts, te) is the token's text span.
+__device__ __forceinline__ bool rec_fetch_op(const u8* rt, const bool minus, u32& cp, u32& x, u32& kc, u32& ts, u32& te) {
+    u32 k = cp, letter = 0;
+    if (minus) { letter = rt[cp - 1]; k = cp - 2; }   // rt[ca - 1] == ':' stops the backward digit walk
+    const u32 k0 = k;
+    const u32 step = minus ? 0xffffffffu : 1u;
+    u32 v = 0, mul = 1, d, edge = 1, firstd = 1;
+    bool any = false;
+    while ((d = (u32)rt[k] - '0') <= 9u) {
+        v = minus ? v + d * mul : v * 10u + d;
+        mul *= 10u;
+        if (!any) firstd = d;
+        any = true;
+        edge = d;
+        k += step;
+    }
+    const u32 nd = minus ? k0 - k : k - k0;
+    const u32 lead = minus ? edge : firstd;   // most significant digit
+    if (minus) { ts = k + 1; te = cp; cp = k + 1; }
+    else { letter = rt[k]; ts = cp; te = k + 1; cp = k + 1; }
+    kc = letter - '=';
+    x = v;
+    return nd != 0 && nd <= 7 && !(nd > 1 && lead == 0) && v != 0 && kc < 28u && ((kOpMask >> kc) & 1u);
+}
+
+// The record walk after the header: steps and ops in normalised order ('-' records walk both
+// columns backwards).  Returns false to delegate.
+struct RecOut {
+    u32 size, nlines;
+};
+__device__ __forceinline__ bool rec_walk(const ShortArgs& a, const u8* rt, const u32 r, const bool minus, const u32 rconst, const u32* p10,
+                                         const u32 pa, const u32 pb, const bool prefixed, const u32 ca, const u32 cb, const i32 qs, i32 ps,
+                                         i32 pe, RecOut& out) {
+    u64 k0, k1;
+    RStep S;
+    if (minus) {   // flip_gaf: mirror the path interval about the summed step lengths (gaf2paf_main.cpp:111-131)
+        u64 total = 0;
+        u32 mp = prefixed ? pa : pa - 1;
+        for (;;) {
+            u32 te = mp + 1;
+            if (prefixed) { while (te < pb && rt[te] != '>' && rt[te] != '<') ++te; } else te = pb;
+            if (!rec_parse_step(rt, mp, te, prefixed, S, k0, k1)) return false;
+            if (S.interval) total += (u32)(S.se - S.sa);
+            else {
+                i64 tl;
+                if (!table_lookup_key16(a.T, k0, k1, S.nl, tl) || tl < 0 || tl > 0x7fffffffLL) return false;
+                total += (u64)tl;
+            }
+            if (te >= pb) break;
+            mp = te;
+        }
+        if (total > 0x7fffffffULL) return false;
+        const i32 nps = (i32)total - pe, npe = (i32)total - ps;
+        ps = nps; pe = npe;
+    }
+    const i32 W = pe - ps;
+    const u32 cend = minus ? ca : cb;   // CIGAR cursor and where it ends
+    u32 cp = minus ? cb : ca;
+    u32 sp = minus ? pb : pa;           // path cursor: the next token starts at sp (forward) / ends at sp (backward)
+    u32 rem = 0, remk = 0;              // unconsumed part of the op cut by the previous boundary
+    u32 qcur = 0, tbc = 0;              // query / target bases consumed by the steps so far
+    u32 size = 0, nlines = 0;
+    bool first = true;
+    for (;;) {
+        // ---- next step token: [mp, te), mp = its marker
+        u32 mp, te;
+        bool last;
+        if (!prefixed) { mp = pa - 1; te = pb; last = true; }
+        else {
+            // forward: from the marker at sp to the next marker or pb; backward: from sp - 1 down to a marker (rt[pa] is one)
+            u32 k = minus ? sp - 1 : sp + 1;
+            const u32 lim = minus ? pa : pb, step = minus ? 0xffffffffu : 1u;
+            while (k != lim && rt[k] != '>' && rt[k] != '<') k += step;
+            if (minus) { mp = k; te = sp; last = k == pa; }
+            else { mp = sp; te = k; last = k == pb; }
+            sp = k;
+        }
+        if (!rec_parse_step(rt, mp, te, prefixed, S, k0, k1)) return false;
+        i64 tl64;
+        if (!table_lookup_key16(a.T, k0, k1, S.nl, tl64) || tl64 < 0 || tl64 > 0x7fffffffLL) return false;
+        const i32 tlen = (i32)tl64;
+        if (!S.interval) { S.sa = 0; S.se = tlen; }
+        const bool rev = (prefixed && rt[mp] == '<') != minus;
+        const i32 slen = S.se - S.sa;
+        // ---- quota (gaf2paf_main.cpp:176-182)
+        const i32 so = first ? ps : 0;
+        i32 quota = slen - so, eo = 0;
+        if (last) { quota = W - (i32)tbc; eo = slen - so - quota; }
+        if (so < 0 || quota < 0 || eo < 0) return false;
+        first = false;
+        if (quota > 0) {
+            // ---- take `quota` target bases of CIGAR (cigar_next_by_target, gaf2paf_main.cpp:71-90)
+            u32 need = (u32)quota, q = 0, nm = 0, nb = 0;
+            LineStep L;
+            L.lenS = 0; L.codeS = 0; L.mid_a = 0; L.mid_b = 0; L.lenE = 0; L.codeE = 0;
+            bool done = false;
+            if (rem) {   // the remainder of a cut op is target-consuming by construction
+                const u32 take = rem < need ? rem : need;
+                if ((kQueryMask >> remk) & 1u) q += take;
+                if ((kMatchMask >> remk) & 1u) nm += take;
+                nb += take;
+                if (rem >= need) { L.lenE = need; L.codeE = (u8)(remk + '='); rem -= need; done = true; }
+                else { L.lenS = rem; L.codeS = (u8)(remk + '='); need -= rem; rem = 0; }
+            }
+            while (!done) {
+                if (cp == cend) return false;   // :80 assert: CIGAR shorter than the path
+                u32 x, kc, ts, tte;
+                if (!rec_fetch_op(rt, minus, cp, x, kc, ts, tte)) return false;
+                const bool tgt = (kTargetMask >> kc) & 1u;
+                if (tgt && x >= need) {
+                    L.lenE = need; L.codeE = (u8)(kc + '=');
+                    rem = x - need; remk = kc;
+                    x = need;
+                    done = true;
+                } else {
+                    if (tgt) need -= x;
+                    if (L.mid_b == 0) { L.mid_a = ts; L.mid_b = tte; }
+                    else if (minus) L.mid_a = ts;
+                    else L.mid_b = tte;
+                }
+                if ((kQueryMask >> kc) & 1u) q += x;
+                if ((kMatchMask >> kc) & 1u) nm += x;
+                nb += x;
+            }
+            if (nm > 0) {   // gaf2paf_main.cpp:225
+                if (nlines >= kSMaxLines) return false;
+                L.rev = rev;
+                L.mid_fwd = rev == minus;
+                L.q0 = (u32)qs + qcur; L.q1 = L.q0 + q;
+                L.name_a = S.name_a; L.nl = S.nl; L.tlen = (u32)tlen;
+                L.ts = (u32)(S.sa + (rev ? eo : so)); L.te = (u32)(S.se - (rev ? so : eo));
+                L.nm = nm; L.nb = nb;
+                const u32 line = rconst + line_step_len(L, p10);
+                store_line_desc(a.sdesc + (size_t)r * kSMaxLines + nlines, r, size, line, L);
+                size += line;
+                ++nlines;
+            }
+            qcur += q;
+            tbc += (u32)quota;
+        }
+        if (last) break;
+    }
+    // the reference parses the whole CIGAR before anything else: what the path left over must be valid too
+    while (cp != cend) {
+        u32 x, kc, ts, tte;
+        if (!rec_fetch_op(rt, minus, cp, x, kc, ts, tte)) return false;
+    }
+    out.size = size; out.nlines = nlines;
+    return true;
+}
+
+__global__ void __launch_bounds__(kRThreads, G2P_REC_CTAS) k_rec(const RecArgs ra) {
+    G2P_DYN_SMEM(smem);
+    __shared__ u32 p10[10];
+    const ShortArgs& a = ra.s;
+    if (threadIdx.x < 10) {
+        u32 v = 1;
+        for (u32 i = 0; i < threadIdx.x; ++i) v *= 10u;
+        p10[threadIdx.x] = v;
+    }
+    const u32 C = ra.chunks, SW = rec_slot_words(C);
+    u32* slots = reinterpret_cast<u32*>(smem);
+    const u32 r0 = blockIdx.x * (u32)kRThreads;
+    // ---- stage: 8 lanes per record, 32 records per pass, 128-bit coalesced loads
+    {
+        const u32 gl = threadIdx.x & (kRStage - 1), grp = threadIdx.x / kRStage;
+        for (u32 rl = grp; rl < (u32)kRThreads; rl += kRThreads / kRStage) {
+            const u32 r = r0 + rl;
+            if (r >= a.nrec) break;
+            const u32 s = a.rec_start[r], e = a.rec_start[r + 1];
+            const u32 A = s & ~15u;
+            const u32 nch = (e - A + 15u) >> 4;   // the record and its '\n'
+            if (e - s > 1u && e - s - 1u <= kSLimit && nch <= C) {
+                u32* dst = slots + (size_t)rl * SW;
+                for (u32 c = gl; c < nch; c += kRStage) {
+                    const uint4 v = ldg_vec_guarded(a.gaf, (u64)A + 16u * c, a.n);
+                    dst[4 * c] = v.x; dst[4 * c + 1] = v.y; dst[4 * c + 2] = v.z; dst[4 * c + 3] = v.w;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const u32 r = r0 + threadIdx.x;
+    if (r >= a.nrec) return;
+    const u32 s = a.rec_start[r], e = a.rec_start[r + 1];
+    const u32 len = e - s - 1, sh = s & 15u;
+    u8* rt = reinterpret_cast<u8*>(slots + (size_t)threadIdx.x * SW) + sh;
+
+    bool ok = false, skip = false;
+    RecOut out;
+    out.size = 0; out.nlines = 0;
+    LineRec R;
+    R.gi = 0; R.gi_n = 0; R.qn_b = 0; R.qlen = R.mapq = R.m = R.b = 0; R.tp_a = R.tp_b = R.rc_a = R.rc_b = 0;
+    do {
+        if (len == 0 || len > kSLimit || ((e - (s & ~15u) + 15u) >> 4) > C) break;   // (k_emit_lines stages kSLimit bytes per record)
+        rt[len] = '\n';   // sentinel also for an unterminated last line
+        if (rt[0] == '*') { skip = true; ok = true; break; }   // gaf2paf_main.cpp:360
+        // ---- columns 1..12 (parse_gaf_record, gafkluge.hpp:84-183)
+        u32 p = 0;
+        u8 c;
+        while ((c = rt[p]) != '\t' && c != '\n') ++p;
+        if (c != '\t' || p == 0 || p > 0xffffu) break;
+        R.qn_b = p;
+        ++p;
+        i32 col[12];
+        u32 pb = 0;
+        bool bad = false;
+#pragma unroll
+        for (int f = 1; f < 12; ++f) {
+            if (f == 4) {   // strand
+                c = rt[p];
+                if ((c != '+' && c != '-') || rt[p + 1] != '\t') bad = true;
+                col[4] = c == '-';
+                p += 2;
+            } else if (f == 5) {   // path
+                col[5] = (i32)p;
+                while ((c = rt[p]) != '\t' && c != '\n') ++p;
+                if (c != '\t' || (u32)col[5] == p) bad = true;
+                pb = p;
+                ++p;
+            } else {
+                i32 v;
+                if (rt[p] == '*') { v = -1; ++p; }
+                else {
+                    u32 x = 0, d;
+                    const u32 p0 = p;
+                    while ((d = (u32)rt[p] - '0') <= 9u) { x = x * 10u + d; ++p; }
+                    if (p == p0 || p - p0 > 9) bad = true;
+                    v = (i32)x;
+                }
+                if (rt[p] != '\t') bad = true;
+                ++p;
+                col[f] = v;
+            }
+            if (bad) break;
+        }
+        if (bad) break;
+        R.qlen = col[1];
+        const i32 qs = col[2], ps = col[7], pe = col[8];
+        const bool minus = col[4] != 0;
+        const u32 pa = (u32)col[5];
+        R.m = col[9]; R.b = col[10];
+        R.mapq = col[11] >= 255 ? -1 : col[11];   // gafkluge.hpp:176-183
+        // ---- optional tags (gafkluge.hpp:185-202): XX:T:value, no duplicates
+        u32 ca = 0, cb = 0;
+        u32 ka = 0, kb = 0, kc_ = 0, kd = 0, ntags = 0;
+        for (;;) {
+            const u32 fa = p;
+            const u8 c0 = rt[p], c1 = rt[p + 1];
+            if (c0 == '\t' || c0 == '\n' || c0 == ':' || c1 == '\t' || c1 == '\n' || c1 == ':') { bad = true; break; }
+            const u8 c3 = rt[p + 3];
+            if (rt[p + 2] != ':' || c3 == '\t' || c3 == '\n' || c3 == ':' || rt[p + 4] != ':') { bad = true; break; }
+            const u32 key = (u32)c0 | ((u32)c1 << 8);
+            const u32 kk = key * 0x00010001u;
+            if (haszero16(ka ^ kk) | haszero16(kb ^ kk) | haszero16(kc_ ^ kk) | haszero16(kd ^ kk)) { bad = true; break; }
+            if (++ntags > kRMaxTags) { bad = true; break; }
+            kd = (kd << 16) | (kc_ >> 16); kc_ = (kc_ << 16) | (kb >> 16); kb = (kb << 16) | (ka >> 16); ka = (ka << 16) | key;
+            p += 5;
+            while ((c = rt[p]) != '\t' && c != '\n') ++p;
+            if (key == ((u32)'c' | ((u32)'g' << 8))) { ca = fa + 5; cb = p; }
+            else if (key == ((u32)'t' | ((u32)'p' << 8))) { R.tp_a = fa + 3; R.tp_b = p; }
+            else if (key == ((u32)'r' | ((u32)'c' << 8))) { R.rc_a = fa + 3; R.rc_b = p; }
+            if (c == '\n') break;
+            ++p;
+        }
+        if (bad || p != len) break;
+        if (cb == 0 || ca >= cb || qs < 0 || ps < 0 || pe < 0) break;
+        const u8 pc0 = rt[pa];
+        const bool prefixed = pc0 == '>' || pc0 == '<';
+        if (!prefixed && pb - pa == 1 && pc0 == '*') break;   // empty path: left to the general kernel
+        R.gi_n = gi_fast(R.m, R.b, R.gi);
+        if (R.gi_n == 0 || !rec_desc_fits(R)) break;
+        const u32 rconst = line_const_len(R, p10);
+        ok = rec_walk(a, rt, r, minus, rconst, p10, pa, pb, prefixed, ca, cb, qs, ps, pe, out);
+    } while (0);
+
+    if (!ok) {
+        a.status[r] = ST_OK;   // overwritten by k_long / the general kernel
+        a.out_off[r] = 0;
+        a.line_off[r] = 0;
+        a.deleg_list[atomicAdd(a.n_deleg, 1u)] = r;
+    } else {
+        const bool fast = !skip && out.size != 0;
+        a.status[r] = (skip ? (u32)ST_SKIP : (u32)ST_OK) | ST_F_FAST | (fast ? (u32)ST_F_DESC : 0u);
+        a.out_off[r] = out.size;
+        a.line_off[r] = fast ? out.nlines : 0u;
+        if (fast) store_rec_desc(a.rdesc + r, R);
+    }
+}
+
+}  // namespace g2p

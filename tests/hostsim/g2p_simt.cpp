@@ -90,7 +90,14 @@ int main(int argc, char** argv) {
     std::vector<RecDesc> rdesc(nrec);
     std::vector<u64> loff(nrec + 1);
     ShortArgs sa{gaf, n, rec.data(), nrec, T, off.data(), loff.data(), status.data(), list.data(), &meta.n_deleg, sdesc.data(), rdesc.data()};
-    hs::launch(dim3(ncta), dim3(kSThreads), kShortSmem, [&] { k_short<kSG>(sa); });
+    // G2P_SIZE_KERNEL=short selects the 8-lanes-per-record kernel, like the library; default: thread-per-record k_rec
+    const char* sk = std::getenv("G2P_SIZE_KERNEL");
+    if (sk && !std::strcmp(sk, "short")) hs::launch(dim3(ncta), dim3(kSThreads), kShortSmem, [&] { k_short<kSG>(sa); });
+    else {
+        const u32 chunks = std::getenv("G2P_REC_CHUNKS") ? (u32)std::atoi(std::getenv("G2P_REC_CHUNKS")) : rec_chunks_for(n, nrec);
+        RecArgs ra{sa, chunks};
+        hs::launch(dim3((nrec + kRThreads - 1) / kRThreads), dim3(kRThreads), rec_smem(chunks), [&] { k_rec(ra); });
+    }
     LongArgs la{gaf, n, rec.data(), T, off.data(), status.data(), nullptr, list.data(), &meta.n_deleg, list2.data(), &meta.n_deleg2,
                 desc.data(), rdesc.data(), &meta.n_desc, desc_cap, &meta.legacy_long};
     const u32 nlong = 2;
