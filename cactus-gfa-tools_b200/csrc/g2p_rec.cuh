@@ -56,41 +56,59 @@ struct RecArgs {
 
 __device__ __forceinline__ u32 haszero16(u32 x) { return (x - 0x00010001u) & ~x & 0x80008000u; }
 
-// One path-step token "[><]name[:start-end]" at rt[mp .. te) (mp = its marker, or pa - 1 for a bare
-// stable name).  Returns false if not canonical.  The name key is left in (k0, k1).
-struct RStep {
-    u32 name_a, nl;
-    i32 sa, se;      // interval (valid after the probe for whole-contig steps)
-    bool interval;
-};
-__device__ __forceinline__ bool rec_parse_step(const u8* rt, u32 mp, u32 te, bool prefixed, RStep& S, u64& k0, u64& k1) {
-    S.name_a = mp + 1;
-    S.interval = false;
-    S.sa = 0; S.se = 0;
-    u32 k = S.name_a;
-    if (prefixed) {
-        while (k < te && rt[k] != ':') ++k;
-    } else k = te;
-    S.nl = k - S.name_a;
-    if (S.nl == 0 || S.nl > 16) return false;
-    u32 w0, w1, w2, w3;
-    lds16_unaligned(rt + S.name_a, w0, w1, w2, w3);
-    w0 = keep_bytes(w0, (int)S.nl); w1 = keep_bytes(w1, (int)S.nl - 4);
-    w2 = keep_bytes(w2, (int)S.nl - 8); w3 = keep_bytes(w3, (int)S.nl - 12);
-    k0 = (u64)w0 | ((u64)w1 << 32); k1 = (u64)w2 | ((u64)w3 << 32);
-    if (k < te) {   // ":start-end" (gafkluge.hpp:131-146), plain digits only
-        S.interval = true;
-        ++k;
-        u32 x = 0, nd = 0, d;
-        while ((d = (u32)rt[k] - '0') <= 9u) { x = x * 10u + d; ++nd; ++k; }
-        if (nd == 0 || nd > 9 || k >= te || rt[k] != '-') return false;
-        S.sa = (i32)x;
-        ++k; x = 0; nd = 0;
-        while ((d = (u32)rt[k] - '0') <= 9u) { x = x * 10u + d; ++nd; ++k; }
-        if (nd == 0 || nd > 9 || k != te) return false;
-        S.se = (i32)x;
-        if (S.se < S.sa) return false;
+// Pass S: the path column, forwards, once per record.  Every step token "[><]name[:start-end]" is
+// scanned with one loop (name end and token end together), its name is probed in the lengths table,
+// and two words per step are left in `stab` (a dead part of the record's own slot):
+//   stab[2i]   = target length | interval flag << 31
+//   stab[2i+1] = marker position | name length << 8 | token end << 16
+// The caller has replaced the tab after the path column by '>' so that the scan needs no bound.
+// Returns false if a token is not canonical or a name is unknown (-> delegate); `total` = sum of
+// the step lengths (flip_gaf's path_target_len, gaf2paf_main.cpp:111-127).
+__device__ __forceinline__ bool rec_steps(const LenTableView& T, const u8* rt, const u32 pa, const u32 pb, const bool prefixed, u32* stab,
+                                          const u32 cap, u32& ns_out, u64& total_out) {
+    u32 ns = 0, mp = prefixed ? pa : pa - 1;
+    u64 total = 0;
+    for (;;) {
+        const u32 name_a = mp + 1;
+        u32 j = pb;
+        u8 c = 0;
+        if (prefixed) {
+            j = name_a;
+            while ((c = rt[j]) != ':' && c != '>' && c != '<') ++j;   // rt[pb] == '>'
+        }
+        const u32 nl = j - name_a;
+        if (nl == 0 || nl > 16) return false;
+        u32 w0, w1, w2, w3;
+        lds16_unaligned(rt + name_a, w0, w1, w2, w3);
+        w0 = keep_bytes(w0, (int)nl); w1 = keep_bytes(w1, (int)nl - 4);
+        w2 = keep_bytes(w2, (int)nl - 8); w3 = keep_bytes(w3, (int)nl - 12);
+        u32 slen = 0;
+        const bool interval = prefixed && c == ':';
+        if (interval) {   // ":start-end" (gafkluge.hpp:131-146), plain digits only
+            u32 k = j + 1, x = 0, d;
+            const u32 k1 = k;
+            while ((d = (u32)rt[k] - '0') <= 9u) { x = x * 10u + d; ++k; }
+            if (k == k1 || k - k1 > 9 || rt[k] != '-') return false;
+            const u32 sa = x;
+            ++k; x = 0;
+            const u32 k2 = k;
+            while ((d = (u32)rt[k] - '0') <= 9u) { x = x * 10u + d; ++k; }
+            if (k == k2 || k - k2 > 9 || (rt[k] != '>' && rt[k] != '<') || x < sa) return false;
+            slen = x - sa;
+            j = k;
+        }
+        i64 tl64;
+        if (!table_lookup_key16(T, (u64)w0 | ((u64)w1 << 32), (u64)w2 | ((u64)w3 << 32), nl, tl64) || tl64 < 0 || tl64 > 0x7fffffffLL) return false;
+        if (!interval) slen = (u32)tl64;
+        total += slen;
+        if (ns >= cap) return false;
+        stab[2 * ns] = (u32)tl64 | (interval ? 0x80000000u : 0u);
+        stab[2 * ns + 1] = (mp & 0xffu) | (nl << 8) | (j << 16);
+        ++ns;
+        if (j >= pb) break;
+        mp = j;
     }
+    ns_out = ns; total_out = total;
     return true;
 }
 
@@ -122,32 +140,15 @@ __device__ __forceinline__ bool rec_fetch_op(const u8* rt, const bool minus, u32
     return nd != 0 && nd <= 7 && !(nd > 1 && lead == 0) && v != 0 && kc < 28u && ((kOpMask >> kc) & 1u);
 }
 
-// The record walk after the header: steps and ops in normalised order ('-' records walk both
-// columns backwards).  Returns false to delegate.
+// The record walk after pass S: steps (from `stab`) and ops in normalised order ('-' records walk
+// both backwards).  Returns false to delegate.
 struct RecOut {
     u32 size, nlines;
 };
 __device__ __forceinline__ bool rec_walk(const ShortArgs& a, const u8* rt, const u32 r, const bool minus, const u32 rconst, const u32* p10,
-                                         const u32 pa, const u32 pb, const bool prefixed, const u32 ca, const u32 cb, const i32 qs, i32 ps,
-                                         i32 pe, RecOut& out) {
-    u64 k0, k1;
-    RStep S;
-    if (minus) {   // flip_gaf: mirror the path interval about the summed step lengths (gaf2paf_main.cpp:111-131)
-        u64 total = 0;
-        u32 mp = prefixed ? pa : pa - 1;
-        for (;;) {
-            u32 te = mp + 1;
-            if (prefixed) { while (te < pb && rt[te] != '>' && rt[te] != '<') ++te; } else te = pb;
-            if (!rec_parse_step(rt, mp, te, prefixed, S, k0, k1)) return false;
-            if (S.interval) total += (u32)(S.se - S.sa);
-            else {
-                i64 tl;
-                if (!table_lookup_key16(a.T, k0, k1, S.nl, tl) || tl < 0 || tl > 0x7fffffffLL) return false;
-                total += (u64)tl;
-            }
-            if (te >= pb) break;
-            mp = te;
-        }
+                                         const bool prefixed, const u32* stab, const u32 ns, const u64 total, const u32 ca, const u32 cb,
+                                         const i32 qs, i32 ps, i32 pe, RecOut& out) {
+    if (minus) {   // flip_gaf: mirror the path interval about the summed step lengths (gaf2paf_main.cpp:128-131)
         if (total > 0x7fffffffULL) return false;
         const i32 nps = (i32)total - pe, npe = (i32)total - ps;
         ps = nps; pe = npe;
@@ -155,38 +156,31 @@ __device__ __forceinline__ bool rec_walk(const ShortArgs& a, const u8* rt, const
     const i32 W = pe - ps;
     const u32 cend = minus ? ca : cb;   // CIGAR cursor and where it ends
     u32 cp = minus ? cb : ca;
-    u32 sp = minus ? pb : pa;           // path cursor: the next token starts at sp (forward) / ends at sp (backward)
     u32 rem = 0, remk = 0;              // unconsumed part of the op cut by the previous boundary
     u32 qcur = 0, tbc = 0;              // query / target bases consumed by the steps so far
     u32 size = 0, nlines = 0;
-    bool first = true;
-    for (;;) {
-        // ---- next step token: [mp, te), mp = its marker
-        u32 mp, te;
-        bool last;
-        if (!prefixed) { mp = pa - 1; te = pb; last = true; }
-        else {
-            // forward: from the marker at sp to the next marker or pb; backward: from sp - 1 down to a marker (rt[pa] is one)
-            u32 k = minus ? sp - 1 : sp + 1;
-            const u32 lim = minus ? pa : pb, step = minus ? 0xffffffffu : 1u;
-            while (k != lim && rt[k] != '>' && rt[k] != '<') k += step;
-            if (minus) { mp = k; te = sp; last = k == pa; }
-            else { mp = sp; te = k; last = k == pb; }
-            sp = k;
+    for (u32 i = 0; i < ns; ++i) {
+        const u32 idx = minus ? ns - 1 - i : i;
+        const u32 sA = stab[2 * idx], sB = stab[2 * idx + 1];
+        const u32 mp = sB & 0xffu, nl = (sB >> 8) & 0xffu;
+        const i32 tlen = (i32)(sA & 0x7fffffffu);
+        i32 sa = 0, se = tlen;
+        if (sA & 0x80000000u) {   // interval: the digits were validated by pass S
+            u32 k = mp + nl + 2, x = 0, d;
+            while ((d = (u32)rt[k] - '0') <= 9u) { x = x * 10u + d; ++k; }
+            sa = (i32)x;
+            ++k; x = 0;
+            while ((d = (u32)rt[k] - '0') <= 9u) { x = x * 10u + d; ++k; }
+            se = (i32)x;
         }
-        if (!rec_parse_step(rt, mp, te, prefixed, S, k0, k1)) return false;
-        i64 tl64;
-        if (!table_lookup_key16(a.T, k0, k1, S.nl, tl64) || tl64 < 0 || tl64 > 0x7fffffffLL) return false;
-        const i32 tlen = (i32)tl64;
-        if (!S.interval) { S.sa = 0; S.se = tlen; }
         const bool rev = (prefixed && rt[mp] == '<') != minus;
-        const i32 slen = S.se - S.sa;
+        const bool last = i + 1 == ns;
+        const i32 slen = se - sa;
         // ---- quota (gaf2paf_main.cpp:176-182)
-        const i32 so = first ? ps : 0;
+        const i32 so = i == 0 ? ps : 0;
         i32 quota = slen - so, eo = 0;
         if (last) { quota = W - (i32)tbc; eo = slen - so - quota; }
         if (so < 0 || quota < 0 || eo < 0) return false;
-        first = false;
         if (quota > 0) {
             // ---- take `quota` target bases of CIGAR (cigar_next_by_target, gaf2paf_main.cpp:71-90)
             u32 need = (u32)quota, q = 0, nm = 0, nb = 0;
@@ -226,8 +220,8 @@ __device__ __forceinline__ bool rec_walk(const ShortArgs& a, const u8* rt, const
                 L.rev = rev;
                 L.mid_fwd = rev == minus;
                 L.q0 = (u32)qs + qcur; L.q1 = L.q0 + q;
-                L.name_a = S.name_a; L.nl = S.nl; L.tlen = (u32)tlen;
-                L.ts = (u32)(S.sa + (rev ? eo : so)); L.te = (u32)(S.se - (rev ? so : eo));
+                L.name_a = mp + 1; L.nl = nl; L.tlen = (u32)tlen;
+                L.ts = (u32)(sa + (rev ? eo : so)); L.te = (u32)(se - (rev ? so : eo));
                 L.nm = nm; L.nb = nb;
                 const u32 line = rconst + line_step_len(L, p10);
                 store_line_desc(a.sdesc + (size_t)r * kSMaxLines + nlines, r, size, line, L);
@@ -237,7 +231,6 @@ __device__ __forceinline__ bool rec_walk(const ShortArgs& a, const u8* rt, const
             qcur += q;
             tbc += (u32)quota;
         }
-        if (last) break;
     }
     // the reference parses the whole CIGAR before anything else: what the path left over must be valid too
     while (cp != cend) {
@@ -301,45 +294,52 @@ __global__ void __launch_bounds__(kRThreads, G2P_REC_CTAS) k_rec(const RecArgs r
         if (c != '\t' || p == 0 || p > 0xffffu) break;
         R.qn_b = p;
         ++p;
-        i32 col[12];
-        u32 pb = 0;
         bool bad = false;
-#pragma unroll
-        for (int f = 1; f < 12; ++f) {
-            if (f == 4) {   // strand
-                c = rt[p];
-                if ((c != '+' && c != '-') || rt[p + 1] != '\t') bad = true;
-                col[4] = c == '-';
-                p += 2;
-            } else if (f == 5) {   // path
-                col[5] = (i32)p;
-                while ((c = rt[p]) != '\t' && c != '\n') ++p;
-                if (c != '\t' || (u32)col[5] == p) bad = true;
-                pb = p;
-                ++p;
-            } else {
-                i32 v;
-                if (rt[p] == '*') { v = -1; ++p; }
-                else {
-                    u32 x = 0, d;
-                    const u32 p0 = p;
-                    while ((d = (u32)rt[p] - '0') <= 9u) { x = x * 10u + d; ++p; }
-                    if (p == p0 || p - p0 > 9) bad = true;
-                    v = (i32)x;
-                }
-                if (rt[p] != '\t') bad = true;
-                ++p;
-                col[f] = v;
-            }
-            if (bad) break;
+        // numeric column at p: plain digits (<= 9) or '*' (-> -1, string_to_int gafkluge.hpp:30), then a tab
+#define G2P_REC_NUM(v)                                                                 \
+        {                                                                              \
+            if (rt[p] == '*') { v = -1; ++p; }                                         \
+            else {                                                                     \
+                u32 x_ = 0, d_;                                                        \
+                const u32 p0_ = p;                                                     \
+                while ((d_ = (u32)rt[p] - '0') <= 9u) { x_ = x_ * 10u + d_; ++p; }     \
+                if (p == p0_ || p - p0_ > 9) bad = true;                               \
+                v = (i32)x_;                                                           \
+            }                                                                          \
+            if (rt[p] != '\t') bad = true;                                             \
+            ++p;                                                                       \
         }
+        i32 qs, qe, plen, ps, pe, mapq;
+        G2P_REC_NUM(R.qlen);
         if (bad) break;
-        R.qlen = col[1];
-        const i32 qs = col[2], ps = col[7], pe = col[8];
-        const bool minus = col[4] != 0;
-        const u32 pa = (u32)col[5];
-        R.m = col[9]; R.b = col[10];
-        R.mapq = col[11] >= 255 ? -1 : col[11];   // gafkluge.hpp:176-183
+        G2P_REC_NUM(qs);
+        if (bad) break;
+        G2P_REC_NUM(qe);
+        if (bad) break;
+        c = rt[p];   // strand
+        if ((c != '+' && c != '-') || rt[p + 1] != '\t') break;
+        const bool minus = c == '-';
+        p += 2;
+        const u32 pa = p;   // path
+        while ((c = rt[p]) != '\t' && c != '\n') ++p;
+        if (c != '\t' || p == pa) break;
+        const u32 pb = p;
+        ++p;
+        G2P_REC_NUM(plen);
+        if (bad) break;
+        G2P_REC_NUM(ps);
+        if (bad) break;
+        G2P_REC_NUM(pe);
+        if (bad) break;
+        G2P_REC_NUM(R.m);
+        if (bad) break;
+        G2P_REC_NUM(R.b);
+        if (bad) break;
+        G2P_REC_NUM(mapq);
+        if (bad) break;
+#undef G2P_REC_NUM
+        (void)qe; (void)plen;
+        R.mapq = mapq >= 255 ? -1 : mapq;   // gafkluge.hpp:176-183
         // ---- optional tags (gafkluge.hpp:185-202): XX:T:value, no duplicates
         u32 ca = 0, cb = 0;
         u32 ka = 0, kb = 0, kc_ = 0, kd = 0, ntags = 0;
@@ -370,7 +370,20 @@ __global__ void __launch_bounds__(kRThreads, G2P_REC_CTAS) k_rec(const RecArgs r
         R.gi_n = gi_fast(R.m, R.b, R.gi);
         if (R.gi_n == 0 || !rec_desc_fits(R)) break;
         const u32 rconst = line_const_len(R, p10);
-        ok = rec_walk(a, rt, r, minus, rconst, p10, pa, pb, prefixed, ca, cb, qs, ps, pe, out);
+        // step table: the larger of the two dead regions of the slot, after the path column up to
+        // "cg:Z" or after the CIGAR (rt[ca - 1] == ':' must survive: it stops the backward CIGAR walk)
+        u32 ta = (sh + pb + 1 + 3) & ~3u, tb = sh + ca - 1;
+        {
+            const u32 ta2 = (sh + cb + 1 + 3) & ~3u, tb2 = sh + len;
+            if (tb2 > ta2 && (tb <= ta || tb2 - ta2 > tb - ta)) { ta = ta2; tb = tb2; }
+        }
+        const u32 cap = tb > ta ? (tb - ta) >> 3 : 0u;
+        u32* stab = reinterpret_cast<u32*>(rt - sh + ta);
+        rt[pb] = '>';   // bounds the token scan of pass S
+        u32 ns;
+        u64 total;
+        if (!rec_steps(a.T, rt, pa, pb, prefixed, stab, cap, ns, total)) break;
+        ok = rec_walk(a, rt, r, minus, rconst, p10, prefixed, stab, ns, total, ca, cb, qs, ps, pe, out);
     } while (0);
 
     if (!ok) {

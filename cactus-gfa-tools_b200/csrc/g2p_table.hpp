@@ -28,7 +28,9 @@ struct HostLenTable {
     }
 
     void reserve_for(u64 n_names) {
-        u64 want = n_names * 5 / 3 + 16;   // load factor <= 0.6
+        // load factor <= 1/3 while the table stays L2-sized (short probe chains keep the lanes of a warp
+        // together: every extra probe of one lane is an extra trip for the whole warp), <= 0.6 beyond
+        u64 want = n_names <= 1000000ULL ? n_names * 3 + 16 : n_names * 5 / 3 + 16;
         if (want > 0xFFFFFFF0ULL) want = 0xFFFFFFF0ULL;
         slots.assign((size_t)want, LenSlot{0, 0, 0, 0, kEmptySlot});
         n_entries = 0;
