@@ -7,7 +7,7 @@ vs the HBM roofline), one JSON line on stdout.
     python bench.py --impl reference ...      # the reference's CPU gaf2paf on the host cores
 
 A step is one pass of the whole device pipeline (line index -> size pass -> scan -> emit
-pass; kernels k_short / k_long / k_convert_list) over one synthetic batch.  `value` is measured with the batch already resident in HBM
+pass; kernels k_rec / k_long / k_convert_list) over one synthetic batch.  `value` is measured with the batch already resident in HBM
 (CUDA events around exactly K steps, max over ranks); `e2e` is the same metric through the
 host-buffer C-ABI call (pinned host input -> H2D -> pipeline -> D2H), i.e. what the
 `gaf2paf` executable does per chunk.  Multi-GPU runs shard by records: every rank converts
@@ -256,9 +256,10 @@ def main():
     peak, peak_src = peaks()
     value = n_records * world * a.steps / (t_ms / 1000.0)
     # dominant kernel: the emit pass (reads the GAF, writes the PAF) or the size pass (reads the GAF);
-    # k_short converts short records, k_long the ones it delegates (res.n_long)
+    # k_rec (or k_short with G2P_SIZE_KERNEL=short) converts short records, k_long the ones it delegates (res.n_long)
     em, sz = statistics.mean(emit_ms), statistics.mean(size_ms)
-    kname = "k_long" if res.n_long * 2 > n_records else "k_short<8>"
+    short_kernel = "k_short<8>" if os.environ.get("G2P_SIZE_KERNEL") == "short" else "k_rec"
+    kname = "k_long" if res.n_long * 2 > n_records else short_kernel
     if em >= sz:   # k_emit_lines: reads descriptors + GAF text, writes the PAF
         dom, dom_ms, dom_bytes, dom_key = "k_emit_lines (emit pass)", em, nbytes + out_bytes, "k_emit_lines"
     else:          # size pass: parses the GAF, writes sizes + line descriptors
@@ -288,7 +289,7 @@ def main():
         "kernel_ms": {"index": statistics.mean(index_ms), "size": sz, "emit": em, "device_pipeline": statistics.mean(dev_ms)},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "algorithmic_bytes_per_launch": dom_bytes, "peak_source": peak_src},
-        "records_by_kernel": {"k_short": int(n_records - res.n_long), "k_long": int(res.n_long - res.n_delegated), "general": int(res.n_delegated)},
+        "records_by_kernel": {short_kernel.split("<")[0]: int(n_records - res.n_long), "k_long": int(res.n_long - res.n_delegated), "general": int(res.n_delegated)},
         "gpu_launches": launches,
         "clocks": clocks,
     }

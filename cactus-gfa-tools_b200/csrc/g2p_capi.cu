@@ -14,6 +14,7 @@
 #include <set>
 #include <thread>
 #include <vector>
+#include <chrono>
 #include <cstring>
 #include <new>
 #include <string>
@@ -454,6 +455,10 @@ int g2p_convert_host(g2p_ctx* ctx, const char* gaf, size_t n, const char** out, 
     // first guess of the output size: keep what earlier calls needed, else 3x the input
     if (ctx->h_out.cap == 0) G2P_CUDA(ctx->h_out.ensure(n * 3 + (1 << 20)));
 
+    // G2P_TRACE=1: host-clock timeline of every chunk on stderr (ms since the call started)
+    const bool trace = std::getenv("G2P_TRACE") != nullptr;
+    const auto t_call = std::chrono::steady_clock::now();
+    auto now_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count(); };
     auto worker = [&](int wi) {
         cudaSetDevice(ctx->device);
         Worker& w = ctx->w[wi];
@@ -463,6 +468,7 @@ int g2p_convert_host(g2p_ctx* ctx, const char* gaf, size_t n, const char** out, 
                 if (i > S.stop_at || S.rc != G2P_OK) break;
             }
             const size_t a = cut[i], len = cut[i + 1] - cut[i];
+            const double t_begin = trace ? now_ms() : 0.0;
             int rc = G2P_OK;
             u8* d_o = nullptr;
             g2p_result r;
@@ -470,6 +476,7 @@ int g2p_convert_host(g2p_ctx* ctx, const char* gaf, size_t n, const char** out, 
             if (w.d_in.ensure(len + 256) != cudaSuccess) rc = G2P_E_CUDA;
             if (rc == G2P_OK && cudaMemcpyAsync(w.d_in.p, gaf + a, len, cudaMemcpyHostToDevice, w.stream) != cudaSuccess) rc = G2P_E_CUDA;
             if (rc == G2P_OK) rc = run_pipeline(ctx, w, static_cast<const u8*>(w.d_in.p), len, w.stream, &r, &d_o);
+            const double t_piped = trace ? now_ms() : 0.0;
             // publish this chunk's output offset (in chunk order)
             std::unique_lock<std::mutex> lk(S.mu);
             S.cv.wait(lk, [&] { return S.published == i || S.rc != G2P_OK || i > S.stop_at; });
@@ -493,9 +500,12 @@ int g2p_convert_host(g2p_ctx* ctx, const char* gaf, size_t n, const char** out, 
             S.published = i + 1;
             S.cv.notify_all();
             lk.unlock();
+            const double t_pub = trace ? now_ms() : 0.0;
             cudaError_t ce = cudaSuccess;
             if (r.out_bytes) ce = cudaMemcpyAsync(dst, d_o, r.out_bytes, cudaMemcpyDeviceToHost, w.stream);
             if (ce == cudaSuccess) ce = cudaStreamSynchronize(w.stream);
+            if (trace) std::fprintf(stderr, "g2p trace: chunk %zu worker %d in %zu out %llu: begin %.2f piped %.2f (device %.2f) published %.2f copied %.2f\n", i, wi, len,
+                                    (unsigned long long)r.out_bytes, t_begin, t_piped, r.device_ms, t_pub, now_ms());
             lk.lock();
             if (ce != cudaSuccess) { S.rc = G2P_E_CUDA; ctx->set_err(std::string("D2H: ") + cudaGetErrorString(ce)); S.cv.notify_all(); break; }
             done[i] = 1;

@@ -35,6 +35,17 @@ constexpr u32 kRMinChunks = 6, kRMaxChunks = 16;   // 16-byte chunks per record 
 #ifndef G2P_REC_CTAS
 #define G2P_REC_CTAS 4
 #endif
+// Variants measured on B200 (tools/gpu_quick.sh): loop-free decoding of <= 3-digit numbers and
+// four-bytes-per-trip scans.  0 = the plain byte loops.
+#ifndef G2P_REC_FAST_OP
+#define G2P_REC_FAST_OP 0
+#endif
+#ifndef G2P_REC_FAST_NUM
+#define G2P_REC_FAST_NUM 0
+#endif
+#ifndef G2P_REC_SCAN4
+#define G2P_REC_SCAN4 1
+#endif
 
 __host__ __device__ __forceinline__ u32 rec_slot_words(u32 chunks) { return 4u * chunks + 1u; }   // odd: conflict-free lane stride
 static inline size_t rec_smem(u32 chunks) { return (size_t)kRThreads * rec_slot_words(chunks) * 4u + 32u; }
@@ -56,6 +67,37 @@ struct RecArgs {
 
 __device__ __forceinline__ u32 haszero16(u32 x) { return (x - 0x00010001u) & ~x & 0x80008000u; }
 
+// First position >= p holding a tab or the record's '\n'; four bytes per trip, loaded together.
+__device__ __forceinline__ u32 rec_scan_field(const u8* rt, u32 p) {
+#if !G2P_REC_SCAN4
+    u32 c;
+    while ((c = rt[p]) != '\t' && c != '\n') ++p;
+    return p;
+#else
+    for (;;) {
+        const u32 c0 = rt[p], c1 = rt[p + 1], c2 = rt[p + 2], c3 = rt[p + 3];
+        const bool t0 = c0 - 9u <= 1u, t1 = c1 - 9u <= 1u, t2 = c2 - 9u <= 1u, t3 = c3 - 9u <= 1u;
+        if (t0 || t1 || t2 || t3) return p + (t0 ? 0u : (t1 ? 1u : (t2 ? 2u : 3u)));
+        p += 4;
+    }
+#endif
+}
+// First position >= p holding ':', '>' or '<' (pass S; the caller planted a '>' after the path column).
+__device__ __forceinline__ u32 rec_scan_step(const u8* rt, u32 p) {
+#if !G2P_REC_SCAN4
+    u32 c;
+    while ((c = rt[p]) != ':' && c != '>' && c != '<') ++p;
+    return p;
+#else
+    for (;;) {
+        const u32 c0 = rt[p], c1 = rt[p + 1], c2 = rt[p + 2], c3 = rt[p + 3];
+        const bool t0 = c0 == ':' || c0 == '>' || c0 == '<', t1 = c1 == ':' || c1 == '>' || c1 == '<';
+        const bool t2 = c2 == ':' || c2 == '>' || c2 == '<', t3 = c3 == ':' || c3 == '>' || c3 == '<';
+        if (t0 || t1 || t2 || t3) return p + (t0 ? 0u : (t1 ? 1u : (t2 ? 2u : 3u)));
+        p += 4;
+    }
+#endif
+}
 // Pass S: the path column, forwards, once per record.  Every step token "[><]name[:start-end]" is
 // scanned with one loop (name end and token end together), its name is probed in the lengths table,
 // and two words per step are left in `stab` (a dead part of the record's own slot):
@@ -73,8 +115,8 @@ __device__ __forceinline__ bool rec_steps(const LenTableView& T, const u8* rt, c
         u32 j = pb;
         u8 c = 0;
         if (prefixed) {
-            j = name_a;
-            while ((c = rt[j]) != ':' && c != '>' && c != '<') ++j;   // rt[pb] == '>'
+            j = rec_scan_step(rt, name_a);   // rt[pb] == '>'
+            c = rt[j];
         }
         const u32 nl = j - name_a;
         if (nl == 0 || nl > 16) return false;
@@ -112,11 +154,17 @@ __device__ __forceinline__ bool rec_steps(const LenTableView& T, const u8* rt, c
     return true;
 }
 
-// One CIGAR token in walk direction.  Forward (dir = +1): "digits letter" starts at cp, cp advances
-// past the letter.  Backward (dir = -1): the token ends at cp (exclusive), cp retreats to its first
-// digit.  One digit loop serves both directions so that '+' and '-' records of a warp stay
-// converged.  [ts, te) is the token's text span.
-__device__ __forceinline__ bool rec_fetch_op(const u8* rt, const bool minus, u32& cp, u32& x, u32& kc, u32& ts, u32& te) {
+// One CIGAR token in walk direction.  Forward: "digits letter" starts at cp, cp advances past the
+// letter.  Backward: the token ends at cp (exclusive), cp retreats to its first digit.  [ts, te) is
+// the token's text span.  Tokens of up to three digits (all of a short read's) are decoded without
+// a loop from the five bytes next to the cursor, loaded together: one shared-memory round trip per
+// op instead of one per digit, and the same instruction stream for '+' and '-' records.
+#if G2P_REC_FAST_OP
+#define G2P_REC_SLOW_INLINE G2P_NOINLINE
+#else
+#define G2P_REC_SLOW_INLINE __forceinline__
+#endif
+__device__ G2P_REC_SLOW_INLINE bool rec_fetch_op_slow(const u8* rt, const bool minus, u32& cp, u32& x, u32& kc, u32& ts, u32& te) {
     u32 k = cp, letter = 0;
     if (minus) { letter = rt[cp - 1]; k = cp - 2; }   // rt[ca - 1] == ':' stops the backward digit walk
     const u32 k0 = k;
@@ -138,6 +186,64 @@ __device__ __forceinline__ bool rec_fetch_op(const u8* rt, const bool minus, u32
     kc = letter - '=';
     x = v;
     return nd != 0 && nd <= 7 && !(nd > 1 && lead == 0) && v != 0 && kc < 28u && ((kOpMask >> kc) & 1u);
+}
+__device__ __forceinline__ bool rec_fetch_op(const u8* rt, const bool minus, u32& cp, u32& x, u32& kc, u32& ts, u32& te) {
+#if !G2P_REC_FAST_OP
+    return rec_fetch_op_slow(rt, minus, cp, x, kc, ts, te);
+#else
+    const u32 step = minus ? 0xffffffffu : 1u;
+    const u32 base = minus ? cp - 1 : cp;
+    const u32 b0 = rt[base], b1 = rt[base + step], b2 = rt[base + 2u * step], b3 = rt[base + 3u * step], b4 = rt[base + 4u * step];
+    // digits in walk order: forward b0 b1 b2 (b3), backward b1 b2 b3 (b4) after the letter b0
+    const u32 d0 = (minus ? b1 : b0) - '0', d1 = (minus ? b2 : b1) - '0', d2 = (minus ? b3 : b2) - '0', d3 = (minus ? b4 : b3) - '0';
+    if (d0 <= 9u && d1 <= 9u && d2 <= 9u && d3 <= 9u) return rec_fetch_op_slow(rt, minus, cp, x, kc, ts, te);   // >= 4 digits
+    const u32 nd = d0 > 9u ? 0u : (d1 > 9u ? 1u : (d2 > 9u ? 2u : 3u));
+    const u32 v2 = minus ? d1 * 10u + d0 : d0 * 10u + d1;
+    const u32 v3 = minus ? d2 * 100u + d1 * 10u + d0 : d0 * 100u + d1 * 10u + d2;
+    const u32 v = nd == 1 ? d0 : (nd == 2 ? v2 : v3);
+    const u32 lead = minus ? (nd == 1 ? d0 : (nd == 2 ? d1 : d2)) : d0;   // most significant digit
+    const u32 letter = minus ? b0 : (nd == 1 ? b1 : (nd == 2 ? b2 : b3));
+    if (minus) { te = cp; ts = cp - nd - 1u; cp = ts; }
+    else { ts = cp; te = cp + nd + 1u; cp = te; }
+    kc = letter - '=';
+    x = v;
+    return nd != 0 && !(nd > 1 && lead == 0) && v != 0 && kc < 28u && ((kOpMask >> kc) & 1u);
+#endif
+}
+
+// Numeric column at p: plain digits (<= 9 of them) or '*' (-> -1, string_to_int gafkluge.hpp:30), then a
+// tab.  Up to three digits are decoded without a loop.  Returns false if not canonical.
+__device__ __forceinline__ bool rec_num(const u8* rt, u32& p, i32& v) {
+#if !G2P_REC_FAST_NUM
+    if (rt[p] == '*') { v = -1; ++p; }
+    else {
+        u32 x = 0, d;
+        const u32 p0 = p;
+        while ((d = (u32)rt[p] - '0') <= 9u) { x = x * 10u + d; ++p; }
+        if (p == p0 || p - p0 > 9) return false;
+        v = (i32)x;
+    }
+    return rt[p++] == '\t';
+#else
+    const u32 c0 = rt[p], c1 = rt[p + 1], c2 = rt[p + 2], c3 = rt[p + 3];
+    const u32 d0 = c0 - '0', d1 = c1 - '0', d2 = c2 - '0', d3 = c3 - '0';
+    if (d0 <= 9u && d1 <= 9u && d2 <= 9u && d3 <= 9u) {   // >= 4 digits
+        u32 x = 0, d;
+        const u32 p0 = p;
+        while ((d = (u32)rt[p] - '0') <= 9u) { x = x * 10u + d; ++p; }
+        v = (i32)x;
+        const bool ok = p - p0 <= 9 && rt[p] == '\t';
+        ++p;
+        return ok;
+    }
+    const u32 nd = d0 > 9u ? 0u : (d1 > 9u ? 1u : (d2 > 9u ? 2u : 3u));
+    const u32 x = nd == 1 ? d0 : (nd == 2 ? d0 * 10u + d1 : d0 * 100u + d1 * 10u + d2);
+    const u32 term = nd == 0 ? c1 : (nd == 1 ? c1 : (nd == 2 ? c2 : c3));
+    const bool star = c0 == '*';
+    v = star ? -1 : (i32)x;
+    p += (star ? 1u : nd) + 1u;
+    return (star || nd != 0) && term == '\t';
+#endif
 }
 
 // The record walk after pass S: steps (from `stab`) and ops in normalised order ('-' records walk
@@ -290,54 +396,31 @@ __global__ void __launch_bounds__(kRThreads, G2P_REC_CTAS) k_rec(const RecArgs r
         // ---- columns 1..12 (parse_gaf_record, gafkluge.hpp:84-183)
         u32 p = 0;
         u8 c;
-        while ((c = rt[p]) != '\t' && c != '\n') ++p;
-        if (c != '\t' || p == 0 || p > 0xffffu) break;
+        p = rec_scan_field(rt, 0);
+        c = rt[p];
+        if (c != '\t' || p == 0) break;
         R.qn_b = p;
         ++p;
         bool bad = false;
-        // numeric column at p: plain digits (<= 9) or '*' (-> -1, string_to_int gafkluge.hpp:30), then a tab
-#define G2P_REC_NUM(v)                                                                 \
-        {                                                                              \
-            if (rt[p] == '*') { v = -1; ++p; }                                         \
-            else {                                                                     \
-                u32 x_ = 0, d_;                                                        \
-                const u32 p0_ = p;                                                     \
-                while ((d_ = (u32)rt[p] - '0') <= 9u) { x_ = x_ * 10u + d_; ++p; }     \
-                if (p == p0_ || p - p0_ > 9) bad = true;                               \
-                v = (i32)x_;                                                           \
-            }                                                                          \
-            if (rt[p] != '\t') bad = true;                                             \
-            ++p;                                                                       \
-        }
         i32 qs, qe, plen, ps, pe, mapq;
-        G2P_REC_NUM(R.qlen);
-        if (bad) break;
-        G2P_REC_NUM(qs);
-        if (bad) break;
-        G2P_REC_NUM(qe);
-        if (bad) break;
+        if (!rec_num(rt, p, R.qlen)) break;
+        if (!rec_num(rt, p, qs)) break;
+        if (!rec_num(rt, p, qe)) break;
         c = rt[p];   // strand
         if ((c != '+' && c != '-') || rt[p + 1] != '\t') break;
         const bool minus = c == '-';
         p += 2;
         const u32 pa = p;   // path
-        while ((c = rt[p]) != '\t' && c != '\n') ++p;
-        if (c != '\t' || p == pa) break;
+        p = rec_scan_field(rt, p);
+        if (rt[p] != '\t' || p == pa) break;
         const u32 pb = p;
         ++p;
-        G2P_REC_NUM(plen);
-        if (bad) break;
-        G2P_REC_NUM(ps);
-        if (bad) break;
-        G2P_REC_NUM(pe);
-        if (bad) break;
-        G2P_REC_NUM(R.m);
-        if (bad) break;
-        G2P_REC_NUM(R.b);
-        if (bad) break;
-        G2P_REC_NUM(mapq);
-        if (bad) break;
-#undef G2P_REC_NUM
+        if (!rec_num(rt, p, plen)) break;
+        if (!rec_num(rt, p, ps)) break;
+        if (!rec_num(rt, p, pe)) break;
+        if (!rec_num(rt, p, R.m)) break;
+        if (!rec_num(rt, p, R.b)) break;
+        if (!rec_num(rt, p, mapq)) break;
         (void)qe; (void)plen;
         R.mapq = mapq >= 255 ? -1 : mapq;   // gafkluge.hpp:176-183
         // ---- optional tags (gafkluge.hpp:185-202): XX:T:value, no duplicates
@@ -354,8 +437,8 @@ __global__ void __launch_bounds__(kRThreads, G2P_REC_CTAS) k_rec(const RecArgs r
             if (haszero16(ka ^ kk) | haszero16(kb ^ kk) | haszero16(kc_ ^ kk) | haszero16(kd ^ kk)) { bad = true; break; }
             if (++ntags > kRMaxTags) { bad = true; break; }
             kd = (kd << 16) | (kc_ >> 16); kc_ = (kc_ << 16) | (kb >> 16); kb = (kb << 16) | (ka >> 16); ka = (ka << 16) | key;
-            p += 5;
-            while ((c = rt[p]) != '\t' && c != '\n') ++p;
+            p = rec_scan_field(rt, p + 5);
+            c = rt[p];
             if (key == ((u32)'c' | ((u32)'g' << 8))) { ca = fa + 5; cb = p; }
             else if (key == ((u32)'t' | ((u32)'p' << 8))) { R.tp_a = fa + 3; R.tp_b = p; }
             else if (key == ((u32)'r' | ((u32)'c' << 8))) { R.rc_a = fa + 3; R.rc_b = p; }

@@ -741,7 +741,10 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 
 constexpr int kEThreads = 256;
 constexpr u32 kEOutCap = 5120;     // staged PAF bytes per warp
-constexpr u32 kETextCap = 4096;    // staged GAF bytes per warp (the records its 32 lines come from)
+#ifndef G2P_EMIT_TEXT_CAP
+#define G2P_EMIT_TEXT_CAP 4096
+#endif
+constexpr u32 kETextCap = G2P_EMIT_TEXT_CAP;    // staged GAF bytes per warp (the records its 32 lines come from); 0: read the text from global
 constexpr size_t kEmitSmem = (size_t)(kEThreads / 32) * (kEOutCap + 16 + kETextCap + 32);
 
 // What k_emit_lines needs to start all its loads at once for a line of a k_short record.

@@ -55,6 +55,10 @@ def test_reference_binary_matches_golden():
     ("stable", 300, {}),
     ("medium", 300, {}),
     ("asm", 2, {"steps_lo": 800, "steps_hi": 1500}),
+    # short records with 4..6-digit numbers (k_rec's loop paths) and with many tiny steps / ops
+    ("short", 1500, {"node_len_lo": 2000, "node_len_hi": 300000, "mrun_lo": 500, "mrun_hi": 150000, "steps_lo": 1, "steps_hi": 3, "max_runs": 4}),
+    ("stable", 1500, {"node_len_lo": 2000, "node_len_hi": 300000, "mrun_lo": 500, "mrun_hi": 150000, "steps_lo": 1, "steps_hi": 3, "max_runs": 4}),
+    ("short_eqx", 1500, {"node_len_lo": 5, "node_len_hi": 40, "mrun_lo": 1, "mrun_hi": 12, "steps_lo": 1, "steps_hi": 7, "max_runs": 12, "indel_lo": 1, "indel_hi": 3}),
 ])
 def test_differential_synthetic(name, count, over):
     """port == hostsim (== reference when built) on seeded synthetic records."""
