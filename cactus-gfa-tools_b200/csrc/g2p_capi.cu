@@ -28,6 +28,22 @@ using namespace g2p;
 
 namespace {
 
+// Pipeline counters go to the host through a kernel that stores into mapped pinned memory, not
+// through cudaMemcpyAsync: a small D2H copy queues on the copy engine BEHIND the 200 MB output copy
+// of another chunk (measured: every pipeline of g2p_convert_host stalled 4-9 ms on its two counter
+// read-backs), a store from a kernel does not.
+__global__ void k_meta_to_host(const g2p::PipelineMeta* __restrict__ src, g2p::PipelineMeta* __restrict__ dst) {
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
+    volatile uint32_t* d = reinterpret_cast<volatile uint32_t*>(dst);
+    for (uint32_t i = threadIdx.x; i < sizeof(g2p::PipelineMeta) / 4; i += blockDim.x) d[i] = s[i];
+    __threadfence_system();
+}
+static_assert(sizeof(g2p::PipelineMeta) % 4 == 0, "PipelineMeta is copied as 32-bit words");
+inline cudaError_t meta_to_host(void* h_meta, const void* d_meta, cudaStream_t st) {
+    k_meta_to_host<<<1, 32, 0, st>>>(static_cast<const g2p::PipelineMeta*>(d_meta), static_cast<g2p::PipelineMeta*>(h_meta));
+    return cudaGetLastError();
+}
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
@@ -51,7 +67,7 @@ struct PinBuf {
         if (p) cudaFreeHost(p);
         p = nullptr; cap = 0;
         size_t want = bytes + bytes / 8 + 4096;
-        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocMapped | cudaHostAllocPortable);   // also device-addressable (unified addressing)
         if (e == cudaSuccess) cap = want;
         return e;
     }
@@ -80,7 +96,7 @@ struct Worker {
 };
 
 constexpr int kWorkers = 3;            // chunks in flight in g2p_convert_host: H2D / kernels / D2H overlap
-constexpr size_t kHostChunk = 96u << 20;   // bytes of GAF per chunk (cut at a newline)
+constexpr size_t kHostChunk = 48u << 20;   // bytes of GAF per chunk (cut at a newline)
 
 struct g2p_ctx {
     int device = 0;
@@ -219,7 +235,7 @@ static int run_index(g2p_ctx* ctx, Worker& w, const u8* d_text, size_t n, cudaSt
         G2P_CUDA(cudaMemsetAsync(d_status, 0, ((size_t)ntiles + 1) * sizeof(u64), st));
         k_index1<<<ntiles, kIdxThreads, 0, st>>>(d_text, n, ntiles, d_status, d_ticket, static_cast<u32*>(w.d_rec.p), (u32)cap64, d_meta);
         ++*launches;
-        G2P_CUDA(cudaMemcpyAsync(w.h_meta.p, d_meta, sizeof(PipelineMeta), cudaMemcpyDeviceToHost, st));
+        G2P_CUDA(meta_to_host(w.h_meta.p, d_meta, st)); ++*launches;
         G2P_CUDA(cudaStreamSynchronize(st));
         G2P_CUDA(cudaGetLastError());
         if ((u64)hm->n_records + 2 <= cap64) return G2P_OK;
@@ -229,7 +245,7 @@ static int run_index(g2p_ctx* ctx, Worker& w, const u8* d_text, size_t n, cudaSt
     if (ntiles) { k_count_lines<<<ntiles, kIdxThreads, 0, st>>>(d_text, n, d_tiles); ++*launches; }
     k_scan_tiles<<<1, 1024, 0, st>>>(d_tiles, ntiles, d_text, n, d_meta);
     ++*launches;
-    G2P_CUDA(cudaMemcpyAsync(w.h_meta.p, d_meta, sizeof(PipelineMeta), cudaMemcpyDeviceToHost, st));
+    G2P_CUDA(meta_to_host(w.h_meta.p, d_meta, st)); ++*launches;
     G2P_CUDA(cudaStreamSynchronize(st));
     G2P_CUDA(w.d_rec.ensure(((size_t)hm->n_records + 2) * sizeof(u32)));
     if (ntiles) {
@@ -327,7 +343,7 @@ static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
     k_scan_blocks2<<<1, 1024, 0, st>>>(d_blocks, d_blocks + nscan, nscan, &d_meta->out_total, &d_meta->lines_total);
     k_scan_apply2<<<nscan, kScanThreads, 0, st>>>(d_off, d_loff, nrec, d_blocks, d_blocks + nscan, &d_meta->out_total, &d_meta->lines_total, d_rec, d_map);
     launches += 3;
-    G2P_CUDA(cudaMemcpyAsync(hm, d_meta, sizeof(PipelineMeta), cudaMemcpyDeviceToHost, st));
+    G2P_CUDA(meta_to_host(w.h_meta.p, d_meta, st)); ++launches;
     G2P_CUDA(cudaStreamSynchronize(st));
     const u64 out_total = hm->out_total;
     res->n_long = hm->n_deleg;
@@ -363,7 +379,7 @@ static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
     if (hm->first_err != 0xFFFFFFFFu) {
         k_diagnose<<<1, 1, 0, st>>>(d_gaf, d_rec, ctx->table, d_off, d_meta);
         ++launches;
-        G2P_CUDA(cudaMemcpyAsync(hm, d_meta, sizeof(PipelineMeta), cudaMemcpyDeviceToHost, st));
+        G2P_CUDA(meta_to_host(w.h_meta.p, d_meta, st)); ++launches;
     }
     G2P_CUDA(cudaStreamSynchronize(st));
     G2P_CUDA(cudaGetLastError());
@@ -411,7 +427,7 @@ int g2p_convert_host(g2p_ctx* ctx, const char* gaf, size_t n, const char** out, 
     G2P_CUDA(cudaSetDevice(ctx->device));
 
     // newline-aligned chunk boundaries.  Chunks must hold enough records to fill the GPU: short
-    // reads do at 96 MB, chromosome-scale records (one warp each in k_long) need more.
+    // reads do at 48 MB, chromosome-scale records (one warp each in k_long) need more.
     size_t chunk = ctx->host_chunk;
     if (!ctx->host_chunk_fixed && n > chunk) {
         const size_t probe = std::min<size_t>(n, 4u << 20);
@@ -422,7 +438,10 @@ int g2p_convert_host(g2p_ctx* ctx, const char* gaf, size_t n, const char** out, 
     }
     std::vector<size_t> cut{0};
     while (cut.back() < n) {
-        size_t e = cut.back() + chunk;
+        // the first chunks are smaller (1/3, 2/3 of a chunk): the output copy, which bounds the call
+        // (PCIe D2H), starts after the first chunk's H2D + kernels
+        const size_t k = cut.size();
+        size_t e = cut.back() + (ctx->host_chunk_fixed || k > 2 ? chunk : chunk * k / 3);
         if (e >= n) e = n;
         else {
             const void* nl = std::memchr(gaf + e - 1, '\n', n - (e - 1));
@@ -668,7 +687,7 @@ static int run_unstable(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
     k_scan_blocks<<<1, 1024, 0, st>>>(d_blocks, nscan, &d_meta->out_total);
     k_scan_apply<<<nscan, kScanThreads, 0, st>>>(d_off, nrec, d_blocks, &d_meta->out_total);
     launches += 3;
-    G2P_CUDA(cudaMemcpyAsync(hm, d_meta, sizeof(PipelineMeta), cudaMemcpyDeviceToHost, st));
+    G2P_CUDA(meta_to_host(w.h_meta.p, d_meta, st)); ++launches;
     G2P_CUDA(cudaStreamSynchronize(st));
     const u64 out_total = hm->out_total;
     G2P_CUDA(w.d_out.ensure(out_total + 256));

@@ -43,6 +43,9 @@ constexpr u32 kRMinChunks = 6, kRMaxChunks = 16;   // 16-byte chunks per record 
 #ifndef G2P_REC_FAST_NUM
 #define G2P_REC_FAST_NUM 0
 #endif
+#ifndef G2P_REC_SORT
+#define G2P_REC_SORT 1   /* order the CTA's records by length before assigning them to threads */
+#endif
 #ifndef G2P_REC_SCAN4
 #define G2P_REC_SCAN4 1
 #endif
@@ -159,7 +162,7 @@ __device__ __forceinline__ bool rec_steps(const LenTableView& T, const u8* rt, c
 // the token's text span.  Tokens of up to three digits (all of a short read's) are decoded without
 // a loop from the five bytes next to the cursor, loaded together: one shared-memory round trip per
 // op instead of one per digit, and the same instruction stream for '+' and '-' records.
-#if G2P_REC_FAST_OP
+#if G2P_REC_FAST_OP == 1
 #define G2P_REC_SLOW_INLINE G2P_NOINLINE
 #else
 #define G2P_REC_SLOW_INLINE __forceinline__
@@ -359,6 +362,45 @@ __global__ void __launch_bounds__(kRThreads, G2P_REC_CTAS) k_rec(const RecArgs r
     const u32 C = ra.chunks, SW = rec_slot_words(C);
     u32* slots = reinterpret_cast<u32*>(smem);
     const u32 r0 = blockIdx.x * (u32)kRThreads;
+    // ---- order the CTA's records by length (counting sort on the byte count): record rl goes to slot
+    // s_slot[rl], thread t converts the record of slot t.  The lanes of a warp then hold records of
+    // similar length, hence with similar numbers of steps and ops and similar field widths, so the
+    // trip counts of the walk's loops (a warp pays the maximum over its lanes) stay close to the mean.
+    __shared__ u32 s_hist[kRThreads];
+    __shared__ u16 s_slot[kRThreads], s_rec[kRThreads];
+    __shared__ u32 s_wsum[kRThreads / 32];
+#if G2P_REC_SORT
+    {
+        const u32 t = threadIdx.x, r = r0 + t;
+        s_hist[t] = 0;
+        __syncthreads();
+        u32 key = 255, pos = 0;
+        if (r < a.nrec) {
+            const u32 l = a.rec_start[r + 1] - a.rec_start[r];
+            key = l < 255u ? l : 255u;
+        }
+        pos = atomicAdd(&s_hist[key], 1u);
+        __syncthreads();
+        // exclusive scan of the 256 bins
+        const u32 h = s_hist[t];
+        u32 inc = h;
+        for (int d = 1; d < 32; d <<= 1) { const u32 v = __shfl_up_sync(0xffffffffu, inc, d); if ((t & 31u) >= (u32)d) inc += v; }
+        if ((t & 31u) == 31u) s_wsum[t >> 5] = inc;
+        __syncthreads();
+        u32 base = 0;
+        for (u32 w = 0; w < (t >> 5); ++w) base += s_wsum[w];
+        __syncthreads();
+        s_hist[t] = base + inc - h;
+        __syncthreads();
+        const u32 slot = s_hist[key] + pos;
+        s_slot[t] = (u16)slot;
+        s_rec[slot] = (u16)t;
+    }
+    __syncthreads();
+#else
+    s_slot[threadIdx.x] = (u16)threadIdx.x; s_rec[threadIdx.x] = (u16)threadIdx.x;
+    __syncthreads();
+#endif
     // ---- stage: 8 lanes per record, 32 records per pass, 128-bit coalesced loads
     {
         const u32 gl = threadIdx.x & (kRStage - 1), grp = threadIdx.x / kRStage;
@@ -369,7 +411,7 @@ __global__ void __launch_bounds__(kRThreads, G2P_REC_CTAS) k_rec(const RecArgs r
             const u32 A = s & ~15u;
             const u32 nch = (e - A + 15u) >> 4;   // the record and its '\n'
             if (e - s > 1u && e - s - 1u <= kSLimit && nch <= C) {
-                u32* dst = slots + (size_t)rl * SW;
+                u32* dst = slots + (size_t)s_slot[rl] * SW;
                 for (u32 c = gl; c < nch; c += kRStage) {
                     const uint4 v = ldg_vec_guarded(a.gaf, (u64)A + 16u * c, a.n);
                     dst[4 * c] = v.x; dst[4 * c + 1] = v.y; dst[4 * c + 2] = v.z; dst[4 * c + 3] = v.w;
@@ -378,7 +420,7 @@ __global__ void __launch_bounds__(kRThreads, G2P_REC_CTAS) k_rec(const RecArgs r
         }
     }
     __syncthreads();
-    const u32 r = r0 + threadIdx.x;
+    const u32 r = r0 + s_rec[threadIdx.x];
     if (r >= a.nrec) return;
     const u32 s = a.rec_start[r], e = a.rec_start[r + 1];
     const u32 len = e - s - 1, sh = s & 15u;
