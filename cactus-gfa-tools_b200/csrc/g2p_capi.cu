@@ -14,7 +14,9 @@
 #include <set>
 #include <thread>
 #include <vector>
+#include <cctype>
 #include <chrono>
+#include <sched.h>
 #include <cstring>
 #include <new>
 #include <string>
@@ -80,7 +82,7 @@ struct PinBuf {
 struct Worker {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
-    DevBuf d_in, d_tiles, d_rec, d_status, d_off, d_blocks, d_out, d_meta, d_list, d_list2, d_desc, d_rdesc, d_sdesc, d_loff, d_map;
+    DevBuf d_in, d_tiles, d_rec, d_status, d_off, d_blocks, d_out, d_meta, d_list, d_list2, d_desc, d_rdesc, d_sdesc, d_loff, d_map, d_lsort, d_perm;
     PinBuf h_meta;
     bool init() {
         if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) return false;
@@ -88,7 +90,7 @@ struct Worker {
         return d_meta.ensure(sizeof(PipelineMeta)) == cudaSuccess && h_meta.ensure(sizeof(PipelineMeta)) == cudaSuccess;
     }
     void release() {
-        for (DevBuf* b : {&d_in, &d_tiles, &d_rec, &d_status, &d_off, &d_blocks, &d_out, &d_meta, &d_list, &d_list2, &d_desc, &d_rdesc, &d_sdesc, &d_loff, &d_map}) b->release();
+        for (DevBuf* b : {&d_in, &d_tiles, &d_rec, &d_status, &d_off, &d_blocks, &d_out, &d_meta, &d_list, &d_list2, &d_desc, &d_rdesc, &d_sdesc, &d_loff, &d_map, &d_lsort, &d_perm}) b->release();
         h_meta.release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
@@ -120,6 +122,7 @@ struct g2p_ctx {
     size_t host_chunk = kHostChunk;
     bool host_chunk_fixed = false;   // G2P_HOST_CHUNK_MB given: no adaptation to the record length
     bool two_pass_index = true;      // default: counting index (count, scan, fill); G2P_ONE_PASS_INDEX=1 selects k_index1 (measured slower, see profiles/r01_summary.md)
+    bool len_sort = false;           // G2P_LEN_SORT=0: k_rec takes the records in input order (in-CTA sort only)
     bool size_kernel_short = false;  // G2P_SIZE_KERNEL=short: k_short (8 lanes per record) instead of k_rec (thread per record)
     uint32_t rec_chunks_override = 0; // G2P_REC_CHUNKS: k_rec slot capacity in 16-byte chunks
     uint64_t desc_cap_override = 0;  // G2P_DESC_CAP (tests): line-descriptor slots, to exercise the overflow fallback
@@ -137,6 +140,49 @@ struct g2p_ctx {
 
 extern "C" {
 
+// Host-side locality: the calling thread (and the worker threads it will start, which inherit its mask)
+// is restricted to the CPUs of the GPU's NUMA node, so that the pinned buffers it allocates are placed in
+// that node's memory and the PCIe copies of several GPUs of one box do not all cross the socket link
+// (8 ranks moved 35 GB of host memory per step at 113 GB/s without it).  G2P_NUMA_BIND=0 turns it off;
+// nothing happens when sysfs has no node for the device or the node's CPUs are not in the current mask.
+static void bind_to_gpu_numa_node(int device) {
+    if (const char* c = std::getenv("G2P_NUMA_BIND")) if (std::atoi(c) == 0) return;
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, (int)sizeof bus, device) != cudaSuccess) return;
+    for (char* q = bus; *q; ++q) *q = (char)std::tolower((unsigned char)*q);
+    char path[160];
+    std::snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* f = std::fopen(path, "r");
+    if (!f) return;
+    int node = -1;
+    const int got = std::fscanf(f, "%d", &node);
+    std::fclose(f);
+    if (got != 1 || node < 0) return;
+    std::snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    f = std::fopen(path, "r");
+    if (!f) return;
+    char list[4096] = {0};
+    const bool have = std::fgets(list, (int)sizeof list, f) != nullptr;
+    std::fclose(f);
+    if (!have) return;
+    cpu_set_t cur, want;
+    CPU_ZERO(&want);
+    if (sched_getaffinity(0, sizeof cur, &cur) != 0) return;
+    int n_want = 0;
+    for (char* q = list; *q;) {   // "0-31,64-95"
+        char* end = nullptr;
+        const long a = std::strtol(q, &end, 10);
+        if (end == q) break;
+        long b = a;
+        q = end;
+        if (*q == '-') { b = std::strtol(q + 1, &end, 10); q = end; }
+        for (long c = a; c <= b && c < CPU_SETSIZE; ++c)
+            if (c >= 0 && CPU_ISSET((int)c, &cur)) { CPU_SET((int)c, &want); ++n_want; }
+        if (*q == ',') ++q; else break;
+    }
+    if (n_want > 0) sched_setaffinity(0, sizeof want, &want);
+}
+
 int g2p_create(int device, g2p_ctx** out) {
     if (!out) return G2P_E_ARG;
     *out = nullptr;
@@ -144,6 +190,7 @@ int g2p_create(int device, g2p_ctx** out) {
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return G2P_E_NO_DEVICE;
     if (cudaSetDevice(device) != cudaSuccess) return G2P_E_NO_DEVICE;
+    bind_to_gpu_numa_node(device);
     g2p_ctx* ctx = new (std::nothrow) g2p_ctx();
     if (!ctx) return G2P_E_ARG;
     ctx->device = device;
@@ -152,6 +199,7 @@ int g2p_create(int device, g2p_ctx** out) {
     cudaFuncSetAttribute(k_short<kSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShortSmem);
     cudaFuncSetAttribute(k_rec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rec_smem(kRMaxChunks));
     if (const char* c = std::getenv("G2P_SIZE_KERNEL")) ctx->size_kernel_short = std::strcmp(c, "short") == 0;
+    if (const char* c = std::getenv("G2P_LEN_SORT")) ctx->len_sort = std::atoi(c) != 0;
     if (const char* c = std::getenv("G2P_REC_CHUNKS")) ctx->rec_chunks_override = (u32)std::min(std::max(std::atoi(c), (int)kRMinChunks), (int)kRMaxChunks);
     cudaFuncSetAttribute(k_emit_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmitSmem);
     cudaFuncSetAttribute(k_long<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)long_smem<true>());
@@ -329,7 +377,23 @@ static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
     if (ctx->size_kernel_short) k_short<kSG><<<ncta, kSThreads, kShortSmem, st>>>(sa);
     else {
         const u32 chunks = ctx->rec_chunks_override ? ctx->rec_chunks_override : rec_chunks_for((u64)n, nrec);
-        RecArgs ra{sa, chunks};
+        const u32* d_perm = nullptr;
+        if (ctx->len_sort && nrec > kRThreads) {   // order the records by length class: counting sort with the u64 scan kernels
+            const u32 nsort = (nrec + kLenSortRecs - 1) / kLenSortRecs, nm = kLenBins * nsort;
+            const u32 nscan_m = (nm + kScanTile - 1) / kScanTile;
+            G2P_CUDA(w.d_lsort.ensure(((size_t)nm + 1 + nscan_m) * sizeof(u64)));
+            G2P_CUDA(w.d_perm.ensure((size_t)nrec * sizeof(u32)));
+            u64* d_m = static_cast<u64*>(w.d_lsort.p);
+            u64* d_mb = d_m + nm + 1;
+            k_len_hist<<<nsort, 256, 0, st>>>(d_rec, nrec, nsort, d_m);
+            k_scan_reduce<<<nscan_m, kScanThreads, 0, st>>>(d_m, nm, d_mb);
+            k_scan_blocks<<<1, 1024, 0, st>>>(d_mb, nscan_m, d_m + nm);
+            k_scan_apply<<<nscan_m, kScanThreads, 0, st>>>(d_m, nm, d_mb, d_m + nm);
+            k_len_scatter<<<nsort, 256, 0, st>>>(d_rec, nrec, nsort, d_m, static_cast<u32*>(w.d_perm.p));
+            launches += 5;
+            d_perm = static_cast<const u32*>(w.d_perm.p);
+        }
+        RecArgs ra{sa, chunks, d_perm};
         k_rec<<<(nrec + kRThreads - 1) / kRThreads, kRThreads, rec_smem(chunks), st>>>(ra);
     }
     k_long<false><<<nlong, kLThreads, long_smem<false>(), st>>>(la);

@@ -95,7 +95,21 @@ int main(int argc, char** argv) {
     if (sk && !std::strcmp(sk, "short")) hs::launch(dim3(ncta), dim3(kSThreads), kShortSmem, [&] { k_short<kSG>(sa); });
     else {
         const u32 chunks = std::getenv("G2P_REC_CHUNKS") ? (u32)std::atoi(std::getenv("G2P_REC_CHUNKS")) : rec_chunks_for(n, nrec);
-        RecArgs ra{sa, chunks};
+        std::vector<u32> perm(nrec);
+        const u32* permp = nullptr;
+        if (!std::getenv("G2P_LEN_SORT") || std::atoi(std::getenv("G2P_LEN_SORT")) != 0) {   // as run_pipeline (g2p_capi.cu)
+            const u32 nsort = (nrec + kLenSortRecs - 1) / kLenSortRecs, nm = kLenBins * nsort;
+            const u32 nscan_m = (nm + kScanTile - 1) / kScanTile;
+            std::vector<u64> m((size_t)nm + 1 + nscan_m);
+            u64* mb = m.data() + nm + 1;
+            hs::launch(dim3(nsort), dim3(256), 0, [&] { k_len_hist(rec.data(), nrec, nsort, m.data()); });
+            hs::launch(dim3(nscan_m), dim3(kScanThreads), 0, [&] { k_scan_reduce(m.data(), nm, mb); });
+            hs::launch(dim3(1), dim3(1024), 0, [&] { k_scan_blocks(mb, nscan_m, m.data() + nm); });
+            hs::launch(dim3(nscan_m), dim3(kScanThreads), 0, [&] { k_scan_apply(m.data(), nm, mb, m.data() + nm); });
+            hs::launch(dim3(nsort), dim3(256), 0, [&] { k_len_scatter(rec.data(), nrec, nsort, m.data(), perm.data()); });
+            permp = perm.data();
+        }
+        RecArgs ra{sa, chunks, permp};
         hs::launch(dim3((nrec + kRThreads - 1) / kRThreads), dim3(kRThreads), rec_smem(chunks), [&] { k_rec(ra); });
     }
     LongArgs la{gaf, n, rec.data(), T, off.data(), status.data(), nullptr, list.data(), &meta.n_deleg, list2.data(), &meta.n_deleg2,
