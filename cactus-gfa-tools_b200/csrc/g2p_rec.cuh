@@ -43,6 +43,10 @@ constexpr u32 kRMinChunks = 6, kRMaxChunks = 16;   // 16-byte chunks per record 
 #ifndef G2P_REC_FAST_NUM
 #define G2P_REC_FAST_NUM 0
 #endif
+#ifndef G2P_REC_STAGE_PASSES
+#define G2P_REC_STAGE_PASSES 2   /* staging passes whose loads are in flight together (1, 2, 4 or 8) */
+#endif
+static_assert(kRMaxChunks <= 2 * kRStage && (kRThreads / (kRThreads / kRStage)) % G2P_REC_STAGE_PASSES == 0, "staging copies a record in two rounds of kRStage lanes");
 #ifndef G2P_REC_SORT
 #define G2P_REC_SORT 1   /* order the CTA's records by length before assigning them to threads */
 #endif
@@ -432,20 +436,40 @@ __global__ void __launch_bounds__(kRThreads, G2P_REC_CTAS) k_rec(const RecArgs r
     s_slot[threadIdx.x] = (u16)threadIdx.x; s_rec[threadIdx.x] = (u16)threadIdx.x;
     __syncthreads();
 #endif
-    // ---- stage: 8 lanes per record, 32 records per pass, 128-bit coalesced loads
+    // ---- stage: 8 lanes per record, 32 records per pass, 128-bit coalesced loads; the loads of two
+    // passes (up to four vectors per thread) are issued before the first store, so that the
+    // rec_start -> text -> shared-memory chains of the passes overlap
     {
         const u32 gl = threadIdx.x & (kRStage - 1), grp = threadIdx.x / kRStage;
-        for (u32 rl = grp; rl < (u32)kRThreads; rl += kRThreads / kRStage) {
-            if (r0 + rl >= a.nrec) break;
-            const u32 r = ra.perm ? ra.perm[r0 + rl] : r0 + rl;
-            const u32 s = a.rec_start[r], e = a.rec_start[r + 1];
-            const u32 A = s & ~15u;
-            const u32 nch = (e - A + 15u) >> 4;   // the record and its '\n'
-            if (e - s > 1u && e - s - 1u <= kSLimit && nch <= C) {
+        constexpr u32 kPer = kRThreads / kRStage;   // records per pass
+#pragma unroll 1
+        for (u32 pass = 0; pass < (u32)kRThreads / kPer; pass += G2P_REC_STAGE_PASSES) {
+            uint4 v0[G2P_REC_STAGE_PASSES], v1[G2P_REC_STAGE_PASSES];
+            u32 nchv[G2P_REC_STAGE_PASSES];
+#pragma unroll
+            for (int u = 0; u < G2P_REC_STAGE_PASSES; ++u) {
+                const u32 rl = (pass + (u32)u) * kPer + grp;
+                nchv[u] = 0;
+                if (r0 + rl < a.nrec) {
+                    const u32 r = ra.perm ? ra.perm[r0 + rl] : r0 + rl;
+                    const u32 s = a.rec_start[r], e = a.rec_start[r + 1];
+                    const u32 A = s & ~15u;
+                    const u32 nch = (e - A + 15u) >> 4;   // the record and its '\n'
+                    if (e - s > 1u && e - s - 1u <= kSLimit && nch <= C) {
+                        nchv[u] = nch;
+                        if (gl < nch) v0[u] = ldg_vec_guarded(a.gaf, (u64)A + 16u * gl, a.n);
+                        if (gl + kRStage < nch) v1[u] = ldg_vec_guarded(a.gaf, (u64)A + 16u * (gl + kRStage), a.n);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < G2P_REC_STAGE_PASSES; ++u) {
+                const u32 rl = (pass + (u32)u) * kPer + grp;
                 u32* dst = slots + (size_t)s_slot[rl] * SW;
-                for (u32 c = gl; c < nch; c += kRStage) {
-                    const uint4 v = ldg_vec_guarded(a.gaf, (u64)A + 16u * c, a.n);
-                    dst[4 * c] = v.x; dst[4 * c + 1] = v.y; dst[4 * c + 2] = v.z; dst[4 * c + 3] = v.w;
+                if (gl < nchv[u]) { dst[4 * gl] = v0[u].x; dst[4 * gl + 1] = v0[u].y; dst[4 * gl + 2] = v0[u].z; dst[4 * gl + 3] = v0[u].w; }
+                if (gl + kRStage < nchv[u]) {
+                    const u32 c = gl + kRStage;
+                    dst[4 * c] = v1[u].x; dst[4 * c + 1] = v1[u].y; dst[4 * c + 2] = v1[u].z; dst[4 * c + 3] = v1[u].w;
                 }
             }
         }

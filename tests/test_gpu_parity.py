@@ -390,3 +390,30 @@ def test_late_delegation(g2p):
             assert (out == ref) if rc != 134 else ref.startswith(out), name
     finally:
         cv.close()
+
+
+@pytest.mark.parametrize("env", [
+    {"G2P_SIZE_KERNEL": "short"},                  # the 8-lanes-per-record size pass
+    {"G2P_LEN_SORT": "1"},                         # k_rec on records ordered by length class
+    {"G2P_REC_CHUNKS": "9"},                       # small k_rec slots: the longer half of the records goes to k_long
+    {"G2P_REC_CHUNKS": "16", "G2P_LEN_SORT": "1"},
+])
+def test_size_pass_variants(g2p, monkeypatch, env):
+    """Every selectable form of the short-record size pass (k_rec with its slot sizes and record orders,
+    k_short) produces the reference's bytes, on node-step records, '=' / 'X' CIGARs, interval steps with
+    5-6 digit numbers and '*' lines."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    big = {"node_len_lo": 2000, "node_len_hi": 300000, "mrun_lo": 500, "mrun_hi": 150000, "steps_lo": 1, "steps_hi": 3, "max_runs": 4}
+    for name, count, over in [("short", 40000, {"pct_star": 2}), ("short_eqx", 20000, {}), ("stable", 6000, big), ("short", 6000, big)]:
+        p = H.preset(name, seed=77, **over)
+        lengths = H.gen_lengths(p)
+        gaf = H.gen_records(p, 0, count)
+        cv = g2p.Converter(0)
+        try:
+            assert cv.load_lengths(lengths)
+            out, res = cv.convert_host(gaf)
+        finally:
+            cv.close()
+        rc, ref, err, kind = H.run_gaf2paf_cpu(gaf, lengths)
+        assert rc == 0 and g2p.exit_code(res) == 0 and out == ref, (env, name)
