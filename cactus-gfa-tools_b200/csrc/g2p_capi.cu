@@ -122,6 +122,8 @@ struct g2p_ctx {
     size_t host_chunk = kHostChunk;
     bool host_chunk_fixed = false;   // G2P_HOST_CHUNK_MB given: no adaptation to the record length
     bool two_pass_index = true;      // default: counting index (count, scan, fill); G2P_ONE_PASS_INDEX=1 selects k_index1 (measured slower, see profiles/r01_summary.md)
+    bool have_cpus = false;          // CPUs of the GPU's NUMA node (G2P_NUMA_BIND=0: none)
+    cpu_set_t cpus;
     bool len_sort = false;           // G2P_LEN_SORT=0: k_rec takes the records in input order (in-CTA sort only)
     bool size_kernel_short = false;  // G2P_SIZE_KERNEL=short: k_short (8 lanes per record) instead of k_rec (thread per record)
     uint32_t rec_chunks_override = 0; // G2P_REC_CHUNKS: k_rec slot capacity in 16-byte chunks
@@ -143,31 +145,44 @@ extern "C" {
 // Host-side locality: the calling thread (and the worker threads it will start, which inherit its mask)
 // is restricted to the CPUs of the GPU's NUMA node, so that the pinned buffers it allocates are placed in
 // that node's memory and the PCIe copies of several GPUs of one box do not all cross the socket link
-// (8 ranks moved 35 GB of host memory per step at 113 GB/s without it).  G2P_NUMA_BIND=0 turns it off;
+// (on the single-NUMA-node VM this round was measured on it is a no-op: 8 ranks move 35 GB of host memory
+// per step at ~115 GB/s with or without it).  G2P_NUMA_BIND=0 turns it off;
 // nothing happens when sysfs has no node for the device or the node's CPUs are not in the current mask.
-static void bind_to_gpu_numa_node(int device) {
-    if (const char* c = std::getenv("G2P_NUMA_BIND")) if (std::atoi(c) == 0) return;
+// The mask is computed once per context against the mask the process had when the first context was
+// created, and applied to the thread that creates the context and to every thread that enters
+// g2p_convert_host with it (several contexts, one host thread per GPU: each thread ends up on its own
+// GPU's node).
+static bool gpu_numa_cpus(int device, cpu_set_t* want) {
+    if (const char* c = std::getenv("G2P_NUMA_BIND")) if (std::atoi(c) == 0) return false;
+    static std::mutex mu;
+    static bool have_orig = false;
+    static cpu_set_t orig;
+    {
+        std::lock_guard<std::mutex> g(mu);
+        if (!have_orig) {
+            if (sched_getaffinity(0, sizeof orig, &orig) != 0) return false;
+            have_orig = true;
+        }
+    }
     char bus[32] = {0};
-    if (cudaDeviceGetPCIBusId(bus, (int)sizeof bus, device) != cudaSuccess) return;
+    if (cudaDeviceGetPCIBusId(bus, (int)sizeof bus, device) != cudaSuccess) return false;
     for (char* q = bus; *q; ++q) *q = (char)std::tolower((unsigned char)*q);
     char path[160];
     std::snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
     FILE* f = std::fopen(path, "r");
-    if (!f) return;
+    if (!f) return false;
     int node = -1;
     const int got = std::fscanf(f, "%d", &node);
     std::fclose(f);
-    if (got != 1 || node < 0) return;
+    if (got != 1 || node < 0) return false;
     std::snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
     f = std::fopen(path, "r");
-    if (!f) return;
+    if (!f) return false;
     char list[4096] = {0};
     const bool have = std::fgets(list, (int)sizeof list, f) != nullptr;
     std::fclose(f);
-    if (!have) return;
-    cpu_set_t cur, want;
-    CPU_ZERO(&want);
-    if (sched_getaffinity(0, sizeof cur, &cur) != 0) return;
+    if (!have) return false;
+    CPU_ZERO(want);
     int n_want = 0;
     for (char* q = list; *q;) {   // "0-31,64-95"
         char* end = nullptr;
@@ -177,10 +192,10 @@ static void bind_to_gpu_numa_node(int device) {
         q = end;
         if (*q == '-') { b = std::strtol(q + 1, &end, 10); q = end; }
         for (long c = a; c <= b && c < CPU_SETSIZE; ++c)
-            if (c >= 0 && CPU_ISSET((int)c, &cur)) { CPU_SET((int)c, &want); ++n_want; }
+            if (c >= 0 && CPU_ISSET((int)c, &orig)) { CPU_SET((int)c, want); ++n_want; }
         if (*q == ',') ++q; else break;
     }
-    if (n_want > 0) sched_setaffinity(0, sizeof want, &want);
+    return n_want > 0;
 }
 
 int g2p_create(int device, g2p_ctx** out) {
@@ -190,10 +205,11 @@ int g2p_create(int device, g2p_ctx** out) {
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return G2P_E_NO_DEVICE;
     if (cudaSetDevice(device) != cudaSuccess) return G2P_E_NO_DEVICE;
-    bind_to_gpu_numa_node(device);
     g2p_ctx* ctx = new (std::nothrow) g2p_ctx();
     if (!ctx) return G2P_E_ARG;
     ctx->device = device;
+    ctx->have_cpus = gpu_numa_cpus(device, &ctx->cpus);
+    if (ctx->have_cpus) sched_setaffinity(0, sizeof ctx->cpus, &ctx->cpus);   // before the pinned buffers are allocated
     for (auto& w : ctx->w)
         if (!w.init()) { g2p_destroy(ctx); return G2P_E_NO_DEVICE; }
     cudaFuncSetAttribute(k_short<kSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShortSmem);
@@ -489,6 +505,7 @@ int g2p_convert_host(g2p_ctx* ctx, const char* gaf, size_t n, const char** out, 
     *out = nullptr;
     std::memset(res, 0, sizeof *res);
     G2P_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->have_cpus) sched_setaffinity(0, sizeof ctx->cpus, &ctx->cpus);   // the worker threads inherit the mask
 
     // newline-aligned chunk boundaries.  Chunks must hold enough records to fill the GPU: short
     // reads do at 48 MB, chromosome-scale records (one warp each in k_long) need more.
