@@ -32,6 +32,9 @@ WORKLOADS = {
     # BASELINE.json configs[2]: synthetic 10M-record short-read GAF on 1 B200
     "short": {"preset": "short", "records": 10_000_000, "desc": "configs[2]: synthetic short-read GAF, 1-5 node steps, short cg CIGARs"},
     # BASELINE.json configs[3] at a record count whose PAF fits one GPU next to the input
+    # shapes of configs[0] / configs[1] (stable-interval and node-coordinate assembly alignments), parity-test sized
+    "stable": {"preset": "stable", "records": 300_000, "desc": "configs[0] shape: stable-interval steps (>contig:start-end), ~2 kB records"},
+    "medium": {"preset": "medium", "records": 100_000, "desc": "configs[1] shape: node-coordinate records of a few hundred steps, ~12 kB"},
     "asm": {"preset": "asm", "records": 4000, "desc": "configs[3] shape: assembly-scale records, 5k-15k steps, 4000 of the 100k records (PAF of all would not fit next to the input)"},
 }
 
@@ -129,7 +132,7 @@ def run_reference(a):
     wl = WORKLOADS[a.workload]
     procs = min(os.cpu_count() or 1, 64)
     # per-step sample sized for ~2-4 s of work per process
-    per_proc = 60000 if a.workload == "short" else 12
+    per_proc = {"short": 60000, "stable": 4000, "medium": 600}.get(a.workload, 12)
     vals = []
     for s in range(a.warmup + a.steps):
         r = cpu_baseline(H, wl["preset"], 1000 + s, per_proc * procs, procs)
@@ -299,7 +302,7 @@ def main():
         line["e2e"] = e2e
     if not a.no_cpu_baseline and world == 1:
         try:
-            line["cpu_baseline"] = cpu_baseline(H, wl["preset"], 1, 600000 if a.workload == "short" else 40, 1)
+            line["cpu_baseline"] = cpu_baseline(H, wl["preset"], 1, {"short": 600000, "stable": 40000, "medium": 6000}.get(a.workload, 40), 1)
         except Exception as ex:   # the baseline must not take the GPU number down with it
             line["cpu_baseline"] = {"error": str(ex)}
     print(json.dumps(line))

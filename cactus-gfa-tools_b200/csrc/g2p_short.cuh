@@ -782,7 +782,10 @@ __global__ void __launch_bounds__(256) k_line_map(const u64* __restrict__ line_o
     for (u64 k = b; k < e; ++k) { m.desc_idx = r * kSMaxLines + (u32)(k - b); map[k] = m; }
 }
 
-__global__ void __launch_bounds__(kEThreads) k_emit_lines(const EmitArgs a) {
+// DENSE = false: the lines of k_rec / k_short records through the line map (a.map); DENSE = true: k_long's
+// 32-slot descriptor blocks (a.map == null).
+template <bool DENSE>
+__global__ void __launch_bounds__(kEThreads, DENSE ? 3 : 4) k_emit_lines(const EmitArgs a) {
     G2P_DYN_SMEM(smem);
     const u32 FULL = 0xffffffffu;
     const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -799,7 +802,7 @@ __global__ void __launch_bounds__(kEThreads) k_emit_lines(const EmitArgs a) {
     u32 rs = 0, re = 0;   // text span of this lane's record
     u64 obase = 0;
     const LineDesc* dp = a.desc + slot;
-    if (a.map && in_range) {   // k_short's lines: one 16-byte entry tells where everything is
+    if (!DENSE && in_range) {   // k_rec's / k_short's lines: one 16-byte entry tells where everything is
         const uint4 m = __ldg(reinterpret_cast<const uint4*>(a.map + slot));
         dp = a.desc + m.x;
         rs = m.y;
@@ -815,17 +818,17 @@ __global__ void __launch_bounds__(kEThreads) k_emit_lines(const EmitArgs a) {
     LineStep L;
     unpack_line_desc(v0, v1, v2, v3, d.rec, d.loff, d.len, L);
     if (!in_range) d.len = 0;
-    const bool valid = a.map ? in_range : (d.rec != kDescInvalid && (__ldg(a.status + d.rec) & ST_F_DESC) != 0);
+    const bool valid = !DENSE ? in_range : (d.rec != kDescInvalid && (__ldg(a.status + d.rec) & ST_F_DESC) != 0);
     const u32 vmask = __ballot_sync(FULL, valid);
     if (vmask == 0) return;
     const int first = __ffs((int)vmask) - 1, last = 31 - __clz((int)vmask);
     u64 o = 0;
-    // text staging can start before the descriptors arrive when the map gave the offsets
+    // The text of the warp's records (one short span: ~14 short records, or the one or two few-kB
+    // records a dense block comes from) is staged in shared memory with one TMA bulk copy.  With the
+    // line map it starts before the descriptors arrive; dense blocks know their record only from them.
     bool text_staged = false, text_tma = false;
     u32 A = 0;
-    if (a.map) {
-        const u32 t0 = __shfl_sync(FULL, rs, first);
-        u32 t1 = __shfl_sync(FULL, re, last);
+    auto stage_text = [&](u32 t0, u32 t1) {
         if ((u64)t1 > a.n) t1 = (u32)a.n;
         A = t0 & ~15u;
         text_staged = t1 > t0 && t1 - A <= kETextCap;
@@ -841,14 +844,16 @@ __global__ void __launch_bounds__(kEThreads) k_emit_lines(const EmitArgs a) {
                 for (u32 v = lane; v < nvec; v += 32) reinterpret_cast<uint4*>(sm_text)[v] = ldg_vec_guarded(a.gaf, (u64)A + 16u * v, a.n);
             }
         }
-    }
+    };
+    if (!DENSE) stage_text(__shfl_sync(FULL, rs, first), __shfl_sync(FULL, re, last));
     if (valid) {
         const uint4* src = reinterpret_cast<const uint4*>(a.rdesc + d.rec);
         const uint4 r0 = __ldg(src), r1 = __ldg(src + 1), r2 = __ldg(src + 2);
-        if (!a.map) { rs = a.rec_start[d.rec]; obase = a.out_off[d.rec]; }
+        if (DENSE) { rs = a.rec_start[d.rec]; re = a.rec_start[d.rec + 1]; obase = a.out_off[d.rec]; }
         o = obase + d.loff;
         unpack_rec_desc(r0, r1, r2, R);
     }
+    if (DENSE) stage_text(__shfl_sync(FULL, rs, first), __shfl_sync(FULL, re, last));
     if (text_staged) {
 #if !defined(G2P_HOSTSIM)
         if (text_tma) {
@@ -865,20 +870,37 @@ __global__ void __launch_bounds__(kEThreads) k_emit_lines(const EmitArgs a) {
     const u64 onext = __shfl_down_sync(FULL, o, 1);
     const bool vnext = __shfl_down_sync(FULL, (u32)valid, 1) != 0 && lane < 31;
     const bool gap = valid && vnext && onext != end;
-    const u64 o0 = __shfl_sync(FULL, o, first), o1 = __shfl_sync(FULL, end, last);
     const bool holes = (vmask >> first) != (0xffffffffu >> (31 - (last - first)));
-    const bool staged = !__any_sync(FULL, gap) && !holes && (o1 - o0) <= kEOutCap;
-    const u32 pad = (u32)(o0 & 15u);
-    if (valid) {
-        // two instantiations so that the common one (staged lines, staged text) works on pointers the
-        // compiler can prove to be shared memory: LDS / STS instead of generic 64-bit LD / ST
-        if (staged && text_staged) write_line(sm + pad + (u32)(o - o0) + d.len, line_src(sm_text + (rs - A), R, L), R, L);
-        else if (staged) write_line(sm + pad + (u32)(o - o0) + d.len, line_src(a.gaf + rs, R, L), R, L);   // long records: text from global
-        else write_line(a.out + o + d.len, line_src(rt, R, L), R, L);
+    const u64 o1 = __shfl_sync(FULL, end, last);
+    // short records: one run that fits the buffer (32 lines of ~130 bytes); anything else goes straight to global
+    if (__any_sync(FULL, gap) || holes || (!DENSE && (o1 - __shfl_sync(FULL, o, first)) + 15u > kEOutCap)) {
+        if (valid) write_line(a.out + o + d.len, line_src(rt, R, L), R, L);
+        return;
     }
-    if (staged) {
-        const u32 total = pad + (u32)(o1 - o0);
-        u8* gb = a.out + (o0 - pad);
+    // The warp's lines are one contiguous run of the output.  It goes through the staging buffer in
+    // sub-runs of at most kEOutCap bytes (one for short reads; the 31 lines of a full batch of a
+    // 2 kB assembly record need two), each formatted in shared memory and flushed with one bulk store.
+    u32 todo = vmask;
+    do {   // (a single pass, known at compile time, for the short records' variant)
+        const int f = DENSE ? __ffs((int)todo) - 1 : first;
+        const u64 ob = __shfl_sync(FULL, o, f);
+        const u32 pad = (u32)(ob & 15u);
+        const bool fits = DENSE ? ((todo >> lane) & 1u) != 0 && (end - ob) + pad <= kEOutCap : valid;
+        const u32 in = DENSE ? __ballot_sync(FULL, fits) : vmask;   // a prefix of `todo`: the lines are in output order
+        if (DENSE && in == 0) {   // one line longer than the buffer
+            if ((int)lane == f) write_line(a.out + o + d.len, line_src(rt, R, L), R, L);
+            todo &= todo - 1u;
+            continue;
+        }
+        const u64 oe = DENSE ? __shfl_sync(FULL, end, 31 - __clz((int)in)) : o1;
+        if (fits) {
+            // two instantiations so that the common one (staged lines, staged text) works on pointers the
+            // compiler can prove to be shared memory: LDS / STS instead of generic 64-bit LD / ST
+            if (text_staged) write_line(sm + pad + (u32)(o - ob) + d.len, line_src(sm_text + (rs - A), R, L), R, L);
+            else write_line(sm + pad + (u32)(o - ob) + d.len, line_src(a.gaf + rs, R, L), R, L);   // long records: text from global
+        }
+        const u32 total = pad + (u32)(oe - ob);
+        u8* gb = a.out + (ob - pad);
         const u32 full_b = total >> 4;
 #if !defined(G2P_HOSTSIM)
         // the 16-byte aligned middle of the run leaves as one TMA bulk store
@@ -897,7 +919,9 @@ __global__ void __launch_bounds__(kEThreads) k_emit_lines(const EmitArgs a) {
 #if !defined(G2P_HOSTSIM)
         if (lane == 0) bulk_wait_read0();   // the staging buffer must outlive the copy's reads
 #endif
-    }
+        __syncwarp();
+        todo &= ~in;
+    } while (DENSE && todo);
 }
 
 }  // namespace g2p

@@ -129,12 +129,12 @@ int main(int argc, char** argv) {
     if (meta.lines_total) {
         const u32 nl = (u32)meta.lines_total;
         EmitArgs ea{gaf, n, rec.data(), off.data(), sdesc.data(), map.data(), rdesc.data(), status.data(), nl, out.data()};
-        hs::launch(dim3((nl + kEThreads - 1) / kEThreads), dim3(kEThreads), kEmitSmem, [&] { k_emit_lines(ea); });
+        hs::launch(dim3((nl + kEThreads - 1) / kEThreads), dim3(kEThreads), kEmitSmem, [&] { k_emit_lines<false>(ea); });
     }
     const u32 n_slots = std::min<u32>(meta.n_desc, desc_cap);
     if (n_slots) {
         EmitArgs ea{gaf, n, rec.data(), off.data(), desc.data(), nullptr, rdesc.data(), status.data(), n_slots, out.data()};
-        hs::launch(dim3((n_slots + kEThreads - 1) / kEThreads), dim3(kEThreads), kEmitSmem, [&] { k_emit_lines(ea); });
+        hs::launch(dim3((n_slots + kEThreads - 1) / kEThreads), dim3(kEThreads), kEmitSmem, [&] { k_emit_lines<true>(ea); });
     }
     if (meta.legacy_long) hs::launch(dim3(nlong), dim3(kLThreads), long_smem<true>(), [&] { k_long<true>(la); });
     if (meta.n_deleg2)

@@ -417,3 +417,42 @@ def test_size_pass_variants(g2p, monkeypatch, env):
             cv.close()
         rc, ref, err, kind = H.run_gaf2paf_cpu(gaf, lengths)
         assert rc == 0 and g2p.exit_code(res) == 0 and out == ref, (env, name)
+
+
+def test_mutation_fuzz_in_batches(g2p):
+    """Mutated (malformed or unusual) records embedded in the middle of batches of valid short records,
+    through the C-ABI in one process: stdout bytes, exit code and the exit(1) message must be the
+    reference's, and the valid records before the bad one must come out (tests/fuzz_vs_ref.py's
+    mutations; its per-process CLI form is the development tool)."""
+    import random
+    import fuzz_vs_ref as F
+    rnd = random.Random(20261018)
+    lengths = F.LENGTHS.encode()
+    seeds = [s.replace(" ", "\t") for s in F.SEEDS]
+    cv = g2p.Converter(0)
+    bad = []
+    try:
+        assert cv.load_lengths(lengths)
+        for case in range(300):
+            line = F.mutate(rnd, rnd.choice(F.SEEDS))
+            if rnd.random() < 0.3:
+                line = F.mutate(rnd, line.replace("\t", " "))
+            pre = [rnd.choice(seeds) for _ in range(rnd.randrange(0, 70))]
+            post = [rnd.choice(seeds) for _ in range(rnd.randrange(0, 40))]
+            gaf = ("\n".join(pre + [line] + post) + "\n").encode("latin-1")
+            out, res = cv.convert_host(gaf)
+            rc, ref_out, ref_err, kind = H.run_gaf2paf_cpu(gaf, lengths)
+            if F.tolerated(line.encode("latin-1"), ref_out, out):
+                continue
+            ok = g2p.exit_code(res) == rc
+            if rc == 134:
+                ok = ok and ref_out.startswith(out) or (ok and out.startswith(ref_out))   # stdout is stdio-buffered when the reference aborts
+            else:
+                ok = ok and out == ref_out
+            if rc == 1:
+                ok = ok and g2p.Converter.format_error(res, gaf) == ref_err
+            if not ok:
+                bad.append((case, line, rc, g2p.exit_code(res)))
+    finally:
+        cv.close()
+    assert not bad, bad[:5]
