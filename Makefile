@@ -17,7 +17,7 @@ HDRS      := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.hpp include/*.h)
 all: $(LIB) $(PKG)/bin/gaf2paf $(PKG)/bin/gaf2unstable $(BUILD)/libgafgen.so $(BUILD)/gafgen hostsim
 
 $(LIB): $(CSRC)/g2p_capi.cu $(HDRS)
-	@mkdir -p $(PKG)/lib
+	@mkdir -p $(PKG)/lib $(BUILD)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -shared -o $@ $(CSRC)/g2p_capi.cu $(wildcard $(CSRC)/g2u_capi.cu) -lcudart 2> $(BUILD)/ptxas.log || (cat $(BUILD)/ptxas.log; false)
 	@grep -E "error|warning" $(BUILD)/ptxas.log || true
 
