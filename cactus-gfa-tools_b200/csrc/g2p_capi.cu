@@ -387,7 +387,7 @@ static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
     u64* d_loff = static_cast<u64*>(w.d_loff.p);
     ShortArgs sa{d_gaf, (u64)n, d_rec, nrec, ctx->table, d_off, d_loff, d_status, d_list, &d_meta->n_deleg, d_sdesc, d_rdesc};
     LongArgs la{d_gaf, (u64)n, d_rec, ctx->table, d_off, d_status, nullptr, d_list, &d_meta->n_deleg, d_list2, &d_meta->n_deleg2,
-                d_desc, d_rdesc, &d_meta->n_desc, desc_cap, &d_meta->legacy_long};
+                d_desc, d_rdesc, &d_meta->n_desc, desc_cap, &d_meta->legacy_long, &d_meta->long_cursor};
 
     // pass 1: sizes, status, line descriptors.  k_short takes the short canonical records, k_long
     // what it left, the general kernel what neither converts (non-canonical or erroneous records).

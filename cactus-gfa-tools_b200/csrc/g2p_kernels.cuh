@@ -31,7 +31,7 @@ struct PipelineMeta {
     u32 n_lines;       // '\n' count
     u32 n_records;     // lines incl. an unterminated last one
     u32 first_err;     // smallest failing record index (0xFFFFFFFF = none)
-    u32 pad;
+    u32 long_cursor;   // next entry of the delegate list a warp of k_long<false> takes
     u64 out_total;     // bytes of PAF for all records
     // k_diagnose
     u32 err_status;
@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(u32* __restrict__ tile_coun
         meta->out_total = 0;
         meta->err_status = 0;
         meta->n_deleg = 0;
+        meta->long_cursor = 0;
         meta->n_deleg2 = 0;
         meta->n_desc = 0;
         meta->legacy_long = 0;
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(kIdxThreads) k_index1(const u8* __restrict__ t
                 meta->first_err = 0xFFFFFFFFu;
                 meta->out_total = 0;
                 meta->err_status = 0;
-                meta->n_deleg = 0; meta->n_deleg2 = 0; meta->n_desc = 0; meta->legacy_long = 0; meta->lines_total = 0;
+                meta->n_deleg = 0; meta->long_cursor = 0; meta->n_deleg2 = 0; meta->n_desc = 0; meta->legacy_long = 0; meta->lines_total = 0;
                 if (recs != lines && recs < cap) rec_start[recs] = (u32)n + 1;   // unterminated last line
             }
             if (tile == 0 && cap) rec_start[0] = 0;

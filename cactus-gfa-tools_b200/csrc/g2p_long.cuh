@@ -239,6 +239,7 @@ struct LongArgs {
     u32* n_desc;
     u32 desc_cap;
     u32* need_legacy;      // set when a record could not be described (array full): k_long<true> emits it
+    u32* cursor;           // size pass: shared cursor into `list` (warps take the next record when they are free)
 };
 
 template <bool EMIT>
@@ -630,6 +631,19 @@ __global__ void __launch_bounds__(kLThreads, EMIT ? 4 : G2P_LONG_CTAS) k_long(co
     const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     LWarpMemT<EMIT>* wm = reinterpret_cast<LWarpMemT<EMIT>*>(smem) + warp;
     const u32 nl = *a.n_list;
+    if (!EMIT && a.cursor) {
+        // records differ in length by orders of magnitude and the grid may hold more warps than are resident:
+        // every warp takes the next unconverted record when it is free
+        for (;;) {
+            u32 k = 0;
+            if (lane == 0) k = atomicAdd(a.cursor, 1u);
+            k = __shfl_sync(0xffffffffu, k, 0);
+            if (k >= nl) break;
+            long_record<EMIT>(a, wm, a.list[k], lane, p10);
+            __syncwarp();
+        }
+        return;
+    }
     for (u32 k = blockIdx.x * kLWarps + warp; k < nl; k += gridDim.x * kLWarps) {
         long_record<EMIT>(a, wm, a.list[k], lane, p10);
         __syncwarp();
