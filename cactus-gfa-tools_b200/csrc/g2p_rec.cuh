@@ -3,18 +3,23 @@
 // k_rec replaces k_short's size pass on the throughput path.  k_short spends ~690 warp
 // instructions per record on coordination (SWAR classification of every byte into three masks,
 // shuffle scans, scatter of token positions, five group votes) with 18 of 32 lanes active.  Here a
-// record is parsed by ONE thread with a plain scalar walk over its text, and the kernel is built
-// so that the 32 lanes of a warp stay in the same loop at the same time:
+// record is parsed by ONE thread with a plain scalar walk over its text (~210 warp instructions per
+// record, 20 lanes active), and the kernel is built so that the 32 lanes of a warp stay in the same
+// loop at the same time:
 //
-//   * staging: the CTA's 256 records are copied from global memory with 128-bit coalesced loads
-//     (8 lanes per record) into per-record shared-memory slots of an ODD number of 32-bit words, so
-//     that lane i's record starts in bank (i * stride) mod 32: byte loads of the 32 lanes at equal
-//     progress hit 32 different banks;
+//   * order: the CTA's 256 records are counting-sorted by length, so that the lanes of a warp hold
+//     records of similar shape (a warp pays the maximum trip count over its lanes);
+//   * staging: the records are copied from global memory with 128-bit coalesced loads (8 lanes per
+//     record) into per-record shared-memory slots of an ODD number of 32-bit words, so that lane
+//     i's record starts in bank (i * stride) mod 32: byte loads of the 32 lanes at equal progress
+//     hit 32 different banks;
 //   * the walk is a fixed sequence of short loops (one per column, one per tag, one per path step,
-//     one per CIGAR op), never a state machine: lanes re-converge after every loop, the trip count
-//     of a loop is the maximum over the warp of a field length, not of a record length;
-//   * '+' records walk the path and the CIGAR forwards, '-' records backwards (flip_gaf,
-//     gaf2paf_main.cpp:92-131, is index arithmetic); a '-' record first sums its step lengths;
+//     one per CIGAR op), never a state machine: lanes re-converge after every loop;
+//   * pass S: the path column is tokenised forwards once, every step name is probed once in the
+//     lengths table, and two words per step are left in a dead part of the record's own slot (the
+//     columns and tags between the path and the CIGAR are not needed again);
+//   * '+' records then walk steps and CIGAR forwards, '-' records backwards (flip_gaf,
+//     gaf2paf_main.cpp:92-131, is index arithmetic) -- one instruction stream for both strands;
 //   * the CIGAR is cut at step boundaries by streaming (cigar_next_by_target, gaf2paf_main.cpp:71-90):
 //     ops are taken until the step's target quota is reached, the op that crosses the boundary is
 //     split and its remainder starts the next step.
