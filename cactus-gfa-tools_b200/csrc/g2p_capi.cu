@@ -124,7 +124,7 @@ struct g2p_ctx {
     bool two_pass_index = true;      // default: counting index (count, scan, fill); G2P_ONE_PASS_INDEX=1 selects k_index1 (measured slower, see profiles/r01_summary.md)
     bool have_cpus = false;          // CPUs of the GPU's NUMA node (G2P_NUMA_BIND=0: none)
     cpu_set_t cpus;
-    bool len_sort = false;           // G2P_LEN_SORT=0: k_rec takes the records in input order (in-CTA sort only)
+    bool len_sort = false;           // G2P_LEN_SORT=1: global counting sort of the records by length class before k_rec (default off: in-CTA sort only)
     bool size_kernel_short = false;  // G2P_SIZE_KERNEL=short: k_short (8 lanes per record) instead of k_rec (thread per record)
     uint32_t rec_chunks_override = 0; // G2P_REC_CHUNKS: k_rec slot capacity in 16-byte chunks
     uint64_t desc_cap_override = 0;  // G2P_DESC_CAP (tests): line-descriptor slots, to exercise the overflow fallback
@@ -142,18 +142,20 @@ struct g2p_ctx {
 
 extern "C" {
 
-// Host-side locality: the calling thread (and the worker threads it will start, which inherit its mask)
+// Host-side locality (opt-in, G2P_NUMA_BIND=1; the default leaves the caller's affinity mask alone):
+// the calling thread (and the worker threads it will start, which inherit its mask)
 // is restricted to the CPUs of the GPU's NUMA node, so that the pinned buffers it allocates are placed in
 // that node's memory and the PCIe copies of several GPUs of one box do not all cross the socket link
 // (on the single-NUMA-node VM this round was measured on it is a no-op: 8 ranks move 35 GB of host memory
-// per step at ~115 GB/s with or without it).  G2P_NUMA_BIND=0 turns it off;
-// nothing happens when sysfs has no node for the device or the node's CPUs are not in the current mask.
+// per step at ~115 GB/s with or without it).
+// Nothing happens when sysfs has no node for the device or the node's CPUs are not in the current mask.
 // The mask is computed once per context against the mask the process had when the first context was
 // created, and applied to the thread that creates the context and to every thread that enters
 // g2p_convert_host with it (several contexts, one host thread per GPU: each thread ends up on its own
 // GPU's node).
 static bool gpu_numa_cpus(int device, cpu_set_t* want) {
-    if (const char* c = std::getenv("G2P_NUMA_BIND")) if (std::atoi(c) == 0) return false;
+    const char* bind = std::getenv("G2P_NUMA_BIND");   // opt-in: a library must not change its host's CPU affinity by default
+    if (!bind || std::atoi(bind) == 0) return false;
     static std::mutex mu;
     static bool have_orig = false;
     static cpu_set_t orig;

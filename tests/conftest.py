@@ -13,6 +13,33 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def _have_gpu():
+    """True when libg2p.so can create a context on device 0 (no torch import needed)."""
+    try:
+        import ctypes
+        import cactus_gfa_tools_b200 as m
+        h = ctypes.c_void_p()
+        rc = m.lib.g2p_create(0, ctypes.byref(h))
+        if rc == 0:
+            m.lib.g2p_destroy(h)
+        return rc == 0
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    """Tests marked `gpu` are skipped (not errored) on a box without a CUDA device, unless they were
+    asked for explicitly with -m gpu: there a missing device must fail loudly (no CPU fallback)."""
+    if "gpu" in (config.getoption("-m") or ""):
+        return
+    gpu_items = [it for it in items if "gpu" in it.keywords]
+    if not gpu_items or _have_gpu():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device (GPU tests run with -m gpu on the B200 box)")
+    for it in gpu_items:
+        it.add_marker(skip)
+
+
 @pytest.fixture(scope="session", autouse=True)
 def _built():
     """Make sure the in-tree artefacts exist (they are prebuilt and travel with the snapshot;
