@@ -21,13 +21,13 @@ $(LIB): $(CSRC)/g2p_capi.cu $(HDRS)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -shared -o $@ $(CSRC)/g2p_capi.cu $(wildcard $(CSRC)/g2u_capi.cu) -lcudart 2> $(BUILD)/ptxas.log || (cat $(BUILD)/ptxas.log; false)
 	@grep -E "error|warning" $(BUILD)/ptxas.log || true
 
-$(PKG)/bin/gaf2paf: $(CSRC)/gaf2paf_main.cpp $(LIB) include/g2p.h
+$(PKG)/bin/gaf2paf: $(CSRC)/gaf2paf_main.cpp $(CSRC)/cli_pipeline.hpp $(LIB) include/g2p.h
 	@mkdir -p $(PKG)/bin
-	$(CXX) $(CXXFLAGS) -o $@ $(CSRC)/gaf2paf_main.cpp -L$(PKG)/lib -lg2p -Wl,-rpath,'$$ORIGIN/../lib'
+	$(CXX) $(CXXFLAGS) -pthread -o $@ $(CSRC)/gaf2paf_main.cpp -L$(PKG)/lib -lg2p -Wl,-rpath,'$$ORIGIN/../lib'
 
-$(PKG)/bin/gaf2unstable: $(CSRC)/gaf2unstable_main.cpp $(LIB) include/g2p.h
+$(PKG)/bin/gaf2unstable: $(CSRC)/gaf2unstable_main.cpp $(CSRC)/cli_pipeline.hpp $(LIB) include/g2p.h
 	@mkdir -p $(PKG)/bin
-	$(CXX) $(CXXFLAGS) -o $@ $(CSRC)/gaf2unstable_main.cpp -L$(PKG)/lib -lg2p -Wl,-rpath,'$$ORIGIN/../lib'
+	$(CXX) $(CXXFLAGS) -pthread -o $@ $(CSRC)/gaf2unstable_main.cpp -L$(PKG)/lib -lg2p -Wl,-rpath,'$$ORIGIN/../lib'
 
 $(BUILD)/libgafgen.so: tools/gafgen.cpp
 	@mkdir -p $(BUILD)
@@ -37,7 +37,11 @@ $(BUILD)/gafgen: tools/gafgen.cpp
 	@mkdir -p $(BUILD)
 	$(CXX) $(CXXFLAGS) -DGAFGEN_MAIN -pthread -o $@ $<
 
-hostsim: $(BUILD)/g2p_hostsim $(BUILD)/g2p_simt $(BUILD)/g2p_simt_long $(BUILD)/g2u_hostsim
+hostsim: $(BUILD)/g2p_hostsim $(BUILD)/g2p_simt $(BUILD)/g2p_simt_long $(BUILD)/g2u_hostsim $(BUILD)/gaf2paf_stub
+# the gaf2paf executable's host logic linked against a CPU stub of the C-ABI (test infrastructure)
+$(BUILD)/gaf2paf_stub: $(CSRC)/gaf2paf_main.cpp $(CSRC)/cli_pipeline.hpp tests/hostsim/g2p_stub_capi.cpp $(HDRS)
+	@mkdir -p $(BUILD)
+	$(CXX) $(CXXFLAGS) -ffp-contract=off -pthread -o $@ $(CSRC)/gaf2paf_main.cpp tests/hostsim/g2p_stub_capi.cpp
 $(BUILD)/g2u_hostsim: tests/hostsim/g2u_hostsim.cpp $(HDRS)
 	@mkdir -p $(BUILD)
 	$(CXX) $(CXXFLAGS) -ffp-contract=off -o $@ $<

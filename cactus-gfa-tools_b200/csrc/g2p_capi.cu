@@ -25,6 +25,7 @@
 #include "g2p_kernels.cuh"
 #include "g2p_table.hpp"
 #include "g2u_rgfa.hpp"
+#include "g2p_errfmt.hpp"
 
 using namespace g2p;
 
@@ -111,7 +112,9 @@ struct g2p_ctx {
     uint64_t table_entries = 0;
     bool have_table = false;
     Worker w[kWorkers];
-    PinBuf h_out;
+    PinBuf h_outs[2];                // pinned result buffers of the host-buffer calls, used alternately: a result stays valid until the next-but-one call
+    int h_cur = 0;
+    PinBuf& next_out() { h_cur ^= 1; return h_outs[h_cur]; }
     // gaf2unstable tables
     DevBuf u_slots, u_arena, u_begin, u_nodes, u_names, u_refoff, u_refnames;
     UnstableView uview{};
@@ -243,7 +246,7 @@ void g2p_destroy(g2p_ctx* ctx) {
     for (DevBuf* b : {&ctx->u_slots, &ctx->u_arena, &ctx->u_begin, &ctx->u_nodes, &ctx->u_names, &ctx->u_refoff, &ctx->u_refnames}) b->release();
     delete ctx->rgfa;
     for (auto& w : ctx->w) w.release();
-    ctx->h_out.release();
+    for (auto& b : ctx->h_outs) b.release();
     delete ctx;
 }
 
@@ -509,6 +512,7 @@ int g2p_convert_host(g2p_ctx* ctx, const char* gaf, size_t n, const char** out, 
     std::memset(res, 0, sizeof *res);
     G2P_CUDA(cudaSetDevice(ctx->device));
     if (ctx->have_cpus) sched_setaffinity(0, sizeof ctx->cpus, &ctx->cpus);   // the worker threads inherit the mask
+    PinBuf& h_out = ctx->next_out();
 
     // newline-aligned chunk boundaries.  Chunks must hold enough records to fill the GPU: short
     // reads do at 48 MB, chromosome-scale records (one warp each in k_long) need more.
@@ -535,8 +539,8 @@ int g2p_convert_host(g2p_ctx* ctx, const char* gaf, size_t n, const char** out, 
     }
     const size_t nchunks = cut.size() - 1;
     if (nchunks == 0) {
-        G2P_CUDA(ctx->h_out.ensure(1));
-        *out = static_cast<const char*>(ctx->h_out.p);
+        G2P_CUDA(h_out.ensure(1));
+        *out = static_cast<const char*>(h_out.p);
         return G2P_OK;
     }
 
@@ -556,7 +560,7 @@ int g2p_convert_host(g2p_ctx* ctx, const char* gaf, size_t n, const char** out, 
     std::vector<g2p_result> cres(nchunks);
     std::vector<char> done(nchunks, 0);
     // first guess of the output size: keep what earlier calls needed, else 3x the input
-    if (ctx->h_out.cap == 0) G2P_CUDA(ctx->h_out.ensure(n * 3 + (1 << 20)));
+    if (h_out.cap == 0) G2P_CUDA(h_out.ensure(n * 3 + (1 << 20)));
 
     // G2P_TRACE=1: host-clock timeline of every chunk on stderr (ms since the call started)
     const bool trace = std::getenv("G2P_TRACE") != nullptr;
@@ -589,17 +593,17 @@ int g2p_convert_host(g2p_ctx* ctx, const char* gaf, size_t n, const char** out, 
             S.off[i + 1] = S.off[i] + r.out_bytes;
             S.recs[i + 1] = S.recs[i] + r.n_records;
             if (r.rec_status != G2P_REC_OK) S.stop_at = i;
-            if (S.off[i + 1] + 1 > ctx->h_out.cap) {
+            if (S.off[i + 1] + 1 > h_out.cap) {
                 // grow the pinned output: wait for the copies of earlier chunks, then move what is there
                 S.cv.wait(lk, [&] { return S.copied == i || S.rc != G2P_OK; });
                 PinBuf nb;
                 if (S.rc == G2P_OK && nb.ensure(S.off[i + 1] + (n - cut[i + 1]) * 4 + (1 << 20)) != cudaSuccess) { S.rc = G2P_E_CUDA; ctx->set_err("pinned output allocation failed"); }
                 if (S.rc != G2P_OK) { S.cv.notify_all(); break; }
-                std::memcpy(nb.p, ctx->h_out.p, S.off[i]);
-                ctx->h_out.release();
-                ctx->h_out = nb;
+                std::memcpy(nb.p, h_out.p, S.off[i]);
+                h_out.release();
+                h_out = nb;
             }
-            char* dst = static_cast<char*>(ctx->h_out.p) + S.off[i];
+            char* dst = static_cast<char*>(h_out.p) + S.off[i];
             S.published = i + 1;
             S.cv.notify_all();
             lk.unlock();
@@ -642,7 +646,7 @@ int g2p_convert_host(g2p_ctx* ctx, const char* gaf, size_t n, const char** out, 
         res->err_name_off = cut[S.stop_at] + r.err_name_off;
         res->err_name_len = r.err_name_len;
     }
-    *out = static_cast<const char*>(ctx->h_out.p);
+    *out = static_cast<const char*>(h_out.p);
     return G2P_OK;
 }
 
@@ -836,15 +840,16 @@ int g2p_unstable_host(g2p_ctx* ctx, const char* gaf, size_t n, const char** out,
     *out = nullptr;
     G2P_CUDA(cudaSetDevice(ctx->device));
     Worker& w = ctx->w[0];
+    PinBuf& h_out = ctx->next_out();
     G2P_CUDA(w.d_in.ensure(n + 256));
     if (n) G2P_CUDA(cudaMemcpyAsync(w.d_in.p, gaf, n, cudaMemcpyHostToDevice, w.stream));
     u8* d_o = nullptr;
     int rc = run_unstable(ctx, w, static_cast<const u8*>(w.d_in.p), n, w.stream, res, &d_o);
     if (rc) return rc;
-    G2P_CUDA(ctx->h_out.ensure(res->out_bytes + 1));
-    if (res->out_bytes) G2P_CUDA(cudaMemcpyAsync(ctx->h_out.p, d_o, res->out_bytes, cudaMemcpyDeviceToHost, w.stream));
+    G2P_CUDA(h_out.ensure(res->out_bytes + 1));
+    if (res->out_bytes) G2P_CUDA(cudaMemcpyAsync(h_out.p, d_o, res->out_bytes, cudaMemcpyDeviceToHost, w.stream));
     G2P_CUDA(cudaStreamSynchronize(w.stream));
-    *out = static_cast<const char*>(ctx->h_out.p);
+    *out = static_cast<const char*>(h_out.p);
     return G2P_OK;
 }
 
@@ -891,25 +896,7 @@ int g2p_format_unstable_warning(g2p_ctx* ctx, const char* line, size_t len, char
 }
 
 int g2p_format_error(const g2p_result* res, const char* gaf, size_t n, char* buf, size_t cap) {
-    if (!res || !buf || cap == 0) return G2P_E_ARG;
-    buf[0] = 0;
-    if (res->rec_status == G2P_REC_ERR_NAME) {
-        std::string name;
-        if (gaf && res->err_name_off + res->err_name_len <= n) name.assign(gaf + res->err_name_off, res->err_name_len);
-        std::snprintf(buf, cap, "[gaf2paf] error: unable to find %s in lengths map\n", name.c_str());
-    } else if (res->rec_status == G2P_REC_ERR_NOCG) {
-        std::snprintf(buf, cap, "[gaf2paf] error: cg cigar not found. This tool only works on output of minigraph -c\n");
-    } else if (res->rec_status >= G2P_REC_ABORT) {
-        static const char* what[] = {"Error parsing GAF column", "Error parsing GAF strand", "Error parsing GAF range", "stol (invalid argument)",
-                                     "stol (out of range)", "Unable to parse optional tag", "Duplicate optional field found",
-                                     "malformed cg cigar", "assertion failed"};
-        unsigned k = res->rec_status - G2P_REC_ABORT;
-        if (res->rec_status == G2P_REC_ABORT)
-            std::snprintf(buf, cap, "terminate: %s %u (record %llu)\n", what[0], res->rec_aux, (unsigned long long)res->err_record);
-        else
-            std::snprintf(buf, cap, "terminate: %s (record %llu)\n", k < 9 ? what[k] : "abort", (unsigned long long)res->err_record);
-    }
-    return G2P_OK;
+    return g2p_errfmt::format_error(res, gaf, n, buf, cap);
 }
 
 }  // extern "C"

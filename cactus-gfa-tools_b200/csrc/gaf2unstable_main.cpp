@@ -7,7 +7,8 @@
 //     -g, --rgfa FILE   (uncompressed) minigraph rGFA
 //     -o FILE           write "node<TAB>length" for every rGFA node (input of gaf2paf -l)
 //
-// Environment: G2P_DEVICE=K (device ordinal), G2P_CHUNK_MB=M (bytes of GAF per GPU call).
+// Environment: G2P_DEVICE=K (device ordinal), G2P_CHUNK_MB=M (bytes of GAF per GPU call, default 128),
+// G2P_IO_THREADS=T.  Host side: the reader -> converter -> writer pipeline of cli_pipeline.hpp.
 #include <fcntl.h>
 #include <getopt.h>
 #include <signal.h>
@@ -20,7 +21,7 @@
 #include <string>
 #include <vector>
 
-#include "../../include/g2p.h"
+#include "cli_pipeline.hpp"
 
 namespace {
 
@@ -33,33 +34,6 @@ void help(char** argv) {
             "    -g, --rGFA FILE           (uncompressed) minigraph rGFA, required to look up unstable mappings\n"
             "    -o, --out-lengths FILE    Output lengths of all minigraph sequences in given file (can be passed to gaf2paf)\n",
             argv[0]);
-}
-
-bool read_file(const std::string& path, std::string& out) {
-    FILE* f = fopen(path.c_str(), "rb");
-    if (!f) return false;
-    char buf[1 << 16];
-    size_t k;
-    while ((k = fread(buf, 1, sizeof buf, f)) > 0) out.append(buf, k);
-    fclose(f);
-    return true;
-}
-
-void write_all(const char* p, size_t n) {
-    while (n) {
-        ssize_t k = ::write(1, p, n);
-        if (k < 0) {
-            if (errno == EINTR) continue;
-            _exit(1);
-        }
-        p += k;
-        n -= (size_t)k;
-    }
-}
-
-long env_long(const char* k, long dflt) {
-    const char* v = getenv(k);
-    return v && *v ? strtol(v, nullptr, 10) : dflt;
 }
 
 }  // namespace
@@ -104,13 +78,18 @@ int main(int argc, char** argv) {
         fprintf(stderr, "[gaf2unstable] error: -g option required\n");
         return 1;
     }
-    FILE* f = in_gaf_path == "-" ? stdin : fopen(in_gaf_path.c_str(), "rb");
-    if (!f) {
-        fprintf(stderr, "[gaf2unstable] error: unable to open input: %s\n", in_gaf_path.c_str());
-        return 1;
+    {   // the reference opens the GAF before it reads the rGFA (gaf2unstable_main.cpp:248-262)
+        if (in_gaf_path != "-") {
+            int fd = open(in_gaf_path.c_str(), O_RDONLY);
+            if (fd == -1) {
+                fprintf(stderr, "[gaf2unstable] error: unable to open input: %s\n", in_gaf_path.c_str());
+                return 1;
+            }
+            close(fd);
+        }
     }
     std::string rgfa;
-    if (!read_file(rgfa_path, rgfa)) {
+    if (!cli::read_file(rgfa_path, rgfa)) {
         fprintf(stderr, "[gaf2unstable] error: Could not open %s\n", rgfa_path.c_str());
         return 1;
     }
@@ -121,7 +100,7 @@ int main(int argc, char** argv) {
     }
 
     g2p_ctx* ctx = nullptr;
-    if (g2p_create((int)env_long("G2P_DEVICE", 0), &ctx) != G2P_OK) {
+    if (g2p_create((int)cli::env_long("G2P_DEVICE", 0), &ctx) != G2P_OK) {
         fprintf(stderr, "[gaf2unstable] error: no usable CUDA device (this build has no CPU path)\n");
         return 1;
     }
@@ -149,64 +128,34 @@ int main(int argc, char** argv) {
         fclose(o);
     }
 
-    const size_t chunk = (size_t)std::max(1L, env_long("G2P_CHUNK_MB", 256)) << 20;
-    size_t cap = chunk + (1 << 20);
-    char* buf = static_cast<char*>(g2p_host_alloc(cap));
-    if (!buf) { fprintf(stderr, "[gaf2unstable] error: cannot allocate pinned host memory\n"); return 1; }
-    std::string carry;
-    bool eof = false;
-    std::vector<char> wmsg(1 << 20);
-    while (!eof) {
-        if (carry.size() + chunk > cap) {
-            size_t want = carry.size() + chunk + (1 << 20);
-            char* nb = static_cast<char*>(g2p_host_alloc(want));
-            if (!nb) { fprintf(stderr, "[gaf2unstable] error: cannot allocate pinned host memory\n"); return 1; }
-            g2p_host_free(buf);
-            buf = nb; cap = want;
-        }
-        memcpy(buf, carry.data(), carry.size());
-        size_t have = carry.size();
-        carry.clear();
-        while (have < cap - 1) {
-            size_t want = std::min(chunk, cap - 1 - have);
-            size_t k = fread(buf + have, 1, want, f);
-            have += k;
-            if (k < want) { eof = true; break; }
-            if (have >= chunk) break;
-        }
-        if (!eof) {
-            size_t cut = have;
-            while (cut > 0 && buf[cut - 1] != '\n') --cut;
-            if (cut == 0) {   // a single line longer than the chunk: keep reading it
-                carry.assign(buf, have);
-                if (carry.size() >= 0xF0000000ULL) { fprintf(stderr, "[gaf2unstable] error: line longer than 4 GiB\n"); return 1; }
-                continue;
-            }
-            carry.assign(buf + cut, have - cut);
-            have = cut;
-        }
-        const char* out = nullptr;
-        g2p_result res;
-        rc = g2p_unstable_host(ctx, buf, have, &out, &res);
-        if (rc != G2P_OK) { fprintf(stderr, "[gaf2unstable] error: GPU conversion failed: %s\n", g2p_last_error(ctx)); return 1; }
+    size_t chunk = (size_t)std::max(1L, cli::env_long("G2P_CHUNK_MB", 128)) << 20;
+    if (cli::env_long("G2P_CHUNK_BYTES", 0) > 0) chunk = (size_t)cli::env_long("G2P_CHUNK_BYTES", 0);   // tests: tiny chunks
+    cli::Pipeline P;
+    P.tool = "gaf2unstable";
+    P.chunk_bytes = chunk;
+    P.ctx.push_back(ctx);
+    P.convert = [](g2p_ctx* cx, cli::Chunk& c) {
+        int r = g2p_unstable_host(cx, c.buf, c.n, &c.out, &c.res);
+        if (r != G2P_OK) return r;
+        // the reference prints its multi-contig warning while it converts the record: keep the texts with the chunk
         const g2p_warn* warns = nullptr;
         size_t nw = 0;
-        g2p_unstable_warnings(ctx, &warns, &nw);
+        g2p_unstable_warnings(cx, &warns, &nw);
+        std::vector<char> wmsg(1 << 16);
         for (size_t i = 0; i < nw; ++i) {
             if (wmsg.size() < warns[i].out_len + 4096) wmsg.resize(warns[i].out_len + 4096);
-            g2p_format_unstable_warning(ctx, out + warns[i].out_off, warns[i].out_len, wmsg.data(), wmsg.size());
-            fputs(wmsg.data(), stderr);
+            g2p_format_unstable_warning(cx, c.out + warns[i].out_off, warns[i].out_len, wmsg.data(), wmsg.size());
+            c.err_text += wmsg.data();
         }
-        write_all(out, res.out_bytes);
-        if (res.rec_status != G2P_REC_OK) {
-            fprintf(stderr, "terminate: gaf2unstable cannot convert record %llu of this block (status %u)\n", (unsigned long long)res.err_record,
-                    res.rec_status);
-            fflush(stderr);
-            abort();   // reference: assert / uncaught exception -> SIGABRT
-        }
-    }
-    if (f != stdin) fclose(f);
-    g2p_host_free(buf);
+        return r;
+    };
+    P.on_record_error = [](cli::Chunk& c) {
+        fprintf(stderr, "terminate: gaf2unstable cannot convert record %llu of this block (status %u)\n", (unsigned long long)c.res.err_record,
+                c.res.rec_status);
+        fflush(stderr);
+        abort();   // reference: assert / uncaught exception -> SIGABRT
+    };
+    const int prc = P.run({in_gaf_path});
     g2p_destroy(ctx);
-    return 0;
+    return prc;
 }

@@ -10,8 +10,10 @@
  * Conventions: plain pointers and sizes only; every function returns 0 on success or
  * a negative G2P_E_* code (no exceptions cross the boundary); the caller owns host
  * buffers it passes in; the library owns every device buffer and the pinned result
- * buffers it hands back (valid until the next call on the same context or
- * g2p_destroy).  One context per GPU; calls on one context must be serialised by the
+ * buffers it hands back.  Device results are valid until the next call on the same
+ * context; the pinned host results of the *_host calls are double-buffered per context
+ * and stay valid until the next-but-one *_host call (or g2p_destroy), so that a caller
+ * can write result i to its sink while call i+1 runs.  One context per GPU; calls on one context must be serialised by the
  * caller; different contexts may be driven from different host threads.
  *
  * There is no CPU fallback: without a CUDA device g2p_create fails with

@@ -18,7 +18,7 @@ BUILD = os.path.join(ROOT, "build")
 class GenParams(ctypes.Structure):
     _fields_ = [("seed", ctypes.c_uint64)] + [(k, ctypes.c_uint32) for k in (
         "n_nodes", "node_len_lo", "node_len_hi", "steps_lo", "steps_hi", "mrun_lo", "mrun_hi", "indel_lo", "indel_hi",
-        "max_runs", "pct_rev", "pct_minus", "use_eqx", "stable", "qlen_min", "pct_star")]
+        "max_runs", "pct_rev", "pct_minus", "use_eqx", "stable", "qlen_min", "pct_star", "mix_every", "qname_len", "extra_tag_len")]
 
 
 _gen = None

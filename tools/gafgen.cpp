@@ -37,6 +37,9 @@ struct gafgen_params {
     uint32_t stable;         // 1: steps are >ctgK:a-b intervals, table holds contigs
     uint32_t qlen_min;       // query length is max(qlen_min, query end)
     uint32_t pct_star;       // percent of extra "*\t..." -S style lines interleaved
+    uint32_t mix_every;      // K > 0: every K-th record has the assembly shape (5k-15k steps) over the same node table
+    uint32_t qname_len;      // > 0: query names are padded to this length (instrument-style read names)
+    uint32_t extra_tag_len;  // > 0: an extra "zd:Z:<text>" tag of this many value bytes before cg
 };
 }
 
@@ -76,7 +79,12 @@ inline void put_u64(std::string& o, u64 v) {
     while (n) o.push_back(b[--n]);
 }
 
-void gen_record(const gafgen_params& P, u64 idx, std::string& o) {
+void gen_record(const gafgen_params& P0, u64 idx, std::string& o) {
+    gafgen_params P = P0;
+    if (P.mix_every && idx % P.mix_every == P.mix_every - 1) {   // the assembly-shaped record of a mixed file (config 5)
+        P.steps_lo = 5000; P.steps_hi = 15000; P.mrun_lo = 20; P.mrun_hi = 800; P.indel_lo = 1; P.indel_hi = 50;
+        P.max_runs = 0; P.qlen_min = 1000000; P.qname_len = 0; P.extra_tag_len = 0;
+    }
     Rng R(mix(P.seed ^ mix(idx + 1)));
     if (P.pct_star && R.pct(P.pct_star)) {
         o += "*\t>s"; put_u64(o, R.range(1, P.n_nodes)); o += "\t97\t12\t0\t6\t92\n";
@@ -149,7 +157,12 @@ void gen_record(const gafgen_params& P, u64 idx, std::string& o) {
     const bool minus = R.pct(P.pct_minus);
     static const int mapqs[5] = {0, 1, 30, 60, 255};
     // line
-    o += "read"; put_u64(o, idx); o.push_back('\t');
+    {
+        const size_t n0 = o.size();
+        o += "read"; put_u64(o, idx);
+        for (u32 k = 0; o.size() - n0 < P.qname_len; ++k) o.push_back(k % 9 == 0 ? ':' : (char)('0' + mix(idx * 131 + k) % 10));
+        o.push_back('\t');
+    }
     put_u64(o, qlen); o.push_back('\t');
     put_u64(o, qs); o.push_back('\t');
     put_u64(o, qe); o.push_back('\t');
@@ -175,6 +188,10 @@ void gen_record(const gafgen_params& P, u64 idx, std::string& o) {
     o += "\ts1:i:"; put_u64(o, R.range(10, 150));
     o += "\ts2:i:"; put_u64(o, R.range(0, 100));
     o += "\tdv:f:0.0"; put_u64(o, R.range(100, 999));
+    if (P.extra_tag_len) {
+        o += "\tzd:Z:";
+        for (u32 k = 0; k < P.extra_tag_len; ++k) o.push_back((char)('A' + mix(idx * 977 + k) % 26));
+    }
     o += "\tcg:Z:"; o += cg;
     o.push_back('\n');
 }
@@ -277,6 +294,11 @@ void gafgen_preset(const char* name, gafgen_params* P) {
         P->n_nodes = 24; P->node_len_lo = 200; P->node_len_hi = 20000; P->stable = 1;
         P->steps_lo = 1; P->steps_hi = 50; P->mrun_lo = 20; P->mrun_hi = 3000; P->indel_lo = 1; P->indel_hi = 50;
         P->qlen_min = 10000;
+    } else if (!std::strcmp(name, "tagged")) {  // short reads with instrument-style names and a long extra tag: 250-500 B records
+        gafgen_preset("short", P); P->qname_len = 40; P->extra_tag_len = 120;
+    } else if (!std::strcmp(name, "mixed")) {   // config 5 shape: ~90 % of the bytes short-read records, ~10 % assembly-scale records, one node table
+        gafgen_preset("short", P);
+        P->n_nodes = 2000000; P->node_len_lo = 50; P->node_len_hi = 2000; P->mix_every = 16400;
     } else if (!std::strcmp(name, "medium")) {  // long-read-like, used for skew tests
         P->n_nodes = 200000; P->node_len_lo = 20; P->node_len_hi = 400;
         P->steps_lo = 20; P->steps_hi = 200; P->mrun_lo = 5; P->mrun_hi = 300; P->indel_lo = 1; P->indel_hi = 10;
@@ -290,7 +312,7 @@ void gafgen_preset(const char* name, gafgen_params* P) {
 // gafgen <preset> <n_records> <out.gaf> <out.lengths.tsv> [seed] [first]
 int main(int argc, char** argv) {
     if (argc < 5) {
-        std::fprintf(stderr, "usage: gafgen <short|short_eqx|asm|stable|medium> <n_records> <out.gaf> <lengths.tsv> [seed] [first] [k=v ...]\n");
+        std::fprintf(stderr, "usage: gafgen <short|short_eqx|tagged|mixed|asm|stable|medium> <n_records> <out.gaf> <lengths.tsv> [seed] [first] [k=v ...]\n");
         return 1;
     }
     gafgen_params P;
@@ -307,6 +329,7 @@ int main(int argc, char** argv) {
         if (k == "n_nodes") P.n_nodes = v; else if (k == "steps_lo") P.steps_lo = v; else if (k == "steps_hi") P.steps_hi = v;
         else if (k == "pct_star") P.pct_star = v; else if (k == "pct_minus") P.pct_minus = v; else if (k == "pct_rev") P.pct_rev = v;
         else if (k == "use_eqx") P.use_eqx = v; else if (k == "node_len_lo") P.node_len_lo = v; else if (k == "node_len_hi") P.node_len_hi = v;
+        else if (k == "mix_every") P.mix_every = v; else if (k == "qname_len") P.qname_len = v; else if (k == "extra_tag_len") P.extra_tag_len = v;
         else if (k == "mrun_lo") P.mrun_lo = v; else if (k == "mrun_hi") P.mrun_hi = v; else if (k == "max_runs") P.max_runs = v;
     }
     unsigned hw = std::thread::hardware_concurrency();
