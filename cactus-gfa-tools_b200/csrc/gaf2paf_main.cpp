@@ -24,6 +24,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "cli_pipeline.hpp"
@@ -87,21 +88,29 @@ int main(int argc, char** argv) {
     cli::Pipeline P;
     P.tool = "gaf2paf";
     P.chunk_bytes = chunk;
+    // one context per GPU, created concurrently (CUDA context creation is the bulk of the start-up time)
+    P.ctx.assign(ngpu, nullptr);
+    std::vector<int> crc(ngpu, G2P_OK), lrc(ngpu, G2P_OK);
+    {
+        std::vector<std::thread> th;
+        for (int g = 0; g < ngpu; ++g)
+            th.emplace_back([&, g] {
+                crc[g] = g2p_create(dev0 + g, &P.ctx[g]);
+                if (crc[g] == G2P_OK) lrc[g] = g2p_load_lengths(P.ctx[g], tsv.data(), tsv.size());
+            });
+        for (auto& t : th) t.join();
+    }
     for (int g = 0; g < ngpu; ++g) {
-        g2p_ctx* ctx = nullptr;
-        int rc = g2p_create(dev0 + g, &ctx);
-        if (rc != G2P_OK) {
+        if (crc[g] != G2P_OK) {
             fprintf(stderr, "[gaf2paf] error: no usable CUDA device %d (this build has no CPU path)\n", dev0 + g);
             return 1;
         }
-        rc = g2p_load_lengths(ctx, tsv.data(), tsv.size());
-        if (rc == G2P_E_TABLE) {
+        if (lrc[g] == G2P_E_TABLE) {
             // get_len_map: std::stol throws -> terminate (reference gaf2paf_main.cpp:35)
             fprintf(stderr, "terminate called after throwing an instance of 'std::invalid_argument'\n  what():  stol\n");
             abort();
         }
-        if (rc != G2P_OK) { fprintf(stderr, "[gaf2paf] error: %s\n", g2p_last_error(ctx)); return 1; }
-        P.ctx.push_back(ctx);
+        if (lrc[g] != G2P_OK) { fprintf(stderr, "[gaf2paf] error: %s\n", g2p_last_error(P.ctx[g])); return 1; }
     }
     P.convert = [](g2p_ctx* ctx, cli::Chunk& c) { return g2p_convert_host(ctx, c.buf, c.n, &c.out, &c.res); };
     P.on_record_error = [](cli::Chunk& c) {
@@ -114,6 +123,7 @@ int main(int argc, char** argv) {
         _exit(1);
     };
     auto t0 = std::chrono::steady_clock::now();
+    if (stats) fprintf(stderr, "[gaf2paf] stats: contexts ready\n");
     const int rc = P.run(in_paths);
     if (stats) {
         double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
