@@ -62,6 +62,8 @@ class Result(ctypes.Structure):
         ("index_ms", ctypes.c_float),
         ("n_delegated", ctypes.c_uint32),
         ("n_long", ctypes.c_uint32),
+        ("fused_ms", ctypes.c_float),
+        ("n_fused", ctypes.c_uint32),
     ]
 
 

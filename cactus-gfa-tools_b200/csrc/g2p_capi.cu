@@ -42,6 +42,11 @@ __global__ void k_meta_to_host(const g2p::PipelineMeta* __restrict__ src, g2p::P
     __threadfence_system();
 }
 static_assert(sizeof(g2p::PipelineMeta) % 4 == 0, "PipelineMeta is copied as 32-bit words");
+__global__ void k_words_to_host(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, uint32_t nwords) {
+    volatile uint32_t* d = dst;
+    for (uint32_t i = threadIdx.x; i < nwords; i += blockDim.x) d[i] = src[i];
+    __threadfence_system();
+}
 inline cudaError_t meta_to_host(void* h_meta, const void* d_meta, cudaStream_t st) {
     k_meta_to_host<<<1, 32, 0, st>>>(static_cast<const g2p::PipelineMeta*>(d_meta), static_cast<g2p::PipelineMeta*>(h_meta));
     return cudaGetLastError();
@@ -82,17 +87,19 @@ struct PinBuf {
 // One pipeline instance: a stream plus the grow-only work buffers of one in-flight chunk.
 struct Worker {
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[8] = {};
-    DevBuf d_in, d_tiles, d_rec, d_status, d_off, d_blocks, d_out, d_meta, d_list, d_list2, d_desc, d_rdesc, d_sdesc, d_loff, d_map, d_lsort, d_perm;
-    PinBuf h_meta;
+    cudaEvent_t ev[8] = {};   // 0..4: general pipeline (index, size, scan, emit), 5..6: k_fuse
+    DevBuf d_in, d_tiles, d_rec, d_status, d_off, d_blocks, d_out, d_meta, d_list, d_list2, d_desc, d_rdesc, d_sdesc, d_loff, d_map, d_lsort, d_perm, d_fuse;
+    PinBuf h_meta, h_fmeta;
     bool init() {
         if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) return false;
         for (auto& e : ev) if (cudaEventCreate(&e) != cudaSuccess) return false;
-        return d_meta.ensure(sizeof(PipelineMeta)) == cudaSuccess && h_meta.ensure(sizeof(PipelineMeta)) == cudaSuccess;
+        return d_meta.ensure(sizeof(PipelineMeta)) == cudaSuccess && h_meta.ensure(sizeof(PipelineMeta)) == cudaSuccess &&
+               h_fmeta.ensure(sizeof(FuseMeta)) == cudaSuccess;
     }
     void release() {
-        for (DevBuf* b : {&d_in, &d_tiles, &d_rec, &d_status, &d_off, &d_blocks, &d_out, &d_meta, &d_list, &d_list2, &d_desc, &d_rdesc, &d_sdesc, &d_loff, &d_map, &d_lsort, &d_perm}) b->release();
+        for (DevBuf* b : {&d_in, &d_tiles, &d_rec, &d_status, &d_off, &d_blocks, &d_out, &d_meta, &d_list, &d_list2, &d_desc, &d_rdesc, &d_sdesc, &d_loff, &d_map, &d_lsort, &d_perm, &d_fuse}) b->release();
         h_meta.release();
+        h_fmeta.release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -131,6 +138,9 @@ struct g2p_ctx {
     bool size_kernel_short = false;  // G2P_SIZE_KERNEL=short: k_short (8 lanes per record) instead of k_rec (thread per record)
     uint32_t rec_chunks_override = 0; // G2P_REC_CHUNKS: k_rec slot capacity in 16-byte chunks
     uint64_t desc_cap_override = 0;  // G2P_DESC_CAP (tests): line-descriptor slots, to exercise the overflow fallback
+    bool use_fuse = true;            // G2P_FUSE=0: skip the one-pass kernel k_fuse, always run the general pipeline
+    u32 fuse_tile = kFTileMax;       // input bytes per CTA of k_fuse: halved (and kept) when a tile holds more records / path steps than its tables (G2P_FUSE_TILE)
+    uint64_t fuse_out_cap_override = 0;   // G2P_FUSE_OUT_CAP (tests): initial output capacity of k_fuse, to exercise the grow-and-rerun path
     void set_err(const std::string& m) { std::lock_guard<std::mutex> g(err_mu); err = m; }
 };
 
@@ -229,6 +239,12 @@ int g2p_create(int device, g2p_ctx** out) {
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
     if (const char* c = std::getenv("G2P_ONE_PASS_INDEX")) ctx->two_pass_index = std::atoi(c) == 0;
     if (const char* c = std::getenv("G2P_DESC_CAP")) ctx->desc_cap_override = std::strtoull(c, nullptr, 10);
+    if (const char* c = std::getenv("G2P_FUSE")) ctx->use_fuse = std::atoi(c) != 0;
+    if (const char* c = std::getenv("G2P_FUSE_OUT_CAP")) ctx->fuse_out_cap_override = std::strtoull(c, nullptr, 10);
+    cudaFuncSetAttribute(k_fuse<32768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FuseCfg<32768>::kSmem);
+    cudaFuncSetAttribute(k_fuse<16384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FuseCfg<16384>::kSmem);
+    cudaFuncSetAttribute(k_fuse<8192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FuseCfg<8192>::kSmem);
+    if (const char* c = std::getenv("G2P_FUSE_TILE")) { const int v = std::atoi(c); if (v == 32768 || v == 16384 || v == 8192) ctx->fuse_tile = (u32)v; }
     if (const char* c = std::getenv("G2P_HOST_CHUNK_MB")) {
         long v = std::atol(c);
         if (v > 0) { ctx->host_chunk = (size_t)v << 20; ctx->host_chunk_fixed = true; }
@@ -341,12 +357,72 @@ int g2p_index_lines(g2p_ctx* ctx, const void* d_text, size_t n, const uint32_t**
     return G2P_OK;
 }
 
+// The one-pass path: k_fuse converts the whole block if every record is a canonical short record.  *done is set
+// when the result is complete; otherwise (some record needs k_long / the general kernel, or fails) nothing of
+// it is used and the caller runs the general pipeline.  The output buffer is sized by a bound (3x the input, or
+// what earlier calls needed) and grown + the kernel run again when the exact size, which k_fuse always reports,
+// exceeds it.
+static void launch_fuse(u32 tile, u32 ntiles, cudaStream_t st, const FuseArgs& fa) {
+    if (tile == 32768) k_fuse<32768><<<ntiles, kFThreads, FuseCfg<32768>::kSmem, st>>>(fa);
+    else if (tile == 16384) k_fuse<16384><<<ntiles, kFThreads, FuseCfg<16384>::kSmem, st>>>(fa);
+    else k_fuse<8192><<<ntiles, kFThreads, FuseCfg<8192>::kSmem, st>>>(fa);
+}
+
+static int run_fused(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cudaStream_t st, g2p_result* res, u8** d_out, bool* done) {
+    *done = false;
+    if (!ctx->use_fuse || n == 0) return G2P_OK;
+    const FuseMeta* hm = static_cast<const FuseMeta*>(w.h_fmeta.p);
+    if (w.d_out.cap == 0 || ctx->fuse_out_cap_override) G2P_CUDA(w.d_out.ensure(ctx->fuse_out_cap_override ? (size_t)ctx->fuse_out_cap_override : n * 3 + (1u << 20)));
+    G2P_CUDA(cudaEventRecord(w.ev[5], st));
+    bool grown = false;
+    for (;;) {
+        const u32 tile = ctx->fuse_tile;
+        const u32 ntiles = (u32)((n + tile - 1) / tile);
+        const size_t fbytes = sizeof(FuseMeta) + 16 + (size_t)ntiles * sizeof(u64);
+        G2P_CUDA(w.d_fuse.ensure(fbytes));
+        u8* fb = static_cast<u8*>(w.d_fuse.p);
+        FuseMeta* d_fm = reinterpret_cast<FuseMeta*>(fb);
+        G2P_CUDA(cudaMemsetAsync(fb, 0, fbytes, st));
+        FuseArgs fa{d_gaf, (u64)n, ntiles, ctx->table, static_cast<u8*>(w.d_out.p), (u64)(ctx->fuse_out_cap_override && !grown ? ctx->fuse_out_cap_override : w.d_out.cap),
+                    reinterpret_cast<u64*>(fb + sizeof(FuseMeta) + 16), reinterpret_cast<u32*>(fb + sizeof(FuseMeta)), d_fm};
+        launch_fuse(tile, ntiles, st, fa);
+        k_words_to_host<<<1, 32, 0, st>>>(reinterpret_cast<const uint32_t*>(d_fm), static_cast<uint32_t*>(w.h_fmeta.p), sizeof(FuseMeta) / 4);
+        res->gpu_launches += 2;
+        G2P_CUDA(cudaEventRecord(w.ev[6], st));
+        G2P_CUDA(cudaStreamSynchronize(st));
+        G2P_CUDA(cudaGetLastError());
+        if (hm->fallback) {
+            // only capacity reasons (records or path steps per tile): a smaller tile converts the same input
+            if (!(hm->fallback & kFuseNotConvertible) && tile > kFTileMin) { ctx->fuse_tile = tile / 2; continue; }
+            return G2P_OK;
+        }
+        if (!hm->overflow) {
+            res->n_records = hm->n_records;
+            res->out_bytes = hm->out_total;
+            res->n_fused = hm->n_records;
+            cudaEventElapsedTime(&res->fused_ms, w.ev[5], w.ev[6]);
+            res->device_ms = res->fused_ms;
+            *d_out = static_cast<u8*>(w.d_out.p);
+            *done = true;
+            return G2P_OK;
+        }
+        if (grown) return G2P_OK;   // (not reached with a consistent out_total; the general pipeline takes over)
+        G2P_CUDA(w.d_out.ensure(hm->out_total + 256));   // the exact size is known now
+        grown = true;
+    }
+}
+
 // The device pipeline on one worker: index, size pass, scan, emit pass.  Returns with the stream
 // synchronised; *d_out is the worker's output buffer.
 static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cudaStream_t st, g2p_result* res, u8** d_out) {
     std::memset(res, 0, sizeof *res);
     *d_out = nullptr;
-    uint32_t launches = 0;
+    {
+        bool done = false;
+        int frc = run_fused(ctx, w, d_gaf, n, st, res, d_out, &done);
+        if (frc || done) return frc;
+    }
+    uint32_t launches = res->gpu_launches;
     G2P_CUDA(cudaEventRecord(w.ev[0], st));
     int rc = run_index(ctx, w, d_gaf, n, st, &launches);
     if (rc) return rc;
@@ -480,7 +556,7 @@ static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
     cudaEventElapsedTime(&res->index_ms, w.ev[0], w.ev[1]);
     cudaEventElapsedTime(&res->size_ms, w.ev[1], w.ev[2]);
     cudaEventElapsedTime(&res->emit_ms, w.ev[3], w.ev[4]);
-    cudaEventElapsedTime(&res->device_ms, w.ev[0], w.ev[4]);
+    cudaEventElapsedTime(&res->device_ms, ctx->use_fuse && n ? w.ev[5] : w.ev[0], w.ev[4]);
     res->gpu_launches = launches;
     *d_out = d_o;
     return G2P_OK;
@@ -636,6 +712,7 @@ int g2p_convert_host(g2p_ctx* ctx, const char* gaf, size_t n, const char** out, 
         res->n_records += r.n_records;
         res->gpu_launches += r.gpu_launches;
         res->device_ms += r.device_ms; res->emit_ms += r.emit_ms; res->size_ms += r.size_ms; res->index_ms += r.index_ms;
+        res->fused_ms += r.fused_ms; res->n_fused += r.n_fused;
         res->n_delegated += r.n_delegated; res->n_long += r.n_long;
     }
     res->out_bytes = S.off[last + 1];

@@ -1,0 +1,795 @@
+// g2p_fuse.cuh — the one-pass conversion kernel for short records.
+//
+// k_fuse reads the GAF text ONCE and writes the PAF text ONCE.  A CTA takes the next byte tile of the input
+// (ticket counter), brings it into shared memory with one TMA bulk copy, and does everything for the records
+// that START in the tile without touching global memory again except for the lengths-table probes:
+//
+//   A  tile load        cp.async.bulk (UBLKCP) of [tile - 16, tile + kFTile + kFTail) + mbarrier
+//   B  line index       SWAR '\n' compare over 128-bit shared loads, block scan of the counts -> record starts
+//                       (the getline loop, gaf2paf_main.cpp:357-363)
+//   C  columns + tags   one thread per record, k_rec's scalar walk (parse_gaf_record, gafkluge.hpp:84-204);
+//                       counts the path steps; block scan -> the record's line slots
+//   D  steps + CIGAR    same thread: every step token is probed once in the lengths table, then steps and ops
+//                       are walked in normalised order ('-' records backwards: flip_gaf, gaf2paf_main.cpp:92-131)
+//                       with the streaming cut of cigar_next_by_target (gaf2paf_main.cpp:71-90); one 48-byte
+//                       slot per step holds the numbers of its PAF line (gaf2paf_main.cpp:157-263) and its length
+//   H  offsets          block scan of the line lengths; ONE decoupled look-back over the tiles' output sizes gives
+//                       the tile's offset in the output
+//   I  format + store   one thread per PAF line formats its line left to right with a 32-bit word accumulator
+//                       (numbers of < 1000 and their separator are one append) into a staging buffer that is
+//                       co-aligned with the output, which then leaves with one TMA bulk store per round
+//
+// Nothing else is written: no record index, no line descriptors, no per-record sizes, no scans in global
+// memory.  The kernel converts only canonical records (same definition as k_rec; additionally the columns it
+// copies verbatim -- query length, matches, block length -- must be plain decimals without leading zeros) of at
+// most kFLimit bytes.  Anything else sets FuseMeta::fallback: the host then runs the general pipeline
+// (k_rec / k_long / k_convert_list + scans + k_emit_lines), which owns every error path of the reference.
+#pragma once
+#include "g2p_rec.cuh"
+
+namespace g2p {
+
+#ifndef G2P_FUSE_CTAS
+#define G2P_FUSE_CTAS 2
+#endif
+constexpr int kFThreads = 256;
+constexpr u32 kFLimit = 1000;              // longest record (bytes, without '\n') converted here
+constexpr u32 kFTail = 1024;               // bytes after the tile its last record may extend into (>= kFLimit + 1)
+constexpr u32 kFMaxRec = 352;              // records per tile (more -> kFuseTooManyRecords)
+constexpr u32 kFMaxSlots = 832;            // path steps per tile (more -> kFuseTooManySteps)
+constexpr u32 kFSmemBudget = (227u * 1024u) / G2P_FUSE_CTAS - 1024u - 512u;    // per CTA: 1 KB reserved by the driver + static shared
+// Shared-memory layout for a tile of TILE input bytes.  The record / step capacities do not depend on the tile:
+// a denser input (shorter records, more steps per byte) is converted with a smaller tile (the host halves it when
+// a tile reports kFuseTooManyRecords / kFuseTooManySteps), which also leaves more room for the staging buffer.
+template <u32 TILE>
+struct FuseCfg {
+    static constexpr u32 kUnits = TILE / 16 / kFThreads;   // 16-byte vectors per thread in the newline scan
+    static_assert(TILE % (16 * kFThreads) == 0, "the newline scan gives every thread whole vectors");
+    static_assert(16 + TILE + kFTail + 64 < 65536, "text positions are 16-bit");
+    static constexpr u32 kTextBytes = 16 + TILE + kFTail + 48;
+    static constexpr u32 kOffStart = kTextBytes;                                      // u16 start[kFMaxRec + 2]
+    static constexpr u32 kOffInfo = (kOffStart + 2 * (kFMaxRec + 2) + 15) & ~15u;     // uint4 info[2 * kFMaxRec]
+    static constexpr u32 kOffSlots = kOffInfo + 32 * kFMaxRec;                        // uint4 slots[3 * kFMaxSlots]
+    static constexpr u32 kOffOff = kOffSlots + 48 * kFMaxSlots;                       // u32 off[kFMaxSlots + 1]
+    static constexpr u32 kOffStage = (kOffOff + 4 * (kFMaxSlots + 1) + 15) & ~15u;
+    static_assert(kFSmemBudget > kOffStage + 8192, "no room for the staging buffer");
+    static constexpr u32 kStage = ((kFSmemBudget - kOffStage - 32) & ~15u);           // staged PAF bytes per round
+    static constexpr size_t kSmem = kOffStage + kStage + 32;
+};
+constexpr u32 kFTileMax = 32768, kFTileMin = 8192;   // instantiated: 32 KiB, 16 KiB, 8 KiB
+
+enum : u32 { kFuseNotConvertible = 1u, kFuseTooManyRecords = 2u, kFuseTooManySteps = 4u };
+
+struct FuseMeta {
+    u32 n_records;    // records seen (sum over the tiles)
+    u32 fallback;     // kFuse* reasons (or-ed): the result is void; capacity reasons alone -> run again with a smaller tile, else the general pipeline
+    u32 overflow;     // the output did not fit out_cap (out_total is still exact): grow and run again
+    u32 n_lines;      // PAF lines written
+    u64 out_total;    // bytes of PAF
+    u64 pad;
+};
+
+struct FuseArgs {
+    const u8* gaf;
+    u64 n;
+    u32 ntiles;
+    LenTableView T;
+    u8* out;
+    u64 out_cap;
+    u64* tile_status;   // look-back words, zeroed before the launch (flag in the top two bits, kIdxFlagAgg / kIdxFlagPre)
+    u32* ticket;        // zeroed before the launch
+    FuseMeta* meta;     // zeroed before the launch
+};
+
+// ---- per-record constants of the lines, 32 bytes in shared memory ---------------------------
+//   w0: start (text position of the record) | pfx_len << 16   ("qname\tqlen\t" is copied verbatim)
+//   w1: m_a | m_len << 16 | b_len << 24                        (columns 10 / 11, copied verbatim)
+//   w2: b_a | (mapq + 1) << 16                                 (mapq -1 .. 254)
+//   w3: tp_a | tp_len << 16          w4: rc_a | rc_len << 16   ("type:value" spans, len 0 = absent)
+//   w5: gi (0 .. 1000: floor(m / b * 1000 + 0.5))
+struct FRec {
+    u32 start, pfx_len, m_a, m_len, b_a, b_len, tp_a, tp_len, rc_a, rc_len, gi;
+    i32 mapq;
+};
+__device__ __forceinline__ void frec_store(uint4* dst, const FRec& r) {
+    dst[0] = make_uint4(r.start | (r.pfx_len << 16), r.m_a | (r.m_len << 16) | (r.b_len << 24), r.b_a | ((u32)(r.mapq + 1) << 16), r.tp_a | (r.tp_len << 16));
+    dst[1] = make_uint4(r.rc_a | (r.rc_len << 16), r.gi, 0u, 0u);
+}
+__device__ __forceinline__ void frec_load(const uint4* src, FRec& r) {
+    const uint4 a = src[0], b = src[1];
+    r.start = a.x & 0xffffu; r.pfx_len = a.x >> 16;
+    r.m_a = a.y & 0xffffu; r.m_len = (a.y >> 16) & 0xffu; r.b_len = a.y >> 24;
+    r.b_a = a.z & 0xffffu; r.mapq = (i32)(a.z >> 16) - 1;
+    r.tp_a = a.w & 0xffffu; r.tp_len = a.w >> 16;
+    r.rc_a = b.x & 0xffffu; r.rc_len = b.x >> 16;
+    r.gi = b.y;
+}
+
+// ---- one line slot (48 bytes) ------------------------------------------------------------------
+//   v0: tlen, ts, te, q0        v1: q1, nm, nb, lenS
+//   v2: lenE, mid_a | mid_len << 16, name_pos | nl << 16 | flags << 24, rec | codeS << 16 | codeE << 24
+// Before the walk v0.x holds tlen | interval << 31 and v2.z the step token (marker position, name length).
+constexpr u32 kFSlotRev = 1u, kFSlotMidFwd = 2u;
+
+// ---- left-to-right line writer: 32-bit words into (word-aligned) shared memory ------------------
+struct WEmit {
+    u32* wp;
+    u32 lo, sh;   // pending bytes: the low `sh` bits of lo (sh in {0, 8, 16, 24})
+    __device__ __forceinline__ void put(u32 v, u32 nbytes) {   // the nbytes low bytes of v (the rest zero), 1 <= nbytes <= 4
+        lo |= v << sh;
+        const u32 hi = __funnelshift_l(v, 0u, sh);   // what does not fit (0 when sh == 0)
+        sh += 8u * nbytes;
+        if (sh >= 32u) { *wp++ = lo; lo = hi; sh -= 32u; }
+    }
+    __device__ __forceinline__ void put4(u32 v) {
+        *wp++ = lo | (v << sh);
+        lo = __funnelshift_l(v, 0u, sh);
+    }
+    // n bytes from an arbitrarily aligned shared-memory address (reads up to 7 bytes past the span)
+    __device__ __forceinline__ void copy(const u8* src, u32 n) {
+        const uintptr_t sa = reinterpret_cast<uintptr_t>(src);
+        const u32* sp = reinterpret_cast<const u32*>(sa & ~(uintptr_t)3);
+        const u32 s8 = (u32)(sa & 3u) * 8u;
+        u32 prev = *sp++;
+        while (n >= 4u) {
+            const u32 cur = *sp++;
+            put4(__funnelshift_r(prev, cur, s8));
+            prev = cur;
+            n -= 4u;
+        }
+        if (n) {
+            const u32 cur = *sp;
+            put(__funnelshift_r(prev, cur, s8) & ((1u << (8u * n)) - 1u), n);
+        }
+    }
+    // decimal digits of x < 10000, zero padded to four, most significant digit in the low byte
+    static __device__ __forceinline__ u32 pack4(u32 x) {
+        const u32 d3 = x / 1000u, r3 = x - d3 * 1000u, d2 = r3 / 100u, r2 = r3 - d2 * 100u, d1 = r2 / 10u, d0 = r2 - d1 * 10u;
+        return (d3 | (d2 << 8) | (d1 << 16) | (d0 << 24)) + 0x30303030u;
+    }
+    __device__ __forceinline__ void num_unpadded4(u32 x) {   // x < 10000
+        const u32 nd = 1u + (u32)(x >= 10u) + (u32)(x >= 100u) + (u32)(x >= 1000u);
+        put(pack4(x) >> (8u * (4u - nd)), nd);
+    }
+    // decimal v followed by the byte sep
+    __device__ __forceinline__ void num(u32 v, u32 sep) {
+        if (v < 1000u) {   // digits and separator in one append
+            const u32 d2 = v / 100u, r = v - d2 * 100u, d1 = r / 10u, d0 = r - d1 * 10u;
+            const u32 nd = 1u + (u32)(v >= 10u) + (u32)(v >= 100u);
+            const u32 w = ((d2 | (d1 << 8) | (d0 << 16)) + 0x303030u) | (sep << 24);
+            put(w >> (8u * (3u - nd)), nd + 1u);
+            return;
+        }
+        const u32 hi = v / 10000u, lo4 = v - hi * 10000u;
+        if (hi == 0u) put4(pack4(lo4));
+        else {
+            const u32 hh = hi / 10000u, hl = hi - hh * 10000u;
+            if (hh == 0u) num_unpadded4(hl);
+            else { num_unpadded4(hh); put4(pack4(hl)); }
+            put4(pack4(lo4));
+        }
+        put(sep, 1u);
+    }
+};
+
+// Pass S of k_rec (rec_steps) writing line slots: the path column forwards, one scan per step token, one
+// table probe per step; step j of the text becomes slot (minus ? ns - 1 - j : j), i.e. slots are in
+// normalised order.  Returns false if a token is not canonical or a name is unknown.
+__device__ __forceinline__ bool fuse_steps(const LenTableView& T, const u8* rt, const u32 pa, const u32 pb, const bool prefixed, const bool minus,
+                                           uint4* slots, const u32 ns, u64& total_out) {
+    u32 j = 0, mp = prefixed ? pa : pa - 1;
+    u64 total = 0;
+    for (;;) {
+        const u32 name_a = mp + 1;
+        u32 e = pb;
+        u8 c = 0;
+        if (prefixed) {
+            e = rec_scan_step(rt, name_a);   // rt[pb] == '>'
+            c = rt[e];
+        }
+        const u32 nl = e - name_a;
+        if (nl == 0 || nl > 16 || j >= ns) return false;
+        u32 w0, w1, w2, w3;
+        lds16_unaligned(rt + name_a, w0, w1, w2, w3);
+        w0 = keep_bytes(w0, (int)nl); w1 = keep_bytes(w1, (int)nl - 4);
+        w2 = keep_bytes(w2, (int)nl - 8); w3 = keep_bytes(w3, (int)nl - 12);
+        u32 slen = 0;
+        const bool interval = prefixed && c == ':';
+        if (interval) {   // ":start-end" (gafkluge.hpp:131-146), plain digits only
+            u32 k = e + 1, x = 0, d;
+            const u32 k1 = k;
+            while ((d = (u32)rt[k] - '0') <= 9u) { x = x * 10u + d; ++k; }
+            if (k == k1 || k - k1 > 9 || rt[k] != '-') return false;
+            const u32 sa = x;
+            ++k; x = 0;
+            const u32 k2 = k;
+            while ((d = (u32)rt[k] - '0') <= 9u) { x = x * 10u + d; ++k; }
+            if (k == k2 || k - k2 > 9 || (rt[k] != '>' && rt[k] != '<') || x < sa) return false;
+            slen = x - sa;
+            e = k;
+        }
+        i64 tl64;
+        if (!table_lookup_key16(T, (u64)w0 | ((u64)w1 << 32), (u64)w2 | ((u64)w3 << 32), nl, tl64) || tl64 < 0 || tl64 > 0x7fffffffLL) return false;
+        if (!interval) slen = (u32)tl64;
+        total += slen;
+        uint4* sl = slots + 3u * (minus ? ns - 1u - j : j);
+        sl[0].x = (u32)tl64 | (interval ? 0x80000000u : 0u);
+        sl[2].z = mp | (nl << 16);
+        ++j;
+        if (e >= pb) break;
+        mp = e;
+    }
+    total_out = total;
+    return j == ns;
+}
+
+// The record walk after fuse_steps (rec_walk of k_rec writing slots): steps (slot i = normalised step i) and
+// ops in normalised order.  Every slot gets its line length in len[i] (0: no line).  Returns false to delegate.
+__device__ __forceinline__ bool fuse_walk(const u8* rt, const u32 rtpos, const u32 rec, const bool minus, const u32 rconst, const u32* p10,
+                                          const bool prefixed, uint4* slots, u32* len, const u32 ns, const u64 total, const u32 ca, const u32 cb,
+                                          const i32 qs, i32 ps, i32 pe, u32& nlines_out) {
+    if (minus) {   // flip_gaf: mirror the path interval about the summed step lengths (gaf2paf_main.cpp:128-131)
+        if (total > 0x7fffffffULL) return false;
+        const i32 nps = (i32)total - pe, npe = (i32)total - ps;
+        ps = nps; pe = npe;
+    }
+    const i32 W = pe - ps;
+    const u32 cend = minus ? ca : cb;   // CIGAR cursor and where it ends
+    u32 cp = minus ? cb : ca;
+    u32 rem = 0, remk = 0;              // unconsumed part of the op cut by the previous boundary
+    u32 qcur = 0, tbc = 0;              // query / target bases consumed by the steps so far
+    u32 nlines = 0;
+    for (u32 i = 0; i < ns; ++i) {
+        uint4* sl = slots + 3u * i;
+        const u32 sA = sl[0].x, sB = sl[2].z;
+        const u32 mp = sB & 0xffffu, nl = (sB >> 16) & 0xffu;
+        const i32 tlen = (i32)(sA & 0x7fffffffu);
+        i32 sa = 0, se = tlen;
+        if (sA & 0x80000000u) {   // interval: the digits were validated by fuse_steps
+            u32 k = mp + nl + 2, x = 0, d;
+            while ((d = (u32)rt[k] - '0') <= 9u) { x = x * 10u + d; ++k; }
+            sa = (i32)x;
+            ++k; x = 0;
+            while ((d = (u32)rt[k] - '0') <= 9u) { x = x * 10u + d; ++k; }
+            se = (i32)x;
+        }
+        const bool rev = (prefixed && rt[mp] == '<') != minus;
+        const bool last = i + 1 == ns;
+        const i32 slen = se - sa;
+        // ---- quota (gaf2paf_main.cpp:176-182)
+        const i32 so = i == 0 ? ps : 0;
+        i32 quota = slen - so, eo = 0;
+        if (last) { quota = W - (i32)tbc; eo = slen - so - quota; }
+        if (so < 0 || quota < 0 || eo < 0) return false;
+        u32 line = 0;
+        if (quota > 0) {
+            // ---- take `quota` target bases of CIGAR (cigar_next_by_target, gaf2paf_main.cpp:71-90)
+            u32 need = (u32)quota, q = 0, nm = 0, nb = 0;
+            LineStep L;
+            L.lenS = 0; L.codeS = 0; L.mid_a = 0; L.mid_b = 0; L.lenE = 0; L.codeE = 0;
+            bool done = false;
+            if (rem) {   // the remainder of a cut op is target-consuming by construction
+                const u32 take = rem < need ? rem : need;
+                if ((kQueryMask >> remk) & 1u) q += take;
+                if ((kMatchMask >> remk) & 1u) nm += take;
+                nb += take;
+                if (rem >= need) { L.lenE = need; L.codeE = (u8)(remk + '='); rem -= need; done = true; }
+                else { L.lenS = rem; L.codeS = (u8)(remk + '='); need -= rem; rem = 0; }
+            }
+            while (!done) {
+                if (cp == cend) return false;   // :80 assert: CIGAR shorter than the path
+                u32 x, kc, ts, tte;
+                if (!rec_fetch_op(rt, minus, cp, x, kc, ts, tte)) return false;
+                const bool tgt = (kTargetMask >> kc) & 1u;
+                if (tgt && x >= need) {
+                    L.lenE = need; L.codeE = (u8)(kc + '=');
+                    rem = x - need; remk = kc;
+                    x = need;
+                    done = true;
+                } else {
+                    if (tgt) need -= x;
+                    if (L.mid_b == 0) { L.mid_a = ts; L.mid_b = tte; }
+                    else if (minus) L.mid_a = ts;
+                    else L.mid_b = tte;
+                }
+                if ((kQueryMask >> kc) & 1u) q += x;
+                if ((kMatchMask >> kc) & 1u) nm += x;
+                nb += x;
+            }
+            if (nm > 0) {   // gaf2paf_main.cpp:225
+                L.rev = rev;
+                L.mid_fwd = rev == minus;
+                L.q0 = (u32)qs + qcur; L.q1 = L.q0 + q;
+                L.name_a = mp + 1; L.nl = nl; L.tlen = (u32)tlen;
+                L.ts = (u32)(sa + (rev ? eo : so)); L.te = (u32)(se - (rev ? so : eo));
+                L.nm = nm; L.nb = nb;
+                line = rconst + line_step_len(L, p10);
+                const u32 mid_len = L.mid_b > L.mid_a ? L.mid_b - L.mid_a : 0u;
+                sl[0] = make_uint4(L.tlen, L.ts, L.te, L.q0);
+                sl[1] = make_uint4(L.q1, L.nm, L.nb, L.lenS);
+                sl[2] = make_uint4(L.lenE, (rtpos + L.mid_a) | (mid_len << 16),
+                                   (rtpos + L.name_a) | (nl << 16) | ((rev ? kFSlotRev : 0u) << 24) | ((L.mid_fwd ? kFSlotMidFwd : 0u) << 24),
+                                   rec | ((u32)L.codeS << 16) | ((u32)L.codeE << 24));
+                ++nlines;
+            }
+            qcur += q;
+            tbc += (u32)quota;
+        }
+        len[i] = line;
+    }
+    // the reference parses the whole CIGAR before anything else: what the path left over must be valid too
+    while (cp != cend) {
+        u32 x, kc, ts, tte;
+        if (!rec_fetch_op(rt, minus, cp, x, kc, ts, tte)) return false;
+    }
+    nlines_out = nlines;
+    return true;
+}
+
+// One PAF line (paf.hpp:83-95 + gaf2paf_main.cpp:228-256), left to right, into `dst` (any alignment) .. dst + len.
+__device__ __forceinline__ void fuse_write_line(u8* dst, const u32 len, const u8* text, const FRec& R, const uint4 v0, const uint4 v1, const uint4 v2) {
+    const u8* rt = text + R.start;
+    // head: the bytes up to the first word boundary go out one by one (the word is shared with the previous line)
+    const u32 head = (4u - ((u32)reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u;
+    for (u32 i = 0; i < head; ++i) dst[i] = rt[i];
+    WEmit E;
+    E.wp = reinterpret_cast<u32*>(dst + head);
+    E.lo = 0; E.sh = 0;
+    E.copy(rt + head, R.pfx_len - head);                       // qname \t qlen \t   (>= 4 bytes)
+    E.num(v0.w, '\t');                                         // query start
+    E.num(v1.x, '\t');                                         // query end
+    const u32 flags = v2.z >> 24;
+    const bool rev = (flags & kFSlotRev) != 0;
+    E.put((rev ? (u32)'-' : (u32)'+') | ((u32)'\t' << 8), 2u);
+    E.copy(text + (v2.z & 0xffffu), (v2.z >> 16) & 0xffu);     // target name
+    E.put('\t', 1u);
+    E.num(v0.x, '\t');                                         // target length
+    E.num(v0.y, '\t');                                         // target start
+    E.num(v0.z, '\t');                                         // target end
+    E.num(v1.y, '\t');                                         // matches
+    E.num(v1.z, '\t');                                         // block length
+    if (R.mapq < 0) E.put((u32)'-' | ((u32)'1' << 8) | ((u32)'\t' << 16), 3u);
+    else E.num((u32)R.mapq, '\t');
+    // (every item below ends with the tab that separates it from the next one)
+    if (R.tp_len) {
+        E.put((u32)'t' | ((u32)'p' << 8) | ((u32)':' << 16), 3u);
+        E.copy(rt + R.tp_a, R.tp_len);
+        E.put('\t', 1u);
+    }
+    if (R.rc_len) {
+        E.put((u32)'r' | ((u32)'c' << 8) | ((u32)':' << 16), 3u);
+        E.copy(rt + R.rc_a, R.rc_len);
+        E.put('\t', 1u);
+    }
+    E.put4((u32)'g' | ((u32)'m' << 8) | ((u32)':' << 16) | ((u32)'i' << 24));
+    E.put(':', 1u);
+    E.copy(rt + R.m_a, R.m_len);
+    E.put4((u32)'\t' | ((u32)'g' << 8) | ((u32)'l' << 16) | ((u32)':' << 24));
+    E.put((u32)'i' | ((u32)':' << 8), 2u);
+    E.copy(rt + R.b_a, R.b_len);
+    E.put4((u32)'\t' | ((u32)'g' << 8) | ((u32)'i' << 16) | ((u32)':' << 24));
+    E.put((u32)'f' | ((u32)':' << 8), 2u);
+    if (R.gi == 0u || R.gi == 1000u) E.put(R.gi ? (u32)'1' : (u32)'0', 1u);
+    else {   // "0." + three decimals, trailing zeros dropped (printf("%g"), gaf2paf_main.cpp:248-253)
+        const u32 d0 = R.gi / 100u, r = R.gi - d0 * 100u, d1 = r / 10u, d2 = r - d1 * 10u;
+        const bool more = (d1 | d2) != 0;
+        E.put((u32)'0' | ((u32)'.' << 8) | ((u32)('0' + d0) << 16) | (more ? (u32)('0' + d1) << 24 : 0u), more ? 4u : 3u);
+        if (d2) E.put('0' + d2, 1u);
+    }
+    E.put4((u32)'\t' | ((u32)'c' << 8) | ((u32)'g' << 16) | ((u32)':' << 24));
+    E.put((u32)'Z' | ((u32)':' << 8), 2u);
+    // CIGAR pieces, reversed for '<' steps (gaf2paf_main.cpp:184-211)
+    const u32 codeS = (v2.w >> 16) & 0xffu, codeE = v2.w >> 24;
+    if (rev) E.num(v2.x, codeE);
+    else if (codeS) E.num(v1.w, codeS);
+    const u32 mid_len = v2.y >> 16;
+    if (mid_len) {
+        const u8* mid = text + (v2.y & 0xffffu);
+        if (flags & kFSlotMidFwd) E.copy(mid, mid_len);
+        else {   // tokens in reverse order: walk the span backwards, one "digits letter" token at a time
+            u32 e = mid_len;
+            while (e) {
+                u32 s = e - 1;
+                while (s > 0 && mid[s - 1] <= '9') --s;   // the previous token's letter (> '9') ends the digits
+                E.copy(mid + s, e - s);
+                e = s;
+            }
+        }
+    }
+    if (rev) { if (codeS) E.num(v1.w, codeS); }
+    else E.num(v2.x, codeE);
+    E.put('\n', 1u);
+    // tail: pending bytes (< 4) one by one
+    u8* tp = reinterpret_cast<u8*>(E.wp);
+    for (u32 i = 0; 8u * i < E.sh; ++i) tp[i] = (u8)(E.lo >> (8u * i));
+    (void)len;
+}
+
+template <u32 TILE>
+__global__ void __launch_bounds__(kFThreads, G2P_FUSE_CTAS) k_fuse(const FuseArgs a) {
+    typedef FuseCfg<TILE> C;
+    constexpr u32 kFTile = TILE, kFUnits = C::kUnits, kFStage = C::kStage;
+    G2P_DYN_SMEM(smem);
+    __shared__ u32 p10[10];
+    __shared__ u32 s_tile, s_flag, s_end, s_lines;
+    __shared__ u32 s_w[kFThreads / 32];
+    __shared__ u64 s_obase;
+#if !defined(G2P_HOSTSIM)
+    __shared__ __align__(8) u64 s_bar;
+#endif
+    const u32 FULL = 0xffffffffu;
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid < 10) {
+        u32 v = 1;
+        for (u32 i = 0; i < tid; ++i) v *= 10u;
+        p10[tid] = v;
+    }
+    if (tid == 0) {
+        s_tile = atomicAdd(a.ticket, 1u);
+        s_flag = 0; s_end = 0xffffffffu; s_lines = 0;
+#if !defined(G2P_HOSTSIM)
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
+#endif
+    }
+    __syncthreads();
+    const u32 tile = s_tile;
+    volatile u64* st = a.tile_status;
+    volatile u32* g_fallback = &a.meta->fallback;
+    if (*g_fallback) {   // the result is void already: only keep the look-back chain alive
+        if (tid == 0) st[tile] = kIdxFlagPre;
+        return;
+    }
+    u8* text = smem;   // text[16 + p] = gaf[base + p]
+    u16* s_start = reinterpret_cast<u16*>(smem + C::kOffStart);
+    uint4* s_info = reinterpret_cast<uint4*>(smem + C::kOffInfo);
+    uint4* s_slots = reinterpret_cast<uint4*>(smem + C::kOffSlots);
+    u32* s_off = reinterpret_cast<u32*>(smem + C::kOffOff);
+    u8* s_stage = smem + C::kOffStage;
+
+    // ---------------- A: tile load
+    const u64 base = (u64)tile * kFTile;
+    {
+        const u64 src0 = tile ? base - 16 : 0;
+        const u32 dst0 = tile ? 0u : 16u;
+        const u64 room = (u64)(tile ? 16u : 0u) + kFTile + kFTail;
+        const u32 avail = (u32)(a.n - src0 < room ? a.n - src0 : room);
+        const u32 full = avail & ~15u;
+#if !defined(G2P_HOSTSIM)
+        if (tid == 0 && full) { mbar_expect_tx(&s_bar, full); bulk_g2s(text + dst0, a.gaf + src0, full, &s_bar); }
+#else
+        for (u32 i = tid; i < full; i += kFThreads) text[dst0 + i] = a.gaf[src0 + i];
+#endif
+        if (tid < avail - full) text[dst0 + full + tid] = a.gaf[src0 + full + tid];   // last partial vector
+        if (tid < 32) text[dst0 + avail + tid] = '\n';   // virtual newline after an unterminated last line (kFTextBytes has the room)
+        if (!tile && tid < 16) text[tid] = '\n';         // the first record starts at position 0
+#if !defined(G2P_HOSTSIM)
+        if (full) { u32 spins = 0; while (!mbar_try_wait(&s_bar, 0)) { if (++spins > (1u << 24)) __trap(); } }
+#endif
+    }
+    __syncthreads();
+
+    // ---------------- B: line index (record starts inside the tile, in text positions relative to text + 16)
+    const u32 limit = (u32)(a.n - base < (u64)kFTile ? a.n - base : (u64)kFTile);   // record starts are < limit
+    u32 R;
+    {
+        u32 m[kFUnits][4];
+        u32 cnt = 0;
+#pragma unroll
+        for (u32 k = 0; k < kFUnits; ++k) {
+            const u32 q0 = 16u * (tid * kFUnits + k);
+            const uint4 v = *reinterpret_cast<const uint4*>(text + 16 + q0);
+            m[k][0] = nl_bits(v.x); m[k][1] = nl_bits(v.y); m[k][2] = nl_bits(v.z); m[k][3] = nl_bits(v.w);
+            if (q0 + 17u > limit) {   // a newline at q starts a record at q + 1 only if q + 1 < limit
+#pragma unroll
+                for (u32 j = 0; j < 4; ++j)
+                    for (u32 b = 0; b < 4; ++b)
+                        if (q0 + 4u * j + b + 1u >= limit) m[k][j] &= ~(0x80u << (8u * b));
+            }
+            cnt += __popc(m[k][0]) + __popc(m[k][1]) + __popc(m[k][2]) + __popc(m[k][3]);
+        }
+        u32 incl = cnt;
+        for (int o = 1; o < 32; o <<= 1) { const u32 up = __shfl_up_sync(FULL, incl, o); if (lane >= (u32)o) incl += up; }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        u32 wpre = 0, total = 0;
+        for (u32 i = 0; i < kFThreads / 32; ++i) { if (i < warp) wpre += s_w[i]; total += s_w[i]; }
+        const u32 head = limit > 0 && text[15] == '\n' ? 1u : 0u;
+        R = head + total;
+        u32 rank = head + wpre + incl - cnt;
+        if (R <= kFMaxRec) {
+            if (tid == 0 && head) s_start[0] = 0;
+#pragma unroll
+            for (u32 k = 0; k < kFUnits; ++k) {
+                const u32 q0 = 16u * (tid * kFUnits + k);
+#pragma unroll
+                for (u32 j = 0; j < 4; ++j) {
+                    u32 mm = m[k][j];
+                    while (mm) {
+                        const u32 bit = (u32)__ffs((int)mm) - 1u;
+                        mm &= mm - 1u;
+                        s_start[rank++] = (u16)(q0 + 4u * j + (bit >> 3) + 1u);
+                    }
+                }
+            }
+        }
+        // the end of the last record: the first newline at or after position limit - 1 (warp 0, one vector per lane and trip)
+        if (warp == 0 && R > 0 && R <= kFMaxRec) {
+            const u32 from = limit - 1u;
+            u32 found = 0xffffffffu;
+            for (u32 u0 = from >> 4; found == 0xffffffffu && 16u * u0 < from + kFLimit + 2u; u0 += 32) {
+                const u32 q0 = 16u * (u0 + lane);
+                u32 mine = 0xffffffffu;
+                if (q0 < kFTile + kFTail + 16u) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(text + 16 + q0);
+                    const u32 w[4] = {v.x, v.y, v.z, v.w};
+                    for (int j = 3; j >= 0; --j) {
+                        u32 mm = nl_bits(w[j]);
+                        while (mm) {
+                            const u32 bit = 31u - (u32)__clz((int)mm);
+                            mm &= ~(1u << bit);
+                            const u32 q = q0 + 4u * (u32)j + (bit >> 3);
+                            if (q >= from) mine = q;   // descending scan: the last assignment is the smallest q >= from
+                        }
+                    }
+                }
+                for (int o = 16; o > 0; o >>= 1) { const u32 t2 = __shfl_xor_sync(FULL, mine, o); mine = t2 < mine ? t2 : mine; }
+                found = mine;
+            }
+            if (lane == 0) s_end = found;
+        }
+    }
+    __syncthreads();
+    if (R > kFMaxRec) {   // too many records for the tile's tables
+        if (tid == 0) { atomicOr(&a.meta->fallback, (u32)kFuseTooManyRecords); st[tile] = kIdxFlagPre; }
+        return;
+    }
+    if (tid == 0 && R) s_start[R] = s_end == 0xffffffffu ? (u16)(s_start[R - 1] + kFLimit + 2u) : (u16)(s_end + 1u);
+    __syncthreads();
+
+    // ---------------- C + D: one thread per record (passes of kFThreads records; the line slots of a pass follow
+    // those of the pass before)
+    u32 nslots = 0;
+    bool bad = false, too_many = false;
+    for (u32 r0 = 0; r0 < R; r0 += kFThreads) {
+        const u32 rec = r0 + tid;
+        const bool have = rec < R;
+        bool ok = !have, skip = false;
+        u32 ns = 0;
+        // state of the record between the two halves of the pass
+        const u8* rt = text + 16;
+        u32 rtpos = 16, len = 0, pa = 0, pb = 0, ca = 0, cb = 0, rconst = 0;
+        i32 qs = 0, ps = 0, pe = 0;
+        bool minus = false, prefixed = false;
+        if (have) do {
+            const u32 s = s_start[rec], e = s_start[rec + 1];
+            rtpos = 16u + s;
+            rt = text + rtpos;
+            len = e - s - 1u;
+            if (len == 0 || len > kFLimit) break;
+            if (rt[0] == '*') { skip = true; ok = true; break; }   // gaf2paf_main.cpp:360
+            // ---- columns 1..12 (parse_gaf_record, gafkluge.hpp:84-183); the record's own '\n' (or the virtual one) ends every scan
+            FRec F;
+            u32 p = rec_scan_field(rt, 0);
+            u8 c = rt[p];
+            if (c != '\t' || p == 0) break;
+            const u32 qn_b = p;
+            ++p;
+            i32 qlen, qe, plen, m, b, mapq;
+            const u32 qlen_a = p;
+            if (!rec_num(rt, p, qlen)) break;
+            if (qlen < 0 || (rt[qlen_a] == '0' && p - qlen_a > 2)) break;   // copied verbatim: plain decimal, no leading zero
+            F.pfx_len = p;
+            if (!rec_num(rt, p, qs)) break;
+            if (!rec_num(rt, p, qe)) break;
+            c = rt[p];   // strand
+            if ((c != '+' && c != '-') || rt[p + 1] != '\t') break;
+            minus = c == '-';
+            p += 2;
+            pa = p;   // path
+            p = rec_scan_field(rt, p);
+            if (rt[p] != '\t' || p == pa) break;
+            pb = p;
+            ++p;
+            if (!rec_num(rt, p, plen)) break;
+            if (!rec_num(rt, p, ps)) break;
+            if (!rec_num(rt, p, pe)) break;
+            F.m_a = p;
+            if (!rec_num(rt, p, m)) break;
+            F.m_len = p - 1u - F.m_a;
+            if (m < 0 || (rt[F.m_a] == '0' && F.m_len > 1)) break;
+            F.b_a = p;
+            if (!rec_num(rt, p, b)) break;
+            F.b_len = p - 1u - F.b_a;
+            if (b < 0 || (rt[F.b_a] == '0' && F.b_len > 1)) break;
+            if (!rec_num(rt, p, mapq)) break;
+            (void)qe; (void)plen;
+            F.mapq = mapq >= 255 ? -1 : mapq;   // gafkluge.hpp:176-183
+            // ---- optional tags (gafkluge.hpp:185-202): XX:T:value, no duplicates
+            u32 tp_a = 0, tp_b = 0, rc_a = 0, rc_b = 0;
+            u32 ka = 0, kb = 0, kc_ = 0, kd = 0, ntags = 0;
+            bool tbad = false;
+            for (;;) {
+                const u32 fa = p;
+                const u8 c0 = rt[p], c1 = rt[p + 1];
+                if (c0 == '\t' || c0 == '\n' || c0 == ':' || c1 == '\t' || c1 == '\n' || c1 == ':') { tbad = true; break; }
+                const u8 c3 = rt[p + 3];
+                if (rt[p + 2] != ':' || c3 == '\t' || c3 == '\n' || c3 == ':' || rt[p + 4] != ':') { tbad = true; break; }
+                const u32 key = (u32)c0 | ((u32)c1 << 8);
+                const u32 kk = key * 0x00010001u;
+                if (haszero16(ka ^ kk) | haszero16(kb ^ kk) | haszero16(kc_ ^ kk) | haszero16(kd ^ kk)) { tbad = true; break; }
+                if (++ntags > kRMaxTags) { tbad = true; break; }
+                kd = (kd << 16) | (kc_ >> 16); kc_ = (kc_ << 16) | (kb >> 16); kb = (kb << 16) | (ka >> 16); ka = (ka << 16) | key;
+                p = rec_scan_field(rt, p + 5);
+                c = rt[p];
+                if (key == ((u32)'c' | ((u32)'g' << 8))) { ca = fa + 5; cb = p; }
+                else if (key == ((u32)'t' | ((u32)'p' << 8))) { tp_a = fa + 3; tp_b = p; }
+                else if (key == ((u32)'r' | ((u32)'c' << 8))) { rc_a = fa + 3; rc_b = p; }
+                if (c == '\n') break;
+                ++p;
+            }
+            if (tbad || p != len) break;
+            if (cb == 0 || ca >= cb || qs < 0 || ps < 0 || pe < 0) break;
+            const u8 pc0 = rt[pa];
+            prefixed = pc0 == '>' || pc0 == '<';
+            if (!prefixed && pb - pa == 1 && pc0 == '*') break;   // empty path: left to the general kernel
+            LineRec Rr;
+            Rr.qn_b = qn_b; Rr.qlen = qlen; Rr.mapq = F.mapq; Rr.m = m; Rr.b = b;
+            Rr.tp_a = tp_a; Rr.tp_b = tp_b; Rr.rc_a = rc_a; Rr.rc_b = rc_b;
+            Rr.gi_n = gi_fast(m, b, Rr.gi);
+            if (Rr.gi_n == 0) break;
+            rconst = line_const_len(Rr, p10);
+            // gi as floor(m / b * 1000 + 0.5) recovered from the text gi_fast produced ("0", "1" or "0.ddd")
+            F.gi = Rr.gi_n == 1 ? ((u32)(Rr.gi & 0xff) == '1' ? 1000u : 0u)
+                                : 100u * ((u32)(Rr.gi >> 16) & 0xfu) + (Rr.gi_n > 3 ? 10u * ((u32)(Rr.gi >> 24) & 0xfu) : 0u) + (Rr.gi_n > 4 ? ((u32)(Rr.gi >> 32) & 0xfu) : 0u);
+            F.start = rtpos;
+            F.tp_a = tp_a; F.tp_len = tp_b - tp_a; F.rc_a = rc_a; F.rc_len = rc_b - rc_a;
+            frec_store(s_info + 2u * rec, F);
+            // ---- count the path steps
+            if (prefixed) {
+                for (u32 k = pa; k < pb; ++k) { const u8 ch = rt[k]; ns += (u32)(ch == '>' || ch == '<'); }
+            } else ns = 1;
+            ok = true;
+        } while (0);
+        if (!ok) { ns = 0; bad = true; }
+        // ---- block scan of the step counts -> first slot of the record
+        u32 incl = ns;
+        for (int o = 1; o < 32; o <<= 1) { const u32 up = __shfl_up_sync(FULL, incl, o); if (lane >= (u32)o) incl += up; }
+        __syncthreads();   // (s_w is free again)
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        u32 wpre = 0, total = 0;
+        for (u32 i = 0; i < kFThreads / 32; ++i) { if (i < warp) wpre += s_w[i]; total += s_w[i]; }
+        const u32 slot0 = nslots + wpre + incl - ns;
+        nslots += total;
+        if (nslots > kFMaxSlots) { too_many = true; break; }   // uniform: every thread sees the same total
+        if (have && ok && !skip) {
+            bool good = false;
+            do {
+                rt = text + rtpos;
+                const_cast<u8*>(rt)[pb] = '>';   // bounds the token scan of fuse_steps
+                u64 total_len;
+                if (!fuse_steps(a.T, rt, pa, pb, prefixed, minus, s_slots + 3u * slot0, ns, total_len)) break;
+                u32 nl_rec;
+                if (!fuse_walk(rt, rtpos, rec, minus, rconst, p10, prefixed, s_slots + 3u * slot0, s_off + slot0, ns, total_len, ca, cb, qs, ps, pe, nl_rec)) break;
+                good = true;
+            } while (0);
+            if (!good) bad = true;
+        }
+    }
+    if (bad) s_flag = 1;
+    __syncthreads();
+    if (s_flag || too_many) {
+        if (tid == 0) { atomicOr(&a.meta->fallback, s_flag ? (u32)kFuseNotConvertible : (u32)kFuseTooManySteps); st[tile] = kIdxFlagPre; }
+        return;
+    }
+
+    // ---------------- H: line lengths -> offsets inside the tile; the tile's offset in the output (look-back)
+    u32 tile_bytes;
+    {
+        const u32 per = (nslots + kFThreads - 1) / kFThreads;
+        const u32 a0 = tid * per, a1 = a0 + per < nslots ? a0 + per : nslots;
+        u32 sum = 0, nl_mine = 0;
+        for (u32 i = a0; i < a1; ++i) { const u32 l = s_off[i]; sum += l; nl_mine += (u32)(l != 0); }
+        u32 incl = sum;
+        for (int o = 1; o < 32; o <<= 1) { const u32 up = __shfl_up_sync(FULL, incl, o); if (lane >= (u32)o) incl += up; }
+        u32 nls = nl_mine;
+        for (int o = 16; o > 0; o >>= 1) nls += __shfl_xor_sync(FULL, nls, o);
+        if (lane == 31) s_w[warp] = incl;
+        if (lane == 0 && nls) atomicAdd(&s_lines, nls);
+        __syncthreads();
+        u32 wpre = 0, total = 0;
+        for (u32 i = 0; i < kFThreads / 32; ++i) { if (i < warp) wpre += s_w[i]; total += s_w[i]; }
+        u32 run = wpre + incl - sum;
+        // s_off[i] becomes the exclusive offset; the length stays recoverable as off[i + 1] - off[i] (off[nslots] = total)
+        for (u32 i = a0; i < a1; ++i) { const u32 l = s_off[i]; s_off[i] = run; run += l; }
+        if (tid == 0) s_off[nslots] = total;   // (no thread's slot range reaches index nslots)
+        tile_bytes = total;
+    }
+    if (warp == 0) {
+        u64 prefix = 0;
+        if (tile > 0) {
+            if (lane == 0) st[tile] = kIdxFlagAgg | (u64)tile_bytes;
+            __syncwarp();
+            int j = (int)tile - 1;
+            for (;;) {
+                const int idx = j - (int)lane;
+                u64 w = kIdxFlagPre;   // tiles before the first: prefix 0
+                if (idx >= 0) {
+                    u32 spins = 0;
+                    while (((w = st[idx]) >> 62) == 0) { if (++spins > (1u << 26)) __trap(); }
+                }
+                const u32 pre = __ballot_sync(FULL, (w >> 62) == 2);
+                const u32 upto = pre ? (u32)__ffs((int)pre) - 1u : 31u;   // lanes 0..upto contribute
+                u64 val = lane <= upto ? (w & kIdxValMask) : 0;
+                for (int o = 16; o > 0; o >>= 1) val += __shfl_down_sync(FULL, val, o);
+                prefix += __shfl_sync(FULL, val, 0);
+                if (pre) break;
+                j -= 32;
+            }
+        }
+        if (lane == 0) {
+            st[tile] = kIdxFlagPre | (prefix + tile_bytes);
+            s_obase = prefix;
+            atomicAdd(&a.meta->n_records, R);
+            if (s_lines) atomicAdd(&a.meta->n_lines, s_lines);
+            if (tile == a.ntiles - 1) a.meta->out_total = prefix + tile_bytes;
+            if (prefix + tile_bytes > a.out_cap) atomicExch(&a.meta->overflow, 1u);
+        }
+    }
+    __syncthreads();
+    const u64 obase = s_obase;
+    if (obase + tile_bytes > a.out_cap || *g_fallback) return;   // nothing may be written (the host grows the buffer / runs the general pipeline)
+
+    // ---------------- I: format and store, in rounds of at most kFThreads slots and kFStage bytes
+    u32 done = 0;
+    while (done < nslots) {
+        const u32 off0 = s_off[done];
+        const u32 pad = (u32)((obase + off0) & 15u);
+        const u32 slot = done + tid;
+        const bool fits = slot < nslots && s_off[slot + 1] - off0 + pad <= kFStage;
+        // slots that fit form a prefix of the round (offsets are monotone): count them
+        const u32 bal = __ballot_sync(FULL, fits);
+        __syncthreads();   // the previous round's staging buffer has been read (its issuer waited before this barrier)
+        if (lane == 0) s_w[warp] = (u32)__popc(bal);
+        __syncthreads();
+        u32 cnt = 0;
+        for (u32 i = 0; i < kFThreads / 32; ++i) cnt += s_w[i];
+        if (cnt == 0) {   // a single line longer than the staging buffer: not a short record after all
+            if (tid == 0) atomicOr(&a.meta->fallback, (u32)kFuseNotConvertible);
+            return;
+        }
+        if (fits) {
+            const u32 o = s_off[slot], l = s_off[slot + 1] - o;
+            if (l) {
+                const uint4* sl = s_slots + 3u * slot;
+                const uint4 v0 = sl[0], v1 = sl[1], v2 = sl[2];
+                FRec F;
+                frec_load(s_info + 2u * (v2.w & 0xffffu), F);
+                fuse_write_line(s_stage + pad + (o - off0), l, text, F, v0, v1, v2);
+            }
+        }
+        const u32 bytes = s_off[done + cnt] - off0;
+        u8* gb = a.out + (obase + off0 - pad);   // 16-byte aligned
+        const u32 total = pad + bytes;
+        const u32 full_b = total >> 4, first_b = pad ? 1u : 0u;
+#if !defined(G2P_HOSTSIM)
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0 && full_b > first_b) { bulk_s2g(gb + 16u * first_b, s_stage + 16u * first_b, 16u * (full_b - first_b)); bulk_commit(); }
+#else
+        __syncthreads();
+        for (u32 u = first_b + tid; u < full_b; u += kFThreads) reinterpret_cast<uint4*>(gb)[u] = reinterpret_cast<const uint4*>(s_stage)[u];
+#endif
+        const u32 head_end = pad ? (total < 16u ? total : 16u) : 0u;
+        for (u32 b = pad + tid; b < head_end; b += kFThreads) gb[b] = s_stage[b];
+        const u32 tail_a = full_b * 16u > head_end ? full_b * 16u : head_end;
+        for (u32 b = tail_a + tid; b < total; b += kFThreads) gb[b] = s_stage[b];
+#if !defined(G2P_HOSTSIM)
+        if (tid == 0) bulk_wait_read0();   // the staging buffer must outlive the copy's reads
+#endif
+        done += cnt;
+    }
+}
+
+}  // namespace g2p

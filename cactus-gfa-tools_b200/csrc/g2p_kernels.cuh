@@ -529,3 +529,5 @@ __global__ void k_diagnose(const u8* __restrict__ gaf, const u32* __restrict__ r
 }
 
 }  // namespace g2p
+
+#include "g2p_fuse.cuh"

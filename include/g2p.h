@@ -65,6 +65,8 @@ typedef struct g2p_result {
     float index_ms;         /* CUDA-event time of the line index kernels */
     uint32_t n_delegated;   /* records converted by the general per-record kernel (non-canonical or erroneous records) */
     uint32_t n_long;        /* records converted by the streaming kernel k_long (incl. those it passed on) */
+    float fused_ms;         /* CUDA-event time of the one-pass kernel k_fuse (0 when it did not produce the result) */
+    uint32_t n_fused;       /* records converted by k_fuse (all of them, or 0 when the general pipeline ran) */
 } g2p_result;
 
 /* Context bound to one CUDA device. */

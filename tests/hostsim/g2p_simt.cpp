@@ -1,5 +1,6 @@
-// g2p_simt — the device pipeline (line index, k_short, k_convert_list, scan, emit) executed on
-// the CPU by the SIMT emulator in cuda_shim.hpp.
+// g2p_simt — the device pipeline (k_fuse; else line index, k_rec / k_long / k_convert_list, scans, k_emit_lines)
+// executed on the CPU by the SIMT emulator in cuda_shim.hpp, with the library's default configuration
+// (G2P_FUSE=0, G2P_ONE_PASS_INDEX=1, G2P_LEN_SORT=1, G2P_SIZE_KERNEL=short select the variants, as in g2p_create).
 //
 // TEST INFRASTRUCTURE ONLY (never linked into libg2p.so or the executables).  The launch
 // sequence below mirrors g2p_convert_device (g2p_capi.cu); the kernels are the product's own
@@ -43,9 +44,11 @@ int main(int argc, char** argv) {
     const LenTableView T = table.view();
 
     std::string gaf_s;
-    for (const char* p : inputs) {
-        if (!slurp(p, gaf_s)) { std::fprintf(stderr, "[gaf2paf] error: unable to open input: %s\n", p); return 1; }
-        if (!gaf_s.empty() && gaf_s.back() != '\n') gaf_s.push_back('\n');
+    for (size_t i = 0; i < inputs.size(); ++i) {
+        if (!slurp(inputs[i], gaf_s)) { std::fprintf(stderr, "[gaf2paf] error: unable to open input: %s\n", inputs[i]); return 1; }
+        // a line never spans two files; the LAST file keeps an unterminated last line as it is (rec_start[nrec] = n + 1,
+        // virtual newline), like the library sees it
+        if (i + 1 < inputs.size() && !gaf_s.empty() && gaf_s.back() != '\n') gaf_s.push_back('\n');
     }
     const u64 n = gaf_s.size();
     // 16-byte aligned copy with slack, like a device allocation
@@ -53,13 +56,46 @@ int main(int argc, char** argv) {
     u8* gaf = reinterpret_cast<u8*>(gaf_buf.data());
     std::memcpy(gaf, gaf_s.data(), n);
 
+    // ---- the one-pass kernel first (run_fused of g2p_capi.cu); G2P_FUSE=0 skips it
+    if (n && !(std::getenv("G2P_FUSE") && std::atoi(std::getenv("G2P_FUSE")) == 0)) {
+        u32 tile = std::getenv("G2P_FUSE_TILE") ? (u32)std::atoi(std::getenv("G2P_FUSE_TILE")) : kFTileMax;
+        u64 cap = std::getenv("G2P_FUSE_OUT_CAP") ? (u64)std::atoll(std::getenv("G2P_FUSE_OUT_CAP")) : n * 3 + (1u << 20);
+        bool grown = false;
+        for (;;) {
+            const u32 ftiles = (u32)((n + tile - 1) / tile);
+            std::vector<u64> fstat(ftiles + 1, 0);
+            u32 fticket = 0;
+            FuseMeta fm;
+            std::memset(&fm, 0, sizeof fm);
+            std::vector<u8> fout(cap + 256, 0xEE);
+            FuseArgs fa{gaf, n, ftiles, T, fout.data(), cap, fstat.data(), &fticket, &fm};
+            if (tile == 32768) hs::launch(dim3(ftiles), dim3(kFThreads), FuseCfg<32768>::kSmem, [&] { k_fuse<32768>(fa); });
+            else if (tile == 16384) hs::launch(dim3(ftiles), dim3(kFThreads), FuseCfg<16384>::kSmem, [&] { k_fuse<16384>(fa); });
+            else hs::launch(dim3(ftiles), dim3(kFThreads), FuseCfg<8192>::kSmem, [&] { k_fuse<8192>(fa); });
+            if (fm.fallback) {
+                if (!(fm.fallback & kFuseNotConvertible) && tile > kFTileMin) { tile /= 2; continue; }
+                break;
+            }
+            if (!fm.overflow) {
+                if (std::getenv("G2P_SIMT_STATS")) std::fprintf(stderr, "g2p_simt: k_fuse converted %u records, %u lines, %llu bytes out (%u tiles of %u bytes)\n", fm.n_records, fm.n_lines, (unsigned long long)fm.out_total, ftiles, tile);
+                std::fwrite(fout.data(), 1, fm.out_total, stdout);
+                std::fflush(stdout);
+                return 0;
+            }
+            if (grown) break;
+            cap = fm.out_total + 256;
+            grown = true;
+        }
+        if (std::getenv("G2P_SIMT_STATS")) std::fprintf(stderr, "g2p_simt: k_fuse fell back to the general pipeline\n");
+    }
+
     PipelineMeta meta;
     std::memset(&meta, 0, sizeof meta);
     const u32 ntiles = (u32)((n + kIdxTile - 1) / kIdxTile);
     std::vector<u32> rec;
     u32 nrec = 0;
     bool indexed = false;
-    if (ntiles && !std::getenv("G2P_TWO_PASS_INDEX")) {   // the emulator exercises the single-pass index by default (the library defaults to the counting kernels)
+    if (ntiles && std::getenv("G2P_ONE_PASS_INDEX") && std::atoi(std::getenv("G2P_ONE_PASS_INDEX")) != 0) {   // default: the counting kernels, like the library
         const u64 cap = std::getenv("G2P_SIMT_INDEX_CAP") ? (u64)std::atol(std::getenv("G2P_SIMT_INDEX_CAP")) : n / 32 + 1024;
         rec.assign(cap + 2, 0xDEADBEEFu);
         std::vector<u64> tstat(ntiles + 1, 0);
@@ -97,7 +133,7 @@ int main(int argc, char** argv) {
         const u32 chunks = std::getenv("G2P_REC_CHUNKS") ? (u32)std::atoi(std::getenv("G2P_REC_CHUNKS")) : rec_chunks_for(n, nrec);
         std::vector<u32> perm(nrec);
         const u32* permp = nullptr;
-        if (!std::getenv("G2P_LEN_SORT") || std::atoi(std::getenv("G2P_LEN_SORT")) != 0) {   // as run_pipeline (g2p_capi.cu)
+        if (std::getenv("G2P_LEN_SORT") && std::atoi(std::getenv("G2P_LEN_SORT")) != 0) {   // off by default, as run_pipeline (g2p_capi.cu)
             const u32 nsort = (nrec + kLenSortRecs - 1) / kLenSortRecs, nm = kLenBins * nsort;
             const u32 nscan_m = (nm + kScanTile - 1) / kScanTile;
             std::vector<u64> m((size_t)nm + 1 + nscan_m);
