@@ -139,7 +139,8 @@ struct g2p_ctx {
     uint32_t rec_chunks_override = 0; // G2P_REC_CHUNKS: k_rec slot capacity in 16-byte chunks
     uint64_t desc_cap_override = 0;  // G2P_DESC_CAP (tests): line-descriptor slots, to exercise the overflow fallback
     bool use_fuse = true;            // G2P_FUSE=0: skip the one-pass kernel k_fuse, always run the general pipeline
-    u32 fuse_tile = kFTileMax;       // input bytes per CTA of k_fuse: halved (and kept) when a tile holds more records / path steps than its tables (G2P_FUSE_TILE)
+    int fuse_cfg = 0;                // k_fuse configuration (tile bytes, table sizes; g2p_fuse.cuh); moves to a denser one, and stays there, when a tile
+                                     // holds more records / path steps than its tables (G2P_FUSE_CFG picks the first one)
     uint64_t fuse_out_cap_override = 0;   // G2P_FUSE_OUT_CAP (tests): initial output capacity of k_fuse, to exercise the grow-and-rerun path
     void set_err(const std::string& m) { std::lock_guard<std::mutex> g(err_mu); err = m; }
 };
@@ -241,10 +242,12 @@ int g2p_create(int device, g2p_ctx** out) {
     if (const char* c = std::getenv("G2P_DESC_CAP")) ctx->desc_cap_override = std::strtoull(c, nullptr, 10);
     if (const char* c = std::getenv("G2P_FUSE")) ctx->use_fuse = std::atoi(c) != 0;
     if (const char* c = std::getenv("G2P_FUSE_OUT_CAP")) ctx->fuse_out_cap_override = std::strtoull(c, nullptr, 10);
-    cudaFuncSetAttribute(k_fuse<32768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FuseCfg<32768>::kSmem);
-    cudaFuncSetAttribute(k_fuse<16384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FuseCfg<16384>::kSmem);
-    cudaFuncSetAttribute(k_fuse<8192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FuseCfg<8192>::kSmem);
-    if (const char* c = std::getenv("G2P_FUSE_TILE")) { const int v = std::atoi(c); if (v == 32768 || v == 16384 || v == 8192) ctx->fuse_tile = (u32)v; }
+    cudaFuncSetAttribute(k_fuse<FuseCfg0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FuseCfg0::kSmem);
+    cudaFuncSetAttribute(k_fuse<FuseCfg1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FuseCfg1::kSmem);
+    cudaFuncSetAttribute(k_fuse<FuseCfg2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FuseCfg2::kSmem);
+    cudaFuncSetAttribute(k_fuse<FuseCfg3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FuseCfg3::kSmem);
+    cudaFuncSetAttribute(k_fuse<FuseCfg4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FuseCfg4::kSmem);
+    if (const char* c = std::getenv("G2P_FUSE_CFG")) { const int v = std::atoi(c); if (v >= 0 && v < kFuseCfgs) ctx->fuse_cfg = v; }
     if (const char* c = std::getenv("G2P_HOST_CHUNK_MB")) {
         long v = std::atol(c);
         if (v > 0) { ctx->host_chunk = (size_t)v << 20; ctx->host_chunk_fixed = true; }
@@ -362,10 +365,14 @@ int g2p_index_lines(g2p_ctx* ctx, const void* d_text, size_t n, const uint32_t**
 // it is used and the caller runs the general pipeline.  The output buffer is sized by a bound (3x the input, or
 // what earlier calls needed) and grown + the kernel run again when the exact size, which k_fuse always reports,
 // exceeds it.
-static void launch_fuse(u32 tile, u32 ntiles, cudaStream_t st, const FuseArgs& fa) {
-    if (tile == 32768) k_fuse<32768><<<ntiles, kFThreads, FuseCfg<32768>::kSmem, st>>>(fa);
-    else if (tile == 16384) k_fuse<16384><<<ntiles, kFThreads, FuseCfg<16384>::kSmem, st>>>(fa);
-    else k_fuse<8192><<<ntiles, kFThreads, FuseCfg<8192>::kSmem, st>>>(fa);
+static void launch_fuse(int cfg, u32 ntiles, cudaStream_t st, const FuseArgs& fa) {
+    switch (cfg) {
+        case 0: k_fuse<FuseCfg0><<<ntiles, kFThreads, FuseCfg0::kSmem, st>>>(fa); break;
+        case 1: k_fuse<FuseCfg1><<<ntiles, kFThreads, FuseCfg1::kSmem, st>>>(fa); break;
+        case 2: k_fuse<FuseCfg2><<<ntiles, kFThreads, FuseCfg2::kSmem, st>>>(fa); break;
+        case 3: k_fuse<FuseCfg3><<<ntiles, kFThreads, FuseCfg3::kSmem, st>>>(fa); break;
+        default: k_fuse<FuseCfg4><<<ntiles, kFThreads, FuseCfg4::kSmem, st>>>(fa); break;
+    }
 }
 
 static int run_fused(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cudaStream_t st, g2p_result* res, u8** d_out, bool* done) {
@@ -376,7 +383,8 @@ static int run_fused(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cudaStr
     G2P_CUDA(cudaEventRecord(w.ev[5], st));
     bool grown = false;
     for (;;) {
-        const u32 tile = ctx->fuse_tile;
+        const int cfg = ctx->fuse_cfg;
+        const u32 tile = fuse_cfg_tile(cfg);
         const u32 ntiles = (u32)((n + tile - 1) / tile);
         const size_t fbytes = sizeof(FuseMeta) + 16 + (size_t)ntiles * sizeof(u64);
         G2P_CUDA(w.d_fuse.ensure(fbytes));
@@ -385,7 +393,7 @@ static int run_fused(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cudaStr
         G2P_CUDA(cudaMemsetAsync(fb, 0, fbytes, st));
         FuseArgs fa{d_gaf, (u64)n, ntiles, ctx->table, static_cast<u8*>(w.d_out.p), (u64)(ctx->fuse_out_cap_override && !grown ? ctx->fuse_out_cap_override : w.d_out.cap),
                     reinterpret_cast<u64*>(fb + sizeof(FuseMeta) + 16), reinterpret_cast<u32*>(fb + sizeof(FuseMeta)), d_fm};
-        launch_fuse(tile, ntiles, st, fa);
+        launch_fuse(cfg, ntiles, st, fa);
         k_words_to_host<<<1, 32, 0, st>>>(reinterpret_cast<const uint32_t*>(d_fm), static_cast<uint32_t*>(w.h_fmeta.p), sizeof(FuseMeta) / 4);
         res->gpu_launches += 2;
         G2P_CUDA(cudaEventRecord(w.ev[6], st));
@@ -393,7 +401,7 @@ static int run_fused(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cudaStr
         G2P_CUDA(cudaGetLastError());
         if (hm->fallback) {
             // only capacity reasons (records or path steps per tile): a smaller tile converts the same input
-            if (!(hm->fallback & kFuseNotConvertible) && tile > kFTileMin) { ctx->fuse_tile = tile / 2; continue; }
+            if (!(hm->fallback & kFuseNotConvertible) && fuse_cfg_denser(cfg) >= 0) { ctx->fuse_cfg = fuse_cfg_denser(cfg); continue; }
             return G2P_OK;
         }
         if (!hm->overflow) {

@@ -29,34 +29,49 @@
 
 namespace g2p {
 
-#ifndef G2P_FUSE_CTAS
-#define G2P_FUSE_CTAS 2
-#endif
 constexpr int kFThreads = 256;
 constexpr u32 kFLimit = 1000;              // longest record (bytes, without '\n') converted here
 constexpr u32 kFTail = 1024;               // bytes after the tile its last record may extend into (>= kFLimit + 1)
-constexpr u32 kFMaxRec = 352;              // records per tile (more -> kFuseTooManyRecords)
-constexpr u32 kFMaxSlots = 832;            // path steps per tile (more -> kFuseTooManySteps)
-constexpr u32 kFSmemBudget = (227u * 1024u) / G2P_FUSE_CTAS - 1024u - 512u;    // per CTA: 1 KB reserved by the driver + static shared
-// Shared-memory layout for a tile of TILE input bytes.  The record / step capacities do not depend on the tile:
-// a denser input (shorter records, more steps per byte) is converted with a smaller tile (the host halves it when
-// a tile reports kFuseTooManyRecords / kFuseTooManySteps), which also leaves more room for the staging buffer.
-template <u32 TILE>
+// Shared-memory layout of one configuration: TILE input bytes per CTA, room for MAXREC records and MAXSLOTS path
+// steps, CTAS resident CTAs per SM (which fixes the shared-memory budget; what the tables leave is the staging buffer).
+template <u32 TILE, u32 MAXREC, u32 MAXSLOTS, int CTAS>
 struct FuseCfg {
+    static constexpr u32 kTile = TILE, kMaxRec = MAXREC, kMaxSlots = MAXSLOTS;
+    static constexpr int kCtas = CTAS;
     static constexpr u32 kUnits = TILE / 16 / kFThreads;   // 16-byte vectors per thread in the newline scan
     static_assert(TILE % (16 * kFThreads) == 0, "the newline scan gives every thread whole vectors");
     static_assert(16 + TILE + kFTail + 64 < 65536, "text positions are 16-bit");
+    static constexpr u32 kBudget = (227u * 1024u) / CTAS - 1024u - 512u;              // per CTA: 1 KB reserved by the driver + static shared
     static constexpr u32 kTextBytes = 16 + TILE + kFTail + 48;
-    static constexpr u32 kOffStart = kTextBytes;                                      // u16 start[kFMaxRec + 2]
-    static constexpr u32 kOffInfo = (kOffStart + 2 * (kFMaxRec + 2) + 15) & ~15u;     // uint4 info[2 * kFMaxRec]
-    static constexpr u32 kOffSlots = kOffInfo + 32 * kFMaxRec;                        // uint4 slots[3 * kFMaxSlots]
-    static constexpr u32 kOffOff = kOffSlots + 48 * kFMaxSlots;                       // u32 off[kFMaxSlots + 1]
-    static constexpr u32 kOffStage = (kOffOff + 4 * (kFMaxSlots + 1) + 15) & ~15u;
-    static_assert(kFSmemBudget > kOffStage + 8192, "no room for the staging buffer");
-    static constexpr u32 kStage = ((kFSmemBudget - kOffStage - 32) & ~15u);           // staged PAF bytes per round
+    static constexpr u32 kOffStart = kTextBytes;                                      // u16 start[MAXREC + 2]
+    static constexpr u32 kOffLidx = (kOffStart + 2 * (MAXREC + 2) + 3) & ~3u;         // u16 lidx[MAXSLOTS]: slots that print a line, in order
+    static constexpr u32 kOffInfo = (kOffLidx + 2 * MAXSLOTS + 15) & ~15u;            // uint4 info[2 * MAXREC]
+    static constexpr u32 kOffSlots = kOffInfo + 32 * MAXREC;                          // uint4 slots[3 * MAXSLOTS]
+    static constexpr u32 kOffOff = kOffSlots + 48 * MAXSLOTS;                         // u32 off[MAXSLOTS + 1]
+    static constexpr u32 kOffStage = (kOffOff + 4 * (MAXSLOTS + 1) + 15) & ~15u;
+    static_assert(kBudget > kOffStage + 8192, "no room for the staging buffer");
+    static constexpr u32 kStage = ((kBudget - kOffStage - 32) & ~15u);                // staged PAF bytes per round
     static constexpr size_t kSmem = kOffStage + kStage + 32;
 };
-constexpr u32 kFTileMax = 32768, kFTileMin = 8192;   // instantiated: 32 KiB, 16 KiB, 8 KiB
+// Configurations.  0-2 are tuning alternatives for ordinary short-read input (G2P_FUSE_CFG); 3 and 4 keep the largest
+// tables on smaller tiles: the host moves to them when a tile reports kFuseTooManyRecords / kFuseTooManySteps
+// (denser input: shorter records or more steps per byte).
+typedef FuseCfg<32768, 352, 832, 2> FuseCfg0;
+typedef FuseCfg<24576, 288, 704, 2> FuseCfg1;
+typedef FuseCfg<16384, 192, 480, 3> FuseCfg2;
+typedef FuseCfg<16384, 352, 832, 2> FuseCfg3;
+typedef FuseCfg<8192, 352, 832, 2> FuseCfg4;
+constexpr int kFuseCfgs = 5, kFuseCfgDense = 3;
+static inline u32 fuse_cfg_tile(int cfg) {
+    static const u32 t[kFuseCfgs] = {FuseCfg0::kTile, FuseCfg1::kTile, FuseCfg2::kTile, FuseCfg3::kTile, FuseCfg4::kTile};
+    return t[cfg];
+}
+static inline size_t fuse_cfg_smem(int cfg) {
+    static const size_t t[kFuseCfgs] = {FuseCfg0::kSmem, FuseCfg1::kSmem, FuseCfg2::kSmem, FuseCfg3::kSmem, FuseCfg4::kSmem};
+    return t[cfg];
+}
+// the configuration to try after `cfg` reported a capacity overflow (-1: none left)
+static inline int fuse_cfg_denser(int cfg) { return cfg < kFuseCfgDense ? kFuseCfgDense : (cfg + 1 < kFuseCfgs ? cfg + 1 : -1); }
 
 enum : u32 { kFuseNotConvertible = 1u, kFuseTooManyRecords = 2u, kFuseTooManySteps = 4u };
 
@@ -86,14 +101,14 @@ struct FuseArgs {
 //   w1: m_a | m_len << 16 | b_len << 24                        (columns 10 / 11, copied verbatim)
 //   w2: b_a | (mapq + 1) << 16                                 (mapq -1 .. 254)
 //   w3: tp_a | tp_len << 16          w4: rc_a | rc_len << 16   ("type:value" spans, len 0 = absent)
-//   w5: gi (0 .. 1000: floor(m / b * 1000 + 0.5))
+//   w5: gi (0 .. 1000: floor(m / b * 1000 + 0.5))     w6: bytes of a line of this record that do not depend on the step
 struct FRec {
-    u32 start, pfx_len, m_a, m_len, b_a, b_len, tp_a, tp_len, rc_a, rc_len, gi;
+    u32 start, pfx_len, m_a, m_len, b_a, b_len, tp_a, tp_len, rc_a, rc_len, gi, rconst;
     i32 mapq;
 };
 __device__ __forceinline__ void frec_store(uint4* dst, const FRec& r) {
     dst[0] = make_uint4(r.start | (r.pfx_len << 16), r.m_a | (r.m_len << 16) | (r.b_len << 24), r.b_a | ((u32)(r.mapq + 1) << 16), r.tp_a | (r.tp_len << 16));
-    dst[1] = make_uint4(r.rc_a | (r.rc_len << 16), r.gi, 0u, 0u);
+    dst[1] = make_uint4(r.rc_a | (r.rc_len << 16), r.gi, r.rconst, 0u);
 }
 __device__ __forceinline__ void frec_load(const uint4* src, FRec& r) {
     const uint4 a = src[0], b = src[1];
@@ -102,7 +117,7 @@ __device__ __forceinline__ void frec_load(const uint4* src, FRec& r) {
     r.b_a = a.z & 0xffffu; r.mapq = (i32)(a.z >> 16) - 1;
     r.tp_a = a.w & 0xffffu; r.tp_len = a.w >> 16;
     r.rc_a = b.x & 0xffffu; r.rc_len = b.x >> 16;
-    r.gi = b.y;
+    r.gi = b.y; r.rconst = b.z;
 }
 
 // ---- one line slot (48 bytes) ------------------------------------------------------------------
@@ -172,158 +187,202 @@ struct WEmit {
     }
 };
 
-// Pass S of k_rec (rec_steps) writing line slots: the path column forwards, one scan per step token, one
-// table probe per step; step j of the text becomes slot (minus ? ns - 1 - j : j), i.e. slots are in
-// normalised order.  Returns false if a token is not canonical or a name is unknown.
-__device__ __forceinline__ bool fuse_steps(const LenTableView& T, const u8* rt, const u32 pa, const u32 pb, const bool prefixed, const bool minus,
-                                           uint4* slots, const u32 ns, u64& total_out) {
+// ---- D1: the path column -> one slot per step token, in normalised order (step j of the text becomes slot
+// (minus ? ns - 1 - j : j): flip_gaf, gaf2paf_main.cpp:92-110, is index arithmetic).  Only positions are recorded
+// (v2.z = marker position | name length << 16, v0.x = interval flag << 31); the table probe and the interval digits
+// are left to one thread per slot (fuse_probe).  The caller has planted a '>' after the path column.
+__device__ __forceinline__ bool fuse_tokens(const u8* rt, const u32 rtpos, const u32 pa, const u32 pb, const bool prefixed, const bool minus,
+                                            uint4* slots, const u32 ns) {
     u32 j = 0, mp = prefixed ? pa : pa - 1;
-    u64 total = 0;
     for (;;) {
         const u32 name_a = mp + 1;
         u32 e = pb;
-        u8 c = 0;
+        bool interval = false;
         if (prefixed) {
             e = rec_scan_step(rt, name_a);   // rt[pb] == '>'
-            c = rt[e];
+            interval = rt[e] == ':';
         }
         const u32 nl = e - name_a;
-        if (nl == 0 || nl > 16 || j >= ns) return false;
-        u32 w0, w1, w2, w3;
-        lds16_unaligned(rt + name_a, w0, w1, w2, w3);
-        w0 = keep_bytes(w0, (int)nl); w1 = keep_bytes(w1, (int)nl - 4);
-        w2 = keep_bytes(w2, (int)nl - 8); w3 = keep_bytes(w3, (int)nl - 12);
-        u32 slen = 0;
-        const bool interval = prefixed && c == ':';
-        if (interval) {   // ":start-end" (gafkluge.hpp:131-146), plain digits only
-            u32 k = e + 1, x = 0, d;
-            const u32 k1 = k;
-            while ((d = (u32)rt[k] - '0') <= 9u) { x = x * 10u + d; ++k; }
-            if (k == k1 || k - k1 > 9 || rt[k] != '-') return false;
-            const u32 sa = x;
-            ++k; x = 0;
-            const u32 k2 = k;
-            while ((d = (u32)rt[k] - '0') <= 9u) { x = x * 10u + d; ++k; }
-            if (k == k2 || k - k2 > 9 || (rt[k] != '>' && rt[k] != '<') || x < sa) return false;
-            slen = x - sa;
-            e = k;
-        }
-        i64 tl64;
-        if (!table_lookup_key16(T, (u64)w0 | ((u64)w1 << 32), (u64)w2 | ((u64)w3 << 32), nl, tl64) || tl64 < 0 || tl64 > 0x7fffffffLL) return false;
-        if (!interval) slen = (u32)tl64;
-        total += slen;
+        if (nl == 0 || nl > 255 || j >= ns) return false;
+        if (interval) e = rec_scan_step(rt, e + 1);   // the token ends at the next marker
+        if (rt[e] == ':') return false;               // a second ':' inside the token: left to the general kernel
         uint4* sl = slots + 3u * (minus ? ns - 1u - j : j);
-        sl[0].x = (u32)tl64 | (interval ? 0x80000000u : 0u);
-        sl[2].z = mp | (nl << 16);
+        sl[0].x = interval ? 0x80000000u : 0u;
+        sl[2].z = (rtpos + mp) | (nl << 16);
         ++j;
         if (e >= pb) break;
         mp = e;
     }
-    total_out = total;
     return j == ns;
 }
 
-// The record walk after fuse_steps (rec_walk of k_rec writing slots): steps (slot i = normalised step i) and
-// ops in normalised order.  Every slot gets its line length in len[i] (0: no line).  Returns false to delegate.
-__device__ __forceinline__ bool fuse_walk(const u8* rt, const u32 rtpos, const u32 rec, const bool minus, const u32 rconst, const u32* p10,
-                                          const bool prefixed, uint4* slots, u32* len, const u32 ns, const u64 total, const u32 ca, const u32 cb,
-                                          const i32 qs, i32 ps, i32 pe, u32& nlines_out) {
-    if (minus) {   // flip_gaf: mirror the path interval about the summed step lengths (gaf2paf_main.cpp:128-131)
+// ---- E: one thread per slot: the step's name is probed once in the lengths table (gaf2paf_main.cpp:162-167) and an
+// interval's ":start-end" (gafkluge.hpp:131-146; plain digits only) is decoded.  v0 = {tlen | interval << 31, start, end, 0}.
+__device__ __forceinline__ bool fuse_probe(const LenTableView& T, const u8* text, uint4* sl) {
+    const u32 z = sl[2].z;
+    const u8* name = text + (z & 0xffffu) + 1u;
+    const u32 nl = (z >> 16) & 0xffu;
+    i64 tl64;
+    if (nl <= 16u) {
+        u32 w0, w1, w2, w3;
+        lds16_unaligned(name, w0, w1, w2, w3);
+        w0 = keep_bytes(w0, (int)nl); w1 = keep_bytes(w1, (int)nl - 4);
+        w2 = keep_bytes(w2, (int)nl - 8); w3 = keep_bytes(w3, (int)nl - 12);
+        if (!table_lookup_key16(T, (u64)w0 | ((u64)w1 << 32), (u64)w2 | ((u64)w3 << 32), nl, tl64)) return false;
+    } else if (!table_lookup(T, name, nl, tl64)) return false;   // long names: 128-bit hash + arena compare
+    if (tl64 < 0 || tl64 > 0x7fffffffLL) return false;
+    u32 sa = 0, se = (u32)tl64;
+    const u32 ivl = sl[0].x & 0x80000000u;
+    if (ivl) {
+        const u8* q = name + nl + 1u;
+        u32 k = 0, x = 0, d;
+        while ((d = (u32)q[k] - '0') <= 9u) { x = x * 10u + d; ++k; }
+        if (k == 0 || k > 9 || q[k] != '-') return false;
+        sa = x;
+        const u32 k2 = ++k;
+        x = 0;
+        while ((d = (u32)q[k] - '0') <= 9u) { x = x * 10u + d; ++k; }
+        if (k == k2 || k - k2 > 9 || (q[k] != '>' && q[k] != '<') || x < sa) return false;
+        se = x;
+    }
+    sl[0] = make_uint4((u32)tl64 | ivl, sa, se, 0u);
+    return true;
+}
+
+// One CIGAR token in walk direction, loop-free for up to three digits (all of a short read's): the five bytes next to
+// the cursor are loaded together.  Forward: "digits letter" starts at cp; backward: the token ends at cp (exclusive).
+__device__ __forceinline__ bool fuse_fetch_op(const u8* rt, const bool minus, u32& cp, u32& x, u32& kc, u32& ts, u32& te) {
+    const u32 step = minus ? 0xffffffffu : 1u;
+    const u32 base = minus ? cp - 1u : cp;
+    const u32 b0 = rt[base], b1 = rt[base + step], b2 = rt[base + 2u * step], b3 = rt[base + 3u * step], b4 = rt[base + 4u * step];
+    // digits in walk order: forward b0 b1 b2 (b3), backward b1 b2 b3 (b4) after the letter b0
+    const u32 d0 = (minus ? b1 : b0) - '0', d1 = (minus ? b2 : b1) - '0', d2 = (minus ? b3 : b2) - '0', d3 = (minus ? b4 : b3) - '0';
+    if (d0 <= 9u && d1 <= 9u && d2 <= 9u && d3 <= 9u) return rec_fetch_op_slow(rt, minus, cp, x, kc, ts, te);   // >= 4 digits
+    const u32 nd = d0 > 9u ? 0u : (d1 > 9u ? 1u : (d2 > 9u ? 2u : 3u));
+    const u32 v2 = minus ? d1 * 10u + d0 : d0 * 10u + d1;
+    const u32 v3 = minus ? d2 * 100u + d1 * 10u + d0 : d0 * 100u + d1 * 10u + d2;
+    const u32 v = nd == 1 ? d0 : (nd == 2 ? v2 : v3);
+    const u32 lead = minus ? (nd == 1 ? d0 : (nd == 2 ? d1 : d2)) : d0;   // most significant digit
+    const u32 letter = minus ? b0 : (nd == 1 ? b1 : (nd == 2 ? b2 : b3));
+    if (minus) { te = cp; ts = cp - nd - 1u; cp = ts; }
+    else { ts = cp; te = cp + nd + 1u; cp = te; }
+    kc = letter - '=';
+    x = v;
+    return nd != 0 && !(nd > 1 && lead == 0) && v != 0 && kc < 28u && ((kOpMask >> kc) & 1u);
+}
+
+// ---- D2: the record walk, one thread per record.  (a) per step: strand, quota and clips (gaf2paf_main.cpp:157-182);
+// (b) ONE loop over the CIGAR ops, in normalised order, that opens / closes the steps as their target quota fills up
+// (cigar_next_by_target, gaf2paf_main.cpp:71-90): every trip fetches at most one op, so the lanes of a warp -- records
+// with similar op counts -- stay in the same loop instead of diverging over nested step / op / digit loops.  Slot i
+// (normalised step i) receives the numbers of its PAF line; kFSlotEmit marks the steps that print one.
+constexpr u32 kFSlotEmit = 4u;
+__device__ __forceinline__ bool fuse_walk2(const u8* rt, const u32 rtpos, const u8* text, const u32 rec, const bool minus, const bool prefixed,
+                                           uint4* slots, const u32 ns, const u32 ca, const u32 cb, const i32 qs, i32 ps, i32 pe) {
+    // (a) step lengths, the mirrored path interval of '-' records (flip_gaf, gaf2paf_main.cpp:111-131), quotas
+    u64 total = 0;
+    for (u32 i = 0; i < ns; ++i) { const uint4 v = slots[3u * i]; total += v.z - v.y; }
+    if (minus) {
         if (total > 0x7fffffffULL) return false;
         const i32 nps = (i32)total - pe, npe = (i32)total - ps;
         ps = nps; pe = npe;
     }
     const i32 W = pe - ps;
-    const u32 cend = minus ? ca : cb;   // CIGAR cursor and where it ends
-    u32 cp = minus ? cb : ca;
-    u32 rem = 0, remk = 0;              // unconsumed part of the op cut by the previous boundary
-    u32 qcur = 0, tbc = 0;              // query / target bases consumed by the steps so far
-    u32 nlines = 0;
+    u32 tbc = 0;
     for (u32 i = 0; i < ns; ++i) {
         uint4* sl = slots + 3u * i;
-        const u32 sA = sl[0].x, sB = sl[2].z;
-        const u32 mp = sB & 0xffffu, nl = (sB >> 16) & 0xffu;
-        const i32 tlen = (i32)(sA & 0x7fffffffu);
-        i32 sa = 0, se = tlen;
-        if (sA & 0x80000000u) {   // interval: the digits were validated by fuse_steps
-            u32 k = mp + nl + 2, x = 0, d;
-            while ((d = (u32)rt[k] - '0') <= 9u) { x = x * 10u + d; ++k; }
-            sa = (i32)x;
-            ++k; x = 0;
-            while ((d = (u32)rt[k] - '0') <= 9u) { x = x * 10u + d; ++k; }
-            se = (i32)x;
-        }
-        const bool rev = (prefixed && rt[mp] == '<') != minus;
-        const bool last = i + 1 == ns;
+        const uint4 v = sl[0];
+        const u32 z = sl[2].z;
+        const i32 tlen = (i32)(v.x & 0x7fffffffu), sa = (i32)v.y, se = (i32)v.z;
+        const bool rev = (prefixed && text[z & 0xffffu] == '<') != minus;
         const i32 slen = se - sa;
-        // ---- quota (gaf2paf_main.cpp:176-182)
         const i32 so = i == 0 ? ps : 0;
         i32 quota = slen - so, eo = 0;
-        if (last) { quota = W - (i32)tbc; eo = slen - so - quota; }
+        if (i + 1 == ns) { quota = W - (i32)tbc; eo = slen - so - quota; }
         if (so < 0 || quota < 0 || eo < 0) return false;
-        u32 line = 0;
-        if (quota > 0) {
-            // ---- take `quota` target bases of CIGAR (cigar_next_by_target, gaf2paf_main.cpp:71-90)
-            u32 need = (u32)quota, q = 0, nm = 0, nb = 0;
-            LineStep L;
-            L.lenS = 0; L.codeS = 0; L.mid_a = 0; L.mid_b = 0; L.lenE = 0; L.codeE = 0;
-            bool done = false;
+        tbc += (u32)quota;
+        sl[0] = make_uint4((u32)tlen, (u32)(sa + (rev ? eo : so)), (u32)(se - (rev ? so : eo)), 0u);
+        sl[1].x = (u32)quota;
+        sl[2].z = ((z & 0xffffu) + 1u) | (z & 0x00ff0000u) | ((rev ? kFSlotRev : 0u) << 24) | ((rev == minus ? kFSlotMidFwd : 0u) << 24);
+    }
+    // (b) ops
+    const u32 cend = minus ? ca : cb;
+    u32 cp = minus ? cb : ca;
+    u32 rem = 0, remk = 0;       // unconsumed part of the op cut by the previous boundary
+    u32 qcur = (u32)qs;          // query position at the start of the open step
+    u32 i = 0, need = 0;         // open step and what is left of its quota (0: no step open)
+    u32 q = 0, nm = 0, nb = 0, lenS = 0, codeS = 0, lenE = 0, codeE = 0, mid_a = 0, mid_b = 0;
+    for (;;) {
+        bool close = false;
+        if (need == 0) {   // open the next step
+            if (i == ns) break;
+            need = slots[3u * i + 1u].x;
+            q = nm = nb = lenS = codeS = lenE = codeE = mid_a = mid_b = 0;
+            if (need == 0) { ++i; continue; }   // no target bases left for it: no line, nothing consumed
             if (rem) {   // the remainder of a cut op is target-consuming by construction
                 const u32 take = rem < need ? rem : need;
                 if ((kQueryMask >> remk) & 1u) q += take;
                 if ((kMatchMask >> remk) & 1u) nm += take;
                 nb += take;
-                if (rem >= need) { L.lenE = need; L.codeE = (u8)(remk + '='); rem -= need; done = true; }
-                else { L.lenS = rem; L.codeS = (u8)(remk + '='); need -= rem; rem = 0; }
+                if (rem >= need) { lenE = need; codeE = remk + '='; rem -= need; close = true; }
+                else { lenS = rem; codeS = remk + '='; need -= rem; rem = 0; }
             }
-            while (!done) {
-                if (cp == cend) return false;   // :80 assert: CIGAR shorter than the path
-                u32 x, kc, ts, tte;
-                if (!rec_fetch_op(rt, minus, cp, x, kc, ts, tte)) return false;
-                const bool tgt = (kTargetMask >> kc) & 1u;
-                if (tgt && x >= need) {
-                    L.lenE = need; L.codeE = (u8)(kc + '=');
-                    rem = x - need; remk = kc;
-                    x = need;
-                    done = true;
-                } else {
-                    if (tgt) need -= x;
-                    if (L.mid_b == 0) { L.mid_a = ts; L.mid_b = tte; }
-                    else if (minus) L.mid_a = ts;
-                    else L.mid_b = tte;
-                }
-                if ((kQueryMask >> kc) & 1u) q += x;
-                if ((kMatchMask >> kc) & 1u) nm += x;
-                nb += x;
+        }
+        if (!close) {   // one op
+            if (cp == cend) return false;   // :80 assert: CIGAR shorter than the path
+            u32 x, kc, ts, tte;
+            if (!fuse_fetch_op(rt, minus, cp, x, kc, ts, tte)) return false;
+            const bool tgt = (kTargetMask >> kc) & 1u;
+            if (tgt && x >= need) {
+                lenE = need; codeE = kc + '=';
+                rem = x - need; remk = kc;
+                x = need;
+                close = true;
+            } else {
+                if (tgt) need -= x;
+                if (mid_b == 0) { mid_a = ts; mid_b = tte; }
+                else if (minus) mid_a = ts;
+                else mid_b = tte;
             }
+            if ((kQueryMask >> kc) & 1u) q += x;
+            if ((kMatchMask >> kc) & 1u) nm += x;
+            nb += x;
+        }
+        if (close) {
+            uint4* sl = slots + 3u * i;
             if (nm > 0) {   // gaf2paf_main.cpp:225
-                L.rev = rev;
-                L.mid_fwd = rev == minus;
-                L.q0 = (u32)qs + qcur; L.q1 = L.q0 + q;
-                L.name_a = mp + 1; L.nl = nl; L.tlen = (u32)tlen;
-                L.ts = (u32)(sa + (rev ? eo : so)); L.te = (u32)(se - (rev ? so : eo));
-                L.nm = nm; L.nb = nb;
-                line = rconst + line_step_len(L, p10);
-                const u32 mid_len = L.mid_b > L.mid_a ? L.mid_b - L.mid_a : 0u;
-                sl[0] = make_uint4(L.tlen, L.ts, L.te, L.q0);
-                sl[1] = make_uint4(L.q1, L.nm, L.nb, L.lenS);
-                sl[2] = make_uint4(L.lenE, (rtpos + L.mid_a) | (mid_len << 16),
-                                   (rtpos + L.name_a) | (nl << 16) | ((rev ? kFSlotRev : 0u) << 24) | ((L.mid_fwd ? kFSlotMidFwd : 0u) << 24),
-                                   rec | ((u32)L.codeS << 16) | ((u32)L.codeE << 24));
-                ++nlines;
+                const u32 mid_len = mid_b > mid_a ? mid_b - mid_a : 0u;
+                sl[0].w = qcur;
+                sl[1] = make_uint4(qcur + q, nm, nb, lenS);
+                sl[2].x = lenE;
+                sl[2].y = (rtpos + mid_a) | (mid_len << 16);
+                sl[2].z |= kFSlotEmit << 24;
+                sl[2].w = rec | (codeS << 16) | (codeE << 24);
             }
             qcur += q;
-            tbc += (u32)quota;
+            need = 0;
+            ++i;
         }
-        len[i] = line;
     }
     // the reference parses the whole CIGAR before anything else: what the path left over must be valid too
     while (cp != cend) {
         u32 x, kc, ts, tte;
-        if (!rec_fetch_op(rt, minus, cp, x, kc, ts, tte)) return false;
+        if (!fuse_fetch_op(rt, minus, cp, x, kc, ts, tte)) return false;
     }
-    nlines_out = nlines;
     return true;
+}
+
+// ---- G: one thread per slot: the byte length of its PAF line (0: the step prints none)
+__device__ __forceinline__ u32 fuse_line_len(const uint4* sl, const uint4* info, const u32* p10) {
+    const uint4 v2 = sl[2];
+    if (!((v2.z >> 24) & kFSlotEmit)) return 0u;
+    const uint4 v0 = sl[0], v1 = sl[1];
+    const u32 rconst = info[2u * (v2.w & 0xffffu) + 1u].z;
+    const u32 codeS = (v2.w >> 16) & 0xffu;
+    u32 n = ((v2.z >> 16) & 0xffu) + dlen_u32(v0.w, p10) + dlen_u32(v1.x, p10) + dlen_u32(v0.x, p10) + dlen_u32(v0.y, p10) + dlen_u32(v0.z, p10) +
+            dlen_u32(v1.y, p10) + dlen_u32(v1.z, p10) + dlen_u32(v2.x, p10) + 1u;
+    if (codeS) n += dlen_u32(v1.w, p10) + 1u;
+    return rconst + n + (v2.y >> 16);
 }
 
 // One PAF line (paf.hpp:83-95 + gaf2paf_main.cpp:228-256), left to right, into `dst` (any alignment) .. dst + len.
@@ -405,13 +464,12 @@ __device__ __forceinline__ void fuse_write_line(u8* dst, const u32 len, const u8
     (void)len;
 }
 
-template <u32 TILE>
-__global__ void __launch_bounds__(kFThreads, G2P_FUSE_CTAS) k_fuse(const FuseArgs a) {
-    typedef FuseCfg<TILE> C;
-    constexpr u32 kFTile = TILE, kFUnits = C::kUnits, kFStage = C::kStage;
+template <class C>
+__global__ void __launch_bounds__(kFThreads, C::kCtas) k_fuse(const FuseArgs a) {
+    constexpr u32 kFTile = C::kTile, kFUnits = C::kUnits, kFStage = C::kStage, kFMaxRec = C::kMaxRec, kFMaxSlots = C::kMaxSlots;
     G2P_DYN_SMEM(smem);
     __shared__ u32 p10[10];
-    __shared__ u32 s_tile, s_flag, s_end, s_lines;
+    __shared__ u32 s_tile, s_flag, s_end;
     __shared__ u32 s_w[kFThreads / 32];
     __shared__ u64 s_obase;
 #if !defined(G2P_HOSTSIM)
@@ -426,7 +484,7 @@ __global__ void __launch_bounds__(kFThreads, G2P_FUSE_CTAS) k_fuse(const FuseArg
     }
     if (tid == 0) {
         s_tile = atomicAdd(a.ticket, 1u);
-        s_flag = 0; s_end = 0xffffffffu; s_lines = 0;
+        s_flag = 0; s_end = 0xffffffffu;
 #if !defined(G2P_HOSTSIM)
         mbar_init(&s_bar, 1);
         fence_mbar_init();
@@ -445,6 +503,7 @@ __global__ void __launch_bounds__(kFThreads, G2P_FUSE_CTAS) k_fuse(const FuseArg
     uint4* s_info = reinterpret_cast<uint4*>(smem + C::kOffInfo);
     uint4* s_slots = reinterpret_cast<uint4*>(smem + C::kOffSlots);
     u32* s_off = reinterpret_cast<u32*>(smem + C::kOffOff);
+    u16* s_lidx = reinterpret_cast<u16*>(smem + C::kOffLidx);
     u8* s_stage = smem + C::kOffStage;
 
     // ---------------- A: tile load
@@ -558,7 +617,7 @@ __global__ void __launch_bounds__(kFThreads, G2P_FUSE_CTAS) k_fuse(const FuseArg
         u32 ns = 0;
         // state of the record between the two halves of the pass
         const u8* rt = text + 16;
-        u32 rtpos = 16, len = 0, pa = 0, pb = 0, ca = 0, cb = 0, rconst = 0;
+        u32 rtpos = 16, len = 0, pa = 0, pb = 0, ca = 0, cb = 0;
         i32 qs = 0, ps = 0, pe = 0;
         bool minus = false, prefixed = false;
         if (have) do {
@@ -638,7 +697,7 @@ __global__ void __launch_bounds__(kFThreads, G2P_FUSE_CTAS) k_fuse(const FuseArg
             Rr.tp_a = tp_a; Rr.tp_b = tp_b; Rr.rc_a = rc_a; Rr.rc_b = rc_b;
             Rr.gi_n = gi_fast(m, b, Rr.gi);
             if (Rr.gi_n == 0) break;
-            rconst = line_const_len(Rr, p10);
+            F.rconst = line_const_len(Rr, p10);
             // gi as floor(m / b * 1000 + 0.5) recovered from the text gi_fast produced ("0", "1" or "0.ddd")
             F.gi = Rr.gi_n == 1 ? ((u32)(Rr.gi & 0xff) == '1' ? 1000u : 0u)
                                 : 100u * ((u32)(Rr.gi >> 16) & 0xfu) + (Rr.gi_n > 3 ? 10u * ((u32)(Rr.gi >> 24) & 0xfu) : 0u) + (Rr.gi_n > 4 ? ((u32)(Rr.gi >> 32) & 0xfu) : 0u);
@@ -661,21 +720,24 @@ __global__ void __launch_bounds__(kFThreads, G2P_FUSE_CTAS) k_fuse(const FuseArg
         u32 wpre = 0, total = 0;
         for (u32 i = 0; i < kFThreads / 32; ++i) { if (i < warp) wpre += s_w[i]; total += s_w[i]; }
         const u32 slot0 = nslots + wpre + incl - ns;
+        const u32 pass_slot0 = nslots;
         nslots += total;
         if (nslots > kFMaxSlots) { too_many = true; break; }   // uniform: every thread sees the same total
-        if (have && ok && !skip) {
-            bool good = false;
-            do {
-                rt = text + rtpos;
-                const_cast<u8*>(rt)[pb] = '>';   // bounds the token scan of fuse_steps
-                u64 total_len;
-                if (!fuse_steps(a.T, rt, pa, pb, prefixed, minus, s_slots + 3u * slot0, ns, total_len)) break;
-                u32 nl_rec;
-                if (!fuse_walk(rt, rtpos, rec, minus, rconst, p10, prefixed, s_slots + 3u * slot0, s_off + slot0, ns, total_len, ca, cb, qs, ps, pe, nl_rec)) break;
-                good = true;
-            } while (0);
-            if (!good) bad = true;
+        const bool live = have && ok && !skip;
+        if (live) {   // D1: step tokens -> slots
+            const_cast<u8*>(rt)[pb] = '>';   // bounds the token scans
+            if (!fuse_tokens(rt, rtpos, pa, pb, prefixed, minus, s_slots + 3u * slot0, ns)) bad = true;
         }
+        if (bad) s_flag = 1;
+        __syncthreads();
+        if (s_flag) break;   // uniform
+        // E: one thread per step slot: table probe + interval digits
+        for (u32 sidx = pass_slot0 + tid; sidx < nslots; sidx += kFThreads)
+            if (!fuse_probe(a.T, text, s_slots + 3u * sidx)) s_flag = 1;
+        __syncthreads();
+        if (s_flag) break;   // uniform
+        // D2: quotas + the op walk
+        if (live && !fuse_walk2(rt, rtpos, text, rec, minus, prefixed, s_slots + 3u * slot0, ns, ca, cb, qs, ps, pe)) bad = true;
     }
     if (bad) s_flag = 1;
     __syncthreads();
@@ -684,27 +746,37 @@ __global__ void __launch_bounds__(kFThreads, G2P_FUSE_CTAS) k_fuse(const FuseArg
         return;
     }
 
-    // ---------------- H: line lengths -> offsets inside the tile; the tile's offset in the output (look-back)
-    u32 tile_bytes;
+    // ---------------- G: one thread per slot: line lengths
+    for (u32 sidx = tid; sidx < nslots; sidx += kFThreads) s_off[sidx] = fuse_line_len(s_slots + 3u * sidx, s_info, p10);
+    __syncthreads();
+
+    // ---------------- H: line lengths -> offsets inside the tile and the list of the slots that print a line (one
+    // block scan over (lines << 32 | bytes)); then the tile's offset in the output (look-back)
+    u32 tile_bytes, nlines;
     {
         const u32 per = (nslots + kFThreads - 1) / kFThreads;
-        const u32 a0 = tid * per, a1 = a0 + per < nslots ? a0 + per : nslots;
-        u32 sum = 0, nl_mine = 0;
-        for (u32 i = a0; i < a1; ++i) { const u32 l = s_off[i]; sum += l; nl_mine += (u32)(l != 0); }
-        u32 incl = sum;
-        for (int o = 1; o < 32; o <<= 1) { const u32 up = __shfl_up_sync(FULL, incl, o); if (lane >= (u32)o) incl += up; }
-        u32 nls = nl_mine;
-        for (int o = 16; o > 0; o >>= 1) nls += __shfl_xor_sync(FULL, nls, o);
-        if (lane == 31) s_w[warp] = incl;
-        if (lane == 0 && nls) atomicAdd(&s_lines, nls);
+        const u32 a0 = tid * per < nslots ? tid * per : nslots, a1 = a0 + per < nslots ? a0 + per : nslots;
+        u64 sum = 0;
+        for (u32 i = a0; i < a1; ++i) { const u32 l = s_off[i]; sum += (u64)l | ((u64)(l != 0) << 32); }
+        u64 incl = sum;
+        for (int o = 1; o < 32; o <<= 1) { const u64 up = __shfl_up_sync(FULL, incl, o); if (lane >= (u32)o) incl += up; }
+        __shared__ u64 s_w64[kFThreads / 32];
+        if (lane == 31) s_w64[warp] = incl;
         __syncthreads();
-        u32 wpre = 0, total = 0;
-        for (u32 i = 0; i < kFThreads / 32; ++i) { if (i < warp) wpre += s_w[i]; total += s_w[i]; }
-        u32 run = wpre + incl - sum;
+        u64 wpre = 0, total = 0;
+        for (u32 i = 0; i < kFThreads / 32; ++i) { if (i < warp) wpre += s_w64[i]; total += s_w64[i]; }
+        u64 run = wpre + incl - sum;
+        u32 rb = (u32)run, rl = (u32)(run >> 32);
         // s_off[i] becomes the exclusive offset; the length stays recoverable as off[i + 1] - off[i] (off[nslots] = total)
-        for (u32 i = a0; i < a1; ++i) { const u32 l = s_off[i]; s_off[i] = run; run += l; }
-        if (tid == 0) s_off[nslots] = total;   // (no thread's slot range reaches index nslots)
-        tile_bytes = total;
+        for (u32 i = a0; i < a1; ++i) {
+            const u32 l = s_off[i];
+            s_off[i] = rb;
+            rb += l;
+            if (l) s_lidx[rl++] = (u16)i;
+        }
+        tile_bytes = (u32)total;
+        nlines = (u32)(total >> 32);
+        if (tid == 0) s_off[nslots] = tile_bytes;   // (no thread's slot range reaches index nslots)
     }
     if (warp == 0) {
         u64 prefix = 0;
@@ -717,7 +789,7 @@ __global__ void __launch_bounds__(kFThreads, G2P_FUSE_CTAS) k_fuse(const FuseArg
                 u64 w = kIdxFlagPre;   // tiles before the first: prefix 0
                 if (idx >= 0) {
                     u32 spins = 0;
-                    while (((w = st[idx]) >> 62) == 0) { if (++spins > (1u << 26)) __trap(); }
+                    while (((w = st[idx]) >> 62) == 0) { __nanosleep(40); if (++spins > (1u << 24)) __trap(); }
                 }
                 const u32 pre = __ballot_sync(FULL, (w >> 62) == 2);
                 const u32 upto = pre ? (u32)__ffs((int)pre) - 1u : 31u;   // lanes 0..upto contribute
@@ -732,7 +804,7 @@ __global__ void __launch_bounds__(kFThreads, G2P_FUSE_CTAS) k_fuse(const FuseArg
             st[tile] = kIdxFlagPre | (prefix + tile_bytes);
             s_obase = prefix;
             atomicAdd(&a.meta->n_records, R);
-            if (s_lines) atomicAdd(&a.meta->n_lines, s_lines);
+            if (nlines) atomicAdd(&a.meta->n_lines, nlines);
             if (tile == a.ntiles - 1) a.meta->out_total = prefix + tile_bytes;
             if (prefix + tile_bytes > a.out_cap) atomicExch(&a.meta->overflow, 1u);
         }
@@ -741,14 +813,21 @@ __global__ void __launch_bounds__(kFThreads, G2P_FUSE_CTAS) k_fuse(const FuseArg
     const u64 obase = s_obase;
     if (obase + tile_bytes > a.out_cap || *g_fallback) return;   // nothing may be written (the host grows the buffer / runs the general pipeline)
 
-    // ---------------- I: format and store, in rounds of at most kFThreads slots and kFStage bytes
+    // ---------------- I: format and store, in rounds of at most kFThreads lines and kFStage bytes
     u32 done = 0;
-    while (done < nslots) {
-        const u32 off0 = s_off[done];
+    while (done < nlines) {
+        const u32 off0 = s_off[s_lidx[done]];
         const u32 pad = (u32)((obase + off0) & 15u);
-        const u32 slot = done + tid;
-        const bool fits = slot < nslots && s_off[slot + 1] - off0 + pad <= kFStage;
-        // slots that fit form a prefix of the round (offsets are monotone): count them
+        const u32 k = done + tid;
+        u32 slot = 0, o = 0, l = 0;
+        bool fits = false;
+        if (k < nlines) {
+            slot = s_lidx[k];
+            o = s_off[slot];
+            l = s_off[slot + 1] - o;
+            fits = o + l - off0 + pad <= kFStage;
+        }
+        // lines that fit form a prefix of the round (offsets are monotone): count them
         const u32 bal = __ballot_sync(FULL, fits);
         __syncthreads();   // the previous round's staging buffer has been read (its issuer waited before this barrier)
         if (lane == 0) s_w[warp] = (u32)__popc(bal);
@@ -760,16 +839,14 @@ __global__ void __launch_bounds__(kFThreads, G2P_FUSE_CTAS) k_fuse(const FuseArg
             return;
         }
         if (fits) {
-            const u32 o = s_off[slot], l = s_off[slot + 1] - o;
-            if (l) {
-                const uint4* sl = s_slots + 3u * slot;
-                const uint4 v0 = sl[0], v1 = sl[1], v2 = sl[2];
-                FRec F;
-                frec_load(s_info + 2u * (v2.w & 0xffffu), F);
-                fuse_write_line(s_stage + pad + (o - off0), l, text, F, v0, v1, v2);
-            }
+            const uint4* sl = s_slots + 3u * slot;
+            const uint4 v0 = sl[0], v1 = sl[1], v2 = sl[2];
+            FRec F;
+            frec_load(s_info + 2u * (v2.w & 0xffffu), F);
+            fuse_write_line(s_stage + pad + (o - off0), l, text, F, v0, v1, v2);
         }
-        const u32 bytes = s_off[done + cnt] - off0;
+        const u32 last = s_lidx[done + cnt - 1u];
+        const u32 bytes = s_off[last + 1u] - off0;
         u8* gb = a.out + (obase + off0 - pad);   // 16-byte aligned
         const u32 total = pad + bytes;
         const u32 full_b = total >> 4, first_b = pad ? 1u : 0u;
@@ -782,9 +859,9 @@ __global__ void __launch_bounds__(kFThreads, G2P_FUSE_CTAS) k_fuse(const FuseArg
         for (u32 u = first_b + tid; u < full_b; u += kFThreads) reinterpret_cast<uint4*>(gb)[u] = reinterpret_cast<const uint4*>(s_stage)[u];
 #endif
         const u32 head_end = pad ? (total < 16u ? total : 16u) : 0u;
-        for (u32 b = pad + tid; b < head_end; b += kFThreads) gb[b] = s_stage[b];
+        for (u32 b2 = pad + tid; b2 < head_end; b2 += kFThreads) gb[b2] = s_stage[b2];
         const u32 tail_a = full_b * 16u > head_end ? full_b * 16u : head_end;
-        for (u32 b = tail_a + tid; b < total; b += kFThreads) gb[b] = s_stage[b];
+        for (u32 b2 = tail_a + tid; b2 < total; b2 += kFThreads) gb[b2] = s_stage[b2];
 #if !defined(G2P_HOSTSIM)
         if (tid == 0) bulk_wait_read0();   // the staging buffer must outlive the copy's reads
 #endif

@@ -58,10 +58,11 @@ int main(int argc, char** argv) {
 
     // ---- the one-pass kernel first (run_fused of g2p_capi.cu); G2P_FUSE=0 skips it
     if (n && !(std::getenv("G2P_FUSE") && std::atoi(std::getenv("G2P_FUSE")) == 0)) {
-        u32 tile = std::getenv("G2P_FUSE_TILE") ? (u32)std::atoi(std::getenv("G2P_FUSE_TILE")) : kFTileMax;
+        int cfg = std::getenv("G2P_FUSE_CFG") ? std::atoi(std::getenv("G2P_FUSE_CFG")) : 0;
         u64 cap = std::getenv("G2P_FUSE_OUT_CAP") ? (u64)std::atoll(std::getenv("G2P_FUSE_OUT_CAP")) : n * 3 + (1u << 20);
         bool grown = false;
         for (;;) {
+            const u32 tile = fuse_cfg_tile(cfg);
             const u32 ftiles = (u32)((n + tile - 1) / tile);
             std::vector<u64> fstat(ftiles + 1, 0);
             u32 fticket = 0;
@@ -69,11 +70,15 @@ int main(int argc, char** argv) {
             std::memset(&fm, 0, sizeof fm);
             std::vector<u8> fout(cap + 256, 0xEE);
             FuseArgs fa{gaf, n, ftiles, T, fout.data(), cap, fstat.data(), &fticket, &fm};
-            if (tile == 32768) hs::launch(dim3(ftiles), dim3(kFThreads), FuseCfg<32768>::kSmem, [&] { k_fuse<32768>(fa); });
-            else if (tile == 16384) hs::launch(dim3(ftiles), dim3(kFThreads), FuseCfg<16384>::kSmem, [&] { k_fuse<16384>(fa); });
-            else hs::launch(dim3(ftiles), dim3(kFThreads), FuseCfg<8192>::kSmem, [&] { k_fuse<8192>(fa); });
+            switch (cfg) {
+                case 0: hs::launch(dim3(ftiles), dim3(kFThreads), FuseCfg0::kSmem, [&] { k_fuse<FuseCfg0>(fa); }); break;
+                case 1: hs::launch(dim3(ftiles), dim3(kFThreads), FuseCfg1::kSmem, [&] { k_fuse<FuseCfg1>(fa); }); break;
+                case 2: hs::launch(dim3(ftiles), dim3(kFThreads), FuseCfg2::kSmem, [&] { k_fuse<FuseCfg2>(fa); }); break;
+                case 3: hs::launch(dim3(ftiles), dim3(kFThreads), FuseCfg3::kSmem, [&] { k_fuse<FuseCfg3>(fa); }); break;
+                default: hs::launch(dim3(ftiles), dim3(kFThreads), FuseCfg4::kSmem, [&] { k_fuse<FuseCfg4>(fa); }); break;
+            }
             if (fm.fallback) {
-                if (!(fm.fallback & kFuseNotConvertible) && tile > kFTileMin) { tile /= 2; continue; }
+                if (!(fm.fallback & kFuseNotConvertible) && fuse_cfg_denser(cfg) >= 0) { cfg = fuse_cfg_denser(cfg); continue; }
                 break;
             }
             if (!fm.overflow) {

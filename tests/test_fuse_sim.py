@@ -60,6 +60,17 @@ def test_every_alignment_of_a_tile_boundary():
         assert out == ref, "shift %d" % shift
 
 
+@pytest.mark.parametrize("cfg", ["1", "2", "3", "4"])
+def test_other_configurations(cfg):
+    """The tuning alternatives (24 KiB tiles; 16 KiB tiles with three CTAs per SM) and the dense-input configurations."""
+    p = H.preset("short", seed=19, pct_star=1)
+    lengths = H.gen_lengths(p)
+    gaf = H.gen_records(p, 0, 4000, threads=1)
+    rc, out, err = simt(gaf, lengths, {"G2P_FUSE_CFG": cfg})
+    rrc, ref, rerr, kind = H.run_gaf2paf_cpu(gaf, lengths)
+    assert rc == rrc == 0 and "k_fuse converted" in err and out == ref
+
+
 def test_output_buffer_grows_and_the_kernel_runs_again():
     p = H.preset("short", seed=29)
     lengths = H.gen_lengths(p)

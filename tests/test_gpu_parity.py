@@ -394,8 +394,9 @@ def test_late_delegation(g2p):
 
 @pytest.mark.parametrize("env", [
     {},                                            # default: the one-pass kernel k_fuse (32 KiB tiles)
-    {"G2P_FUSE_TILE": "16384"},                    # k_fuse on 16 KiB tiles
-    {"G2P_FUSE_TILE": "8192", "G2P_FUSE_OUT_CAP": "65536"},   # 8 KiB tiles; the output buffer starts too small: grow and run again
+    {"G2P_FUSE_CFG": "1"},                         # k_fuse on 24 KiB tiles
+    {"G2P_FUSE_CFG": "2"},                         # 16 KiB tiles, three CTAs per SM
+    {"G2P_FUSE_CFG": "4", "G2P_FUSE_OUT_CAP": "65536"},   # 8 KiB tiles; the output buffer starts too small: grow and run again
     {"G2P_FUSE": "0"},                             # the general two-pass pipeline alone (k_rec + scans + k_emit_lines)
     {"G2P_FUSE": "0", "G2P_SIZE_KERNEL": "short"},                  # the 8-lanes-per-record size pass
     {"G2P_FUSE": "0", "G2P_LEN_SORT": "1"},                         # k_rec on records ordered by length class
