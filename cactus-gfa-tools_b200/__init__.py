@@ -38,6 +38,7 @@ EXPORTED_SYMBOLS = (
     "g2p_create", "g2p_destroy", "g2p_last_error", "g2p_host_alloc", "g2p_host_free", "g2p_load_lengths",
     "g2p_table_entries", "g2p_copy_to_device", "g2p_copy_to_host", "g2p_convert_device", "g2p_convert_host", "g2p_index_lines", "g2p_format_error",
     "g2p_load_rgfa", "g2p_rgfa_node_lengths", "g2p_unstable_device", "g2p_unstable_host", "g2p_unstable_warnings", "g2p_format_unstable_warning",
+    "g2p_unstable_convert_device", "g2p_unstable_convert_host", "g2p_unstable_convert_warnings",
 )
 
 
@@ -64,6 +65,9 @@ class Result(ctypes.Structure):
         ("n_long", ctypes.c_uint32),
         ("fused_ms", ctypes.c_float),
         ("n_fused", ctypes.c_uint32),
+        ("unstable_ms", ctypes.c_float),
+        ("stage", ctypes.c_uint32),
+        ("mid_bytes", ctypes.c_uint64),
     ]
 
 
@@ -112,6 +116,12 @@ def _load():
     lib.g2p_unstable_device.restype = ctypes.c_int
     lib.g2p_unstable_host.argtypes = [vp, vp, sz, ctypes.POINTER(vp), ctypes.POINTER(Result)]
     lib.g2p_unstable_host.restype = ctypes.c_int
+    lib.g2p_unstable_convert_device.argtypes = [vp, vp, sz, ctypes.POINTER(vp), ctypes.POINTER(Result), vp]
+    lib.g2p_unstable_convert_device.restype = ctypes.c_int
+    lib.g2p_unstable_convert_host.argtypes = [vp, vp, sz, ctypes.POINTER(vp), ctypes.POINTER(Result)]
+    lib.g2p_unstable_convert_host.restype = ctypes.c_int
+    lib.g2p_unstable_convert_warnings.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(sz)]
+    lib.g2p_unstable_convert_warnings.restype = ctypes.c_int
     lib.g2p_unstable_warnings.argtypes = [vp, ctypes.POINTER(ctypes.POINTER(Warn)), ctypes.POINTER(sz)]
     lib.g2p_unstable_warnings.restype = ctypes.c_int
     lib.g2p_format_unstable_warning.argtypes = [vp, vp, sz, vp, sz]
@@ -241,6 +251,32 @@ class Converter:
             lib.g2p_format_unstable_warning(self._h, line, len(line), buf, len(buf))
             warns.append(buf.value.decode("latin-1"))
         return data, res, warns
+
+    def unstable_convert_host(self, gaf):
+        """``gaf2unstable gaf -g rgfa -o L | gaf2paf - -l L`` in one call (the intermediate GAF stays on the device):
+        -> (paf bytes, Result, stderr text of the gaf2unstable stage)."""
+        addr, n, keep = _buf_ptr(gaf)
+        out = ctypes.c_void_p()
+        res = Result()
+        self._check(lib.g2p_unstable_convert_host(self._h, addr, n, ctypes.byref(out), ctypes.byref(res)))
+        return _bytes_at(out.value, res.out_bytes), res, self._convert_warnings()
+
+    def unstable_convert_host_raw(self, addr, n):
+        out = ctypes.c_void_p()
+        res = Result()
+        self._check(lib.g2p_unstable_convert_host(self._h, addr, n, ctypes.byref(out), ctypes.byref(res)))
+        return out.value, res
+
+    def unstable_convert_device(self, d_ptr, n, stream=0):
+        out = ctypes.c_void_p()
+        res = Result()
+        self._check(lib.g2p_unstable_convert_device(self._h, d_ptr, n, ctypes.byref(out), ctypes.byref(res), stream or None))
+        return out.value, res
+
+    def _convert_warnings(self):
+        p, n = ctypes.c_void_p(), ctypes.c_size_t()
+        self._check(lib.g2p_unstable_convert_warnings(self._h, ctypes.byref(p), ctypes.byref(n)))
+        return ctypes.string_at(p.value, n.value).decode("latin-1") if n.value else ""
 
     @staticmethod
     def format_error(res, gaf):

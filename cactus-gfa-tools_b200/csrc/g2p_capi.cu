@@ -88,7 +88,7 @@ struct PinBuf {
 struct Worker {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};   // 0..4: general pipeline (index, size, scan, emit), 5..6: k_fuse
-    DevBuf d_in, d_tiles, d_rec, d_status, d_off, d_blocks, d_out, d_meta, d_list, d_list2, d_desc, d_rdesc, d_sdesc, d_loff, d_map, d_lsort, d_perm, d_fuse;
+    DevBuf d_mid, d_in, d_tiles, d_rec, d_status, d_off, d_blocks, d_out, d_meta, d_list, d_list2, d_desc, d_rdesc, d_sdesc, d_loff, d_map, d_lsort, d_perm, d_fuse;
     PinBuf h_meta, h_fmeta;
     bool init() {
         if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) return false;
@@ -97,7 +97,7 @@ struct Worker {
                h_fmeta.ensure(sizeof(FuseMeta)) == cudaSuccess;
     }
     void release() {
-        for (DevBuf* b : {&d_in, &d_tiles, &d_rec, &d_status, &d_off, &d_blocks, &d_out, &d_meta, &d_list, &d_list2, &d_desc, &d_rdesc, &d_sdesc, &d_loff, &d_map, &d_lsort, &d_perm, &d_fuse}) b->release();
+        for (DevBuf* b : {&d_mid, &d_in, &d_tiles, &d_rec, &d_status, &d_off, &d_blocks, &d_out, &d_meta, &d_list, &d_list2, &d_desc, &d_rdesc, &d_sdesc, &d_loff, &d_map, &d_lsort, &d_perm, &d_fuse}) b->release();
         h_meta.release();
         h_fmeta.release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -124,6 +124,9 @@ struct g2p_ctx {
     PinBuf& next_out() { h_cur ^= 1; return h_outs[h_cur]; }
     // gaf2unstable tables
     DevBuf u_slots, u_arena, u_begin, u_nodes, u_names, u_refoff, u_refnames;
+    DevBuf n_slots, n_arena;              // node name -> length table of the rGFA (what gaf2unstable -o writes, loaded like gaf2paf -l)
+    LenTableView node_table{nullptr, nullptr, 0};
+    std::string warn_text;                // stderr text of the gaf2unstable stage of the last g2p_unstable_convert_* call
     UnstableView uview{};
     bool have_rgfa = false;
     RgfaTables* rgfa = nullptr;
@@ -262,7 +265,7 @@ void g2p_destroy(g2p_ctx* ctx) {
     cudaDeviceSynchronize();
     ctx->d_slots.release();
     ctx->d_arena.release();
-    for (DevBuf* b : {&ctx->u_slots, &ctx->u_arena, &ctx->u_begin, &ctx->u_nodes, &ctx->u_names, &ctx->u_refoff, &ctx->u_refnames}) b->release();
+    for (DevBuf* b : {&ctx->u_slots, &ctx->u_arena, &ctx->u_begin, &ctx->u_nodes, &ctx->u_names, &ctx->u_refoff, &ctx->u_refnames, &ctx->n_slots, &ctx->n_arena}) b->release();
     delete ctx->rgfa;
     for (auto& w : ctx->w) w.release();
     for (auto& b : ctx->h_outs) b.release();
@@ -814,6 +817,15 @@ int g2p_load_rgfa(g2p_ctx* ctx, const char* rgfa, size_t n, int* ref_exit_code, 
     ctx->uview.node_names = static_cast<const u8*>(ctx->u_names.p);
     ctx->uview.ref_off = static_cast<const u32*>(ctx->u_refoff.p);
     ctx->uview.ref_names = static_cast<const u8*>(ctx->u_refnames.p);
+    {   // the node-lengths table of the fused gaf2unstable | gaf2paf path: exactly what `gaf2paf -l <the -o file>` would load
+        HostLenTable nt;
+        if (build_len_table(ctx->node_lengths.data(), ctx->node_lengths.size(), nt) != ST_OK) { ctx->set_err("node lengths table"); return G2P_E_TABLE; }
+        G2P_CUDA(up(ctx->n_slots, nt.slots.data(), nt.slots.size() * sizeof(LenSlot)));
+        G2P_CUDA(up(ctx->n_arena, nt.arena.data(), nt.arena.size()));
+        ctx->node_table.slots = static_cast<const LenSlot*>(ctx->n_slots.p);
+        ctx->node_table.arena = static_cast<const u8*>(ctx->n_arena.p);
+        ctx->node_table.nslots = (u32)nt.slots.size();
+    }
     ctx->have_rgfa = true;
     return G2P_OK;
 }
@@ -935,6 +947,85 @@ int g2p_unstable_host(g2p_ctx* ctx, const char* gaf, size_t n, const char** out,
     if (res->out_bytes) G2P_CUDA(cudaMemcpyAsync(h_out.p, d_o, res->out_bytes, cudaMemcpyDeviceToHost, w.stream));
     G2P_CUDA(cudaStreamSynchronize(w.stream));
     *out = static_cast<const char*>(h_out.p);
+    return G2P_OK;
+}
+
+// ---- N2: gaf2unstable | gaf2paf without the intermediate text leaving the device (README.md:55-58 pipeline) -------
+// Stage 1 (k_unstable) writes the node-space GAF into a device buffer, stage 2 (the gaf2paf pipeline, with the node
+// lengths of the same rGFA as its -l table) reads it from there: no D2H / host / H2D round trip of the intermediate.
+static int run_unstable_convert(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cudaStream_t st, g2p_result* res, u8** d_out) {
+    g2p_result r1;
+    u8* d_mid = nullptr;
+    ctx->warn_text.clear();
+    int rc = run_unstable(ctx, w, d_gaf, n, st, &r1, &d_mid);
+    if (rc) return rc;
+    // the stage-1 warnings (gaf2unstable_main.cpp:165-171) quote the record it wrote: fetch those lines (rare)
+    for (const g2p_warn& wn : ctx->warns) {
+        std::vector<char> line(wn.out_len + 1), msg(wn.out_len + 4096);
+        G2P_CUDA(cudaMemcpy(line.data(), d_mid + wn.out_off, wn.out_len, cudaMemcpyDeviceToHost));
+        g2p_format_unstable_warning(ctx, line.data(), wn.out_len, msg.data(), msg.size());
+        ctx->warn_text += msg.data();
+    }
+    std::swap(w.d_out, w.d_mid);   // the intermediate GAF stays in d_mid; the converter writes d_out
+    const LenTableView saved = ctx->table;
+    const bool saved_have = ctx->have_table;
+    ctx->table = ctx->node_table;
+    ctx->have_table = true;
+    rc = run_pipeline(ctx, w, static_cast<const u8*>(w.d_mid.p), (size_t)r1.out_bytes, st, res, d_out);
+    ctx->table = saved;
+    ctx->have_table = saved_have;
+    if (rc) return rc;
+    res->unstable_ms = r1.device_ms;
+    res->device_ms += r1.device_ms;
+    res->gpu_launches += r1.gpu_launches;
+    res->mid_bytes = r1.out_bytes;
+    if (res->rec_status != G2P_REC_OK) res->stage = 2;
+    else if (r1.rec_status != G2P_REC_OK) {   // stage 1 stopped at a record: everything before it was converted
+        res->rec_status = r1.rec_status; res->rec_aux = r1.rec_aux; res->err_record = r1.err_record;
+        res->stage = 1;
+    }
+    // stage 2 counts the records of the intermediate GAF ('*' lines are dropped by stage 1)
+    return G2P_OK;
+}
+
+int g2p_unstable_convert_device(g2p_ctx* ctx, const void* d_gaf_v, size_t n, void** d_out, g2p_result* res, void* stream) {
+    if (!ctx || !res || !d_out) return G2P_E_ARG;
+    if (!ctx->have_rgfa) return G2P_E_NOTABLE;
+    if (n >= 0xFFFFFFF0ULL) return G2P_E_TOOBIG;
+    if ((reinterpret_cast<uintptr_t>(d_gaf_v) & 15) != 0) { ctx->set_err("d_gaf must be 16-byte aligned"); return G2P_E_ARG; }
+    G2P_CUDA(cudaSetDevice(ctx->device));
+    Worker& w = ctx->w[0];
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : w.stream;
+    u8* d_o = nullptr;
+    int rc = run_unstable_convert(ctx, w, static_cast<const u8*>(d_gaf_v), n, st, res, &d_o);
+    *d_out = d_o;
+    return rc;
+}
+
+int g2p_unstable_convert_host(g2p_ctx* ctx, const char* gaf, size_t n, const char** out, g2p_result* res) {
+    if (!ctx || !res || !out || (!gaf && n)) return G2P_E_ARG;
+    if (!ctx->have_rgfa) return G2P_E_NOTABLE;
+    if (n >= 0xFFFFFFF0ULL) return G2P_E_TOOBIG;
+    *out = nullptr;
+    G2P_CUDA(cudaSetDevice(ctx->device));
+    Worker& w = ctx->w[0];
+    PinBuf& h_out = ctx->next_out();
+    G2P_CUDA(w.d_in.ensure(n + 256));
+    if (n) G2P_CUDA(cudaMemcpyAsync(w.d_in.p, gaf, n, cudaMemcpyHostToDevice, w.stream));
+    u8* d_o = nullptr;
+    int rc = run_unstable_convert(ctx, w, static_cast<const u8*>(w.d_in.p), n, w.stream, res, &d_o);
+    if (rc) return rc;
+    G2P_CUDA(h_out.ensure(res->out_bytes + 1));
+    if (res->out_bytes) G2P_CUDA(cudaMemcpyAsync(h_out.p, d_o, res->out_bytes, cudaMemcpyDeviceToHost, w.stream));
+    G2P_CUDA(cudaStreamSynchronize(w.stream));
+    *out = static_cast<const char*>(h_out.p);
+    return G2P_OK;
+}
+
+int g2p_unstable_convert_warnings(g2p_ctx* ctx, const char** text, size_t* n) {
+    if (!ctx || !text || !n) return G2P_E_ARG;
+    *text = ctx->warn_text.data();
+    *n = ctx->warn_text.size();
     return G2P_OK;
 }
 

@@ -191,29 +191,40 @@ struct WEmit {
 // (minus ? ns - 1 - j : j): flip_gaf, gaf2paf_main.cpp:92-110, is index arithmetic).  Only positions are recorded
 // (v2.z = marker position | name length << 16, v0.x = interval flag << 31); the table probe and the interval digits
 // are left to one thread per slot (fuse_probe).  The caller has planted a '>' after the path column.
-__device__ __forceinline__ bool fuse_tokens(const u8* rt, const u32 rtpos, const u32 pa, const u32 pb, const bool prefixed, const bool minus,
-                                            uint4* slots, const u32 ns) {
+// CONVERGENCE: these per-record functions are called by ALL lanes of a warp (`live` = the lane has a record) and
+// never leave a loop by `return`: an early return inside divergent code moves the reconvergence point of the
+// compiler's BSSY / BSYNC pairs to the end of the function, after which the lanes of a warp run one by one (ncu:
+// 3 of 32 lanes active in the op walk).  Failures set a flag; every data-dependent loop runs `while any lane is in
+// it` (__any_sync is also the reconvergence point of the trip).
+__device__ __forceinline__ bool fuse_tokens(const bool live, const u8* rt, const u32 rtpos, const u32 pa, const u32 pb, const bool prefixed,
+                                            const bool minus, uint4* slots, const u32 ns) {
+    const u32 FULL = 0xffffffffu;
     u32 j = 0, mp = prefixed ? pa : pa - 1;
-    for (;;) {
-        const u32 name_a = mp + 1;
-        u32 e = pb;
-        bool interval = false;
-        if (prefixed) {
-            e = rec_scan_step(rt, name_a);   // rt[pb] == '>'
-            interval = rt[e] == ':';
+    bool going = live, ok = true;
+    while (__any_sync(FULL, going)) {
+        if (going) {
+            const u32 name_a = mp + 1;
+            u32 e = pb;
+            bool interval = false;
+            if (prefixed) {
+                e = rec_scan_step(rt, name_a);   // rt[pb] == '>'
+                interval = rt[e] == ':';
+            }
+            const u32 nl = e - name_a;
+            if (interval) e = rec_scan_step(rt, e + 1);   // the token ends at the next marker
+            // (a second ':' inside the token is left to the general kernel)
+            if (nl == 0 || nl > 255 || j >= ns || rt[e] == ':') { ok = false; going = false; }
+            else {
+                uint4* sl = slots + 3u * (minus ? ns - 1u - j : j);
+                sl[0].x = interval ? 0x80000000u : 0u;
+                sl[2].z = (rtpos + mp) | (nl << 16);
+                ++j;
+                if (e >= pb) going = false;
+                mp = e;
+            }
         }
-        const u32 nl = e - name_a;
-        if (nl == 0 || nl > 255 || j >= ns) return false;
-        if (interval) e = rec_scan_step(rt, e + 1);   // the token ends at the next marker
-        if (rt[e] == ':') return false;               // a second ':' inside the token: left to the general kernel
-        uint4* sl = slots + 3u * (minus ? ns - 1u - j : j);
-        sl[0].x = interval ? 0x80000000u : 0u;
-        sl[2].z = (rtpos + mp) | (nl << 16);
-        ++j;
-        if (e >= pb) break;
-        mp = e;
     }
-    return j == ns;
+    return ok && (!live || j == ns);
 }
 
 // ---- E: one thread per slot: the step's name is probed once in the lengths table (gaf2paf_main.cpp:162-167) and an
@@ -257,7 +268,12 @@ __device__ __forceinline__ bool fuse_fetch_op(const u8* rt, const bool minus, u3
     const u32 b0 = rt[base], b1 = rt[base + step], b2 = rt[base + 2u * step], b3 = rt[base + 3u * step], b4 = rt[base + 4u * step];
     // digits in walk order: forward b0 b1 b2 (b3), backward b1 b2 b3 (b4) after the letter b0
     const u32 d0 = (minus ? b1 : b0) - '0', d1 = (minus ? b2 : b1) - '0', d2 = (minus ? b3 : b2) - '0', d3 = (minus ? b4 : b3) - '0';
-    if (d0 <= 9u && d1 <= 9u && d2 <= 9u && d3 <= 9u) return rec_fetch_op_slow(rt, minus, cp, x, kc, ts, te);   // >= 4 digits
+    if (d0 <= 9u && d1 <= 9u && d2 <= 9u && d3 <= 9u) {   // >= 4 digits (rare: no reconvergence needed inside)
+        u32 cp2 = cp, x2, kc2, ts2, te2;
+        const bool r = rec_fetch_op_slow(rt, minus, cp2, x2, kc2, ts2, te2);
+        cp = cp2; x = x2; kc = kc2; ts = ts2; te = te2;
+        return r;
+    }
     const u32 nd = d0 > 9u ? 0u : (d1 > 9u ? 1u : (d2 > 9u ? 2u : 3u));
     const u32 v2 = minus ? d1 * 10u + d0 : d0 * 10u + d1;
     const u32 v3 = minus ? d2 * 100u + d1 * 10u + d0 : d0 * 100u + d1 * 10u + d2;
@@ -277,33 +293,39 @@ __device__ __forceinline__ bool fuse_fetch_op(const u8* rt, const bool minus, u3
 // with similar op counts -- stay in the same loop instead of diverging over nested step / op / digit loops.  Slot i
 // (normalised step i) receives the numbers of its PAF line; kFSlotEmit marks the steps that print one.
 constexpr u32 kFSlotEmit = 4u;
-__device__ __forceinline__ bool fuse_walk2(const u8* rt, const u32 rtpos, const u8* text, const u32 rec, const bool minus, const bool prefixed,
-                                           uint4* slots, const u32 ns, const u32 ca, const u32 cb, const i32 qs, i32 ps, i32 pe) {
+__device__ __forceinline__ bool fuse_walk2(const bool live, const u8* rt, const u32 rtpos, const u8* text, const u32 rec, const bool minus,
+                                           const bool prefixed, uint4* slots, const u32 ns_in, const u32 ca, const u32 cb, const i32 qs, i32 ps, i32 pe) {
+    const u32 FULL = 0xffffffffu;
+    const u32 ns = live ? ns_in : 0u;
+    bool ok = true;
     // (a) step lengths, the mirrored path interval of '-' records (flip_gaf, gaf2paf_main.cpp:111-131), quotas
     u64 total = 0;
-    for (u32 i = 0; i < ns; ++i) { const uint4 v = slots[3u * i]; total += v.z - v.y; }
+    for (u32 i = 0; __any_sync(FULL, i < ns); ++i)
+        if (i < ns) { const uint4 v = slots[3u * i]; total += v.z - v.y; }
     if (minus) {
-        if (total > 0x7fffffffULL) return false;
+        if (total > 0x7fffffffULL) ok = false;
         const i32 nps = (i32)total - pe, npe = (i32)total - ps;
         ps = nps; pe = npe;
     }
     const i32 W = pe - ps;
     u32 tbc = 0;
-    for (u32 i = 0; i < ns; ++i) {
-        uint4* sl = slots + 3u * i;
-        const uint4 v = sl[0];
-        const u32 z = sl[2].z;
-        const i32 tlen = (i32)(v.x & 0x7fffffffu), sa = (i32)v.y, se = (i32)v.z;
-        const bool rev = (prefixed && text[z & 0xffffu] == '<') != minus;
-        const i32 slen = se - sa;
-        const i32 so = i == 0 ? ps : 0;
-        i32 quota = slen - so, eo = 0;
-        if (i + 1 == ns) { quota = W - (i32)tbc; eo = slen - so - quota; }
-        if (so < 0 || quota < 0 || eo < 0) return false;
-        tbc += (u32)quota;
-        sl[0] = make_uint4((u32)tlen, (u32)(sa + (rev ? eo : so)), (u32)(se - (rev ? so : eo)), 0u);
-        sl[1].x = (u32)quota;
-        sl[2].z = ((z & 0xffffu) + 1u) | (z & 0x00ff0000u) | ((rev ? kFSlotRev : 0u) << 24) | ((rev == minus ? kFSlotMidFwd : 0u) << 24);
+    for (u32 i = 0; __any_sync(FULL, i < ns); ++i) {
+        if (i < ns) {
+            uint4* sl = slots + 3u * i;
+            const uint4 v = sl[0];
+            const u32 z = sl[2].z;
+            const i32 tlen = (i32)(v.x & 0x7fffffffu), sa = (i32)v.y, se = (i32)v.z;
+            const bool rev = (prefixed && text[z & 0xffffu] == '<') != minus;
+            const i32 slen = se - sa;
+            const i32 so = i == 0 ? ps : 0;
+            i32 quota = slen - so, eo = 0;
+            if (i + 1 == ns) { quota = W - (i32)tbc; eo = slen - so - quota; }
+            if (so < 0 || quota < 0 || eo < 0) { ok = false; quota = 0; }
+            tbc += (u32)quota;
+            sl[0] = make_uint4((u32)tlen, (u32)(sa + (rev ? eo : so)), (u32)(se - (rev ? so : eo)), 0u);
+            sl[1].x = (u32)quota;
+            sl[2].z = ((z & 0xffffu) + 1u) | (z & 0x00ff0000u) | ((rev ? kFSlotRev : 0u) << 24) | ((rev == minus ? kFSlotMidFwd : 0u) << 24);
+        }
     }
     // (b) ops
     const u32 cend = minus ? ca : cb;
@@ -312,64 +334,79 @@ __device__ __forceinline__ bool fuse_walk2(const u8* rt, const u32 rtpos, const 
     u32 qcur = (u32)qs;          // query position at the start of the open step
     u32 i = 0, need = 0;         // open step and what is left of its quota (0: no step open)
     u32 q = 0, nm = 0, nb = 0, lenS = 0, codeS = 0, lenE = 0, codeE = 0, mid_a = 0, mid_b = 0;
-    for (;;) {
-        bool close = false;
-        if (need == 0) {   // open the next step
-            if (i == ns) break;
-            need = slots[3u * i + 1u].x;
-            q = nm = nb = lenS = codeS = lenE = codeE = mid_a = mid_b = 0;
-            if (need == 0) { ++i; continue; }   // no target bases left for it: no line, nothing consumed
-            if (rem) {   // the remainder of a cut op is target-consuming by construction
-                const u32 take = rem < need ? rem : need;
-                if ((kQueryMask >> remk) & 1u) q += take;
-                if ((kMatchMask >> remk) & 1u) nm += take;
-                nb += take;
-                if (rem >= need) { lenE = need; codeE = remk + '='; rem -= need; close = true; }
-                else { lenS = rem; codeS = remk + '='; need -= rem; rem = 0; }
+    bool going = live && ok;
+    while (__any_sync(FULL, going)) {
+        if (going) {
+            bool fetch = true, close = false;
+            if (need == 0) {   // open the next step
+                fetch = false;
+                if (i == ns) going = false;
+                else {
+                    need = slots[3u * i + 1u].x;
+                    q = nm = nb = lenS = codeS = lenE = codeE = mid_a = mid_b = 0;
+                    if (need == 0) ++i;   // no target bases left for it: no line, nothing consumed
+                    else {
+                        fetch = true;
+                        if (rem) {   // the remainder of a cut op is target-consuming by construction
+                            const u32 take = rem < need ? rem : need;
+                            if ((kQueryMask >> remk) & 1u) q += take;
+                            if ((kMatchMask >> remk) & 1u) nm += take;
+                            nb += take;
+                            if (rem >= need) { lenE = need; codeE = remk + '='; rem -= need; close = true; fetch = false; }
+                            else { lenS = rem; codeS = remk + '='; need -= rem; rem = 0; }
+                        }
+                    }
+                }
             }
-        }
-        if (!close) {   // one op
-            if (cp == cend) return false;   // :80 assert: CIGAR shorter than the path
-            u32 x, kc, ts, tte;
-            if (!fuse_fetch_op(rt, minus, cp, x, kc, ts, tte)) return false;
-            const bool tgt = (kTargetMask >> kc) & 1u;
-            if (tgt && x >= need) {
-                lenE = need; codeE = kc + '=';
-                rem = x - need; remk = kc;
-                x = need;
-                close = true;
-            } else {
-                if (tgt) need -= x;
-                if (mid_b == 0) { mid_a = ts; mid_b = tte; }
-                else if (minus) mid_a = ts;
-                else mid_b = tte;
+            if (fetch) {   // one op
+                u32 x = 0, kc = 0, ts = 0, tte = 0;
+                // (:80 assert: CIGAR shorter than the path)
+                if (cp == cend || !fuse_fetch_op(rt, minus, cp, x, kc, ts, tte)) { ok = false; going = false; }
+                else {
+                    const bool tgt = (kTargetMask >> kc) & 1u;
+                    if (tgt && x >= need) {
+                        lenE = need; codeE = kc + '=';
+                        rem = x - need; remk = kc;
+                        x = need;
+                        close = true;
+                    } else {
+                        if (tgt) need -= x;
+                        if (mid_b == 0) { mid_a = ts; mid_b = tte; }
+                        else if (minus) mid_a = ts;
+                        else mid_b = tte;
+                    }
+                    if ((kQueryMask >> kc) & 1u) q += x;
+                    if ((kMatchMask >> kc) & 1u) nm += x;
+                    nb += x;
+                }
             }
-            if ((kQueryMask >> kc) & 1u) q += x;
-            if ((kMatchMask >> kc) & 1u) nm += x;
-            nb += x;
-        }
-        if (close) {
-            uint4* sl = slots + 3u * i;
-            if (nm > 0) {   // gaf2paf_main.cpp:225
-                const u32 mid_len = mid_b > mid_a ? mid_b - mid_a : 0u;
-                sl[0].w = qcur;
-                sl[1] = make_uint4(qcur + q, nm, nb, lenS);
-                sl[2].x = lenE;
-                sl[2].y = (rtpos + mid_a) | (mid_len << 16);
-                sl[2].z |= kFSlotEmit << 24;
-                sl[2].w = rec | (codeS << 16) | (codeE << 24);
+            if (close) {
+                uint4* sl = slots + 3u * i;
+                if (nm > 0) {   // gaf2paf_main.cpp:225
+                    const u32 mid_len = mid_b > mid_a ? mid_b - mid_a : 0u;
+                    sl[0].w = qcur;
+                    sl[1] = make_uint4(qcur + q, nm, nb, lenS);
+                    sl[2].x = lenE;
+                    sl[2].y = (rtpos + mid_a) | (mid_len << 16);
+                    sl[2].z |= kFSlotEmit << 24;
+                    sl[2].w = rec | (codeS << 16) | (codeE << 24);
+                }
+                qcur += q;
+                need = 0;
+                ++i;
             }
-            qcur += q;
-            need = 0;
-            ++i;
         }
     }
     // the reference parses the whole CIGAR before anything else: what the path left over must be valid too
-    while (cp != cend) {
-        u32 x, kc, ts, tte;
-        if (!fuse_fetch_op(rt, minus, cp, x, kc, ts, tte)) return false;
+    going = live && ok && cp != cend;
+    while (__any_sync(FULL, going)) {
+        if (going) {
+            u32 x, kc, ts, tte;
+            if (!fuse_fetch_op(rt, minus, cp, x, kc, ts, tte)) { ok = false; going = false; }
+            else if (cp == cend) going = false;
+        }
     }
-    return true;
+    return ok;
 }
 
 // ---- G: one thread per slot: the byte length of its PAF line (0: the step prints none)
@@ -724,10 +761,9 @@ __global__ void __launch_bounds__(kFThreads, C::kCtas) k_fuse(const FuseArgs a) 
         nslots += total;
         if (nslots > kFMaxSlots) { too_many = true; break; }   // uniform: every thread sees the same total
         const bool live = have && ok && !skip;
-        if (live) {   // D1: step tokens -> slots
-            const_cast<u8*>(rt)[pb] = '>';   // bounds the token scans
-            if (!fuse_tokens(rt, rtpos, pa, pb, prefixed, minus, s_slots + 3u * slot0, ns)) bad = true;
-        }
+        // D1: step tokens -> slots (all lanes: see CONVERGENCE)
+        if (live) const_cast<u8*>(rt)[pb] = '>';   // bounds the token scans
+        if (!fuse_tokens(live, rt, rtpos, pa, pb, prefixed, minus, s_slots + 3u * slot0, ns)) bad = true;
         if (bad) s_flag = 1;
         __syncthreads();
         if (s_flag) break;   // uniform
@@ -737,7 +773,7 @@ __global__ void __launch_bounds__(kFThreads, C::kCtas) k_fuse(const FuseArgs a) 
         __syncthreads();
         if (s_flag) break;   // uniform
         // D2: quotas + the op walk
-        if (live && !fuse_walk2(rt, rtpos, text, rec, minus, prefixed, s_slots + 3u * slot0, ns, ca, cb, qs, ps, pe)) bad = true;
+        if (!fuse_walk2(live, rt, rtpos, text, rec, minus, prefixed, s_slots + 3u * slot0, ns, ca, cb, qs, ps, pe)) bad = true;
     }
     if (bad) s_flag = 1;
     __syncthreads();

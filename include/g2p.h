@@ -67,6 +67,9 @@ typedef struct g2p_result {
     uint32_t n_long;        /* records converted by the streaming kernel k_long (incl. those it passed on) */
     float fused_ms;         /* CUDA-event time of the one-pass kernel k_fuse (0 when it did not produce the result) */
     uint32_t n_fused;       /* records converted by k_fuse (all of them, or 0 when the general pipeline ran) */
+    float unstable_ms;      /* g2p_unstable_convert_*: CUDA-event time of the gaf2unstable stage (included in device_ms) */
+    uint32_t stage;         /* g2p_unstable_convert_*: 1 / 2 = rec_status comes from the gaf2unstable / gaf2paf stage */
+    uint64_t mid_bytes;     /* g2p_unstable_convert_*: bytes of the intermediate node-space GAF (it never leaves the device) */
 } g2p_result;
 
 /* Context bound to one CUDA device. */
@@ -141,6 +144,17 @@ typedef struct g2p_warn {
 int g2p_unstable_warnings(g2p_ctx* ctx, const g2p_warn** warns, size_t* n);
 /* The reference's stderr text for one such output line. */
 int g2p_format_unstable_warning(g2p_ctx* ctx, const char* out_line, size_t len, char* buf, size_t cap);
+
+/* The reference's two-stage pipeline `gaf2unstable in.gaf -g graph.gfa -o L | gaf2paf - -l L` (README.md:55-58,
+ * test/gaf2paf.t:36-37) as ONE call: stage 1 (gaf2unstable_main.cpp:109-175) writes the node-space GAF into device
+ * memory, stage 2 (gaf2paf_main.cpp:134-264) converts it from there with the node lengths of the same rGFA as its
+ * lengths table -- the intermediate text makes no device->host->device round trip.  Needs g2p_load_rgfa; the -l table
+ * of g2p_load_lengths is not touched.  Output: the PAF bytes of the pipeline; res->stage tells which stage stopped at
+ * a record (stage 1: the reference's gaf2unstable aborts; the records before it are converted). */
+int g2p_unstable_convert_device(g2p_ctx* ctx, const void* d_gaf, size_t n, void** d_out, g2p_result* res, void* stream);
+int g2p_unstable_convert_host(g2p_ctx* ctx, const char* gaf, size_t n, const char** out, g2p_result* res);
+/* stderr text of the gaf2unstable stage of the last g2p_unstable_convert_* call (its multi-contig warnings). */
+int g2p_unstable_convert_warnings(g2p_ctx* ctx, const char** text, size_t* n);
 
 /* Formats the stderr line the reference prints for a failed record (empty for aborts,
  * whose text comes from the C++ runtime).  `gaf` is the host copy of the input. */

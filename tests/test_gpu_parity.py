@@ -299,6 +299,52 @@ def test_gaf2unstable_synthetic_and_two_stage(g2p, seed, aligned):
         cv.close()
 
 
+@pytest.mark.parametrize("seed", [31, 32])
+def test_fused_unstable_convert_equals_the_two_stage_pipeline(g2p, seed):
+    """N2: `gaf2unstable in.gaf -g g.gfa -o L | gaf2paf - -l L` as one call whose intermediate GAF stays in
+    device memory == the reference's two processes (README.md:55-58), including the stage-1 warnings and a record on
+    which the reference's gaf2unstable aborts."""
+    import torch
+    rgfa, gaf = H.gen_rgfa_case(seed, n_records=6000, aligned=True, multi_ref_pct=4)
+    rc, ugaf, err, nl = H.run_gaf2unstable_ref(gaf, rgfa, want_lengths=True)
+    rc2, paf_ref, err2, kind = H.run_gaf2paf_cpu(ugaf, nl)
+    assert rc == 0 and rc2 == 0
+    cv = g2p.Converter(0)
+    try:
+        ok, code, msg = cv.load_rgfa(rgfa)
+        assert ok
+        paf, res, warn_text = cv.unstable_convert_host(gaf)
+        assert g2p.exit_code(res) == 0 and res.stage == 0
+        assert paf == paf_ref
+        assert warn_text == err
+        assert res.mid_bytes == len(ugaf) and res.unstable_ms > 0
+        # device-resident entry point
+        t = torch.empty(len(gaf) + 16, dtype=torch.uint8, device="cuda")
+        g2p.copy_to_device(t.data_ptr(), gaf)
+        torch.cuda.synchronize()
+        d_out, res2 = cv.unstable_convert_device(t.data_ptr(), len(gaf), torch.cuda.current_stream().cuda_stream)
+        assert g2p.copy_to_host(d_out, res2.out_bytes) == paf_ref
+        # the -l table of the context is not touched by the fused call
+        p = H.preset("short", seed=3)
+        lengths = H.gen_lengths(p)
+        g = H.gen_records(p, 0, 2000)
+        assert cv.load_lengths(lengths)
+        cv.unstable_convert_host(gaf)
+        out, r3 = cv.convert_host(g)
+        assert out == H.run_gaf2paf_cpu(g, lengths)[1]
+        # stage 1 stops at a record (unknown contig: the reference's gaf2unstable aborts): what came before is converted
+        lines = gaf.split(b"\n")
+        k = len(lines) // 2
+        bad = b"\n".join(lines[:k] + [b"q\t100\t0\t15\t+\t>nosuchcontig:0-15\t15\t0\t15\t15\t15\t60\tcg:Z:15M"] + lines[k:])
+        paf_b, res_b, _ = cv.unstable_convert_host(bad)
+        head = b"\n".join(lines[:k]) + b"\n"
+        rc, ugaf_h, err_h, nl_h = H.run_gaf2unstable_ref(head, rgfa, want_lengths=True)
+        assert g2p.exit_code(res_b) == 134 and res_b.stage == 1
+        assert paf_b == H.run_gaf2paf_cpu(ugaf_h, nl_h)[1]
+    finally:
+        cv.close()
+
+
 def test_gaf2unstable_abort_and_cli(g2p):
     rgfa, gaf = H.gen_rgfa_case(21, n_records=1500, aligned=True)
     bad = gaf + b"q\t100\t0\t15\t+\t>nosuchcontig:0-15\t15\t0\t15\t15\t15\t60\tcg:Z:15M\n" + gaf[:2000]
