@@ -2,7 +2,7 @@
 """bench.py — gaf2paf throughput on B200 (BASELINE.json metric: GAF records/s and input GB/s
 vs the HBM roofline), one JSON line on stdout.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload short|tagged|mixed|stable|medium|asm] [--records R]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload short|tagged|mixed|stable|medium|asm|unstable] [--records R]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...      # the reference's CPU gaf2paf on the host cores
 
@@ -51,6 +51,9 @@ WORKLOADS = {
     # shapes of configs[0] / configs[1] (stable-interval and node-coordinate assembly alignments)
     "stable": {"preset": "stable", "records": 300_000, "desc": "configs[0] shape: stable-interval steps (>contig:start-end), ~2 kB records", "cpu_records": 40_000},
     "medium": {"preset": "medium", "records": 100_000, "desc": "configs[1] shape: node-coordinate records of 20-200 steps, ~2 kB", "cpu_records": 6_000},
+    # BASELINE.json configs[1]: gaf2unstable + gaf2paf on an rGFA, as ONE device-resident call (N2)
+    "unstable": {"kind": "unstable", "preset": None, "records": 300_000, "cpu_records": 100_000,
+                 "desc": "configs[1] shape: gaf2unstable | gaf2paf fused (stable-interval GAF + rGFA -> node-space PAF, the intermediate GAF stays on the device)"},
     "asm": {"preset": "asm", "records": 4000, "desc": "configs[3] shape: assembly-scale records, 5k-15k steps, 4000 of the 100k records (PAF of all would not fit next to the input)",
             "cpu_records": 40},
 }
@@ -132,15 +135,31 @@ class CpuArm:
 
     def __init__(self, H, preset_name, seed, per_proc, procs):
         self.binary, self.kind = H.oracle_path()
-        p = H.preset(preset_name, seed=seed)
         self.per, self.procs = max(1, per_proc), procs
-        self.td = tempfile.TemporaryDirectory(dir=scratch_dir(self.per * procs * 300))
+        self.td = tempfile.TemporaryDirectory(dir=scratch_dir(max(self.per * procs * 300, 1 << 30)))
         td = self.td.name
         self.lp = os.path.join(td, "l.tsv")
-        open(self.lp, "wb").write(H.gen_lengths(p))
         self.empty = os.path.join(td, "empty.gaf")
         open(self.empty, "wb").close()
         self.files, self.nbytes = [], 0
+        self.unstable = preset_name is None
+        if self.unstable:
+            # the reference's two-stage pipeline, stage after stage: gaf2unstable in.gaf -g g.gfa -o L > u.gaf; gaf2paf u.gaf -l L
+            self.binary_u, _ = H.oracle_path("auto", "gaf2unstable")
+            rgfa, gaf = H.gen_rgfa_case(seed, n_contigs=24, n_records=self.per, aligned=True)
+            self.gp = os.path.join(td, "g.gfa")
+            open(self.gp, "wb").write(rgfa)
+            open(self.lp, "wb").close()
+            for i in range(procs):
+                fp = os.path.join(td, "s%d.gaf" % i)
+                open(fp, "wb").write(gaf)
+                self.files.append(fp)
+                self.nbytes += len(gaf)
+            self.per = gaf.count(b"\n")
+            self.table_load_s = 0.0
+            return
+        p = H.preset(preset_name, seed=seed)
+        open(self.lp, "wb").write(H.gen_lengths(p))
         for i in range(procs):
             g = H.gen_records(p, i * self.per, self.per)
             fp = os.path.join(td, "s%d.gaf" % i)
@@ -158,6 +177,15 @@ class CpuArm:
         self.table_load_s = min(ts)
 
     def step(self):
+        if self.unstable:
+            t0 = time.perf_counter()
+            cmd = '"%s" "$0" -g "%s" -o "$0.L" > "$0.u" 2>/dev/null && "%s" "$0.u" -l "$0.L" > /dev/null' % (self.binary_u, self.gp, self.binary)
+            ps = [subprocess.Popen(["bash", "-c", cmd, fp]) for fp in self.files]
+            rcs = [q.wait() for q in ps]
+            dt = time.perf_counter() - t0
+            if any(rcs):
+                raise RuntimeError("cpu baseline (gaf2unstable | gaf2paf) failed: rc %r" % rcs)
+            return dt
         t0 = time.perf_counter()
         ps = [subprocess.Popen([self.binary, fp, "-l", self.lp], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for fp in self.files]
         rcs = [q.wait() for q in ps]
@@ -188,7 +216,7 @@ def run_reference(a):
         return 0
     wl = WORKLOADS[a.workload]
     procs = min(os.cpu_count() or 1, 64)
-    arm = CpuArm(H, wl["preset"], 1000, wl["cpu_records"], procs)
+    arm = CpuArm(H, wl["preset"], 1000 if wl["preset"] else 7, wl["cpu_records"], procs)
     try:
         dts = []
         for s in range(a.warmup + a.steps):
@@ -319,17 +347,32 @@ def main():
 
     wl = WORKLOADS[a.workload]
     nrec = a.records or wl["records"]
-    p = H.preset(wl["preset"], seed=1)
-    lengths = H.gen_lengths(p)
+    unstable = wl.get("kind") == "unstable"
     cv = g2p.Converter(local)
-    t0 = time.perf_counter()
-    assert cv.load_lengths(lengths)
-    table_load_s = time.perf_counter() - t0
-
-    # ---- ONE logical input: rank r generates records [r*nrec, (r+1)*nrec) into a shared tmpfs file at its byte
-    # offset; the file is then cut into `world` newline-aligned byte ranges and rank r takes range r.
     threads = max(1, (os.cpu_count() or 8) // max(1, world))
-    addr, gen_bytes = H.gen_records_raw(p, rank * nrec, nrec, threads=min(64, threads))
+    if unstable:
+        # stable-interval GAF + rGFA (tests/helpers.py gen_rgfa_case, minigraph-like, node-aligned intervals); every rank
+        # holds one copy of the same block, the logical input is the block repeated `world` times
+        rgfa, block = H.gen_rgfa_case(7, n_contigs=24, n_records=nrec, aligned=True)
+        t0 = time.perf_counter()
+        ok, code, msg = cv.load_rgfa(rgfa)
+        assert ok, msg
+        table_load_s = time.perf_counter() - t0
+        lengths = cv.node_lengths()
+        keep_block = ctypes.create_string_buffer(block, len(block))
+        addr, gen_bytes = ctypes.addressof(keep_block), len(block)
+        a.no_cli = True   # the reference's interface for this path is two executables and a pipe
+        dev_call, host_call = cv.unstable_convert_device, cv.unstable_convert_host_raw
+    else:
+        p = H.preset(wl["preset"], seed=1)
+        lengths = H.gen_lengths(p)
+        t0 = time.perf_counter()
+        assert cv.load_lengths(lengths)
+        table_load_s = time.perf_counter() - t0
+        # ---- ONE logical input: rank r generates records [r*nrec, (r+1)*nrec) into a shared tmpfs file at its byte
+        # offset; the file is then cut into `world` newline-aligned byte ranges and rank r takes range r.
+        addr, gen_bytes = H.gen_records_raw(p, rank * nrec, nrec, threads=min(64, threads))
+        dev_call, host_call = cv.convert_device, cv.convert_host_raw
     sizes = gather_int(gen_bytes)
     total_in = sum(sizes)
     want_cli = not a.no_cli
@@ -355,11 +398,11 @@ def main():
             pinned = g2p.lib.g2p_host_alloc(nbytes + 16)
             ctypes.memmove(pinned, base + a_off, nbytes)
             mm.close()
-        H.gen_free(addr)
     else:
         a_off, nbytes = 0, gen_bytes
         pinned = g2p.lib.g2p_host_alloc(nbytes + 16)
         ctypes.memmove(pinned, addr, nbytes)
+    if not unstable:
         H.gen_free(addr)
     d_in = torch.empty(nbytes + 16, dtype=torch.uint8, device="cuda")
     assert g2p.lib.g2p_copy_to_device(d_in.data_ptr(), pinned, nbytes) == 0
@@ -369,7 +412,7 @@ def main():
     # ---- device-resident timing (value)
     res = None
     for _ in range(a.warmup):
-        d_out, res = cv.convert_device(d_in.data_ptr(), nbytes, stream)
+        d_out, res = dev_call(d_in.data_ptr(), nbytes, stream)
     assert g2p.exit_code(res) == 0, "synthetic workload must convert cleanly"
     out_bytes = res.out_bytes
     n_records = res.n_records
@@ -382,11 +425,11 @@ def main():
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ms = {k: [] for k in ("emit_ms", "size_ms", "index_ms", "device_ms", "fused_ms")}
+    ms = {k: [] for k in ("emit_ms", "size_ms", "index_ms", "device_ms", "fused_ms", "unstable_ms")}
     launches = 0
     e0.record()
     for _ in range(a.steps):
-        d_out, res = cv.convert_device(d_in.data_ptr(), nbytes, stream)
+        d_out, res = dev_call(d_in.data_ptr(), nbytes, stream)
         for k in ms:
             ms[k].append(getattr(res, k, 0.0))
         launches += res.gpu_launches
@@ -400,11 +443,11 @@ def main():
     e2e = None
     if not a.no_e2e:
         for _ in range(2):
-            cv.convert_host_raw(pinned, nbytes)
+            host_call(pinned, nbytes)
         barrier()
         w0 = time.perf_counter()
         for _ in range(a.steps):
-            o_addr, r2 = cv.convert_host_raw(pinned, nbytes)
+            o_addr, r2 = host_call(pinned, nbytes)
         torch.cuda.synchronize()
         w_s = max_float(time.perf_counter() - w0)
         assert r2.out_bytes == out_bytes
@@ -469,7 +512,8 @@ def main():
         "input_GBps": total_in * a.steps / (t_ms / 1000.0) / 1e9,
         "pipeline_in_plus_out_GBps": (total_in + tot_out) * a.steps / (t_ms / 1000.0) / 1e9,
         "pipeline_frac_of_hbm_peak": (nbytes + out_bytes) * a.steps / (t_ms / 1000.0) / 1e9 / peak,
-        "kernel_ms": {"index": mean["index_ms"], "size": mean["size_ms"], "emit": mean["emit_ms"], "fused": mean["fused_ms"], "device_pipeline": mean["device_ms"]},
+        "kernel_ms": {"index": mean["index_ms"], "size": mean["size_ms"], "emit": mean["emit_ms"], "fused": mean["fused_ms"],
+                      "gaf2unstable_stage": mean["unstable_ms"], "device_pipeline": mean["device_ms"]},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "algorithmic_bytes_per_launch": dom_bytes, "peak_source": peak_src},
         "records_by_kernel": {"k_fuse": n_fused, short_kernel.split("<")[0]: int(n_records - res.n_long - n_fused) if n_fused == 0 else 0,
@@ -484,7 +528,7 @@ def main():
         line["cli"] = cli
     if not a.no_cpu_baseline and world == 1:
         try:
-            arm = CpuArm(H, wl["preset"], 1, wl["cpu_records"] * (2 if a.workload == "short" else 1), 1)
+            arm = CpuArm(H, wl["preset"], 1 if wl["preset"] else 7, wl["cpu_records"] * (2 if a.workload == "short" else 1), 1)
             try:
                 line["cpu_baseline"] = arm.result([arm.step()])
             finally:

@@ -250,6 +250,7 @@ int g2p_create(int device, g2p_ctx** out) {
     cudaFuncSetAttribute(k_fuse<FuseCfg2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FuseCfg2::kSmem);
     cudaFuncSetAttribute(k_fuse<FuseCfg3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FuseCfg3::kSmem);
     cudaFuncSetAttribute(k_fuse<FuseCfg4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FuseCfg4::kSmem);
+    cudaFuncSetAttribute(k_fuse<FuseCfg5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FuseCfg5::kSmem);
     if (const char* c = std::getenv("G2P_FUSE_CFG")) { const int v = std::atoi(c); if (v >= 0 && v < kFuseCfgs) ctx->fuse_cfg = v; }
     if (const char* c = std::getenv("G2P_HOST_CHUNK_MB")) {
         long v = std::atol(c);
@@ -374,7 +375,8 @@ static void launch_fuse(int cfg, u32 ntiles, cudaStream_t st, const FuseArgs& fa
         case 1: k_fuse<FuseCfg1><<<ntiles, kFThreads, FuseCfg1::kSmem, st>>>(fa); break;
         case 2: k_fuse<FuseCfg2><<<ntiles, kFThreads, FuseCfg2::kSmem, st>>>(fa); break;
         case 3: k_fuse<FuseCfg3><<<ntiles, kFThreads, FuseCfg3::kSmem, st>>>(fa); break;
-        default: k_fuse<FuseCfg4><<<ntiles, kFThreads, FuseCfg4::kSmem, st>>>(fa); break;
+        case 4: k_fuse<FuseCfg4><<<ntiles, kFThreads, FuseCfg4::kSmem, st>>>(fa); break;
+        default: k_fuse<FuseCfg5><<<ntiles, kFThreads, FuseCfg5::kSmem, st>>>(fa); break;
     }
 }
 

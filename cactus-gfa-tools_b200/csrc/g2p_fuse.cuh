@@ -53,7 +53,7 @@ struct FuseCfg {
     static constexpr u32 kStage = ((kBudget - kOffStage - 32) & ~15u);                // staged PAF bytes per round
     static constexpr size_t kSmem = kOffStage + kStage + 32;
 };
-// Configurations.  0-2 are tuning alternatives for ordinary short-read input (G2P_FUSE_CFG); 3 and 4 keep the largest
+// Configurations.  0-2 and 5 are tuning alternatives for ordinary short-read input (G2P_FUSE_CFG); 3 and 4 keep the largest
 // tables on smaller tiles: the host moves to them when a tile reports kFuseTooManyRecords / kFuseTooManySteps
 // (denser input: shorter records or more steps per byte).
 typedef FuseCfg<32768, 352, 832, 2> FuseCfg0;
@@ -61,17 +61,18 @@ typedef FuseCfg<24576, 288, 704, 2> FuseCfg1;
 typedef FuseCfg<16384, 192, 480, 3> FuseCfg2;
 typedef FuseCfg<16384, 352, 832, 2> FuseCfg3;
 typedef FuseCfg<8192, 352, 832, 2> FuseCfg4;
-constexpr int kFuseCfgs = 5, kFuseCfgDense = 3;
+typedef FuseCfg<28672, 288, 736, 2> FuseCfg5;
+constexpr int kFuseCfgs = 6, kFuseCfgDense = 3;
 static inline u32 fuse_cfg_tile(int cfg) {
-    static const u32 t[kFuseCfgs] = {FuseCfg0::kTile, FuseCfg1::kTile, FuseCfg2::kTile, FuseCfg3::kTile, FuseCfg4::kTile};
+    static const u32 t[kFuseCfgs] = {FuseCfg0::kTile, FuseCfg1::kTile, FuseCfg2::kTile, FuseCfg3::kTile, FuseCfg4::kTile, FuseCfg5::kTile};
     return t[cfg];
 }
 static inline size_t fuse_cfg_smem(int cfg) {
-    static const size_t t[kFuseCfgs] = {FuseCfg0::kSmem, FuseCfg1::kSmem, FuseCfg2::kSmem, FuseCfg3::kSmem, FuseCfg4::kSmem};
+    static const size_t t[kFuseCfgs] = {FuseCfg0::kSmem, FuseCfg1::kSmem, FuseCfg2::kSmem, FuseCfg3::kSmem, FuseCfg4::kSmem, FuseCfg5::kSmem};
     return t[cfg];
 }
 // the configuration to try after `cfg` reported a capacity overflow (-1: none left)
-static inline int fuse_cfg_denser(int cfg) { return cfg < kFuseCfgDense ? kFuseCfgDense : (cfg + 1 < kFuseCfgs ? cfg + 1 : -1); }
+static inline int fuse_cfg_denser(int cfg) { return cfg == 3 ? 4 : (cfg == 4 ? -1 : kFuseCfgDense); }
 
 enum : u32 { kFuseNotConvertible = 1u, kFuseTooManyRecords = 2u, kFuseTooManySteps = 4u };
 
@@ -134,7 +135,11 @@ struct WEmit {
         lo |= v << sh;
         const u32 hi = __funnelshift_l(v, 0u, sh);   // what does not fit (0 when sh == 0)
         sh += 8u * nbytes;
-        if (sh >= 32u) { *wp++ = lo; lo = hi; sh -= 32u; }
+        const u32 full = sh >> 5;                    // 0 or 1; straight-line code: one predicated store, selects
+        if (full) *wp = lo;
+        wp += full;
+        lo = full ? hi : lo;
+        sh &= 31u;
     }
     __device__ __forceinline__ void put4(u32 v) {
         *wp++ = lo | (v << sh);
@@ -260,31 +265,37 @@ __device__ __forceinline__ bool fuse_probe(const LenTableView& T, const u8* text
     return true;
 }
 
-// One CIGAR token in walk direction, loop-free for up to three digits (all of a short read's): the five bytes next to
-// the cursor are loaded together.  Forward: "digits letter" starts at cp; backward: the token ends at cp (exclusive).
+// One CIGAR token in walk direction, loop-free for up to four digits (all of a short read's).  Forward: "digits
+// letter" starts at cp; backward: the token ends at cp (exclusive).  One unaligned 32-bit window of the text holds the
+// digits either way -- forward the four bytes at cp (digits first), backward the four bytes before the letter (digits
+// last); SWAR finds how many of them are digits, the window is shifted so that the last digit sits in the top byte,
+// and the value is four multiply-adds.  Tokens of five or more digits take the byte loop of k_rec.
+__device__ __forceinline__ u32 lds32_unaligned(const u8* p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const u32* q = reinterpret_cast<const u32*>(a & ~(uintptr_t)3);
+    return __funnelshift_r(q[0], q[1], (u32)(a & 3u) * 8u);
+}
 __device__ __forceinline__ bool fuse_fetch_op(const u8* rt, const bool minus, u32& cp, u32& x, u32& kc, u32& ts, u32& te) {
-    const u32 step = minus ? 0xffffffffu : 1u;
-    const u32 base = minus ? cp - 1u : cp;
-    const u32 b0 = rt[base], b1 = rt[base + step], b2 = rt[base + 2u * step], b3 = rt[base + 3u * step], b4 = rt[base + 4u * step];
-    // digits in walk order: forward b0 b1 b2 (b3), backward b1 b2 b3 (b4) after the letter b0
-    const u32 d0 = (minus ? b1 : b0) - '0', d1 = (minus ? b2 : b1) - '0', d2 = (minus ? b3 : b2) - '0', d3 = (minus ? b4 : b3) - '0';
-    if (d0 <= 9u && d1 <= 9u && d2 <= 9u && d3 <= 9u) {   // >= 4 digits (rare: no reconvergence needed inside)
+    const u32 w = lds32_unaligned(rt + (minus ? cp - 5u : cp));   // (the bytes before "cg:Z:" belong to the record: always readable)
+    const u32 nd_mask = nondigit_bytes(w);                        // 0x80 in every byte that is not '0'..'9'
+    // forward: digits are the leading bytes; backward: the trailing ones
+    const u32 nd = minus ? ((u32)__clz((int)nd_mask) >> 3) : (nd_mask ? ((u32)__ffs((int)nd_mask) - 1u) >> 3 : 4u);
+    const u32 letter = rt[minus ? cp - 1u : cp + nd];
+    if (nd == 4u && (minus ? (u32)rt[cp - 6u] - '0' <= 9u : letter - '0' <= 9u)) {   // >= 5 digits (rare)
         u32 cp2 = cp, x2, kc2, ts2, te2;
         const bool r = rec_fetch_op_slow(rt, minus, cp2, x2, kc2, ts2, te2);
         cp = cp2; x = x2; kc = kc2; ts = ts2; te = te2;
         return r;
     }
-    const u32 nd = d0 > 9u ? 0u : (d1 > 9u ? 1u : (d2 > 9u ? 2u : 3u));
-    const u32 v2 = minus ? d1 * 10u + d0 : d0 * 10u + d1;
-    const u32 v3 = minus ? d2 * 100u + d1 * 10u + d0 : d0 * 100u + d1 * 10u + d2;
-    const u32 v = nd == 1 ? d0 : (nd == 2 ? v2 : v3);
-    const u32 lead = minus ? (nd == 1 ? d0 : (nd == 2 ? d1 : d2)) : d0;   // most significant digit
-    const u32 letter = minus ? b0 : (nd == 1 ? b1 : (nd == 2 ? b2 : b3));
+    // last digit in the top byte, zeros below the first digit
+    const u32 al = nd ? (minus ? w >> (8u * (4u - nd)) << (8u * (4u - nd)) : w << (8u * (4u - nd))) : 0u;
+    const u32 v = ((al >> 24) & 15u) + 10u * ((al >> 16) & 15u) + 100u * ((al >> 8) & 15u) + 1000u * (al & 15u);
+    const u32 lead = nd ? (al >> (8u * (4u - nd))) & 0xffu : 0u;   // most significant digit (as a character)
     if (minus) { te = cp; ts = cp - nd - 1u; cp = ts; }
     else { ts = cp; te = cp + nd + 1u; cp = te; }
     kc = letter - '=';
     x = v;
-    return nd != 0 && !(nd > 1 && lead == 0) && v != 0 && kc < 28u && ((kOpMask >> kc) & 1u);
+    return nd != 0 && !(nd > 1 && lead == '0') && v != 0 && kc < 28u && ((kOpMask >> kc) & 1u);
 }
 
 // ---- D2: the record walk, one thread per record.  (a) per step: strand, quota and clips (gaf2paf_main.cpp:157-182);
