@@ -127,6 +127,8 @@ struct g2p_ctx {
     DevBuf n_slots, n_arena;              // node name -> length table of the rGFA (what gaf2unstable -o writes, loaded like gaf2paf -l)
     LenTableView node_table{nullptr, nullptr, 0};
     std::string warn_text;                // stderr text of the gaf2unstable stage of the last g2p_unstable_convert_* call
+    const u8* warn_mid = nullptr;         // (built on demand from the intermediate GAF, which stays in the worker's d_mid buffer)
+    bool warn_pending = false;
     UnstableView uview{};
     bool have_rgfa = false;
     RgfaTables* rgfa = nullptr;
@@ -251,6 +253,9 @@ int g2p_create(int device, g2p_ctx** out) {
     cudaFuncSetAttribute(k_fuse<FuseCfg3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FuseCfg3::kSmem);
     cudaFuncSetAttribute(k_fuse<FuseCfg4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FuseCfg4::kSmem);
     cudaFuncSetAttribute(k_fuse<FuseCfg5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FuseCfg5::kSmem);
+    cudaFuncSetAttribute(k_fuse<FuseCfg6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FuseCfg6::kSmem);
+    cudaFuncSetAttribute(k_fuse<FuseCfg7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FuseCfg7::kSmem);
+    cudaFuncSetAttribute(k_fuse<FuseCfg8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FuseCfg8::kSmem);
     if (const char* c = std::getenv("G2P_FUSE_CFG")) { const int v = std::atoi(c); if (v >= 0 && v < kFuseCfgs) ctx->fuse_cfg = v; }
     if (const char* c = std::getenv("G2P_HOST_CHUNK_MB")) {
         long v = std::atol(c);
@@ -376,7 +381,10 @@ static void launch_fuse(int cfg, u32 ntiles, cudaStream_t st, const FuseArgs& fa
         case 2: k_fuse<FuseCfg2><<<ntiles, kFThreads, FuseCfg2::kSmem, st>>>(fa); break;
         case 3: k_fuse<FuseCfg3><<<ntiles, kFThreads, FuseCfg3::kSmem, st>>>(fa); break;
         case 4: k_fuse<FuseCfg4><<<ntiles, kFThreads, FuseCfg4::kSmem, st>>>(fa); break;
-        default: k_fuse<FuseCfg5><<<ntiles, kFThreads, FuseCfg5::kSmem, st>>>(fa); break;
+        case 5: k_fuse<FuseCfg5><<<ntiles, kFThreads, FuseCfg5::kSmem, st>>>(fa); break;
+        case 6: k_fuse<FuseCfg6><<<ntiles, kFThreads, FuseCfg6::kSmem, st>>>(fa); break;
+        case 7: k_fuse<FuseCfg7><<<ntiles, kFThreads, FuseCfg7::kSmem, st>>>(fa); break;
+        default: k_fuse<FuseCfg8><<<ntiles, kFThreads, FuseCfg8::kSmem, st>>>(fa); break;
     }
 }
 
@@ -961,14 +969,10 @@ static int run_unstable_convert(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t
     ctx->warn_text.clear();
     int rc = run_unstable(ctx, w, d_gaf, n, st, &r1, &d_mid);
     if (rc) return rc;
-    // the stage-1 warnings (gaf2unstable_main.cpp:165-171) quote the record it wrote: fetch those lines (rare)
-    for (const g2p_warn& wn : ctx->warns) {
-        std::vector<char> line(wn.out_len + 1), msg(wn.out_len + 4096);
-        G2P_CUDA(cudaMemcpy(line.data(), d_mid + wn.out_off, wn.out_len, cudaMemcpyDeviceToHost));
-        g2p_format_unstable_warning(ctx, line.data(), wn.out_len, msg.data(), msg.size());
-        ctx->warn_text += msg.data();
-    }
-    std::swap(w.d_out, w.d_mid);   // the intermediate GAF stays in d_mid; the converter writes d_out
+    (void)d_mid;
+    std::swap(w.d_out, w.d_mid);   // the intermediate GAF stays in d_mid (until the next call); the converter writes d_out
+    ctx->warn_mid = static_cast<const u8*>(w.d_mid.p);
+    ctx->warn_pending = !ctx->warns.empty();
     const LenTableView saved = ctx->table;
     const bool saved_have = ctx->have_table;
     ctx->table = ctx->node_table;
@@ -1026,6 +1030,18 @@ int g2p_unstable_convert_host(g2p_ctx* ctx, const char* gaf, size_t n, const cha
 
 int g2p_unstable_convert_warnings(g2p_ctx* ctx, const char** text, size_t* n) {
     if (!ctx || !text || !n) return G2P_E_ARG;
+    if (ctx->warn_pending) {
+        // the stage-1 warnings (gaf2unstable_main.cpp:165-171) quote the record it wrote: fetch those lines from the
+        // intermediate GAF -- here, not inside the conversion call
+        G2P_CUDA(cudaSetDevice(ctx->device));
+        for (const g2p_warn& wn : ctx->warns) {
+            std::vector<char> line(wn.out_len + 1), msg(wn.out_len + 4096);
+            G2P_CUDA(cudaMemcpy(line.data(), ctx->warn_mid + wn.out_off, wn.out_len, cudaMemcpyDeviceToHost));
+            g2p_format_unstable_warning(ctx, line.data(), wn.out_len, msg.data(), msg.size());
+            ctx->warn_text += msg.data();
+        }
+        ctx->warn_pending = false;
+    }
     *text = ctx->warn_text.data();
     *n = ctx->warn_text.size();
     return G2P_OK;

@@ -34,10 +34,11 @@ constexpr u32 kFLimit = 1000;              // longest record (bytes, without '\n
 constexpr u32 kFTail = 1024;               // bytes after the tile its last record may extend into (>= kFLimit + 1)
 // Shared-memory layout of one configuration: TILE input bytes per CTA, room for MAXREC records and MAXSLOTS path
 // steps, CTAS resident CTAs per SM (which fixes the shared-memory budget; what the tables leave is the staging buffer).
-template <u32 TILE, u32 MAXREC, u32 MAXSLOTS, int CTAS>
+template <u32 TILE, u32 MAXREC, u32 MAXSLOTS, int CTAS, bool DIRECT = false>
 struct FuseCfg {
     static constexpr u32 kTile = TILE, kMaxRec = MAXREC, kMaxSlots = MAXSLOTS;
     static constexpr int kCtas = CTAS;
+    static constexpr bool kDirect = DIRECT;   // lines are written straight to global memory (32-bit words), no staging buffer / TMA store
     static constexpr u32 kUnits = TILE / 16 / kFThreads;   // 16-byte vectors per thread in the newline scan
     static_assert(TILE % (16 * kFThreads) == 0, "the newline scan gives every thread whole vectors");
     static_assert(16 + TILE + kFTail + 64 < 65536, "text positions are 16-bit");
@@ -49,8 +50,8 @@ struct FuseCfg {
     static constexpr u32 kOffSlots = kOffInfo + 32 * MAXREC;                          // uint4 slots[3 * MAXSLOTS]
     static constexpr u32 kOffOff = kOffSlots + 48 * MAXSLOTS;                         // u32 off[MAXSLOTS + 1]
     static constexpr u32 kOffStage = (kOffOff + 4 * (MAXSLOTS + 1) + 15) & ~15u;
-    static_assert(kBudget > kOffStage + 8192, "no room for the staging buffer");
-    static constexpr u32 kStage = ((kBudget - kOffStage - 32) & ~15u);                // staged PAF bytes per round
+    static_assert(DIRECT ? kBudget >= kOffStage + 64 : kBudget > kOffStage + 8192, "no room for the staging buffer");
+    static constexpr u32 kStage = DIRECT ? 32u : ((kBudget - kOffStage - 32) & ~15u);   // staged PAF bytes per round
     static constexpr size_t kSmem = kOffStage + kStage + 32;
 };
 // Configurations.  0-2 and 5 are tuning alternatives for ordinary short-read input (G2P_FUSE_CFG); 3 and 4 keep the largest
@@ -62,13 +63,16 @@ typedef FuseCfg<16384, 192, 480, 3> FuseCfg2;
 typedef FuseCfg<16384, 352, 832, 2> FuseCfg3;
 typedef FuseCfg<8192, 352, 832, 2> FuseCfg4;
 typedef FuseCfg<28672, 288, 736, 2> FuseCfg5;
-constexpr int kFuseCfgs = 6, kFuseCfgDense = 3;
+typedef FuseCfg<24576, 288, 704, 3, true> FuseCfg6;
+typedef FuseCfg<32768, 352, 832, 2, true> FuseCfg7;
+typedef FuseCfg<16384, 192, 480, 4, true> FuseCfg8;
+constexpr int kFuseCfgs = 9, kFuseCfgDense = 3;
 static inline u32 fuse_cfg_tile(int cfg) {
-    static const u32 t[kFuseCfgs] = {FuseCfg0::kTile, FuseCfg1::kTile, FuseCfg2::kTile, FuseCfg3::kTile, FuseCfg4::kTile, FuseCfg5::kTile};
+    static const u32 t[kFuseCfgs] = {FuseCfg0::kTile, FuseCfg1::kTile, FuseCfg2::kTile, FuseCfg3::kTile, FuseCfg4::kTile, FuseCfg5::kTile, FuseCfg6::kTile, FuseCfg7::kTile, FuseCfg8::kTile};
     return t[cfg];
 }
 static inline size_t fuse_cfg_smem(int cfg) {
-    static const size_t t[kFuseCfgs] = {FuseCfg0::kSmem, FuseCfg1::kSmem, FuseCfg2::kSmem, FuseCfg3::kSmem, FuseCfg4::kSmem, FuseCfg5::kSmem};
+    static const size_t t[kFuseCfgs] = {FuseCfg0::kSmem, FuseCfg1::kSmem, FuseCfg2::kSmem, FuseCfg3::kSmem, FuseCfg4::kSmem, FuseCfg5::kSmem, FuseCfg6::kSmem, FuseCfg7::kSmem, FuseCfg8::kSmem};
     return t[cfg];
 }
 // the configuration to try after `cfg` reported a capacity overflow (-1: none left)
@@ -161,6 +165,18 @@ struct WEmit {
             const u32 cur = *sp;
             put(__funnelshift_r(prev, cur, s8) & ((1u << (8u * n)) - 1u), n);
         }
+    }
+    // n <= 8 bytes (the short verbatim fields: tag values, column texts): no loop
+    __device__ __forceinline__ void copy_small(const u8* src, u32 n) {
+        const uintptr_t sa = reinterpret_cast<uintptr_t>(src);
+        const u32* sp = reinterpret_cast<const u32*>(sa & ~(uintptr_t)3);
+        const u32 s8 = (u32)(sa & 3u) * 8u;
+        const u32 x0 = sp[0], x1 = sp[1];
+        const u32 w0 = __funnelshift_r(x0, x1, s8);
+        if (n <= 4u) { put(n == 4u ? w0 : w0 & ((1u << (8u * n)) - 1u), n); return; }
+        const u32 w1 = __funnelshift_r(x1, sp[2], s8);
+        put4(w0);
+        put(n == 8u ? w1 : w1 & ((1u << (8u * (n - 4u))) - 1u), n - 4u);
     }
     // decimal digits of x < 10000, zero padded to four, most significant digit in the low byte
     static __device__ __forceinline__ u32 pack4(u32 x) {
@@ -263,6 +279,22 @@ __device__ __forceinline__ bool fuse_probe(const LenTableView& T, const u8* text
     }
     sl[0] = make_uint4((u32)tl64 | ivl, sa, se, 0u);
     return true;
+}
+
+// First position >= p holding a tab or '\n' (the record's own newline, or the virtual one, bounds the scan): aligned
+// 32-bit words, SWAR compare, four bytes per trip.
+__device__ __forceinline__ u32 fuse_scan_field(const u8* rt, const u32 p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(rt + p);
+    const u32* q = reinterpret_cast<const u32*>(a & ~(uintptr_t)3);
+    const u32 off = (u32)(a & 3u);
+    u32 w = *q | ((1u << (8u * off)) - 1u);   // the bytes before p read as 0xFF
+    u32 base = p - off;
+    for (;;) {
+        const u32 m = zero_bytes(w ^ 0x09090909u) | zero_bytes(w ^ 0x0A0A0A0Au);
+        if (m) return base + (((u32)__ffs((int)m) - 1u) >> 3);
+        base += 4u;
+        w = *++q;
+    }
 }
 
 // One CIGAR token in walk direction, loop-free for up to four digits (all of a short read's).  Forward: "digits
@@ -448,7 +480,10 @@ __device__ __forceinline__ void fuse_write_line(u8* dst, const u32 len, const u8
     const u32 flags = v2.z >> 24;
     const bool rev = (flags & kFSlotRev) != 0;
     E.put((rev ? (u32)'-' : (u32)'+') | ((u32)'\t' << 8), 2u);
-    E.copy(text + (v2.z & 0xffffu), (v2.z >> 16) & 0xffu);     // target name
+    {                                                          // target name
+        const u32 nl = (v2.z >> 16) & 0xffu;
+        if (nl <= 8u) E.copy_small(text + (v2.z & 0xffffu), nl); else E.copy(text + (v2.z & 0xffffu), nl);
+    }
     E.put('\t', 1u);
     E.num(v0.x, '\t');                                         // target length
     E.num(v0.y, '\t');                                         // target start
@@ -460,7 +495,7 @@ __device__ __forceinline__ void fuse_write_line(u8* dst, const u32 len, const u8
     // (every item below ends with the tab that separates it from the next one)
     if (R.tp_len) {
         E.put((u32)'t' | ((u32)'p' << 8) | ((u32)':' << 16), 3u);
-        E.copy(rt + R.tp_a, R.tp_len);
+        if (R.tp_len <= 8u) E.copy_small(rt + R.tp_a, R.tp_len); else E.copy(rt + R.tp_a, R.tp_len);
         E.put('\t', 1u);
     }
     if (R.rc_len) {
@@ -470,10 +505,10 @@ __device__ __forceinline__ void fuse_write_line(u8* dst, const u32 len, const u8
     }
     E.put4((u32)'g' | ((u32)'m' << 8) | ((u32)':' << 16) | ((u32)'i' << 24));
     E.put(':', 1u);
-    E.copy(rt + R.m_a, R.m_len);
+    if (R.m_len <= 8u) E.copy_small(rt + R.m_a, R.m_len); else E.copy(rt + R.m_a, R.m_len);
     E.put4((u32)'\t' | ((u32)'g' << 8) | ((u32)'l' << 16) | ((u32)':' << 24));
     E.put((u32)'i' | ((u32)':' << 8), 2u);
-    E.copy(rt + R.b_a, R.b_len);
+    if (R.b_len <= 8u) E.copy_small(rt + R.b_a, R.b_len); else E.copy(rt + R.b_a, R.b_len);
     E.put4((u32)'\t' | ((u32)'g' << 8) | ((u32)'i' << 16) | ((u32)':' << 24));
     E.put((u32)'f' | ((u32)':' << 8), 2u);
     if (R.gi == 0u || R.gi == 1000u) E.put(R.gi ? (u32)'1' : (u32)'0', 1u);
@@ -677,10 +712,9 @@ __global__ void __launch_bounds__(kFThreads, C::kCtas) k_fuse(const FuseArgs a) 
             if (rt[0] == '*') { skip = true; ok = true; break; }   // gaf2paf_main.cpp:360
             // ---- columns 1..12 (parse_gaf_record, gafkluge.hpp:84-183); the record's own '\n' (or the virtual one) ends every scan
             FRec F;
-            u32 p = rec_scan_field(rt, 0);
+            u32 p = fuse_scan_field(rt, 0);
             u8 c = rt[p];
             if (c != '\t' || p == 0) break;
-            const u32 qn_b = p;
             ++p;
             i32 qlen, qe, plen, m, b, mapq;
             const u32 qlen_a = p;
@@ -694,7 +728,7 @@ __global__ void __launch_bounds__(kFThreads, C::kCtas) k_fuse(const FuseArgs a) 
             minus = c == '-';
             p += 2;
             pa = p;   // path
-            p = rec_scan_field(rt, p);
+            p = fuse_scan_field(rt, p);
             if (rt[p] != '\t' || p == pa) break;
             pb = p;
             ++p;
@@ -727,7 +761,7 @@ __global__ void __launch_bounds__(kFThreads, C::kCtas) k_fuse(const FuseArgs a) 
                 if (haszero16(ka ^ kk) | haszero16(kb ^ kk) | haszero16(kc_ ^ kk) | haszero16(kd ^ kk)) { tbad = true; break; }
                 if (++ntags > kRMaxTags) { tbad = true; break; }
                 kd = (kd << 16) | (kc_ >> 16); kc_ = (kc_ << 16) | (kb >> 16); kb = (kb << 16) | (ka >> 16); ka = (ka << 16) | key;
-                p = rec_scan_field(rt, p + 5);
+                p = fuse_scan_field(rt, p + 5);
                 c = rt[p];
                 if (key == ((u32)'c' | ((u32)'g' << 8))) { ca = fa + 5; cb = p; }
                 else if (key == ((u32)'t' | ((u32)'p' << 8))) { tp_a = fa + 3; tp_b = p; }
@@ -740,21 +774,49 @@ __global__ void __launch_bounds__(kFThreads, C::kCtas) k_fuse(const FuseArgs a) 
             const u8 pc0 = rt[pa];
             prefixed = pc0 == '>' || pc0 == '<';
             if (!prefixed && pb - pa == 1 && pc0 == '*') break;   // empty path: left to the general kernel
-            LineRec Rr;
-            Rr.qn_b = qn_b; Rr.qlen = qlen; Rr.mapq = F.mapq; Rr.m = m; Rr.b = b;
-            Rr.tp_a = tp_a; Rr.tp_b = tp_b; Rr.rc_a = rc_a; Rr.rc_b = rc_b;
-            Rr.gi_n = gi_fast(m, b, Rr.gi);
-            if (Rr.gi_n == 0) break;
-            F.rconst = line_const_len(Rr, p10);
-            // gi as floor(m / b * 1000 + 0.5) recovered from the text gi_fast produced ("0", "1" or "0.ddd")
-            F.gi = Rr.gi_n == 1 ? ((u32)(Rr.gi & 0xff) == '1' ? 1000u : 0u)
-                                : 100u * ((u32)(Rr.gi >> 16) & 0xfu) + (Rr.gi_n > 3 ? 10u * ((u32)(Rr.gi >> 24) & 0xfu) : 0u) + (Rr.gi_n > 4 ? ((u32)(Rr.gi >> 32) & 0xfu) : 0u);
+            // gi = floor(m / b * 1000 + 0.5) / 1000 printed with %g (gaf2paf_main.cpp:248-253).  In integers:
+            // K = (2000 m + b) / (2 b).  The reference's three rounded double operations can only differ from it when
+            // m / b * 1000 + 0.5 is an integer exactly (any other value is >= 1 / (2 b) > 2e-10 away from one, the rounding
+            // error is < 4e-13): those ties, and large m, take the double path of k_rec.
+            u32 gk, gi_n;
+            if (b <= 0) { gk = 0; gi_n = 1; }
+            else {
+                bool exact = false;
+                gk = 0;
+                if (m < (1 << 20)) {
+                    const u32 num = 2000u * (u32)m + (u32)b, den = 2u * (u32)b;
+                    gk = num / den;
+                    exact = num - gk * den != 0u;
+                }
+                if (!exact) {
+                    u64 pack;
+                    const u32 n1 = gi_fast(m, b, pack);
+                    if (n1 == 0) break;
+                    gk = n1 == 1 ? ((u32)(pack & 0xff) == '1' ? 1000u : 0u) : 100u * ((u32)(pack >> 16) & 0xfu) + 10u * ((u32)(pack >> 24) & 0xfu) + ((u32)(pack >> 32) & 0xfu);
+                }
+                if (gk > 1000u) break;
+                const u32 r100 = gk % 100u;
+                gi_n = gk == 0u || gk == 1000u ? 1u : (gk % 10u ? 5u : (r100 ? 4u : 3u));
+            }
+            F.gi = gk;
+            // bytes of a line that do not depend on the step (line_const_len of k_rec; the verbatim columns by their text length)
+            F.rconst = F.pfx_len - 2u + 12u + dlen_i32(F.mapq, p10) + (tp_b ? 4u + (tp_b - tp_a) : 0u) + (rc_b ? 4u + (rc_b - rc_a) : 0u) +
+                       6u + F.m_len + 6u + F.b_len + 6u + gi_n + 6u + 1u;
             F.start = rtpos;
             F.tp_a = tp_a; F.tp_len = tp_b - tp_a; F.rc_a = rc_a; F.rc_len = rc_b - rc_a;
             frec_store(s_info + 2u * rec, F);
             // ---- count the path steps
-            if (prefixed) {
-                for (u32 k = pa; k < pb; ++k) { const u8 ch = rt[k]; ns += (u32)(ch == '>' || ch == '<'); }
+            if (prefixed) {   // '<' = 0x3C, '>' = 0x3E: (byte & 0xFD) == 0x3C, four bytes per trip on aligned words
+                const uintptr_t a0 = reinterpret_cast<uintptr_t>(rt + pa), a1 = reinterpret_cast<uintptr_t>(rt + pb);
+                const u32* q = reinterpret_cast<const u32*>(a0 & ~(uintptr_t)3);
+                const u32* qe2 = reinterpret_cast<const u32*>((a1 + 3u) & ~(uintptr_t)3);
+                const u32 head_skip = (u32)(a0 & 3u), tail_skip = (u32)((0u - (u32)a1) & 3u);
+                for (const u32* w = q; w < qe2; ++w) {
+                    u32 mk = zero_bytes((*w & 0xFDFDFDFDu) ^ 0x3C3C3C3Cu);
+                    if (w == q) mk &= 0xffffffffu << (8u * head_skip);
+                    if (w + 1 == qe2 && tail_skip) mk &= 0xffffffffu >> (8u * tail_skip);
+                    ns += (u32)__popc(mk);
+                }
             } else ns = 1;
             ok = true;
         } while (0);
@@ -860,6 +922,18 @@ __global__ void __launch_bounds__(kFThreads, C::kCtas) k_fuse(const FuseArgs a) 
     const u64 obase = s_obase;
     if (obase + tile_bytes > a.out_cap || *g_fallback) return;   // nothing may be written (the host grows the buffer / runs the general pipeline)
 
+    if (C::kDirect) {   // ---------------- I (direct): every line straight to its place in the output
+        for (u32 k = tid; k < nlines; k += kFThreads) {
+            const u32 slot = s_lidx[k];
+            const u32 o = s_off[slot], l = s_off[slot + 1] - o;
+            const uint4* sl = s_slots + 3u * slot;
+            const uint4 v0 = sl[0], v1 = sl[1], v2 = sl[2];
+            FRec F;
+            frec_load(s_info + 2u * (v2.w & 0xffffu), F);
+            fuse_write_line(a.out + obase + o, l, text, F, v0, v1, v2);
+        }
+        return;
+    }
     // ---------------- I: format and store, in rounds of at most kFThreads lines and kFStage bytes
     u32 done = 0;
     while (done < nlines) {

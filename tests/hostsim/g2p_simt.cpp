@@ -76,7 +76,10 @@ int main(int argc, char** argv) {
                 case 2: hs::launch(dim3(ftiles), dim3(kFThreads), FuseCfg2::kSmem, [&] { k_fuse<FuseCfg2>(fa); }); break;
                 case 3: hs::launch(dim3(ftiles), dim3(kFThreads), FuseCfg3::kSmem, [&] { k_fuse<FuseCfg3>(fa); }); break;
                 case 4: hs::launch(dim3(ftiles), dim3(kFThreads), FuseCfg4::kSmem, [&] { k_fuse<FuseCfg4>(fa); }); break;
-                default: hs::launch(dim3(ftiles), dim3(kFThreads), FuseCfg5::kSmem, [&] { k_fuse<FuseCfg5>(fa); }); break;
+                case 5: hs::launch(dim3(ftiles), dim3(kFThreads), FuseCfg5::kSmem, [&] { k_fuse<FuseCfg5>(fa); }); break;
+                case 6: hs::launch(dim3(ftiles), dim3(kFThreads), FuseCfg6::kSmem, [&] { k_fuse<FuseCfg6>(fa); }); break;
+                case 7: hs::launch(dim3(ftiles), dim3(kFThreads), FuseCfg7::kSmem, [&] { k_fuse<FuseCfg7>(fa); }); break;
+                default: hs::launch(dim3(ftiles), dim3(kFThreads), FuseCfg8::kSmem, [&] { k_fuse<FuseCfg8>(fa); }); break;
             }
             if (fm.fallback) {
                 if (!(fm.fallback & kFuseNotConvertible) && fuse_cfg_denser(cfg) >= 0) { cfg = fuse_cfg_denser(cfg); continue; }

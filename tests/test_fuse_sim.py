@@ -60,7 +60,7 @@ def test_every_alignment_of_a_tile_boundary():
         assert out == ref, "shift %d" % shift
 
 
-@pytest.mark.parametrize("cfg", ["1", "2", "3", "4", "5"])
+@pytest.mark.parametrize("cfg", ["1", "2", "3", "4", "5", "6", "7"])
 def test_other_configurations(cfg):
     """The tuning alternatives (24 KiB tiles; 16 KiB tiles with three CTAs per SM) and the dense-input configurations."""
     p = H.preset("short", seed=19, pct_star=1)
