@@ -143,7 +143,9 @@ struct Chunk {
 
 struct Pipeline {
     std::vector<g2p_ctx*> ctx;          // one per GPU
-    size_t chunk_bytes = 128u << 20;
+    size_t chunk_bytes = 16u << 20;
+    bool chunk_auto = true;             // size the chunks from the records: short reads 16 MB (small pinned buffers, early overlap of
+                                        // read / convert / write), long records up to 512 MB (a GPU call must hold enough of them)
     const char* tool = "gaf2paf";
     // one C-ABI call: fills c.out, c.res (and c.err_text); returns G2P_*
     std::function<int(g2p_ctx*, Chunk&)> convert;
@@ -207,6 +209,14 @@ struct Pipeline {
                 if (regular) {
                     const size_t size = (size_t)st.st_size;
                     size_t pos = 0;
+                    if (chunk_auto) {   // mean record length of the first MiB
+                        std::vector<char> probe(std::min<size_t>(size, 1u << 20));
+                        const ssize_t got = ::pread(fd, probe.data(), probe.size(), 0);
+                        size_t nl = 1;
+                        for (ssize_t i = 0; i < got; ++i) nl += probe[i] == '\n';
+                        const size_t mean = got > 0 ? (size_t)got / nl : 128;
+                        chunk_bytes = std::min<size_t>(std::max<size_t>(mean * 65536u, 16u << 20), 512u << 20);
+                    }
                     while (pos < size) {
                         Chunk* c = acquire();
                         if (!c) { aborted = true; break; }

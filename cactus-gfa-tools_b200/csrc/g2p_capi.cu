@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -143,8 +144,13 @@ struct g2p_ctx {
     bool size_kernel_short = false;  // G2P_SIZE_KERNEL=short: k_short (8 lanes per record) instead of k_rec (thread per record)
     uint32_t rec_chunks_override = 0; // G2P_REC_CHUNKS: k_rec slot capacity in 16-byte chunks
     uint64_t desc_cap_override = 0;  // G2P_DESC_CAP (tests): line-descriptor slots, to exercise the overflow fallback
-    bool use_fuse = true;            // G2P_FUSE=0: skip the one-pass kernel k_fuse, always run the general pipeline
-    int fuse_cfg = 0;                // k_fuse configuration (tile bytes, table sizes; g2p_fuse.cuh); moves to a denser one, and stays there, when a tile
+    int fuse_mode = 1;               // G2P_FUSE: 0 never run the one-pass kernel k_fuse; 2 always try it first; 1 (default) when it pays:
+                                     // k_fuse takes records of up to 1000 bytes at one speed, the two-pass pipeline is faster on records its
+                                     // thread-per-record size pass k_rec takes (<= 240 bytes: 7.2 vs 9.3 ms per 10 M records) and ~9x slower on
+                                     // longer ones (k_long) -- so: mean record length > 200 bytes, or the previous call sent > 1/32 of its
+                                     // records to k_long
+    std::atomic<int> prefer_fuse{0};
+    int fuse_cfg = 6;                // k_fuse configuration (tile bytes, table sizes; g2p_fuse.cuh); moves to a denser one, and stays there, when a tile
                                      // holds more records / path steps than its tables (G2P_FUSE_CFG picks the first one)
     uint64_t fuse_out_cap_override = 0;   // G2P_FUSE_OUT_CAP (tests): initial output capacity of k_fuse, to exercise the grow-and-rerun path
     void set_err(const std::string& m) { std::lock_guard<std::mutex> g(err_mu); err = m; }
@@ -245,7 +251,7 @@ int g2p_create(int device, g2p_ctx** out) {
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
     if (const char* c = std::getenv("G2P_ONE_PASS_INDEX")) ctx->two_pass_index = std::atoi(c) == 0;
     if (const char* c = std::getenv("G2P_DESC_CAP")) ctx->desc_cap_override = std::strtoull(c, nullptr, 10);
-    if (const char* c = std::getenv("G2P_FUSE")) ctx->use_fuse = std::atoi(c) != 0;
+    if (const char* c = std::getenv("G2P_FUSE")) ctx->fuse_mode = std::min(2, std::max(0, std::atoi(c)));
     if (const char* c = std::getenv("G2P_FUSE_OUT_CAP")) ctx->fuse_out_cap_override = std::strtoull(c, nullptr, 10);
     cudaFuncSetAttribute(k_fuse<FuseCfg0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FuseCfg0::kSmem);
     cudaFuncSetAttribute(k_fuse<FuseCfg1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FuseCfg1::kSmem);
@@ -388,9 +394,10 @@ static void launch_fuse(int cfg, u32 ntiles, cudaStream_t st, const FuseArgs& fa
     }
 }
 
-static int run_fused(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cudaStream_t st, g2p_result* res, u8** d_out, bool* done) {
+static int run_fused(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cudaStream_t st, g2p_result* res, u8** d_out, bool* done, bool* not_convertible) {
     *done = false;
-    if (!ctx->use_fuse || n == 0) return G2P_OK;
+    *not_convertible = false;
+    if (n == 0) return G2P_OK;
     const FuseMeta* hm = static_cast<const FuseMeta*>(w.h_fmeta.p);
     if (w.d_out.cap == 0 || ctx->fuse_out_cap_override) G2P_CUDA(w.d_out.ensure(ctx->fuse_out_cap_override ? (size_t)ctx->fuse_out_cap_override : n * 3 + (1u << 20)));
     G2P_CUDA(cudaEventRecord(w.ev[5], st));
@@ -415,6 +422,8 @@ static int run_fused(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cudaStr
         if (hm->fallback) {
             // only capacity reasons (records or path steps per tile): a smaller tile converts the same input
             if (!(hm->fallback & kFuseNotConvertible) && fuse_cfg_denser(cfg) >= 0) { ctx->fuse_cfg = fuse_cfg_denser(cfg); continue; }
+            *not_convertible = (hm->fallback & kFuseNotConvertible) != 0;
+            cudaEventElapsedTime(&res->fused_ms, w.ev[5], w.ev[6]);   // (time spent on the attempt; n_fused stays 0)
             return G2P_OK;
         }
         if (!hm->overflow) {
@@ -422,7 +431,7 @@ static int run_fused(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cudaStr
             res->out_bytes = hm->out_total;
             res->n_fused = hm->n_records;
             cudaEventElapsedTime(&res->fused_ms, w.ev[5], w.ev[6]);
-            res->device_ms = res->fused_ms;
+            res->device_ms += res->fused_ms;
             *d_out = static_cast<u8*>(w.d_out.p);
             *done = true;
             return G2P_OK;
@@ -438,10 +447,12 @@ static int run_fused(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cudaStr
 static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cudaStream_t st, g2p_result* res, u8** d_out) {
     std::memset(res, 0, sizeof *res);
     *d_out = nullptr;
-    {
+    bool fuse_tried = false, fuse_nc = false;
+    if (ctx->fuse_mode == 2) {   // always: before anything else
         bool done = false;
-        int frc = run_fused(ctx, w, d_gaf, n, st, res, d_out, &done);
+        int frc = run_fused(ctx, w, d_gaf, n, st, res, d_out, &done, &fuse_nc);
         if (frc || done) return frc;
+        fuse_tried = true;
     }
     uint32_t launches = res->gpu_launches;
     G2P_CUDA(cudaEventRecord(w.ev[0], st));
@@ -452,6 +463,20 @@ static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
     PipelineMeta* d_meta = static_cast<PipelineMeta*>(w.d_meta.p);
     const u32 nrec = hm->n_records;
     res->n_records = nrec;
+    if (ctx->fuse_mode == 1 && nrec && ((u64)n / nrec > 200 || ctx->prefer_fuse.load())) {   // when it pays (see g2p_ctx::fuse_mode)
+        res->gpu_launches = launches;
+        bool done = false;
+        int frc = run_fused(ctx, w, d_gaf, n, st, res, d_out, &done, &fuse_nc);
+        if (frc) return frc;
+        if (done) {
+            cudaEventElapsedTime(&res->index_ms, w.ev[0], w.ev[1]);
+            res->device_ms += res->index_ms;
+            return G2P_OK;
+        }
+        launches = res->gpu_launches;
+        fuse_tried = true;
+        if (fuse_nc) ctx->prefer_fuse.store(0);
+    }
     if (nrec == 0) {
         G2P_CUDA(w.d_out.ensure(256));
         *d_out = static_cast<u8*>(w.d_out.p);
@@ -475,9 +500,9 @@ static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
     const u32 nlong = (u32)ctx->n_sm * 6u;
     const u32 nlist = std::min<u32>((nrec + kListThreads - 1) / kListThreads, (u32)ctx->n_sm * 16u);
     // line descriptors: k_short's records own kSMaxLines slots each (sparse, addressed through the
-    // line map); k_long reserves 32-slot blocks in a dense array (~1 line per 40 bytes of text) and
-    // falls back to its streaming emit when that array is full
-    const u64 desc_cap64 = std::min<u64>((u64)n / 16 + 1024, 0xFFFFFF00ULL);
+    // line map); k_long reserves one block per batch in a dense array, as many slots as the batch has lines
+    // (~1 line per 40 bytes of text), and falls back to its streaming emit when that array is full
+    const u64 desc_cap64 = std::min<u64>((u64)n / 8 + 2048, 0xFFFFFF00ULL);   // two halves: full batches / small batches
     const u32 desc_cap = ctx->desc_cap_override ? (u32)std::min<u64>(ctx->desc_cap_override, desc_cap64) : (u32)desc_cap64;
     G2P_CUDA(w.d_desc.ensure((size_t)desc_cap * sizeof(LineDesc)));
     G2P_CUDA(w.d_sdesc.ensure((size_t)nrec * kSMaxLines * sizeof(LineDesc)));
@@ -489,7 +514,7 @@ static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
     u64* d_loff = static_cast<u64*>(w.d_loff.p);
     ShortArgs sa{d_gaf, (u64)n, d_rec, nrec, ctx->table, d_off, d_loff, d_status, d_list, &d_meta->n_deleg, d_sdesc, d_rdesc};
     LongArgs la{d_gaf, (u64)n, d_rec, ctx->table, d_off, d_status, nullptr, d_list, &d_meta->n_deleg, d_list2, &d_meta->n_deleg2,
-                d_desc, d_rdesc, &d_meta->n_desc, desc_cap, &d_meta->legacy_long, &d_meta->long_cursor};
+                d_desc, d_rdesc, &d_meta->n_desc, &d_meta->n_desc2, desc_cap, &d_meta->legacy_long, &d_meta->long_cursor};
 
     // pass 1: sizes, status, line descriptors.  k_short takes the short canonical records, k_long
     // what it left, the general kernel what neither converts (non-canonical or erroneous records).
@@ -543,10 +568,17 @@ static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
         k_emit_lines<false><<<(nl + kEThreads - 1) / kEThreads, kEThreads, kEmitSmem, st>>>(ea);
         ++launches;
     }
-    const u32 n_slots = std::min<u32>(hm->n_desc, desc_cap);
-    if (n_slots) {           // k_long's records: dense 32-slot blocks
+    const u32 half = desc_cap / 2u;
+    const u32 n_slots = std::min<u32>(hm->n_desc, half);
+    if (n_slots) {           // k_long's records, full batches: dense 32-slot blocks
         EmitArgs ea{d_gaf, (u64)n, d_rec, d_off, d_desc, nullptr, d_rdesc, d_status, n_slots, d_o};
         k_emit_lines<true><<<(n_slots + kEThreads - 1) / kEThreads, kEThreads, kEmitSmem, st>>>(ea);
+        ++launches;
+    }
+    const u32 n_slots2 = std::min<u32>(hm->n_desc2, desc_cap - half);
+    if (n_slots2) {          // ... and their small batches
+        EmitArgs ea{d_gaf, (u64)n, d_rec, d_off, d_desc + half, nullptr, d_rdesc, d_status, n_slots2, d_o};
+        k_emit_lines<true><<<(n_slots2 + kEThreads - 1) / kEThreads, kEThreads, kEmitSmem, st>>>(ea);
         ++launches;
     }
     if (hm->legacy_long) {   // records k_long could not describe (descriptor array full)
@@ -577,8 +609,11 @@ static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
     cudaEventElapsedTime(&res->index_ms, w.ev[0], w.ev[1]);
     cudaEventElapsedTime(&res->size_ms, w.ev[1], w.ev[2]);
     cudaEventElapsedTime(&res->emit_ms, w.ev[3], w.ev[4]);
-    cudaEventElapsedTime(&res->device_ms, ctx->use_fuse && n ? w.ev[5] : w.ev[0], w.ev[4]);
+    cudaEventElapsedTime(&res->device_ms, fuse_tried ? w.ev[5] : w.ev[0], w.ev[4]);
+    if (fuse_tried && ctx->fuse_mode == 1) cudaEventElapsedTime(&res->device_ms, w.ev[0], w.ev[4]);   // (the attempt came after the index)
     res->gpu_launches = launches;
+    // many records needed k_long and nothing says k_fuse cannot take them: try it first next time
+    if (ctx->fuse_mode == 1 && !fuse_nc) ctx->prefer_fuse.store((u64)res->n_long * 32u > nrec ? 1 : 0);
     *d_out = d_o;
     return G2P_OK;
 }

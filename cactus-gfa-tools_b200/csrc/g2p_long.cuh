@@ -237,6 +237,7 @@ struct LongArgs {
     LineDesc* desc;        // size pass: line descriptors for k_emit_lines (one padded 32-slot block per batch)
     RecDesc* rdesc;
     u32* n_desc;
+    u32* n_desc2;          // small batches (<= 16 lines) take blocks from the upper half of the array: desc_cap / 2 + ...
     u32 desc_cap;
     u32* need_legacy;      // set when a record could not be described (array full): k_long<true> emits it
     u32* cursor;           // size pass: shared cursor into `list` (warps take the next record when they are free)
@@ -548,19 +549,28 @@ __device__ __forceinline__ void long_record(const LongArgs& a, LWarpMemT<EMIT>* 
             const u32 lincl = wscan32(line, lane);
             const u32 btot = __shfl_sync(FULL, lincl, 31);
             if (!EMIT && btot && !desc_fail) {
-                // describe the batch's lines for k_emit_lines: one 32-slot block, lines first
+                // describe the batch's lines for k_emit_lines.  Full batches take one 32-slot block from the lower half of
+                // the array (one block = one warp of k_emit_lines = one contiguous run of the output); batches of at most
+                // 16 lines (the only batch of a 250-1000 byte record, the last batch of a long one) take as many slots as
+                // they have lines, rounded up to four, from the upper half -- a fixed 32 per batch starved such records.
+                const u32 em = __ballot_sync(FULL, emit_line);
+                const u32 nem = (u32)__popc(em);
+                const bool small = nem <= 16u;
+                const u32 nalloc = small ? (nem + 3u) & ~3u : 32u;
+                const u32 half = a.desc_cap / 2u;
                 u32 base = 0;
-                if (lane == 0) base = atomicAdd(a.n_desc, 32u);
+                if (lane == 0) base = atomicAdd(small ? a.n_desc2 : a.n_desc, nalloc);
                 base = __shfl_sync(FULL, base, 0);
                 const u64 lo64 = run + (lincl - line);
-                if (base > a.desc_cap || a.desc_cap - base < 32u || run + btot > 0xffffffffULL) {
+                const u32 room = small ? a.desc_cap - half : half;
+                LineDesc* blk = a.desc + (small ? half : 0u) + base;
+                if (base > room || room - base < nalloc || run + btot > 0xffffffffULL) {
                     desc_fail = true;
-                    if (base < a.desc_cap) { const u32 k = base + lane; if (k < a.desc_cap) a.desc[k].rec = kDescInvalid; }
+                    if (base < room && lane < nalloc && base + lane < room) blk[lane].rec = kDescInvalid;
                 } else {
-                    const u32 em = __ballot_sync(FULL, emit_line);
                     const u32 rank = (u32)__popc(em & ((1u << lane) - 1u));
-                    if (emit_line) store_line_desc(a.desc + base + rank, r, (u32)lo64, line, Ls);
-                    if (lane >= (u32)__popc(em)) a.desc[base + lane].rec = kDescInvalid;
+                    if (emit_line) store_line_desc(blk + rank, r, (u32)lo64, line, Ls);
+                    if (lane >= nem && lane < nalloc) blk[lane].rec = kDescInvalid;
                 }
             }
             if (EMIT && btot) {

@@ -853,7 +853,15 @@ __global__ void __launch_bounds__(kEThreads, DENSE ? 3 : 4) k_emit_lines(const E
         o = obase + d.loff;
         unpack_rec_desc(r0, r1, r2, R);
     }
-    if (DENSE) stage_text(__shfl_sync(FULL, rs, first), __shfl_sync(FULL, re, last));
+    if (DENSE) {   // the warp's slots may belong to several records in any order (small batches): stage the span that covers them all
+        u32 t0 = valid ? rs : 0xffffffffu, t1 = valid ? re : 0u;
+        for (int o2 = 16; o2 > 0; o2 >>= 1) {
+            const u32 x0 = __shfl_xor_sync(FULL, t0, o2), x1 = __shfl_xor_sync(FULL, t1, o2);
+            t0 = x0 < t0 ? x0 : t0;
+            t1 = x1 > t1 ? x1 : t1;
+        }
+        stage_text(t0, t1);
+    }
     if (text_staged) {
 #if !defined(G2P_HOSTSIM)
         if (text_tma) {

@@ -10,7 +10,7 @@
 //   G2P_GPUS=N        shard the input over the first N GPUs of the box by newline-aligned
 //                     byte ranges; outputs are concatenated in input order (default 1)
 //   G2P_DEVICE=K      first device ordinal (default 0)
-//   G2P_CHUNK_MB=M    bytes of GAF per GPU call (default 128)
+//   G2P_CHUNK_MB=M    bytes of GAF per GPU call (default: 16 for short records, up to 512 for long ones)
 //   G2P_IO_THREADS=T  threads of the parallel pread / pwrite of regular files (default: half the cores, <= 16)
 //   G2P_STATS=1       timing summary on stderr
 //
@@ -81,13 +81,14 @@ int main(int argc, char** argv) {
 
     const int ngpu = (int)std::max(1L, cli::env_long("G2P_GPUS", 1));
     const int dev0 = (int)cli::env_long("G2P_DEVICE", 0);
-    size_t chunk = (size_t)std::max(1L, cli::env_long("G2P_CHUNK_MB", 128)) << 20;
+    size_t chunk = (size_t)std::max(1L, cli::env_long("G2P_CHUNK_MB", 16)) << 20;
     if (cli::env_long("G2P_CHUNK_BYTES", 0) > 0) chunk = (size_t)cli::env_long("G2P_CHUNK_BYTES", 0);   // tests: tiny chunks
     const bool stats = cli::env_long("G2P_STATS", 0) != 0;
 
     cli::Pipeline P;
     P.tool = "gaf2paf";
     P.chunk_bytes = chunk;
+    P.chunk_auto = !getenv("G2P_CHUNK_MB") && !getenv("G2P_CHUNK_BYTES");
     // one context per GPU, created concurrently (CUDA context creation is the bulk of the start-up time)
     P.ctx.assign(ngpu, nullptr);
     std::vector<int> crc(ngpu, G2P_OK), lrc(ngpu, G2P_OK);

@@ -7,7 +7,7 @@
 //     -g, --rgfa FILE   (uncompressed) minigraph rGFA
 //     -o FILE           write "node<TAB>length" for every rGFA node (input of gaf2paf -l)
 //
-// Environment: G2P_DEVICE=K (device ordinal), G2P_CHUNK_MB=M (bytes of GAF per GPU call, default 128),
+// Environment: G2P_DEVICE=K (device ordinal), G2P_CHUNK_MB=M (bytes of GAF per GPU call; default 16 for short records, up to 512 for long ones),
 // G2P_IO_THREADS=T.  Host side: the reader -> converter -> writer pipeline of cli_pipeline.hpp.
 #include <fcntl.h>
 #include <getopt.h>
@@ -128,11 +128,12 @@ int main(int argc, char** argv) {
         fclose(o);
     }
 
-    size_t chunk = (size_t)std::max(1L, cli::env_long("G2P_CHUNK_MB", 128)) << 20;
+    size_t chunk = (size_t)std::max(1L, cli::env_long("G2P_CHUNK_MB", 16)) << 20;
     if (cli::env_long("G2P_CHUNK_BYTES", 0) > 0) chunk = (size_t)cli::env_long("G2P_CHUNK_BYTES", 0);   // tests: tiny chunks
     cli::Pipeline P;
     P.tool = "gaf2unstable";
     P.chunk_bytes = chunk;
+    P.chunk_auto = !getenv("G2P_CHUNK_MB") && !getenv("G2P_CHUNK_BYTES");
     P.ctx.push_back(ctx);
     P.convert = [](g2p_ctx* cx, cli::Chunk& c) {
         int r = g2p_unstable_host(cx, c.buf, c.n, &c.out, &c.res);

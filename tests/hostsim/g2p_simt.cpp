@@ -56,9 +56,13 @@ int main(int argc, char** argv) {
     u8* gaf = reinterpret_cast<u8*>(gaf_buf.data());
     std::memcpy(gaf, gaf_s.data(), n);
 
-    // ---- the one-pass kernel first (run_fused of g2p_capi.cu); G2P_FUSE=0 skips it
-    if (n && !(std::getenv("G2P_FUSE") && std::atoi(std::getenv("G2P_FUSE")) == 0)) {
-        int cfg = std::getenv("G2P_FUSE_CFG") ? std::atoi(std::getenv("G2P_FUSE_CFG")) : 0;
+    // ---- the one-pass kernel (run_fused of g2p_capi.cu).  G2P_FUSE as in g2p_create: 0 never, 2 always, default: when the
+    // mean record length exceeds 200 bytes
+    const int fuse_mode = std::getenv("G2P_FUSE") ? std::atoi(std::getenv("G2P_FUSE")) : 1;
+    u64 n_nl = 0;
+    for (u64 i = 0; i < n; ++i) n_nl += gaf[i] == '\n';
+    if (n && (fuse_mode == 2 || (fuse_mode == 1 && n / (n_nl ? n_nl : 1) > 200))) {
+        int cfg = std::getenv("G2P_FUSE_CFG") ? std::atoi(std::getenv("G2P_FUSE_CFG")) : 6;
         u64 cap = std::getenv("G2P_FUSE_OUT_CAP") ? (u64)std::atoll(std::getenv("G2P_FUSE_OUT_CAP")) : n * 3 + (1u << 20);
         bool grown = false;
         for (;;) {
@@ -130,7 +134,7 @@ int main(int argc, char** argv) {
     const u32 ncta = (nrec + kShortRecsPerCta - 1) / kShortRecsPerCta;
     const u32 nlist = std::min<u32>((nrec + kListThreads - 1) / kListThreads, 8u);
     // G2P_SIMT_DESC_CAP=<slots> shrinks k_long's descriptor array to exercise the overflow fallback
-    const u32 desc_cap = std::getenv("G2P_SIMT_DESC_CAP") ? (u32)std::atol(std::getenv("G2P_SIMT_DESC_CAP")) : (u32)(n / 16) + 1024;
+    const u32 desc_cap = std::getenv("G2P_SIMT_DESC_CAP") ? (u32)std::atol(std::getenv("G2P_SIMT_DESC_CAP")) : (u32)(n / 8) + 2048;
     std::vector<LineDesc> desc(desc_cap + 1), sdesc((size_t)nrec * kSMaxLines);
     std::vector<RecDesc> rdesc(nrec);
     std::vector<u64> loff(nrec + 1);
@@ -158,7 +162,7 @@ int main(int argc, char** argv) {
         hs::launch(dim3((nrec + kRThreads - 1) / kRThreads), dim3(kRThreads), rec_smem(chunks), [&] { k_rec(ra); });
     }
     LongArgs la{gaf, n, rec.data(), T, off.data(), status.data(), nullptr, list.data(), &meta.n_deleg, list2.data(), &meta.n_deleg2,
-                desc.data(), rdesc.data(), &meta.n_desc, desc_cap, &meta.legacy_long, &meta.long_cursor};
+                desc.data(), rdesc.data(), &meta.n_desc, &meta.n_desc2, desc_cap, &meta.legacy_long, &meta.long_cursor};
     const u32 nlong = 2;
     hs::launch(dim3(nlong), dim3(kLThreads), long_smem<false>(), [&] { k_long<false>(la); });
     hs::launch(dim3(nlist), dim3(kListThreads), 0, [&] { k_convert_list<false>(gaf, rec.data(), T, off.data(), status.data(), nullptr, &meta, list2.data(), &meta.n_deleg2); });
@@ -176,10 +180,16 @@ int main(int argc, char** argv) {
         EmitArgs ea{gaf, n, rec.data(), off.data(), sdesc.data(), map.data(), rdesc.data(), status.data(), nl, out.data()};
         hs::launch(dim3((nl + kEThreads - 1) / kEThreads), dim3(kEThreads), kEmitSmem, [&] { k_emit_lines<false>(ea); });
     }
-    const u32 n_slots = std::min<u32>(meta.n_desc, desc_cap);
+    const u32 half = desc_cap / 2u;
+    const u32 n_slots = std::min<u32>(meta.n_desc, half);
     if (n_slots) {
         EmitArgs ea{gaf, n, rec.data(), off.data(), desc.data(), nullptr, rdesc.data(), status.data(), n_slots, out.data()};
         hs::launch(dim3((n_slots + kEThreads - 1) / kEThreads), dim3(kEThreads), kEmitSmem, [&] { k_emit_lines<true>(ea); });
+    }
+    const u32 n_slots2 = std::min<u32>(meta.n_desc2, desc_cap - half);
+    if (n_slots2) {
+        EmitArgs ea{gaf, n, rec.data(), off.data(), desc.data() + half, nullptr, rdesc.data(), status.data(), n_slots2, out.data()};
+        hs::launch(dim3((n_slots2 + kEThreads - 1) / kEThreads), dim3(kEThreads), kEmitSmem, [&] { k_emit_lines<true>(ea); });
     }
     if (meta.legacy_long) hs::launch(dim3(nlong), dim3(kLThreads), long_smem<true>(), [&] { k_long<true>(la); });
     if (meta.n_deleg2)
@@ -189,7 +199,7 @@ int main(int argc, char** argv) {
         hs::launch(dim3(1), dim3(1), 0, [&] { k_diagnose(gaf, rec.data(), T, off.data(), &meta); });
         out_bytes = meta.err_out_end;
     }
-    if (std::getenv("G2P_SIMT_STATS")) std::fprintf(stderr, "g2p_simt: %u records, %u to k_long, %u to the general kernel, %llu short lines, %u long line slots (cap %u), %llu bytes out\n", nrec, meta.n_deleg, meta.n_deleg2, (unsigned long long)meta.lines_total, meta.n_desc, desc_cap, (unsigned long long)out_bytes);
+    if (std::getenv("G2P_SIMT_STATS")) std::fprintf(stderr, "g2p_simt: %u records, %u to k_long, %u to the general kernel, %llu short lines, %u + %u long line slots (cap %u), %llu bytes out\n", nrec, meta.n_deleg, meta.n_deleg2, (unsigned long long)meta.lines_total, meta.n_desc, meta.n_desc2, desc_cap, (unsigned long long)out_bytes);
     std::fwrite(out.data(), 1, out_bytes, stdout);
     std::fflush(stdout);
     if (meta.first_err != 0xFFFFFFFFu) {

@@ -15,7 +15,7 @@ TILE = 32768
 
 
 def simt(gaf, lengths, env=None):
-    e = dict(os.environ, G2P_SIMT_STATS="1")
+    e = dict(os.environ, G2P_SIMT_STATS="1", G2P_FUSE="2")   # always try k_fuse first (the default does when it pays)
     e.update(env or {})
     with tempfile.TemporaryDirectory() as td:
         lp = os.path.join(td, "l.tsv")
@@ -111,6 +111,31 @@ def test_falls_back_to_the_general_pipeline(kind):
         assert out == ref
     if rc == 1:
         assert err.splitlines()[-1] + "\n" == rerr
+
+
+def test_default_dispatch_picks_the_kernel_that_pays():
+    """G2P_FUSE unset: records of <= 240 bytes stay with the two-pass pipeline (k_rec), 250-500 byte records go to k_fuse."""
+    for name, want in (("short", "to k_long"), ("tagged", "k_fuse converted")):
+        p = H.preset(name, seed=41)
+        lengths = H.gen_lengths(p)
+        gaf = H.gen_records(p, 0, 2500, threads=1)
+        e = dict(os.environ, G2P_SIMT_STATS="1")
+        e.pop("G2P_FUSE", None)
+        with tempfile.TemporaryDirectory() as td:
+            lp = os.path.join(td, "l.tsv")
+            open(lp, "wb").write(lengths)
+            pr = subprocess.run([SIMT, "-l", lp, "-"], input=gaf, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=e)
+        rrc, ref, rerr, kind = H.run_gaf2paf_cpu(gaf, lengths)
+        assert pr.returncode == 0 and pr.stdout == ref
+        assert want in pr.stderr.decode(), pr.stderr.decode()
+
+
+def test_mutation_fuzz_through_k_fuse():
+    """tests/fuzz_vs_ref.py with k_fuse forced first: every mutated record is either converted by it identically or handed on."""
+    env = dict(os.environ, G2P_FUSE="2")
+    pr = subprocess.run([os.sys.executable, os.path.join(H.ROOT, "tests", "fuzz_vs_ref.py"), "--n", "400", "--seed", "3", "--bin", SIMT],
+                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env)
+    assert pr.returncode == 0 and b" 0 mismatches" in pr.stdout, pr.stdout[-500:]
 
 
 def test_general_pipeline_alone_still_matches():

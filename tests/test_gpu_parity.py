@@ -439,10 +439,11 @@ def test_late_delegation(g2p):
 
 
 @pytest.mark.parametrize("env", [
-    {},                                            # default: the one-pass kernel k_fuse (32 KiB tiles)
-    {"G2P_FUSE_CFG": "1"},                         # k_fuse on 24 KiB tiles
-    {"G2P_FUSE_CFG": "2"},                         # 16 KiB tiles, three CTAs per SM
-    {"G2P_FUSE_CFG": "4", "G2P_FUSE_OUT_CAP": "65536"},   # 8 KiB tiles; the output buffer starts too small: grow and run again
+    {},                                            # default dispatch (k_fuse when it pays, else the two-pass pipeline)
+    {"G2P_FUSE": "2"},                             # the one-pass kernel k_fuse first, default configuration (24 KiB tiles, direct stores)
+    {"G2P_FUSE": "2", "G2P_FUSE_CFG": "0"},        # 32 KiB tiles, staged lines + TMA bulk store
+    {"G2P_FUSE": "2", "G2P_FUSE_CFG": "2"},        # 16 KiB tiles, three CTAs per SM
+    {"G2P_FUSE": "2", "G2P_FUSE_CFG": "4", "G2P_FUSE_OUT_CAP": "65536"},   # 8 KiB tiles; the output buffer starts too small: grow and run again
     {"G2P_FUSE": "0"},                             # the general two-pass pipeline alone (k_rec + scans + k_emit_lines)
     {"G2P_FUSE": "0", "G2P_SIZE_KERNEL": "short"},                  # the 8-lanes-per-record size pass
     {"G2P_FUSE": "0", "G2P_LEN_SORT": "1"},                         # k_rec on records ordered by length class
@@ -470,7 +471,7 @@ def test_size_pass_variants(g2p, monkeypatch, env):
         assert rc == 0 and g2p.exit_code(res) == 0 and out == ref, (env, name)
         if env.get("G2P_FUSE") == "0":
             assert res.n_fused == 0
-        elif name.startswith("short") and "node_len_lo" not in over:
+        elif env.get("G2P_FUSE") == "2" and name.startswith("short") and "node_len_lo" not in over:
             assert res.n_fused == res.n_records, "short canonical records are converted by k_fuse"
 
 

@@ -73,6 +73,20 @@ def test_whole_output_md5_matches_reference(g2p, name, count, over):
     assert got == ref, "PAF md5 differs from the %s oracle" % kind
 
 
+def test_default_dispatch_sends_250_to_1000_byte_records_to_k_fuse(g2p):
+    p = H.preset("tagged", seed=15)
+    lengths = H.gen_lengths(p)
+    gaf = H.gen_records(p, 0, 50000)
+    cv = g2p.Converter(0)
+    try:
+        assert cv.load_lengths(lengths)
+        out, res = cv.convert_host(gaf)
+        assert res.n_fused == res.n_records == 50000 and res.n_long == 0
+        assert out == H.run_gaf2paf_cpu(gaf, lengths)[1]
+    finally:
+        cv.close()
+
+
 def n_gpus():
     try:
         out = subprocess.run(["nvidia-smi", "-L"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
