@@ -143,6 +143,7 @@ struct g2p_ctx {
     bool len_sort = false;           // G2P_LEN_SORT=1: global counting sort of the records by length class before k_rec (default off: in-CTA sort only)
     bool size_kernel_short = false;  // G2P_SIZE_KERNEL=short: k_short (8 lanes per record) instead of k_rec (thread per record)
     uint32_t rec_chunks_override = 0; // G2P_REC_CHUNKS: k_rec slot capacity in 16-byte chunks
+    u32 long_small_max = 8;          // G2P_LONG_SMALL: k_long batches of at most this many lines take a small descriptor block (0: always 32 slots)
     uint64_t desc_cap_override = 0;  // G2P_DESC_CAP (tests): line-descriptor slots, to exercise the overflow fallback
     int fuse_mode = 1;               // G2P_FUSE: 0 never run the one-pass kernel k_fuse; 2 always try it first; 1 (default) when it pays:
                                      // k_fuse takes records of up to 1000 bytes at one speed, the two-pass pipeline is faster on records its
@@ -250,6 +251,7 @@ int g2p_create(int device, g2p_ctx** out) {
     cudaFuncSetAttribute(k_long<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)long_smem<false>());
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
     if (const char* c = std::getenv("G2P_ONE_PASS_INDEX")) ctx->two_pass_index = std::atoi(c) == 0;
+    if (const char* c = std::getenv("G2P_LONG_SMALL")) ctx->long_small_max = (u32)std::min(16, std::max(0, std::atoi(c)));
     if (const char* c = std::getenv("G2P_DESC_CAP")) ctx->desc_cap_override = std::strtoull(c, nullptr, 10);
     if (const char* c = std::getenv("G2P_FUSE")) ctx->fuse_mode = std::min(2, std::max(0, std::atoi(c)));
     if (const char* c = std::getenv("G2P_FUSE_OUT_CAP")) ctx->fuse_out_cap_override = std::strtoull(c, nullptr, 10);
@@ -423,6 +425,8 @@ static int run_fused(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cudaStr
             // only capacity reasons (records or path steps per tile): a smaller tile converts the same input
             if (!(hm->fallback & kFuseNotConvertible) && fuse_cfg_denser(cfg) >= 0) { ctx->fuse_cfg = fuse_cfg_denser(cfg); continue; }
             *not_convertible = (hm->fallback & kFuseNotConvertible) != 0;
+            if (hm->fallback & (kFuseTimeoutLoad | kFuseTimeoutLookback))
+                std::fprintf(stderr, "libg2p: k_fuse gave up a spin wait (flags 0x%x); the general pipeline converts this block\n", hm->fallback);
             cudaEventElapsedTime(&res->fused_ms, w.ev[5], w.ev[6]);   // (time spent on the attempt; n_fused stays 0)
             return G2P_OK;
         }
@@ -463,7 +467,8 @@ static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
     PipelineMeta* d_meta = static_cast<PipelineMeta*>(w.d_meta.p);
     const u32 nrec = hm->n_records;
     res->n_records = nrec;
-    if (ctx->fuse_mode == 1 && nrec && ((u64)n / nrec > 200 || ctx->prefer_fuse.load())) {   // when it pays (see g2p_ctx::fuse_mode)
+    // when it pays (see g2p_ctx::fuse_mode); a mean above k_fuse's record limit says it cannot take the block at all
+    if (ctx->fuse_mode == 1 && nrec && (u64)n / nrec <= kFLimit && ((u64)n / nrec > 200 || ctx->prefer_fuse.load())) {
         res->gpu_launches = launches;
         bool done = false;
         int frc = run_fused(ctx, w, d_gaf, n, st, res, d_out, &done, &fuse_nc);
@@ -514,7 +519,7 @@ static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
     u64* d_loff = static_cast<u64*>(w.d_loff.p);
     ShortArgs sa{d_gaf, (u64)n, d_rec, nrec, ctx->table, d_off, d_loff, d_status, d_list, &d_meta->n_deleg, d_sdesc, d_rdesc};
     LongArgs la{d_gaf, (u64)n, d_rec, ctx->table, d_off, d_status, nullptr, d_list, &d_meta->n_deleg, d_list2, &d_meta->n_deleg2,
-                d_desc, d_rdesc, &d_meta->n_desc, &d_meta->n_desc2, desc_cap, &d_meta->legacy_long, &d_meta->long_cursor};
+                d_desc, d_rdesc, &d_meta->n_desc, &d_meta->n_desc2, desc_cap, ctx->long_small_max, &d_meta->legacy_long, &d_meta->long_cursor};
 
     // pass 1: sizes, status, line descriptors.  k_short takes the short canonical records, k_long
     // what it left, the general kernel what neither converts (non-canonical or erroneous records).

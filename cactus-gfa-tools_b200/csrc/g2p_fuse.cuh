@@ -4,7 +4,8 @@
 // (ticket counter), brings it into shared memory with one TMA bulk copy, and does everything for the records
 // that START in the tile without touching global memory again except for the lengths-table probes:
 //
-//   A  tile load        cp.async.bulk (UBLKCP) of [tile - 16, tile + kFTile + kFTail) + mbarrier
+//   A  tile load        128-bit coalesced loads of [tile - 16, tile + kFTile + kFTail) into shared memory (a TMA bulk copy with
+//                       G2P_FUSE_TMA_LOAD=1)
 //   B  line index       SWAR '\n' compare over 128-bit shared loads, block scan of the counts -> record starts
 //                       (the getline loop, gaf2paf_main.cpp:357-363)
 //   C  columns + tags   one thread per record, k_rec's scalar walk (parse_gaf_record, gafkluge.hpp:84-204);
@@ -29,6 +30,9 @@
 
 namespace g2p {
 
+#ifndef G2P_FUSE_TMA_LOAD
+#define G2P_FUSE_TMA_LOAD 0
+#endif
 constexpr int kFThreads = 256;
 constexpr u32 kFLimit = 1000;              // longest record (bytes, without '\n') converted here
 constexpr u32 kFTail = 1024;               // bytes after the tile its last record may extend into (>= kFLimit + 1)
@@ -78,7 +82,8 @@ static inline size_t fuse_cfg_smem(int cfg) {
 // the configuration to try after `cfg` reported a capacity overflow (-1: none left)
 static inline int fuse_cfg_denser(int cfg) { return cfg == 3 ? 4 : (cfg == 4 ? -1 : kFuseCfgDense); }
 
-enum : u32 { kFuseNotConvertible = 1u, kFuseTooManyRecords = 2u, kFuseTooManySteps = 4u };
+enum : u32 { kFuseNotConvertible = 1u, kFuseTooManyRecords = 2u, kFuseTooManySteps = 4u,
+             kFuseTimeoutLoad = 16u, kFuseTimeoutLookback = 32u };   // a spin wait gave up (never expected; reported, the general pipeline takes over)
 
 struct FuseMeta {
     u32 n_records;    // records seen (sum over the tiles)
@@ -130,83 +135,6 @@ __device__ __forceinline__ void frec_load(const uint4* src, FRec& r) {
 //   v2: lenE, mid_a | mid_len << 16, name_pos | nl << 16 | flags << 24, rec | codeS << 16 | codeE << 24
 // Before the walk v0.x holds tlen | interval << 31 and v2.z the step token (marker position, name length).
 constexpr u32 kFSlotRev = 1u, kFSlotMidFwd = 2u;
-
-// ---- left-to-right line writer: 32-bit words into (word-aligned) shared memory ------------------
-struct WEmit {
-    u32* wp;
-    u32 lo, sh;   // pending bytes: the low `sh` bits of lo (sh in {0, 8, 16, 24})
-    __device__ __forceinline__ void put(u32 v, u32 nbytes) {   // the nbytes low bytes of v (the rest zero), 1 <= nbytes <= 4
-        lo |= v << sh;
-        const u32 hi = __funnelshift_l(v, 0u, sh);   // what does not fit (0 when sh == 0)
-        sh += 8u * nbytes;
-        const u32 full = sh >> 5;                    // 0 or 1; straight-line code: one predicated store, selects
-        if (full) *wp = lo;
-        wp += full;
-        lo = full ? hi : lo;
-        sh &= 31u;
-    }
-    __device__ __forceinline__ void put4(u32 v) {
-        *wp++ = lo | (v << sh);
-        lo = __funnelshift_l(v, 0u, sh);
-    }
-    // n bytes from an arbitrarily aligned shared-memory address (reads up to 7 bytes past the span)
-    __device__ __forceinline__ void copy(const u8* src, u32 n) {
-        const uintptr_t sa = reinterpret_cast<uintptr_t>(src);
-        const u32* sp = reinterpret_cast<const u32*>(sa & ~(uintptr_t)3);
-        const u32 s8 = (u32)(sa & 3u) * 8u;
-        u32 prev = *sp++;
-        while (n >= 4u) {
-            const u32 cur = *sp++;
-            put4(__funnelshift_r(prev, cur, s8));
-            prev = cur;
-            n -= 4u;
-        }
-        if (n) {
-            const u32 cur = *sp;
-            put(__funnelshift_r(prev, cur, s8) & ((1u << (8u * n)) - 1u), n);
-        }
-    }
-    // n <= 8 bytes (the short verbatim fields: tag values, column texts): no loop
-    __device__ __forceinline__ void copy_small(const u8* src, u32 n) {
-        const uintptr_t sa = reinterpret_cast<uintptr_t>(src);
-        const u32* sp = reinterpret_cast<const u32*>(sa & ~(uintptr_t)3);
-        const u32 s8 = (u32)(sa & 3u) * 8u;
-        const u32 x0 = sp[0], x1 = sp[1];
-        const u32 w0 = __funnelshift_r(x0, x1, s8);
-        if (n <= 4u) { put(n == 4u ? w0 : w0 & ((1u << (8u * n)) - 1u), n); return; }
-        const u32 w1 = __funnelshift_r(x1, sp[2], s8);
-        put4(w0);
-        put(n == 8u ? w1 : w1 & ((1u << (8u * (n - 4u))) - 1u), n - 4u);
-    }
-    // decimal digits of x < 10000, zero padded to four, most significant digit in the low byte
-    static __device__ __forceinline__ u32 pack4(u32 x) {
-        const u32 d3 = x / 1000u, r3 = x - d3 * 1000u, d2 = r3 / 100u, r2 = r3 - d2 * 100u, d1 = r2 / 10u, d0 = r2 - d1 * 10u;
-        return (d3 | (d2 << 8) | (d1 << 16) | (d0 << 24)) + 0x30303030u;
-    }
-    __device__ __forceinline__ void num_unpadded4(u32 x) {   // x < 10000
-        const u32 nd = 1u + (u32)(x >= 10u) + (u32)(x >= 100u) + (u32)(x >= 1000u);
-        put(pack4(x) >> (8u * (4u - nd)), nd);
-    }
-    // decimal v followed by the byte sep
-    __device__ __forceinline__ void num(u32 v, u32 sep) {
-        if (v < 1000u) {   // digits and separator in one append
-            const u32 d2 = v / 100u, r = v - d2 * 100u, d1 = r / 10u, d0 = r - d1 * 10u;
-            const u32 nd = 1u + (u32)(v >= 10u) + (u32)(v >= 100u);
-            const u32 w = ((d2 | (d1 << 8) | (d0 << 16)) + 0x303030u) | (sep << 24);
-            put(w >> (8u * (3u - nd)), nd + 1u);
-            return;
-        }
-        const u32 hi = v / 10000u, lo4 = v - hi * 10000u;
-        if (hi == 0u) put4(pack4(lo4));
-        else {
-            const u32 hh = hi / 10000u, hl = hi - hh * 10000u;
-            if (hh == 0u) num_unpadded4(hl);
-            else { num_unpadded4(hh); put4(pack4(hl)); }
-            put4(pack4(lo4));
-        }
-        put(sep, 1u);
-    }
-};
 
 // ---- D1: the path column -> one slot per step token, in normalised order (step j of the text becomes slot
 // (minus ? ns - 1 - j : j): flip_gaf, gaf2paf_main.cpp:92-110, is index arithmetic).  Only positions are recorded
@@ -555,7 +483,7 @@ __global__ void __launch_bounds__(kFThreads, C::kCtas) k_fuse(const FuseArgs a) 
     __shared__ u32 s_tile, s_flag, s_end;
     __shared__ u32 s_w[kFThreads / 32];
     __shared__ u64 s_obase;
-#if !defined(G2P_HOSTSIM)
+#if G2P_FUSE_TMA_LOAD && !defined(G2P_HOSTSIM)
     __shared__ __align__(8) u64 s_bar;
 #endif
     const u32 FULL = 0xffffffffu;
@@ -568,7 +496,7 @@ __global__ void __launch_bounds__(kFThreads, C::kCtas) k_fuse(const FuseArgs a) 
     if (tid == 0) {
         s_tile = atomicAdd(a.ticket, 1u);
         s_flag = 0; s_end = 0xffffffffu;
-#if !defined(G2P_HOSTSIM)
+#if G2P_FUSE_TMA_LOAD && !defined(G2P_HOSTSIM)
         mbar_init(&s_bar, 1);
         fence_mbar_init();
 #endif
@@ -597,16 +525,25 @@ __global__ void __launch_bounds__(kFThreads, C::kCtas) k_fuse(const FuseArgs a) 
         const u64 room = (u64)(tile ? 16u : 0u) + kFTile + kFTail;
         const u32 avail = (u32)(a.n - src0 < room ? a.n - src0 : room);
         const u32 full = avail & ~15u;
-#if !defined(G2P_HOSTSIM)
+#if G2P_FUSE_TMA_LOAD && !defined(G2P_HOSTSIM)
         if (tid == 0 && full) { mbar_expect_tx(&s_bar, full); bulk_g2s(text + dst0, a.gaf + src0, full, &s_bar); }
 #else
-        for (u32 i = tid; i < full; i += kFThreads) text[dst0 + i] = a.gaf[src0 + i];
+        // 128-bit coalesced loads (source and destination are 16-byte aligned).  The TMA bulk copy this replaces
+        // (G2P_FUSE_TMA_LOAD=1) is no faster here and, on B200 / driver 580, its mbarrier was seen not to complete
+        // (rarely, in launches whose CTAs mostly leave at once: inputs with long records, concurrent streams) -- see DESIGN.md.
+        for (u32 i = tid; i < (full >> 4); i += kFThreads)
+            reinterpret_cast<uint4*>(text + dst0)[i] = __ldg(reinterpret_cast<const uint4*>(a.gaf + src0) + i);
 #endif
         if (tid < avail - full) text[dst0 + full + tid] = a.gaf[src0 + full + tid];   // last partial vector
         if (tid < 32) text[dst0 + avail + tid] = '\n';   // virtual newline after an unterminated last line (kFTextBytes has the room)
         if (!tile && tid < 16) text[tid] = '\n';         // the first record starts at position 0
-#if !defined(G2P_HOSTSIM)
-        if (full) { u32 spins = 0; while (!mbar_try_wait(&s_bar, 0)) { if (++spins > (1u << 24)) __trap(); } }
+#if G2P_FUSE_TMA_LOAD && !defined(G2P_HOSTSIM)
+        if (full) {
+            u32 spins = 0;
+            while (!mbar_try_wait(&s_bar, 0)) {
+                if (++spins > (1u << 22)) { atomicOr(&a.meta->fallback, (u32)(kFuseNotConvertible | kFuseTimeoutLoad)); break; }
+            }
+        }
 #endif
     }
     __syncthreads();
@@ -898,7 +835,14 @@ __global__ void __launch_bounds__(kFThreads, C::kCtas) k_fuse(const FuseArgs a) 
                 u64 w = kIdxFlagPre;   // tiles before the first: prefix 0
                 if (idx >= 0) {
                     u32 spins = 0;
-                    while (((w = st[idx]) >> 62) == 0) { __nanosleep(40); if (++spins > (1u << 24)) __trap(); }
+                    while (((w = st[idx]) >> 62) == 0) {
+                        __nanosleep(64);
+                        if (++spins > (1u << 22) || *g_fallback) {   // the result is void anyway once the fallback flag is up: do not wait for anyone
+                            if (spins > (1u << 22)) atomicOr(&a.meta->fallback, (u32)(kFuseNotConvertible | kFuseTimeoutLookback));
+                            w = kIdxFlagPre;
+                            break;
+                        }
+                    }
                 }
                 const u32 pre = __ballot_sync(FULL, (w >> 62) == 2);
                 const u32 upto = pre ? (u32)__ffs((int)pre) - 1u : 31u;   // lanes 0..upto contribute

@@ -41,7 +41,7 @@ struct PipelineMeta {
     u32 n_deleg;       // records k_short left to k_long
     u32 n_deleg2;      // records k_long left to the general kernel
     u32 n_desc;        // line-descriptor slots reserved by k_long for full batches (32 per batch, lower half of the array)
-    u32 n_desc2;       // ... and for batches of at most 16 lines (as many as needed, rounded up to four; upper half)
+    u32 n_desc2;       // ... and for batches of at most 8 lines (as many as needed, rounded up to four; upper half)
     u32 pad_meta;
     u32 legacy_long;   // some k_long record is not described: run k_long<true>
     u64 lines_total;   // PAF lines of the records k_short converted

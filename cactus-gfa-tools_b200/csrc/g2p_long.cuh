@@ -237,8 +237,9 @@ struct LongArgs {
     LineDesc* desc;        // size pass: line descriptors for k_emit_lines (one padded 32-slot block per batch)
     RecDesc* rdesc;
     u32* n_desc;
-    u32* n_desc2;          // small batches (<= 16 lines) take blocks from the upper half of the array: desc_cap / 2 + ...
+    u32* n_desc2;          // small batches (<= 8 lines) take blocks from the upper half of the array: desc_cap / 2 + ...
     u32 desc_cap;
+    u32 small_max;         // batches of at most this many lines take a small block (0: every batch takes 32 slots)
     u32* need_legacy;      // set when a record could not be described (array full): k_long<true> emits it
     u32* cursor;           // size pass: shared cursor into `list` (warps take the next record when they are free)
 };
@@ -551,11 +552,11 @@ __device__ __forceinline__ void long_record(const LongArgs& a, LWarpMemT<EMIT>* 
             if (!EMIT && btot && !desc_fail) {
                 // describe the batch's lines for k_emit_lines.  Full batches take one 32-slot block from the lower half of
                 // the array (one block = one warp of k_emit_lines = one contiguous run of the output); batches of at most
-                // 16 lines (the only batch of a 250-1000 byte record, the last batch of a long one) take as many slots as
+                // 8 lines (the only batch of a 250-1000 byte record, the last batch of a long one) take as many slots as
                 // they have lines, rounded up to four, from the upper half -- a fixed 32 per batch starved such records.
                 const u32 em = __ballot_sync(FULL, emit_line);
                 const u32 nem = (u32)__popc(em);
-                const bool small = nem <= 16u;
+                const bool small = nem <= a.small_max;
                 const u32 nalloc = small ? (nem + 3u) & ~3u : 32u;
                 const u32 half = a.desc_cap / 2u;
                 u32 base = 0;

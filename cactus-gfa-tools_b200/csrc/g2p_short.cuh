@@ -307,6 +307,83 @@ __device__ __forceinline__ u8* write_line(u8* pend, const LineSrc& S, const Line
     return p;
 }
 
+// ---- left-to-right line writer: 32-bit words into (word-aligned) shared memory ------------------
+struct WEmit {
+    u32* wp;
+    u32 lo, sh;   // pending bytes: the low `sh` bits of lo (sh in {0, 8, 16, 24})
+    __device__ __forceinline__ void put(u32 v, u32 nbytes) {   // the nbytes low bytes of v (the rest zero), 1 <= nbytes <= 4
+        lo |= v << sh;
+        const u32 hi = __funnelshift_l(v, 0u, sh);   // what does not fit (0 when sh == 0)
+        sh += 8u * nbytes;
+        const u32 full = sh >> 5;                    // 0 or 1; straight-line code: one predicated store, selects
+        if (full) *wp = lo;
+        wp += full;
+        lo = full ? hi : lo;
+        sh &= 31u;
+    }
+    __device__ __forceinline__ void put4(u32 v) {
+        *wp++ = lo | (v << sh);
+        lo = __funnelshift_l(v, 0u, sh);
+    }
+    // n bytes from an arbitrarily aligned shared-memory address (reads up to 7 bytes past the span)
+    __device__ __forceinline__ void copy(const u8* src, u32 n) {
+        const uintptr_t sa = reinterpret_cast<uintptr_t>(src);
+        const u32* sp = reinterpret_cast<const u32*>(sa & ~(uintptr_t)3);
+        const u32 s8 = (u32)(sa & 3u) * 8u;
+        u32 prev = *sp++;
+        while (n >= 4u) {
+            const u32 cur = *sp++;
+            put4(__funnelshift_r(prev, cur, s8));
+            prev = cur;
+            n -= 4u;
+        }
+        if (n) {
+            const u32 cur = *sp;
+            put(__funnelshift_r(prev, cur, s8) & ((1u << (8u * n)) - 1u), n);
+        }
+    }
+    // n <= 8 bytes (the short verbatim fields: tag values, column texts): no loop
+    __device__ __forceinline__ void copy_small(const u8* src, u32 n) {
+        const uintptr_t sa = reinterpret_cast<uintptr_t>(src);
+        const u32* sp = reinterpret_cast<const u32*>(sa & ~(uintptr_t)3);
+        const u32 s8 = (u32)(sa & 3u) * 8u;
+        const u32 x0 = sp[0], x1 = sp[1];
+        const u32 w0 = __funnelshift_r(x0, x1, s8);
+        if (n <= 4u) { put(n == 4u ? w0 : w0 & ((1u << (8u * n)) - 1u), n); return; }
+        const u32 w1 = __funnelshift_r(x1, sp[2], s8);
+        put4(w0);
+        put(n == 8u ? w1 : w1 & ((1u << (8u * (n - 4u))) - 1u), n - 4u);
+    }
+    // decimal digits of x < 10000, zero padded to four, most significant digit in the low byte
+    static __device__ __forceinline__ u32 pack4(u32 x) {
+        const u32 d3 = x / 1000u, r3 = x - d3 * 1000u, d2 = r3 / 100u, r2 = r3 - d2 * 100u, d1 = r2 / 10u, d0 = r2 - d1 * 10u;
+        return (d3 | (d2 << 8) | (d1 << 16) | (d0 << 24)) + 0x30303030u;
+    }
+    __device__ __forceinline__ void num_unpadded4(u32 x) {   // x < 10000
+        const u32 nd = 1u + (u32)(x >= 10u) + (u32)(x >= 100u) + (u32)(x >= 1000u);
+        put(pack4(x) >> (8u * (4u - nd)), nd);
+    }
+    // decimal v followed by the byte sep
+    __device__ __forceinline__ void num(u32 v, u32 sep) {
+        if (v < 1000u) {   // digits and separator in one append
+            const u32 d2 = v / 100u, r = v - d2 * 100u, d1 = r / 10u, d0 = r - d1 * 10u;
+            const u32 nd = 1u + (u32)(v >= 10u) + (u32)(v >= 100u);
+            const u32 w = ((d2 | (d1 << 8) | (d0 << 16)) + 0x303030u) | (sep << 24);
+            put(w >> (8u * (3u - nd)), nd + 1u);
+            return;
+        }
+        const u32 hi = v / 10000u, lo4 = v - hi * 10000u;
+        if (hi == 0u) put4(pack4(lo4));
+        else {
+            const u32 hh = hi / 10000u, hl = hi - hh * 10000u;
+            if (hh == 0u) num_unpadded4(hl);
+            else { num_unpadded4(hh); put4(pack4(hl)); }
+            put4(pack4(lo4));
+        }
+        put(sep, 1u);
+    }
+};
+
 // ---- line descriptors: what the size pass hands to k_emit_lines ---------------------------
 // One 64-byte descriptor per PAF line and one 32-byte header per record; k_emit_lines formats
 // one line per thread from them without parsing the record again.

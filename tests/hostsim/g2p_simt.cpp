@@ -162,7 +162,7 @@ int main(int argc, char** argv) {
         hs::launch(dim3((nrec + kRThreads - 1) / kRThreads), dim3(kRThreads), rec_smem(chunks), [&] { k_rec(ra); });
     }
     LongArgs la{gaf, n, rec.data(), T, off.data(), status.data(), nullptr, list.data(), &meta.n_deleg, list2.data(), &meta.n_deleg2,
-                desc.data(), rdesc.data(), &meta.n_desc, &meta.n_desc2, desc_cap, &meta.legacy_long, &meta.long_cursor};
+                desc.data(), rdesc.data(), &meta.n_desc, &meta.n_desc2, desc_cap, 8u, &meta.legacy_long, &meta.long_cursor};
     const u32 nlong = 2;
     hs::launch(dim3(nlong), dim3(kLThreads), long_smem<false>(), [&] { k_long<false>(la); });
     hs::launch(dim3(nlist), dim3(kListThreads), 0, [&] { k_convert_list<false>(gaf, rec.data(), T, off.data(), status.data(), nullptr, &meta, list2.data(), &meta.n_deleg2); });
