@@ -63,7 +63,7 @@ inline void write_seq(int fd, const char* p, size_t n) {
 
 // smallest span one I/O thread gets (tests lower it to exercise the parallel paths on small files)
 inline size_t io_min_bytes() {
-    static const size_t v = (size_t)std::max(1L, env_long("G2P_IO_MIN_BYTES", 8L << 20));
+    static const size_t v = (size_t)std::max(1L, env_long("G2P_IO_MIN_BYTES", 1L << 20));
     return v;
 }
 
