@@ -14,7 +14,7 @@ CXXFLAGS  := -O2 -std=c++17 -Wall -fPIC
 LIB       := $(PKG)/lib/libg2p.so
 HDRS      := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.hpp include/*.h)
 
-all: $(LIB) $(PKG)/bin/gaf2paf $(PKG)/bin/gaf2unstable $(BUILD)/libgafgen.so $(BUILD)/gafgen hostsim
+all: $(LIB) $(PKG)/bin/gaf2paf $(PKG)/bin/gaf2unstable $(PKG)/bin/gaffilter $(BUILD)/libgafgen.so $(BUILD)/gafgen hostsim
 
 $(LIB): $(CSRC)/g2p_capi.cu $(HDRS)
 	@mkdir -p $(PKG)/lib $(BUILD)
@@ -29,6 +29,10 @@ $(PKG)/bin/gaf2unstable: $(CSRC)/gaf2unstable_main.cpp $(CSRC)/cli_pipeline.hpp 
 	@mkdir -p $(PKG)/bin
 	$(CXX) $(CXXFLAGS) -pthread -o $@ $(CSRC)/gaf2unstable_main.cpp -L$(PKG)/lib -lg2p -Wl,-rpath,'$$ORIGIN/../lib'
 
+$(PKG)/bin/gaffilter: $(CSRC)/gaffilter_main.cpp $(CSRC)/cli_pipeline.hpp $(LIB) include/g2p.h
+	@mkdir -p $(PKG)/bin
+	$(CXX) $(CXXFLAGS) -pthread -o $@ $(CSRC)/gaffilter_main.cpp -L$(PKG)/lib -lg2p -Wl,-rpath,'$$$$ORIGIN/../lib'
+
 $(BUILD)/libgafgen.so: tools/gafgen.cpp
 	@mkdir -p $(BUILD)
 	$(CXX) $(CXXFLAGS) -shared -pthread -o $@ $<
@@ -37,7 +41,10 @@ $(BUILD)/gafgen: tools/gafgen.cpp
 	@mkdir -p $(BUILD)
 	$(CXX) $(CXXFLAGS) -DGAFGEN_MAIN -pthread -o $@ $<
 
-hostsim: $(BUILD)/g2p_hostsim $(BUILD)/g2p_simt $(BUILD)/g2p_simt_long $(BUILD)/g2u_hostsim $(BUILD)/gaf2paf_stub
+hostsim: $(BUILD)/g2p_hostsim $(BUILD)/g2p_simt $(BUILD)/g2p_simt_long $(BUILD)/g2u_hostsim $(BUILD)/gaf2paf_stub $(BUILD)/g2p_filter_simt
+$(BUILD)/g2p_filter_simt: tests/hostsim/g2p_filter_simt.cpp tests/hostsim/cuda_shim.hpp $(HDRS)
+	@mkdir -p $(BUILD)
+	$(CXX) -O1 -g -std=c++17 -ffp-contract=off -Wall -Wno-unused-function -Wno-unknown-pragmas -Itests/hostsim -o $@ $<
 # the gaf2paf executable's host logic linked against a CPU stub of the C-ABI (test infrastructure)
 $(BUILD)/gaf2paf_stub: $(CSRC)/gaf2paf_main.cpp $(CSRC)/cli_pipeline.hpp tests/hostsim/g2p_stub_capi.cpp $(HDRS)
 	@mkdir -p $(BUILD)

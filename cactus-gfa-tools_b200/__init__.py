@@ -39,6 +39,7 @@ EXPORTED_SYMBOLS = (
     "g2p_table_entries", "g2p_copy_to_device", "g2p_copy_to_host", "g2p_convert_device", "g2p_convert_host", "g2p_index_lines", "g2p_format_error",
     "g2p_load_rgfa", "g2p_rgfa_node_lengths", "g2p_unstable_device", "g2p_unstable_host", "g2p_unstable_warnings", "g2p_format_unstable_warning",
     "g2p_unstable_convert_device", "g2p_unstable_convert_host", "g2p_unstable_convert_warnings",
+    "g2p_filter_device", "g2p_filter_host",
 )
 
 
@@ -69,6 +70,20 @@ class Result(ctypes.Structure):
         ("stage", ctypes.c_uint32),
         ("mid_bytes", ctypes.c_uint64),
     ]
+
+
+class FilterParams(ctypes.Structure):
+    """struct g2p_filter_params (include/g2p.h): gaffilter's options."""
+    _fields_ = [("ratio", ctypes.c_double), ("min_overlap_pct", ctypes.c_double), ("min_identity", ctypes.c_double),
+                ("min_overlap_len", ctypes.c_int64), ("min_block_len", ctypes.c_int64), ("min_mapq", ctypes.c_int64),
+                ("is_paf", ctypes.c_int32), ("pad", ctypes.c_int32)]
+
+
+class FilterResult(ctypes.Structure):
+    """struct g2p_filter_result (include/g2p.h)."""
+    _fields_ = [("n_loaded", ctypes.c_uint64), ("n_filtered", ctypes.c_uint64), ("filtered_len", ctypes.c_uint64), ("out_bytes", ctypes.c_uint64),
+                ("rec_status", ctypes.c_uint32), ("gpu_launches", ctypes.c_uint32), ("err_record", ctypes.c_uint64),
+                ("device_ms", ctypes.c_float), ("pad", ctypes.c_uint32)]
 
 
 class Warn(ctypes.Structure):
@@ -122,6 +137,10 @@ def _load():
     lib.g2p_unstable_convert_host.restype = ctypes.c_int
     lib.g2p_unstable_convert_warnings.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(sz)]
     lib.g2p_unstable_convert_warnings.restype = ctypes.c_int
+    lib.g2p_filter_device.argtypes = [vp, vp, sz, ctypes.POINTER(FilterParams), ctypes.POINTER(vp), ctypes.POINTER(FilterResult), vp]
+    lib.g2p_filter_device.restype = ctypes.c_int
+    lib.g2p_filter_host.argtypes = [vp, vp, sz, ctypes.POINTER(FilterParams), ctypes.POINTER(vp), ctypes.POINTER(FilterResult)]
+    lib.g2p_filter_host.restype = ctypes.c_int
     lib.g2p_unstable_warnings.argtypes = [vp, ctypes.POINTER(ctypes.POINTER(Warn)), ctypes.POINTER(sz)]
     lib.g2p_unstable_warnings.restype = ctypes.c_int
     lib.g2p_format_unstable_warning.argtypes = [vp, vp, sz, vp, sz]
@@ -277,6 +296,28 @@ class Converter:
         p, n = ctypes.c_void_p(), ctypes.c_size_t()
         self._check(lib.g2p_unstable_convert_warnings(self._h, ctypes.byref(p), ctypes.byref(n)))
         return ctypes.string_at(p.value, n.value).decode("latin-1") if n.value else ""
+
+    # ---- gaffilter
+    @staticmethod
+    def filter_params(ratio=0.0, min_overlap=0.0, min_identity=0.0, min_overlap_length=0, min_block_length=0, min_mapq=0, paf=False):
+        """gaffilter's options; -r / -m / -i go through std::stof in the reference: the values are rounded to float here too."""
+        f32 = lambda x: ctypes.c_float(x).value
+        return FilterParams(f32(ratio), f32(min_overlap), f32(min_identity), int(min_overlap_length), int(min_block_length), int(min_mapq), 1 if paf else 0, 0)
+
+    def filter_host(self, text, params):
+        """``gaffilter [options] <text>``: -> (kept records as the reference prints them, FilterResult)."""
+        addr, n, keep = _buf_ptr(text)
+        out = ctypes.c_void_p()
+        res = FilterResult()
+        self._check(lib.g2p_filter_host(self._h, addr, n, ctypes.byref(params), ctypes.byref(out), ctypes.byref(res)))
+        return _bytes_at(out.value, res.out_bytes), res
+
+    def filter_device(self, d_ptr, n, params, stream=0):
+        """Filter text that is already on the device (e.g. the PAF g2p_convert_device just made): -> (device address, FilterResult)."""
+        out = ctypes.c_void_p()
+        res = FilterResult()
+        self._check(lib.g2p_filter_device(self._h, d_ptr, n, ctypes.byref(params), ctypes.byref(out), ctypes.byref(res), stream or None))
+        return out.value, res
 
     @staticmethod
     def format_error(res, gaf):

@@ -89,6 +89,7 @@ struct PinBuf {
 struct Worker {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};   // 0..4: general pipeline (index, size, scan, emit), 5..6: k_fuse
+    DevBuf f_rows, f_keys, f_keys2, f_vals, f_vals2, f_pmax, f_keep, f_hist, f_meta;   // gaffilter
     DevBuf d_mid, d_in, d_tiles, d_rec, d_status, d_off, d_blocks, d_out, d_meta, d_list, d_list2, d_desc, d_rdesc, d_sdesc, d_loff, d_map, d_lsort, d_perm, d_fuse;
     PinBuf h_meta, h_fmeta;
     bool init() {
@@ -98,7 +99,7 @@ struct Worker {
                h_fmeta.ensure(sizeof(FuseMeta)) == cudaSuccess;
     }
     void release() {
-        for (DevBuf* b : {&d_mid, &d_in, &d_tiles, &d_rec, &d_status, &d_off, &d_blocks, &d_out, &d_meta, &d_list, &d_list2, &d_desc, &d_rdesc, &d_sdesc, &d_loff, &d_map, &d_lsort, &d_perm, &d_fuse}) b->release();
+        for (DevBuf* b : {&f_rows, &f_keys, &f_keys2, &f_vals, &f_vals2, &f_pmax, &f_keep, &f_hist, &f_meta, &d_mid, &d_in, &d_tiles, &d_rec, &d_status, &d_off, &d_blocks, &d_out, &d_meta, &d_list, &d_list2, &d_desc, &d_rdesc, &d_sdesc, &d_loff, &d_map, &d_lsort, &d_perm, &d_fuse}) b->release();
         h_meta.release();
         h_fmeta.release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -1126,6 +1127,131 @@ int g2p_format_unstable_warning(g2p_ctx* ctx, const char* line, size_t len, char
     m.append(line, ll);
     m += "\n";
     std::snprintf(buf, cap, "%s", m.c_str());
+    return G2P_OK;
+}
+
+// ---- N1: gaffilter on the device ------------------------------------------------------------------------
+static int run_filter(g2p_ctx* ctx, Worker& w, const u8* d_text, size_t n, const g2p_filter_params* gp, cudaStream_t st, g2p_filter_result* res, u8** d_out) {
+    std::memset(res, 0, sizeof *res);
+    *d_out = nullptr;
+    uint32_t launches = 0;
+    G2P_CUDA(cudaEventRecord(w.ev[0], st));
+    int rc = run_index(ctx, w, d_text, n, st, &launches);
+    if (rc) return rc;
+    const u32 nrec = static_cast<const PipelineMeta*>(w.h_meta.p)->n_records;
+    G2P_CUDA(w.d_out.ensure(256));
+    *d_out = static_cast<u8*>(w.d_out.p);
+    if (nrec == 0) { G2P_CUDA(cudaStreamSynchronize(st)); res->gpu_launches = launches; return G2P_OK; }
+    const u32 nblk = (nrec + kRsTile - 1) / kRsTile, nh = 16u * nblk;
+    const u32 nscan_h = (nh + kScanTile - 1) / kScanTile, nscan_r = (nrec + kScanTile - 1) / kScanTile;
+    G2P_CUDA(w.f_rows.ensure((size_t)nrec * sizeof(FRow)));
+    G2P_CUDA(w.f_keys.ensure((size_t)nrec * 8)); G2P_CUDA(w.f_keys2.ensure((size_t)nrec * 8));
+    G2P_CUDA(w.f_vals.ensure((size_t)nrec * 4)); G2P_CUDA(w.f_vals2.ensure((size_t)nrec * 4));
+    G2P_CUDA(w.f_pmax.ensure((size_t)nrec * 8));
+    G2P_CUDA(w.f_keep.ensure((size_t)nrec));
+    G2P_CUDA(w.f_hist.ensure(((size_t)nh + 2 + nscan_h + nscan_r) * 8));
+    G2P_CUDA(w.f_meta.ensure(sizeof(FilterMeta)));
+    G2P_CUDA(w.d_off.ensure(((size_t)nrec + 1) * sizeof(u64)));
+    G2P_CUDA(w.d_blocks.ensure((size_t)std::max(nscan_r, nscan_h) * 2 * sizeof(u64)));
+    FilterMeta* d_fm = static_cast<FilterMeta*>(w.f_meta.p);
+    FilterMeta init;
+    std::memset(&init, 0, sizeof init);
+    init.first_err = 0xFFFFFFFFu;
+    G2P_CUDA(cudaMemcpyAsync(d_fm, &init, sizeof init, cudaMemcpyHostToDevice, st));
+    FilterParams P{gp->ratio, gp->min_overlap_pct, gp->min_identity, gp->min_overlap_len, gp->min_block_len, gp->min_mapq, gp->is_paf ? 1u : 0u};
+    u64* keys = static_cast<u64*>(w.f_keys.p);
+    u64* keys2 = static_cast<u64*>(w.f_keys2.p);
+    u32* vals = static_cast<u32*>(w.f_vals.p);
+    u32* vals2 = static_cast<u32*>(w.f_vals2.p);
+    FRow* rows = static_cast<FRow*>(w.f_rows.p);
+    const u32* d_rec = static_cast<const u32*>(w.d_rec.p);
+    const u32 grid = std::min<u32>((nrec + 127) / 128, (u32)ctx->n_sm * 16u);
+    FilterArgs fa{d_text, d_rec, nrec, P, rows, keys, vals, d_fm};
+    k_filter_parse<<<grid, 128, 0, st>>>(fa);
+    ++launches;
+    // sort by (hash32, query_start): 16 passes of 4 bits
+    u64* hist = static_cast<u64*>(w.f_hist.p);
+    u64* d_blocks = static_cast<u64*>(w.d_blocks.p);
+    for (u32 shift = 0; shift < 64; shift += 4) {
+        k_rs_hist<<<nblk, kRsThreads, 0, st>>>(keys, nrec, shift, hist, nblk);
+        k_scan_reduce<<<nscan_h, kScanThreads, 0, st>>>(hist, nh, d_blocks);
+        k_scan_blocks<<<1, 1024, 0, st>>>(d_blocks, nscan_h, hist + nh + 1);
+        k_scan_apply<<<nscan_h, kScanThreads, 0, st>>>(hist, nh, d_blocks, hist + nh + 1);
+        k_rs_scatter<<<nblk, kRsThreads, 0, st>>>(keys, vals, keys2, vals2, nrec, shift, hist, nblk);
+        std::swap(keys, keys2);
+        std::swap(vals, vals2);
+        launches += 5;
+    }
+    i64* pmax = static_cast<i64*>(w.f_pmax.p);
+    u8* keep = static_cast<u8*>(w.f_keep.p);
+    k_filter_prefmax<<<grid, 256, 0, st>>>(keys, vals, rows, nrec, pmax);
+    G2P_CUDA(cudaMemsetAsync(keep, 0, nrec, st));
+    k_filter_sweep<<<grid, 128, 0, st>>>(keys, vals, rows, pmax, nrec, P, keep, d_fm);
+    u64* d_off = static_cast<u64*>(w.d_off.p);
+    k_filter_emit<false><<<grid, 128, 0, st>>>(d_text, d_rec, nrec, P.is_paf, keep, d_off, nullptr);
+    k_scan_reduce<<<nscan_r, kScanThreads, 0, st>>>(d_off, nrec, d_blocks);
+    k_scan_blocks<<<1, 1024, 0, st>>>(d_blocks, nscan_r, &d_fm->out_total);
+    k_scan_apply<<<nscan_r, kScanThreads, 0, st>>>(d_off, nrec, d_blocks, &d_fm->out_total);
+    k_filter_diagnose<<<1, 1, 0, st>>>(fa);
+    launches += 7;
+    FilterMeta hm;
+    G2P_CUDA(cudaMemcpyAsync(&hm, d_fm, sizeof hm, cudaMemcpyDeviceToHost, st));
+    G2P_CUDA(cudaStreamSynchronize(st));
+    G2P_CUDA(cudaGetLastError());
+    if (hm.unsupported) { ctx->set_err("gaffilter: a query_start outside [0, 2^32) is not supported by the device sort"); return G2P_E_ARG; }
+    res->n_loaded = hm.n_loaded;
+    if (hm.first_err != 0xFFFFFFFFu) {   // the reference dies while it loads the records: nothing is printed
+        res->rec_status = hm.err_status & 0xff;
+        if (res->rec_status < G2P_REC_ABORT) res->rec_status = G2P_REC_ABORT + 8;
+        res->err_record = hm.first_err;
+        res->gpu_launches = launches;
+        return G2P_OK;
+    }
+    res->n_filtered = hm.n_filtered;
+    res->filtered_len = hm.filtered_len;
+    res->out_bytes = hm.out_total;
+    G2P_CUDA(w.d_out.ensure(hm.out_total + 256));
+    u8* d_o = static_cast<u8*>(w.d_out.p);
+    k_filter_emit<true><<<grid, 128, 0, st>>>(d_text, d_rec, nrec, P.is_paf, keep, d_off, d_o);
+    ++launches;
+    G2P_CUDA(cudaEventRecord(w.ev[4], st));
+    G2P_CUDA(cudaStreamSynchronize(st));
+    G2P_CUDA(cudaGetLastError());
+    cudaEventElapsedTime(&res->device_ms, w.ev[0], w.ev[4]);
+    res->gpu_launches = launches;
+    *d_out = d_o;
+    return G2P_OK;
+}
+
+int g2p_filter_device(g2p_ctx* ctx, const void* d_text, size_t n, const g2p_filter_params* params, void** d_out, g2p_filter_result* res, void* stream) {
+    if (!ctx || !res || !d_out || !params) return G2P_E_ARG;
+    if (n >= 0xFFFFFFF0ULL) return G2P_E_TOOBIG;
+    if ((reinterpret_cast<uintptr_t>(d_text) & 15) != 0) { ctx->set_err("d_text must be 16-byte aligned"); return G2P_E_ARG; }
+    G2P_CUDA(cudaSetDevice(ctx->device));
+    Worker& w = ctx->w[1];   // (not worker 0: the text may be worker 0's own output buffer, a PAF made by g2p_convert_device)
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : w.stream;
+    u8* d_o = nullptr;
+    int rc = run_filter(ctx, w, static_cast<const u8*>(d_text), n, params, st, res, &d_o);
+    *d_out = d_o;
+    return rc;
+}
+
+int g2p_filter_host(g2p_ctx* ctx, const char* text, size_t n, const g2p_filter_params* params, const char** out, g2p_filter_result* res) {
+    if (!ctx || !res || !out || !params || (!text && n)) return G2P_E_ARG;
+    if (n >= 0xFFFFFFF0ULL) return G2P_E_TOOBIG;
+    *out = nullptr;
+    G2P_CUDA(cudaSetDevice(ctx->device));
+    Worker& w = ctx->w[1];
+    PinBuf& h_out = ctx->next_out();
+    G2P_CUDA(w.d_in.ensure(n + 256));
+    if (n) G2P_CUDA(cudaMemcpyAsync(w.d_in.p, text, n, cudaMemcpyHostToDevice, w.stream));
+    u8* d_o = nullptr;
+    int rc = run_filter(ctx, w, static_cast<const u8*>(w.d_in.p), n, params, w.stream, res, &d_o);
+    if (rc) return rc;
+    G2P_CUDA(h_out.ensure(res->out_bytes + 1));
+    if (res->out_bytes) G2P_CUDA(cudaMemcpyAsync(h_out.p, d_o, res->out_bytes, cudaMemcpyDeviceToHost, w.stream));
+    G2P_CUDA(cudaStreamSynchronize(w.stream));
+    *out = static_cast<const char*>(h_out.p);
     return G2P_OK;
 }
 

@@ -534,3 +534,4 @@ __global__ void k_diagnose(const u8* __restrict__ gaf, const u32* __restrict__ r
 }  // namespace g2p
 
 #include "g2p_fuse.cuh"
+#include "g2p_filter.cuh"

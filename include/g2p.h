@@ -156,6 +156,36 @@ int g2p_unstable_convert_host(g2p_ctx* ctx, const char* gaf, size_t n, const cha
 /* stderr text of the gaf2unstable stage of the last g2p_unstable_convert_* call (its multi-contig warnings). */
 int g2p_unstable_convert_warnings(g2p_ctx* ctx, const char** text, size_t* n);
 
+/* ---- gaffilter: the query-overlap filter on GAF or PAF text that is already on the device ----------
+ * Replaces the whole of gaffilter's main() after option parsing (gaffilter_main.cpp:186-343): load all records, one
+ * interval tree per query, keep a record iff it dominates every qualifying overlapping record (dominates :31-60,
+ * dominates_mzgaf2paf :63-66), print the kept records in input order re-serialised like operator<<(GafRecord) /
+ * operator<<(PafLine).  Parameters as the reference's options (-r/-m/-i go through std::stof there: pass the float
+ * value widened to double).  A PAF made by g2p_convert_device can be filtered where it lies: no D2H of the unfiltered PAF. */
+typedef struct g2p_filter_params {
+    double ratio;              /* -r */
+    double min_overlap_pct;    /* -m */
+    double min_identity;       /* -i */
+    int64_t min_overlap_len;   /* -o */
+    int64_t min_block_len;     /* -b */
+    int64_t min_mapq;          /* -q */
+    int32_t is_paf;            /* -p */
+    int32_t pad;
+} g2p_filter_params;
+typedef struct g2p_filter_result {
+    uint64_t n_loaded;         /* "[gaffilter]: Loaded N ... records" */
+    uint64_t n_filtered;       /* "[gaffilter]: filtered X / N. total block lengths filtered: Y" */
+    uint64_t filtered_len;
+    uint64_t out_bytes;
+    uint32_t rec_status;       /* 0, or >= G2P_REC_ABORT: the reference dies on line err_record (nothing is printed) */
+    uint32_t gpu_launches;
+    uint64_t err_record;
+    float device_ms;
+    uint32_t pad;
+} g2p_filter_result;
+int g2p_filter_device(g2p_ctx* ctx, const void* d_text, size_t n, const g2p_filter_params* params, void** d_out, g2p_filter_result* res, void* stream);
+int g2p_filter_host(g2p_ctx* ctx, const char* text, size_t n, const g2p_filter_params* params, const char** out, g2p_filter_result* res);
+
 /* Formats the stderr line the reference prints for a failed record (empty for aborts,
  * whose text comes from the C++ runtime).  `gaf` is the host copy of the input. */
 int g2p_format_error(const g2p_result* res, const char* gaf, size_t n, char* buf, size_t cap);

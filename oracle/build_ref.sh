@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# Build the UNMODIFIED reference gaf2paf / gaf2unstable binaries into oracle/_ref/
+# Build the UNMODIFIED reference gaf2paf / gaf2unstable / gaffilter binaries into oracle/_ref/
 # straight from the sources where they lie under /root/reference (nothing is copied
 # into this repository).  Test infrastructure only: the product never calls these.
 #
@@ -21,6 +21,7 @@ mkdir -p "$OUT"
 FLAGS="-O3 -std=c++14 -pthread -w -I$REF"
 $CXX $FLAGS "$REF/gaf2paf_main.cpp" -o "$OUT/gaf2paf" &
 $CXX $FLAGS "$REF/gaf2unstable_main.cpp" "$REF/rgfa-split.cpp" -o "$OUT/gaf2unstable" &
+$CXX $FLAGS "$REF/gaffilter_main.cpp" -o "$OUT/gaffilter" &   # SURVEY.md §8f N1 (Makefile: gaffilter_main.o alone)
 wait
-strip "$OUT/gaf2paf" "$OUT/gaf2unstable"
+strip "$OUT/gaf2paf" "$OUT/gaf2unstable" "$OUT/gaffilter"
 ls -la "$OUT" >&2

@@ -52,6 +52,7 @@ def _built():
         os.path.join(ROOT, "build", "g2p_simt_long"),
         os.path.join(ROOT, "build", "g2u_hostsim"),
         os.path.join(ROOT, "build", "gaf2paf_stub"),
+        os.path.join(ROOT, "build", "g2p_filter_simt"),
     ]
     if not all(os.path.exists(p) for p in need):
         subprocess.check_call(["make", "-C", ROOT], stdout=subprocess.DEVNULL)

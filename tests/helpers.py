@@ -237,3 +237,39 @@ def run_gaf2unstable_ref(gaf, rgfa, want_lengths=False):
         if want_lengths:
             return rc, out, err, open(lp, "rb").read() if os.path.exists(lp) else b""
     return rc, out, err
+
+
+# ---- gaffilter: records whose query intervals overlap (several alignments per query, primary / secondary, mixed mapq) ----
+def gen_filter_case(seed, n_records=3000, n_queries=150, paf=False):
+    """GAF (or, paf=True, the PAF that gaf2paf makes of it: -> (text, lengths)) in which many records share a query name,
+    so that gaffilter has overlaps to resolve."""
+    import random
+    rnd = random.Random(seed)
+    p = preset("short", seed=seed)
+    lengths = gen_lengths(p)
+    lines = gen_records(p, 0, n_records, threads=1).split(b"\n")[:-1]
+    out = []
+    for i, ln in enumerate(lines):
+        f = ln.split(b"\t")
+        f[0] = b"q%d" % rnd.randrange(n_queries)
+        if rnd.random() < 0.3:
+            f = [x if not x.startswith(b"tp:A:") else b"tp:A:S" for x in f]
+        if rnd.random() < 0.1:
+            f = [x for x in f if not x.startswith(b"tp:A:")]
+        f[11] = str(rnd.choice([0, 1, 5, 20, 60, 255])).encode()
+        if rnd.random() < 0.2:
+            f.insert(12, b"rc:Z:chr%d" % rnd.randrange(3))
+        out.append(b"\t".join(f))
+        if rnd.random() < 0.01:
+            out.append(b"*\t>s43\t97\t12\t0\t6\t92")
+    gaf = b"\n".join(out) + b"\n"
+    if not paf:
+        return gaf, lengths
+    rc, paf_text, err, kind = run_gaf2paf_cpu(gaf, lengths)
+    assert rc == 0, err
+    return paf_text, lengths
+
+
+def run_gaffilter_ref(text, args):
+    binary = os.path.join(REF_BIN, "gaffilter")
+    return run_tool(binary, ["-"] + list(args), text)
