@@ -425,7 +425,7 @@ def main():
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ms = {k: [] for k in ("emit_ms", "size_ms", "index_ms", "device_ms", "fused_ms", "unstable_ms")}
+    ms = {k: [] for k in ("emit_ms", "size_ms", "index_ms", "device_ms", "fused_ms", "unstable_ms", "par_ms")}
     launches = 0
     e0.record()
     for _ in range(a.steps):
@@ -490,7 +490,7 @@ def main():
     elif mean["emit_ms"] >= mean["size_ms"]:
         dom, dom_ms, dom_bytes, dom_key = "k_emit_lines (emit pass)", mean["emit_ms"], nbytes + out_bytes, "k_emit_lines"
     else:
-        kname = "k_long" if res.n_long * 2 > n_records else short_kernel
+        kname = ("k_par" if res.n_par * 2 > res.n_long else "k_long") if res.n_long * 2 > n_records else short_kernel
         dom, dom_ms, dom_bytes, dom_key = kname + " (size pass)", mean["size_ms"], nbytes, kname.split("<")[0] + "_size"
     traffic = None
     try:
@@ -512,12 +512,12 @@ def main():
         "input_GBps": total_in * a.steps / (t_ms / 1000.0) / 1e9,
         "pipeline_in_plus_out_GBps": (total_in + tot_out) * a.steps / (t_ms / 1000.0) / 1e9,
         "pipeline_frac_of_hbm_peak": (nbytes + out_bytes) * a.steps / (t_ms / 1000.0) / 1e9 / peak,
-        "kernel_ms": {"index": mean["index_ms"], "size": mean["size_ms"], "emit": mean["emit_ms"], "fused": mean["fused_ms"],
+        "kernel_ms": {"index": mean["index_ms"], "size": mean["size_ms"], "emit": mean["emit_ms"], "fused": mean["fused_ms"], "par": mean["par_ms"],
                       "gaf2unstable_stage": mean["unstable_ms"], "device_pipeline": mean["device_ms"]},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "algorithmic_bytes_per_launch": dom_bytes, "peak_source": peak_src},
         "records_by_kernel": {"k_fuse": n_fused, short_kernel.split("<")[0]: int(n_records - res.n_long - n_fused) if n_fused == 0 else 0,
-                              "k_long": int(res.n_long - res.n_delegated), "general": int(res.n_delegated)},
+                              "k_par": int(res.n_par), "k_long": int(res.n_long - res.n_par - res.n_delegated), "general": int(res.n_delegated)},
         "gpu_launches": launches,
         "clocks": clocks,
         "table_load_s": table_load_s,

@@ -69,6 +69,8 @@ class Result(ctypes.Structure):
         ("unstable_ms", ctypes.c_float),
         ("stage", ctypes.c_uint32),
         ("mid_bytes", ctypes.c_uint64),
+        ("par_ms", ctypes.c_float),
+        ("n_par", ctypes.c_uint32),
     ]
 
 

@@ -88,20 +88,22 @@ struct PinBuf {
 // One pipeline instance: a stream plus the grow-only work buffers of one in-flight chunk.
 struct Worker {
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[8] = {};   // 0..4: general pipeline (index, size, scan, emit), 5..6: k_fuse
+    cudaEvent_t ev[10] = {};  // 0..4: general pipeline (index, size, scan, emit), 5..6: k_fuse, 8..9: k_par
     DevBuf f_rows, f_keys, f_keys2, f_vals, f_vals2, f_pmax, f_keep, f_hist, f_meta;   // gaffilter
     DevBuf d_mid, d_in, d_tiles, d_rec, d_status, d_off, d_blocks, d_out, d_meta, d_list, d_list2, d_desc, d_rdesc, d_sdesc, d_loff, d_map, d_lsort, d_perm, d_fuse;
-    PinBuf h_meta, h_fmeta;
+    DevBuf p_recs, p_tb, p_toff, p_bs, p_step, p_op, d_list3;   // k_par (g2p_par.cuh)
+    PinBuf h_meta, h_fmeta, h_par;
     bool init() {
         if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) return false;
         for (auto& e : ev) if (cudaEventCreate(&e) != cudaSuccess) return false;
         return d_meta.ensure(sizeof(PipelineMeta)) == cudaSuccess && h_meta.ensure(sizeof(PipelineMeta)) == cudaSuccess &&
-               h_fmeta.ensure(sizeof(FuseMeta)) == cudaSuccess;
+               h_fmeta.ensure(sizeof(FuseMeta)) == cudaSuccess && h_par.ensure(64) == cudaSuccess;
     }
     void release() {
-        for (DevBuf* b : {&f_rows, &f_keys, &f_keys2, &f_vals, &f_vals2, &f_pmax, &f_keep, &f_hist, &f_meta, &d_mid, &d_in, &d_tiles, &d_rec, &d_status, &d_off, &d_blocks, &d_out, &d_meta, &d_list, &d_list2, &d_desc, &d_rdesc, &d_sdesc, &d_loff, &d_map, &d_lsort, &d_perm, &d_fuse}) b->release();
+        for (DevBuf* b : {&f_rows, &f_keys, &f_keys2, &f_vals, &f_vals2, &f_pmax, &f_keep, &f_hist, &f_meta, &d_mid, &d_in, &d_tiles, &d_rec, &d_status, &d_off, &d_blocks, &d_out, &d_meta, &d_list, &d_list2, &d_desc, &d_rdesc, &d_sdesc, &d_loff, &d_map, &d_lsort, &d_perm, &d_fuse, &p_recs, &p_tb, &p_toff, &p_bs, &p_step, &p_op, &d_list3}) b->release();
         h_meta.release();
         h_fmeta.release();
+        h_par.release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -144,6 +146,7 @@ struct g2p_ctx {
     bool len_sort = false;           // G2P_LEN_SORT=1: global counting sort of the records by length class before k_rec (default off: in-CTA sort only)
     bool size_kernel_short = false;  // G2P_SIZE_KERNEL=short: k_short (8 lanes per record) instead of k_rec (thread per record)
     uint32_t rec_chunks_override = 0; // G2P_REC_CHUNKS: k_rec slot capacity in 16-byte chunks
+    bool par = true;                 // G2P_PAR=0: records k_rec does not take go straight to k_long (one warp per record) instead of the token-parallel kernels
     u32 long_small_max = 8;          // G2P_LONG_SMALL: k_long batches of at most this many lines take a small descriptor block (0: always 32 slots)
     uint64_t desc_cap_override = 0;  // G2P_DESC_CAP (tests): line-descriptor slots, to exercise the overflow fallback
     int fuse_mode = 1;               // G2P_FUSE: 0 never run the one-pass kernel k_fuse; 2 always try it first; 1 (default) when it pays:
@@ -252,6 +255,7 @@ int g2p_create(int device, g2p_ctx** out) {
     cudaFuncSetAttribute(k_long<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)long_smem<false>());
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
     if (const char* c = std::getenv("G2P_ONE_PASS_INDEX")) ctx->two_pass_index = std::atoi(c) == 0;
+    if (const char* c = std::getenv("G2P_PAR")) ctx->par = std::atoi(c) != 0;
     if (const char* c = std::getenv("G2P_LONG_SMALL")) ctx->long_small_max = (u32)std::min(16, std::max(0, std::atoi(c)));
     if (const char* c = std::getenv("G2P_DESC_CAP")) ctx->desc_cap_override = std::strtoull(c, nullptr, 10);
     if (const char* c = std::getenv("G2P_FUSE")) ctx->fuse_mode = std::min(2, std::max(0, std::atoi(c)));
@@ -449,6 +453,120 @@ static int run_fused(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cudaStr
 
 // The device pipeline on one worker: index, size pass, scan, emit pass.  Returns with the stream
 // synchronised; *d_out is the worker's output buffer.
+// three 64-bit device words -> pinned host memory (same reason as k_meta_to_host)
+__global__ void k_par_counts_to_host(const u64* a, const u64* b, const u64* c, u64* dst) {
+    volatile u64* d = dst;
+    if (threadIdx.x == 0) { d[0] = a ? *a : 0; d[1] = b ? *b : 0; d[2] = c ? *c : 0; }
+    __threadfence_system();
+}
+
+// The token-parallel kernels (g2p_par.cuh) on the `nlist` records k_rec left: sizes, status and line descriptors
+// for the canonical ones, the rest listed in w.d_list3 / meta->n_reject for k_long.  *done = false: nothing was
+// converted (no room for the descriptors, or nothing to do) and k_long takes the whole list.
+static int run_par(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cudaStream_t st, u32 nlist, LongArgs& la, PipelineMeta* d_meta, u32* launches, bool* done) {
+    *done = false;
+    auto scan64 = [&](u64* x, u32 cnt) {
+        const u32 nb = (cnt + kScanTile - 1) / kScanTile;
+        k_scan_reduce<<<nb, kScanThreads, 0, st>>>(x, cnt, static_cast<u64*>(w.p_bs.p));
+        k_scan_blocks<<<1, 1024, 0, st>>>(static_cast<u64*>(w.p_bs.p), nb, x + cnt);
+        k_scan_apply<<<nb, kScanThreads, 0, st>>>(x, cnt, static_cast<u64*>(w.p_bs.p), x + cnt);
+        *launches += 3;
+    };
+    auto scan4 = [&](uint4* x, u32 cnt) {
+        const u32 nb = (cnt + kScanTile - 1) / kScanTile;
+        k_scan4_reduce<<<nb, kScanThreads, 0, st>>>(x, cnt, static_cast<uint4*>(w.p_bs.p));
+        k_scan4_blocks<<<1, 1024, 0, st>>>(static_cast<uint4*>(w.p_bs.p), nb, x + cnt);
+        k_scan4_apply<<<nb, kScanThreads, 0, st>>>(x, cnt, static_cast<uint4*>(w.p_bs.p));
+        *launches += 3;
+    };
+    G2P_CUDA(w.p_recs.ensure((size_t)nlist * sizeof(ParRec)));
+    G2P_CUDA(w.p_tb.ensure(((size_t)nlist + 1) * 2 * sizeof(u64)));
+    G2P_CUDA(w.p_bs.ensure(((size_t)nlist / kScanTile + 2) * sizeof(uint4)));
+    G2P_CUDA(w.d_list3.ensure((size_t)nlist * sizeof(u32)));
+    ParArgs pa;
+    std::memset(&pa, 0, sizeof pa);
+    pa.gaf = d_gaf; pa.n = (u64)n; pa.rec_start = la.rec_start; pa.T = la.T; pa.list = la.list; pa.nlist = nlist;
+    pa.recs = static_cast<ParRec*>(w.p_recs.p);
+    pa.tile_base = static_cast<u64*>(w.p_tb.p); pa.slot_scan = pa.tile_base + nlist + 1;
+    pa.out_off = la.out_off; pa.status = la.status; pa.rdesc = la.rdesc; pa.desc = la.desc;
+    pa.reject_list = static_cast<u32*>(w.d_list3.p); pa.n_reject = &d_meta->n_reject; pa.n_desc = la.n_desc; pa.n_desc2 = la.n_desc2;
+    pa.small_max = ctx->long_small_max ? ctx->long_small_max : 0u;
+    const u32 grec = (nlist + 255) / 256;
+    volatile u64* hp = static_cast<volatile u64*>(w.h_par.p);
+    k_par_plan<<<grec, 256, 0, st>>>(pa); ++*launches;
+    scan64(pa.tile_base, nlist);
+    k_par_counts_to_host<<<1, 32, 0, st>>>(pa.tile_base + nlist, nullptr, nullptr, static_cast<u64*>(w.h_par.p)); ++*launches;
+    G2P_CUDA(cudaStreamSynchronize(st));
+    const u64 ntiles = hp[0];
+    if (ntiles == 0 || ntiles > 0x7FFFFF00ULL) return G2P_OK;
+    pa.ntiles = (u32)ntiles;
+    G2P_CUDA(w.p_toff.ensure(((size_t)ntiles + 1) * (sizeof(u64) + sizeof(uint2))));
+    G2P_CUDA(w.p_bs.ensure(((size_t)ntiles / kScanTile + 2) * sizeof(uint4)));
+    pa.tile_off = static_cast<u64*>(w.p_toff.p);
+    pa.tile_map = reinterpret_cast<uint2*>(pa.tile_off + ntiles + 1);
+    k_par_tilemap<<<grec, 256, 0, st>>>(pa); ++*launches;
+    k_par_tabs<<<pa.ntiles, kPThreads, 0, st>>>(pa);
+    k_par_head<<<(nlist + 127) / 128, 128, 0, st>>>(pa);
+    k_par_count<<<pa.ntiles, kPThreads, 0, st>>>(pa);
+    *launches += 3;
+    scan64(pa.tile_off, pa.ntiles);
+    k_par_ranges<<<grec, 256, 0, st>>>(pa); ++*launches;
+    scan64(pa.slot_scan, nlist);
+    k_par_counts_to_host<<<1, 32, 0, st>>>(pa.tile_off + pa.ntiles, pa.slot_scan + nlist, nullptr, static_cast<u64*>(w.h_par.p)); ++*launches;
+    G2P_CUDA(cudaStreamSynchronize(st));
+    pa.nsteps = (u32)hp[0]; pa.nops = (u32)(hp[0] >> 32);
+    const u64 big = (u32)hp[1], small = hp[1] >> 32;
+    if (pa.nsteps == 0 || pa.nops == 0) return G2P_OK;
+    // room for the records' descriptor runs in both halves of the array (k_long's blocks follow them), at most 12 bytes of descriptors per input byte
+    const u64 need = 2 * std::max<u64>(std::max<u64>(big, small) + 2048, la.desc_cap / 2u);
+    if (need > la.desc_cap) {
+        if (ctx->desc_cap_override || need > 3 * (u64)n / 16 + 8192 || need > 0xFFFFFF00ULL) return G2P_OK;
+        G2P_CUDA(w.d_desc.ensure((size_t)need * sizeof(LineDesc)));
+        la.desc = static_cast<LineDesc*>(w.d_desc.p);
+        la.desc_cap = (u32)need;
+        pa.desc = la.desc;
+    }
+    pa.half = la.desc_cap / 2u;
+    // per step: spos, srec (4 + 4), sval, sx (16 + 16), lx (8); per op: opos, orec (4 + 4), ox (16)
+    const size_t ns1 = (size_t)pa.nsteps + 1, no1 = (size_t)pa.nops + 1;
+    G2P_CUDA(w.p_step.ensure(ns1 * 48 + 64));
+    G2P_CUDA(w.p_op.ensure(no1 * 24 + 64));
+    G2P_CUDA(w.p_bs.ensure((std::max(ns1, no1) / kScanTile + 2) * sizeof(uint4)));
+    {
+        u8* b = static_cast<u8*>(w.p_step.p);
+        pa.sval = reinterpret_cast<uint4*>(b); b += ns1 * 16;
+        pa.sx = reinterpret_cast<uint4*>(b); b += ns1 * 16;
+        pa.lx = reinterpret_cast<u64*>(b); b += ns1 * 8;
+        pa.spos = reinterpret_cast<u32*>(b); b += ns1 * 4;
+        pa.srec = reinterpret_cast<u32*>(b);
+        u8* c = static_cast<u8*>(w.p_op.p);
+        pa.ox = reinterpret_cast<uint4*>(c); c += no1 * 16;
+        pa.opos = reinterpret_cast<u32*>(c); c += no1 * 4;
+        pa.orec = reinterpret_cast<u32*>(c);
+    }
+    const u32 gmax = (u32)ctx->n_sm * 16u;
+    const u32 gstep = std::min<u32>((pa.nsteps + 127) / 128, gmax), gop = std::min<u32>((pa.nops + 127) / 128, gmax);
+    k_par_slots<<<grec, 256, 0, st>>>(pa);
+    k_par_fill<<<pa.ntiles, kPThreads, 0, st>>>(pa);
+    k_par_steps<<<gstep, 128, 0, st>>>(pa);
+    k_par_ops<<<gop, 128, 0, st>>>(pa);
+    *launches += 4;
+    scan4(pa.sx, pa.nsteps);
+    scan4(pa.ox, pa.nops);
+    k_par_totals<<<grec, 256, 0, st>>>(pa);
+    k_par_lines<<<gstep, 128, 0, st>>>(pa);
+    *launches += 2;
+    scan64(pa.lx, pa.nsteps);
+    k_par_finish<<<grec, 256, 0, st>>>(pa);
+    k_par_place<<<gstep, 128, 0, st>>>(pa);
+    *launches += 2;
+    G2P_CUDA(cudaGetLastError());
+    la.list = pa.reject_list;
+    la.n_list = &d_meta->n_reject;
+    *done = true;
+    return G2P_OK;
+}
+
 static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cudaStream_t st, g2p_result* res, u8** d_out) {
     std::memset(res, 0, sizeof *res);
     *d_out = nullptr;
@@ -546,9 +664,32 @@ static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
         RecArgs ra{sa, chunks, d_perm};
         k_rec<<<(nrec + kRThreads - 1) / kRThreads, kRThreads, rec_smem(chunks), st>>>(ra);
     }
-    k_long<false><<<nlong, kLThreads, long_smem<false>(), st>>>(la);
-    k_convert_list<false><<<nlist, kListThreads, 0, st>>>(d_gaf, d_rec, ctx->table, d_off, d_status, nullptr, d_meta, d_list2, &d_meta->n_deleg2);
-    launches += 3;
+    ++launches;
+    u32 desc_cap_now = desc_cap;
+    bool par_done = false;
+    if (ctx->par && !ctx->size_kernel_short) {
+        // how many records did k_rec leave?  (one small read-back; the stream is synchronised again before the emit pass anyway)
+        k_words_to_host<<<1, 32, 0, st>>>(&d_meta->n_deleg, &hm->n_deleg, 1); ++launches;
+        G2P_CUDA(cudaStreamSynchronize(st));
+        const u32 n_left = hm->n_deleg;
+        if (n_left) {
+            G2P_CUDA(cudaEventRecord(w.ev[8], st));
+            rc = run_par(ctx, w, d_gaf, n, st, n_left, la, d_meta, &launches, &par_done);
+            if (rc) return rc;
+            G2P_CUDA(cudaEventRecord(w.ev[9], st));
+            d_desc = la.desc;
+            desc_cap_now = la.desc_cap;
+        }
+        if (n_left) {
+            k_long<false><<<nlong, kLThreads, long_smem<false>(), st>>>(la);
+            k_convert_list<false><<<nlist, kListThreads, 0, st>>>(d_gaf, d_rec, ctx->table, d_off, d_status, nullptr, d_meta, d_list2, &d_meta->n_deleg2);
+            launches += 2;
+        }
+    } else {
+        k_long<false><<<nlong, kLThreads, long_smem<false>(), st>>>(la);
+        k_convert_list<false><<<nlist, kListThreads, 0, st>>>(d_gaf, d_rec, ctx->table, d_off, d_status, nullptr, d_meta, d_list2, &d_meta->n_deleg2);
+        launches += 2;
+    }
     G2P_CUDA(cudaEventRecord(w.ev[2], st));
     // exclusive scans: byte counts -> output offsets, line counts -> line slots (+ the line map)
     G2P_CUDA(w.d_map.ensure((size_t)nrec * kSMaxLines * sizeof(LineMapEnt)));
@@ -562,6 +703,8 @@ static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
     const u64 out_total = hm->out_total;
     res->n_long = hm->n_deleg;
     res->n_delegated = hm->n_deleg2;
+    res->n_par = par_done ? hm->n_deleg - hm->n_reject : 0u;
+    if (par_done) cudaEventElapsedTime(&res->par_ms, w.ev[8], w.ev[9]);
     G2P_CUDA(w.d_out.ensure(out_total + 256));
     u8* d_o = static_cast<u8*>(w.d_out.p);
     // pass 2: emit
@@ -574,14 +717,14 @@ static int run_pipeline(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
         k_emit_lines<false><<<(nl + kEThreads - 1) / kEThreads, kEThreads, kEmitSmem, st>>>(ea);
         ++launches;
     }
-    const u32 half = desc_cap / 2u;
+    const u32 half = desc_cap_now / 2u;
     const u32 n_slots = std::min<u32>(hm->n_desc, half);
-    if (n_slots) {           // k_long's records, full batches: dense 32-slot blocks
+    if (n_slots) {           // k_par's / k_long's records, full batches: dense 32-slot blocks
         EmitArgs ea{d_gaf, (u64)n, d_rec, d_off, d_desc, nullptr, d_rdesc, d_status, n_slots, d_o};
         k_emit_lines<true><<<(n_slots + kEThreads - 1) / kEThreads, kEThreads, kEmitSmem, st>>>(ea);
         ++launches;
     }
-    const u32 n_slots2 = std::min<u32>(hm->n_desc2, desc_cap - half);
+    const u32 n_slots2 = std::min<u32>(hm->n_desc2, desc_cap_now - half);
     if (n_slots2) {          // ... and their small batches
         EmitArgs ea{d_gaf, (u64)n, d_rec, d_off, d_desc + half, nullptr, d_rdesc, d_status, n_slots2, d_o};
         k_emit_lines<true><<<(n_slots2 + kEThreads - 1) / kEThreads, kEThreads, kEmitSmem, st>>>(ea);

@@ -42,7 +42,7 @@ struct PipelineMeta {
     u32 n_deleg2;      // records k_long left to the general kernel
     u32 n_desc;        // line-descriptor slots reserved by k_long for full batches (32 per batch, lower half of the array)
     u32 n_desc2;       // ... and for batches of at most 8 lines (as many as needed, rounded up to four; upper half)
-    u32 pad_meta;
+    u32 n_reject;      // records k_par left to k_long
     u32 legacy_long;   // some k_long record is not described: run k_long<true>
     u64 lines_total;   // PAF lines of the records k_short converted
 };
@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(u32* __restrict__ tile_coun
         meta->n_deleg2 = 0;
         meta->n_desc = 0;
         meta->n_desc2 = 0;
+        meta->n_reject = 0;
         meta->legacy_long = 0;
         meta->lines_total = 0;
     }
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(kIdxThreads) k_index1(const u8* __restrict__ t
                 meta->first_err = 0xFFFFFFFFu;
                 meta->out_total = 0;
                 meta->err_status = 0;
-                meta->n_deleg = 0; meta->long_cursor = 0; meta->n_deleg2 = 0; meta->n_desc = 0; meta->n_desc2 = 0; meta->legacy_long = 0; meta->lines_total = 0;
+                meta->n_deleg = 0; meta->long_cursor = 0; meta->n_deleg2 = 0; meta->n_desc = 0; meta->n_desc2 = 0; meta->n_reject = 0; meta->legacy_long = 0; meta->lines_total = 0;
                 if (recs != lines && recs < cap) rec_start[recs] = (u32)n + 1;   // unterminated last line
             }
             if (tile == 0 && cap) rec_start[0] = 0;
@@ -534,4 +535,5 @@ __global__ void k_diagnose(const u8* __restrict__ gaf, const u32* __restrict__ r
 }  // namespace g2p
 
 #include "g2p_fuse.cuh"
+#include "g2p_par.cuh"
 #include "g2p_filter.cuh"

@@ -70,6 +70,8 @@ typedef struct g2p_result {
     float unstable_ms;      /* g2p_unstable_convert_*: CUDA-event time of the gaf2unstable stage (included in device_ms) */
     uint32_t stage;         /* g2p_unstable_convert_*: 1 / 2 = rec_status comes from the gaf2unstable / gaf2paf stage */
     uint64_t mid_bytes;     /* g2p_unstable_convert_*: bytes of the intermediate node-space GAF (it never leaves the device) */
+    float par_ms;           /* CUDA-event time of the token-parallel kernels k_par_* (part of size_ms) */
+    uint32_t n_par;         /* records converted by them (n_long counts what k_rec left; n_long - n_par went on to k_long) */
 } g2p_result;
 
 /* Context bound to one CUDA device. */

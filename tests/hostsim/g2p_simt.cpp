@@ -134,7 +134,7 @@ int main(int argc, char** argv) {
     const u32 ncta = (nrec + kShortRecsPerCta - 1) / kShortRecsPerCta;
     const u32 nlist = std::min<u32>((nrec + kListThreads - 1) / kListThreads, 8u);
     // G2P_SIMT_DESC_CAP=<slots> shrinks k_long's descriptor array to exercise the overflow fallback
-    const u32 desc_cap = std::getenv("G2P_SIMT_DESC_CAP") ? (u32)std::atol(std::getenv("G2P_SIMT_DESC_CAP")) : (u32)(n / 8) + 2048;
+    u32 desc_cap = std::getenv("G2P_SIMT_DESC_CAP") ? (u32)std::atol(std::getenv("G2P_SIMT_DESC_CAP")) : (u32)(n / 8) + 2048;
     std::vector<LineDesc> desc(desc_cap + 1), sdesc((size_t)nrec * kSMaxLines);
     std::vector<RecDesc> rdesc(nrec);
     std::vector<u64> loff(nrec + 1);
@@ -163,6 +163,78 @@ int main(int argc, char** argv) {
     }
     LongArgs la{gaf, n, rec.data(), T, off.data(), status.data(), nullptr, list.data(), &meta.n_deleg, list2.data(), &meta.n_deleg2,
                 desc.data(), rdesc.data(), &meta.n_desc, &meta.n_desc2, desc_cap, 8u, &meta.legacy_long, &meta.long_cursor};
+    // ---- the token-parallel kernels (run_par of g2p_capi.cu) take k_rec's delegates first; G2P_PAR=0: k_long takes them all
+    std::vector<u32> list3(nrec);
+    u32 par_steps = 0, par_ops = 0;
+    if (meta.n_deleg && !(std::getenv("G2P_PAR") && std::atoi(std::getenv("G2P_PAR")) == 0)) do {
+        auto scan64 = [&](u64* x, u32 cnt) {
+            const u32 nb = (cnt + kScanTile - 1) / kScanTile;
+            std::vector<u64> bs(nb + 1);
+            hs::launch(dim3(nb), dim3(kScanThreads), 0, [&] { k_scan_reduce(x, cnt, bs.data()); });
+            hs::launch(dim3(1), dim3(1024), 0, [&] { k_scan_blocks(bs.data(), nb, x + cnt); });
+            hs::launch(dim3(nb), dim3(kScanThreads), 0, [&] { k_scan_apply(x, cnt, bs.data(), x + cnt); });
+        };
+        auto scan4 = [&](uint4* x, u32 cnt) {
+            const u32 nb = (cnt + kScanTile - 1) / kScanTile;
+            std::vector<uint4> bs(nb + 1);
+            hs::launch(dim3(nb), dim3(kScanThreads), 0, [&] { k_scan4_reduce(x, cnt, bs.data()); });
+            hs::launch(dim3(1), dim3(1024), 0, [&] { k_scan4_blocks(bs.data(), nb, x + cnt); });
+            hs::launch(dim3(nb), dim3(kScanThreads), 0, [&] { k_scan4_apply(x, cnt, bs.data()); });
+        };
+        const u32 npl = meta.n_deleg;
+        std::vector<ParRec> precs(npl);
+        std::vector<u64> tile_base(npl + 1), slot_scan(npl + 1);
+        ParArgs pa;
+        std::memset(&pa, 0, sizeof pa);
+        pa.gaf = gaf; pa.n = n; pa.rec_start = rec.data(); pa.T = T; pa.list = list.data(); pa.nlist = npl;
+        pa.recs = precs.data(); pa.tile_base = tile_base.data(); pa.slot_scan = slot_scan.data();
+        pa.out_off = off.data(); pa.status = status.data(); pa.rdesc = rdesc.data(); pa.desc = desc.data();
+        pa.reject_list = list3.data(); pa.n_reject = &meta.n_reject; pa.n_desc = &meta.n_desc; pa.n_desc2 = &meta.n_desc2; pa.small_max = 8;
+        const u32 grec = (npl + 255) / 256;
+        hs::launch(dim3(grec), dim3(256), 0, [&] { k_par_plan(pa); });
+        scan64(tile_base.data(), npl);
+        const u64 ptiles = tile_base[npl];
+        if (ptiles == 0 || ptiles > 0xFFFFFF00ULL) break;
+        pa.ntiles = (u32)ptiles;
+        std::vector<u64> tile_off(ptiles + 1);
+        pa.tile_off = tile_off.data();
+        std::vector<uint2> tile_map(ptiles);
+        pa.tile_map = tile_map.data();
+        hs::launch(dim3(grec), dim3(256), 0, [&] { k_par_tilemap(pa); });
+        hs::launch(dim3(pa.ntiles), dim3(kPThreads), 0, [&] { k_par_tabs(pa); });
+        hs::launch(dim3((npl + 127) / 128), dim3(128), 0, [&] { k_par_head(pa); });
+        hs::launch(dim3(pa.ntiles), dim3(kPThreads), 0, [&] { k_par_count(pa); });
+        scan64(tile_off.data(), pa.ntiles);
+        hs::launch(dim3(grec), dim3(256), 0, [&] { k_par_ranges(pa); });
+        scan64(slot_scan.data(), npl);
+        pa.nsteps = (u32)tile_off[ptiles]; pa.nops = (u32)(tile_off[ptiles] >> 32);
+        if (pa.nsteps == 0 || pa.nops == 0) break;
+        {   // room for the records' descriptor runs in both halves (k_long's blocks follow them); bounded by 12 bytes of descriptors per input byte
+            const u64 big = (u32)slot_scan[npl], small = slot_scan[npl] >> 32;
+            const u64 need = 2 * std::max<u64>(std::max<u64>(big, small) + 2048, desc_cap / 2u);
+            if (std::getenv("G2P_SIMT_DESC_CAP") ? need > desc_cap : need > 3 * n / 16 + 8192) break;
+            if (need > desc_cap) { desc_cap = (u32)need; desc.resize(desc_cap + 1); la.desc = desc.data(); la.desc_cap = desc_cap; pa.desc = desc.data(); }
+        }
+        pa.half = desc_cap / 2u; pa.small_max = 8;
+        std::vector<u32> spos(pa.nsteps), srec(pa.nsteps), opos(pa.nops), orec(pa.nops);
+        std::vector<uint4> sval(pa.nsteps), sx(pa.nsteps + 1), ox(pa.nops + 1);
+        std::vector<u64> lx(pa.nsteps + 1);
+        pa.spos = spos.data(); pa.srec = srec.data(); pa.opos = opos.data(); pa.orec = orec.data();
+        pa.sval = sval.data(); pa.sx = sx.data(); pa.ox = ox.data(); pa.lx = lx.data();
+        hs::launch(dim3(grec), dim3(256), 0, [&] { k_par_slots(pa); });
+        hs::launch(dim3(pa.ntiles), dim3(kPThreads), 0, [&] { k_par_fill(pa); });
+        hs::launch(dim3(std::min<u32>((pa.nsteps + 127) / 128, 8u)), dim3(128), 0, [&] { k_par_steps(pa); });
+        hs::launch(dim3(std::min<u32>((pa.nops + 127) / 128, 8u)), dim3(128), 0, [&] { k_par_ops(pa); });
+        scan4(sx.data(), pa.nsteps);
+        scan4(ox.data(), pa.nops);
+        hs::launch(dim3(grec), dim3(256), 0, [&] { k_par_totals(pa); });
+        hs::launch(dim3(std::min<u32>((pa.nsteps + 127) / 128, 8u)), dim3(128), 0, [&] { k_par_lines(pa); });
+        scan64(lx.data(), pa.nsteps);
+        hs::launch(dim3(grec), dim3(256), 0, [&] { k_par_finish(pa); });
+        hs::launch(dim3(std::min<u32>((pa.nsteps + 127) / 128, 8u)), dim3(128), 0, [&] { k_par_place(pa); });
+        par_steps = pa.nsteps; par_ops = pa.nops;
+        la.list = list3.data(); la.n_list = &meta.n_reject;
+    } while (0);
     const u32 nlong = 2;
     hs::launch(dim3(nlong), dim3(kLThreads), long_smem<false>(), [&] { k_long<false>(la); });
     hs::launch(dim3(nlist), dim3(kListThreads), 0, [&] { k_convert_list<false>(gaf, rec.data(), T, off.data(), status.data(), nullptr, &meta, list2.data(), &meta.n_deleg2); });
@@ -199,7 +271,7 @@ int main(int argc, char** argv) {
         hs::launch(dim3(1), dim3(1), 0, [&] { k_diagnose(gaf, rec.data(), T, off.data(), &meta); });
         out_bytes = meta.err_out_end;
     }
-    if (std::getenv("G2P_SIMT_STATS")) std::fprintf(stderr, "g2p_simt: %u records, %u to k_long, %u to the general kernel, %llu short lines, %u + %u long line slots (cap %u), %llu bytes out\n", nrec, meta.n_deleg, meta.n_deleg2, (unsigned long long)meta.lines_total, meta.n_desc, meta.n_desc2, desc_cap, (unsigned long long)out_bytes);
+    if (std::getenv("G2P_SIMT_STATS")) std::fprintf(stderr, "g2p_simt: %u records, %u to k_par (%u steps, %u ops), %u to k_long, %u to the general kernel, %llu short lines, %u + %u long line slots (cap %u), %llu bytes out\n", nrec, meta.n_deleg, par_steps, par_ops, par_steps ? meta.n_reject : meta.n_deleg, meta.n_deleg2, (unsigned long long)meta.lines_total, meta.n_desc, meta.n_desc2, desc_cap, (unsigned long long)out_bytes);
     std::fwrite(out.data(), 1, out_bytes, stdout);
     std::fflush(stdout);
     if (meta.first_err != 0xFFFFFFFFu) {
