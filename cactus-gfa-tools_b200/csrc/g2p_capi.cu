@@ -500,9 +500,10 @@ static int run_par(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cudaStrea
     const u64 ntiles = hp[0];
     if (ntiles == 0 || ntiles > 0x7FFFFF00ULL) return G2P_OK;
     pa.ntiles = (u32)ntiles;
-    G2P_CUDA(w.p_toff.ensure(((size_t)ntiles + 1) * (sizeof(u64) + sizeof(uint2))));
+    G2P_CUDA(w.p_toff.ensure(((size_t)ntiles + 1) * (sizeof(uint4) + sizeof(u64) + sizeof(uint2))));
     G2P_CUDA(w.p_bs.ensure(((size_t)ntiles / kScanTile + 2) * sizeof(uint4)));
-    pa.tile_off = static_cast<u64*>(w.p_toff.p);
+    pa.tile_osum = static_cast<uint4*>(w.p_toff.p);
+    pa.tile_off = reinterpret_cast<u64*>(pa.tile_osum + ntiles + 1);
     pa.tile_map = reinterpret_cast<uint2*>(pa.tile_off + ntiles + 1);
     k_par_tilemap<<<grec, 256, 0, st>>>(pa); ++*launches;
     k_par_tabs<<<pa.ntiles, kPThreads, 0, st>>>(pa);
@@ -510,6 +511,7 @@ static int run_par(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cudaStrea
     k_par_count<<<pa.ntiles, kPThreads, 0, st>>>(pa);
     *launches += 3;
     scan64(pa.tile_off, pa.ntiles);
+    scan4(pa.tile_osum, pa.ntiles);
     k_par_ranges<<<grec, 256, 0, st>>>(pa); ++*launches;
     scan64(pa.slot_scan, nlist);
     k_par_counts_to_host<<<1, 32, 0, st>>>(pa.tile_off + pa.ntiles, pa.slot_scan + nlist, nullptr, static_cast<u64*>(w.h_par.p)); ++*launches;
@@ -527,32 +529,30 @@ static int run_par(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cudaStrea
         pa.desc = la.desc;
     }
     pa.half = la.desc_cap / 2u;
-    // per step: spos, srec (4 + 4), sval, sx (16 + 16), lx (8); per op: opos, orec (4 + 4), ox (16)
+    // per step: sval (16), sx, lx (8 + 8), spos, srec (4 + 4); per op: ox (16), opos, ot (4 + 4)
     const size_t ns1 = (size_t)pa.nsteps + 1, no1 = (size_t)pa.nops + 1;
-    G2P_CUDA(w.p_step.ensure(ns1 * 48 + 64));
+    G2P_CUDA(w.p_step.ensure(ns1 * 40 + 64));
     G2P_CUDA(w.p_op.ensure(no1 * 24 + 64));
-    G2P_CUDA(w.p_bs.ensure((std::max(ns1, no1) / kScanTile + 2) * sizeof(uint4)));
+    G2P_CUDA(w.p_bs.ensure((ns1 / kScanTile + 2) * sizeof(uint4)));
     {
         u8* b = static_cast<u8*>(w.p_step.p);
         pa.sval = reinterpret_cast<uint4*>(b); b += ns1 * 16;
-        pa.sx = reinterpret_cast<uint4*>(b); b += ns1 * 16;
+        pa.sx = reinterpret_cast<u64*>(b); b += ns1 * 8;
         pa.lx = reinterpret_cast<u64*>(b); b += ns1 * 8;
         pa.spos = reinterpret_cast<u32*>(b); b += ns1 * 4;
         pa.srec = reinterpret_cast<u32*>(b);
         u8* c = static_cast<u8*>(w.p_op.p);
         pa.ox = reinterpret_cast<uint4*>(c); c += no1 * 16;
         pa.opos = reinterpret_cast<u32*>(c); c += no1 * 4;
-        pa.orec = reinterpret_cast<u32*>(c);
+        pa.ot = reinterpret_cast<u32*>(c);
     }
     const u32 gmax = (u32)ctx->n_sm * 16u;
-    const u32 gstep = std::min<u32>((pa.nsteps + 127) / 128, gmax), gop = std::min<u32>((pa.nops + 127) / 128, gmax);
+    const u32 gstep = std::min<u32>((pa.nsteps + 127) / 128, gmax);
     k_par_slots<<<grec, 256, 0, st>>>(pa);
     k_par_fill<<<pa.ntiles, kPThreads, 0, st>>>(pa);
     k_par_steps<<<gstep, 128, 0, st>>>(pa);
-    k_par_ops<<<gop, 128, 0, st>>>(pa);
-    *launches += 4;
-    scan4(pa.sx, pa.nsteps);
-    scan4(pa.ox, pa.nops);
+    *launches += 3;
+    scan64(pa.sx, pa.nsteps);
     k_par_totals<<<grec, 256, 0, st>>>(pa);
     k_par_lines<<<gstep, 128, 0, st>>>(pa);
     *launches += 2;

@@ -9,13 +9,14 @@
 //   k_par_tilemap  thread / record      tile -> (record, text position)
 //   k_par_tabs     thread / 16 bytes    tab positions -> the record's (small) tab list
 //   k_par_head     thread / record      columns 1-12, tags, path and cg spans, RecDesc                   (parse_gaf_record)
-//   k_par_count    thread / 16 bytes    '>' '<' markers inside the path column, op letters inside the cg value
+//   k_par_count    thread / 16 bytes    '>' '<' markers inside the path column, op letters inside the cg value            + u64, uint4 scans
 //   k_par_ranges   thread / record      its steps / ops in the flat arrays, its run of line descriptors  + u64 scans
 //   k_par_fill     thread / 16 bytes    ... the positions of the markers and letters, in text order
 //   k_par_steps    thread / path step   name, ":start-end", ONE table probe                              (gaf2paf_main.cpp:157-170)
-//   k_par_ops      thread / CIGAR op    length and class -> (target, query, match, block) contributions   (for_each_cg)
-//   uint4 scans                         exclusive prefix sums of both (mod 2^32: differences inside a record are exact,
-//                                       records whose sums do not fit 31 bits are recognised by 64-bit totals and left alone)
+//   (k_par_count and k_par_fill also parse the CIGAR ops, for_each_cg: the first sums their (target, query, match, block)
+//    contributions per tile, the second -- after a scan over the tiles -- writes every op's exclusive prefix sums.  All
+//    sums are mod 2^32: differences inside a record are exact, and records whose sums do not fit 31 bits are
+//    recognised by 64-bit totals and left alone)
 //   k_par_totals   thread / record      summed step lengths, mirrored path interval of '-' records       (flip_gaf)
 //   k_par_lines    thread / path step   boundary B_i -> lower_bound in the cumulative target length of the ops
 //                                       (cigar_next_by_target as a binary search), sums by prefix differences, the
@@ -36,14 +37,14 @@ constexpr u32 kPTile = 2048, kPThreads = 128;   // 16 bytes per thread
 constexpr u32 kPMaxTabs = 40;
 
 struct __align__(16) ParRec {
+    u32 pa, pb, ca, cb;       // path column and cg value, absolute text positions (one 16-byte load in the tile kernels)
     u32 r, s, len, ntabs;     // record ordinal, text start, length without '\n'
-    u32 status;               // 0 ok, 1 not canonical (-> k_long)
-    u32 pa, pb, ca, cb;       // path column and cg value, absolute text positions
     u32 s0, ns, g0, no;       // its steps / ops in the flat arrays
+    u32 status;               // 0 ok, 1 not canonical (-> k_long)
     i32 qs, ps, pe;           // ps / pe mirrored for '-' records by k_par_totals
     u32 total, rconst, minus;
     u32 slot0, nslots;        // descriptor run
-    u32 pad0;
+    u32 pad0, pad1, pad2;
     unsigned long long sum_steps, sum_ops;   // 64-bit totals (overflow guards of the 32-bit prefix sums)
     u32 tabs[kPMaxTabs];
 };
@@ -61,11 +62,13 @@ struct ParArgs {
     uint2* tile_map;        // [ntiles] record (list index), first text position
     u64* slot_scan;         // [nlist + 1] descriptor run starts (32-padded runs | small runs << 32)
     u32 ntiles;
+    uint4* tile_osum;       // [ntiles + 1] exclusive sums of the tiles' op contributions
     u32* spos; u32* srec;   // per step: marker position, record (list index)
-    u32* opos; u32* orec;   // per op: letter position, record
+    u32* opos;              // per op: letter position
     uint4* sval;            // per step: tlen, sa, se, nl | '<' << 16                        (k_par_steps)
-    uint4* sx;              // per step (+1): {slen, 0, 0, 0}, scanned
-    uint4* ox;              // per op (+1): {target, query, match, block}, scanned
+    u64* sx;                // per step (+1): step length, scanned
+    uint4* ox;              // per op (+1): exclusive prefix sums of {target, query, match, block}  (k_par_fill, from the tile sums)
+    u32* ot;                // per op (+1): ox[].x alone, what the boundary search reads
     u64* lx;                // per step (+1), normalised order: line_len | emit << 32, scanned
     u32 nsteps, nops;
     // outputs shared with k_long
@@ -155,7 +158,7 @@ __global__ void __launch_bounds__(256) k_par_tilemap(const ParArgs a) {
     }
 }
 __device__ __forceinline__ u32 par_tile_record(const ParArgs& a, u32 tile, u32& pos0) {
-    const uint2 m = a.tile_map[tile];
+    const uint2 m = __ldg(a.tile_map + tile);
     pos0 = m.y;
     return m.x;
 }
@@ -182,11 +185,9 @@ __device__ __forceinline__ u32 par_nondigit_mask(const ParChunk& c) {
 }
 
 __global__ void __launch_bounds__(kPThreads) k_par_tabs(const ParArgs a) {
-    __shared__ u32 s_k, s_pos;
-    if (threadIdx.x == 0) { u32 p; s_k = par_tile_record(a, blockIdx.x, p); s_pos = p; }
-    __syncthreads();
-    ParRec& R = a.recs[s_k];
-    const ParChunk c = par_chunk(a, s_pos);
+    u32 t_pos;
+    ParRec& R = a.recs[par_tile_record(a, blockIdx.x, t_pos)];
+    const ParChunk c = par_chunk(a, t_pos);
     u32 m = par_eq_mask(c, 0x09090909u) & par_range(c, R.s, R.s + R.len);
     while (m) {
         const u32 b = (u32)__ffs((int)m) - 1u;
@@ -254,6 +255,7 @@ __global__ void __launch_bounds__(128) k_par_head(const ParArgs a) {
                 else if (t[x] == 'r' && t[x + 1] == 'c') { L.rc_a = x + 3; L.rc_b = y; }
             }
             if (bad || cb == 0 || ca >= cb || qs < 0 || ps < 0 || pe < 0) break;
+            if ((u32)t[cb - 1] - '0' <= 9u) break;   // digits after the last op letter
             L.gi_n = gi_fast(L.m, L.b, L.gi);
             if (L.gi_n == 0 || !rec_desc_fits(L)) break;
             R.pa = R.s + pa; R.pb = R.s + pb; R.ca = R.s + ca; R.cb = R.s + cb;
@@ -267,25 +269,99 @@ __global__ void __launch_bounds__(128) k_par_head(const ParArgs a) {
 }
 
 // marker bits inside the path column, op-letter bits inside the cg value
-__device__ __forceinline__ void par_masks(const ParRec& R, const ParChunk& c, u32& mm, u32& om) {
-    mm = om = 0;
-    if (R.status) return;
-    const u32 pr = par_range(c, R.pa, R.pb), cr = par_range(c, R.ca, R.cb);
+__device__ __forceinline__ void par_masks(const uint4 sp, const ParChunk& c, u32& mm, u32& om) {
+    mm = om = 0;   // (records k_par_head rejected have empty spans; a status set later must not change what is counted)
+    const u32 pr = par_range(c, sp.x, sp.y), cr = par_range(c, sp.z, sp.w);
     if (pr) mm = (par_eq_mask(c, 0x3E3E3E3Eu) | par_eq_mask(c, 0x3C3C3C3Cu)) & pr;
     if (cr) om = par_nondigit_mask(c) & cr;
 }
-__global__ void __launch_bounds__(kPThreads) k_par_count(const ParArgs a) {
-    __shared__ u32 s_k, s_pos;
-    __shared__ u64 ws[kPThreads / 32];
-    if (threadIdx.x == 0) { u32 p; s_k = par_tile_record(a, blockIdx.x, p); s_pos = p; }
+// The CTA's tile in shared memory behind a 16-byte halo (the text just before the tile), so that the digits of an op
+// are read from there whichever thread or tile they begin in.  Returns the calling thread's chunk.
+__device__ __forceinline__ ParChunk par_stage(const ParArgs& a, u32 tile_pos, u8* sm) {
+    const ParChunk c = par_chunk(a, tile_pos);
+    reinterpret_cast<uint4*>(sm)[1 + threadIdx.x] = make_uint4(c.w0, c.w1, c.w2, c.w3);
+    if (threadIdx.x == 0) reinterpret_cast<uint4*>(sm)[0] = tile_pos >= 16u ? ldg_vec_guarded(a.gaf, (u64)tile_pos - 16u, a.n) : make_uint4(0, 0, 0, 0);
     __syncthreads();
+    return c;
+}
+// One CIGAR op (for_each_cg, gafkluge.hpp:226-239), its letter at offset `off` of the staged tile.  The digits before it
+// come from one unaligned 4-byte window when there are at most three (the byte before the first digit is a letter or
+// the ':' of "cg:Z:"), else from a byte loop.  Returns length | class << 24 (kPOpT / Q / M: consumes target / query /
+// counts as match; kPOpValid), or 0 if it is not a canonical op.
+constexpr u32 kPOpT = 1u << 24, kPOpQ = 1u << 25, kPOpM = 1u << 26, kPOpValid = 1u << 27;
+__device__ __forceinline__ u32 par_op(const u8* sm, u32 off) {
+    const u32 kc = (u32)sm[off] - '=';
+    const u32 o4 = off - 4u;
+    const u32* q = reinterpret_cast<const u32*>(sm + (o4 & ~3u));
+    const u32 W = __funnelshift_r(q[0], q[1], (o4 & 3u) * 8u);   // byte 3 = the last digit
+    const u32 F = nondigit_bytes(W);
+    u32 x, nd, first;
+    if (F) {   // at most three digits
+        nd = (u32)__clz((int)F) >> 3;
+        const u32 D = W & 0x0F0F0F0Fu;
+        const u32 d3 = D >> 24, d2 = (D >> 16) & 0xffu, d1 = (D >> 8) & 0xffu;
+        x = d3 + (nd > 1 ? d2 * 10u : 0u) + (nd > 2 ? d1 * 100u : 0u);
+        first = nd > 2 ? d1 : d2;
+    } else {
+        x = 0; nd = 0; first = 0;
+        u32 p = 1;
+        while (nd < 8u) {
+            const u32 d = (u32)sm[off - 1u - nd] - '0';
+            if (d > 9u) break;
+            x += d * p; p *= 10u; first = d; ++nd;
+        }
+    }
+    if (!(kc < 28u && ((kOpMask >> kc) & 1u)) || nd == 0 || nd > 7 || (nd > 1 && first == 0) || x == 0) return 0u;
+    return x | kPOpValid | (((kTargetMask >> kc) & 1u) ? kPOpT : 0u) | (((kQueryMask >> kc) & 1u) ? kPOpQ : 0u) | (((kMatchMask >> kc) & 1u) ? kPOpM : 0u);
+}
+// ... its (target, query, match, block) contributions
+__device__ __forceinline__ uint4 par_op_sums(u32 op) {
+    const u32 x = op & 0xffffffu;
+    return make_uint4(op & kPOpT ? x : 0u, op & kPOpQ ? x : 0u, op & kPOpM ? x : 0u, x);
+}
+// sum over the CTA, valid in thread 0
+__device__ __forceinline__ uint4 par_block_sum4(uint4 v) {
+    __shared__ uint4 ws4[kPThreads / 32];
+    for (int o = 16; o > 0; o >>= 1) {
+        v.x += __shfl_down_sync(0xffffffffu, v.x, o); v.y += __shfl_down_sync(0xffffffffu, v.y, o);
+        v.z += __shfl_down_sync(0xffffffffu, v.z, o); v.w += __shfl_down_sync(0xffffffffu, v.w, o);
+    }
+    if ((threadIdx.x & 31) == 0) ws4[threadIdx.x >> 5] = v;
+    __syncthreads();
+    uint4 s = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) for (u32 i = 0; i < kPThreads / 32; ++i) s = add4(s, ws4[i]);
+    return s;
+}
+__global__ void __launch_bounds__(kPThreads) k_par_count(const ParArgs a) {
+    __shared__ u64 ws[kPThreads / 32];
+    __shared__ __align__(16) u8 s_text[16 + kPTile];
+    u32 t_pos;
+    ParRec& R = a.recs[par_tile_record(a, blockIdx.x, t_pos)];   // (every thread reads the same map entry: no barrier before the loads below)
+    const uint4 spans = __ldg(reinterpret_cast<const uint4*>(&R));
+    const ParChunk ch = par_stage(a, t_pos, s_text);
     u32 mm, om;
-    par_masks(a.recs[s_k], par_chunk(a, s_pos), mm, om);
+    par_masks(spans, ch, mm, om);
     u64 c = (u64)__popc(mm) | ((u64)__popc(om) << 32);
+    uint4 sum = make_uint4(0, 0, 0, 0);
+    bool bad = false;
+    while (om) {
+        const u32 b = (u32)__ffs((int)om) - 1u;
+        om &= om - 1u;
+        const u32 op = par_op(s_text, 16u + threadIdx.x * 16u + b);
+        if (!op) bad = true;
+        sum = add4(sum, par_op_sums(op));
+    }
+    if (bad) atomicExch(&R.status, 1u);   // (k_par_fill sees the same ops and contributes the same zeros)
     for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
     if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
-    __syncthreads();
-    if (threadIdx.x == 0) { u64 s = 0; for (u32 i = 0; i < kPThreads / 32; ++i) s += ws[i]; a.tile_off[blockIdx.x] = s; }
+    const uint4 tot = par_block_sum4(sum);   // (contains the barrier that orders ws)
+    if (threadIdx.x == 0) {
+        u64 s = 0;
+        for (u32 i = 0; i < kPThreads / 32; ++i) s += ws[i];
+        a.tile_off[blockIdx.x] = s;
+        a.tile_osum[blockIdx.x] = tot;
+        if (tot.w) atomicAdd(&R.sum_ops, (unsigned long long)tot.w);   // (a tile's block length fits 32 bits: 1024 ops of < 10^7)
+    }
 }
 // the record's ranges in the flat arrays; its descriptor run (one slot per step, padded to 32)
 __global__ void __launch_bounds__(256) k_par_ranges(const ParArgs a) {
@@ -304,14 +380,14 @@ __global__ void __launch_bounds__(256) k_par_ranges(const ParArgs a) {
     }
 }
 __global__ void __launch_bounds__(kPThreads) k_par_fill(const ParArgs a) {
-    __shared__ u32 s_k, s_pos;
     __shared__ u64 ws[kPThreads / 32];
-    if (threadIdx.x == 0) { u32 p; s_k = par_tile_record(a, blockIdx.x, p); s_pos = p; }
-    __syncthreads();
-    const u32 k = s_k;
-    const ParChunk ch = par_chunk(a, s_pos);
+    __shared__ __align__(16) u8 s_text[16 + kPTile];
+    u32 t_pos;
+    const u32 k = par_tile_record(a, blockIdx.x, t_pos);
+    const uint4 spans = __ldg(reinterpret_cast<const uint4*>(a.recs + k));
+    const ParChunk ch = par_stage(a, t_pos, s_text);
     u32 mm, om;
-    par_masks(a.recs[k], ch, mm, om);
+    par_masks(spans, ch, mm, om);
     const u64 c = (u64)__popc(mm) | ((u64)__popc(om) << 32);
     u64 incl = c;
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -323,7 +399,36 @@ __global__ void __launch_bounds__(kPThreads) k_par_fill(const ParArgs a) {
     const u64 base = a.tile_off[blockIdx.x] + pre + incl - c;
     u32 si = (u32)base, oi = (u32)(base >> 32);
     while (mm) { const u32 b = (u32)__ffs((int)mm) - 1u; mm &= mm - 1u; a.spos[si] = ch.pos + b; a.srec[si] = k; ++si; }
-    while (om) { const u32 b = (u32)__ffs((int)om) - 1u; om &= om - 1u; a.opos[oi] = ch.pos + b; a.orec[oi] = k; ++oi; }
+    // the ops: values as in k_par_count, prefix = tile prefix (scanned) + the threads before this one + the ops before this one
+    // (parsed once; a canonical chunk holds at most 8 ops -- with more, one of them has no digits and the record is rejected)
+    __shared__ u32 s_ops[kPThreads * 8];
+    const u32 soff = 16u + threadIdx.x * 16u;
+    uint4 vals = make_uint4(0, 0, 0, 0);
+    {
+        u32 j = 0;
+        for (u32 m = om; m; ++j) {
+            const u32 b = (u32)__ffs((int)m) - 1u;
+            m &= m - 1u;
+            const u32 op = par_op(s_text, soff + b);
+            if (j < 8u) s_ops[threadIdx.x * 8u + j] = op;
+            vals = add4(vals, par_op_sums(op));
+        }
+    }
+    uint4 inc4 = vals;
+    for (int o = 1; o < 32; o <<= 1) { const uint4 up = shfl_up4(inc4, o); if (lane >= (u32)o) inc4 = add4(inc4, up); }
+    __shared__ uint4 ws4[kPThreads / 32];
+    if (lane == 31) ws4[warp] = inc4;
+    __syncthreads();
+    uint4 run = add4(a.tile_osum[blockIdx.x], sub4(inc4, vals));
+    for (u32 i = 0; i < warp; ++i) run = add4(run, ws4[i]);
+    for (u32 j = 0; om; ++j) {
+        const u32 b = (u32)__ffs((int)om) - 1u;
+        om &= om - 1u;
+        a.opos[oi] = ch.pos + b; a.ox[oi] = run; a.ot[oi] = run.x;
+        run = add4(run, par_op_sums(j < 8u ? s_ops[threadIdx.x * 8u + j] : 0u));
+        ++oi;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { const uint4 t = a.tile_osum[a.ntiles]; a.ox[a.nops] = t; a.ot[a.nops] = t.x; }
 }
 // (slot_scan scanned) -> the records' descriptor runs
 __global__ void __launch_bounds__(256) k_par_slots(const ParArgs a) {
@@ -346,74 +451,75 @@ __device__ __forceinline__ void par_sum64(unsigned long long* dst, u32 key, u32 
     } else if (active && v) atomicAdd(dst, (unsigned long long)v);
 }
 
-// one path step: "[><]name[:start-end]", one table probe
+// one path step: "[><]name[:start-end]", one table probe.  (Flags instead of early exits: the probe, a dependent random
+// access, must be issued once for the whole warp, not once per divergent path that leads to it.)
 __global__ void __launch_bounds__(128) k_par_steps(const ParArgs a) {
     const u32 nround = (a.nsteps + 31u) & ~31u;
+    const u8* g = a.gaf;
     for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < nround; s += gridDim.x * blockDim.x) {
         const bool in = s < a.nsteps;
         const u32 k = in ? a.srec[s] : 0u;
         ParRec& R = a.recs[k];
-        uint4 v = make_uint4(0, 0, 0, 0);
-        u32 slen = 0;
-        bool ok = false;
         const bool live = in && !R.status;
-        if (live) do {
-            const u8* g = a.gaf;
-            const u32 mp = a.spos[s];
-            const u32 end = s + 1 < R.s0 + R.ns ? a.spos[s + 1] : R.pb;
-            u32 e = mp + 1;
-            while (e < end && g[e] != ':') ++e;
-            const u32 nl = e - (mp + 1);
-            if (nl == 0 || nl > 255) break;
-            i64 tl64;
-            if (!table_lookup(a.T, g + mp + 1, nl, tl64) || tl64 < 0 || tl64 > 0x7fffffffLL) break;
-            u32 sa = 0, se = (u32)tl64;
-            if (e < end) {   // ":start-end" (gafkluge.hpp:131-146), plain digits only
-                u32 q = e + 1, x = 0;
-                const u32 q1 = q;
-                while (q < end && (u32)g[q] - '0' <= 9u && q - q1 < 10) { x = x * 10u + ((u32)g[q] - '0'); ++q; }
-                if (q == q1 || q - q1 > 9 || q >= end || g[q] != '-') break;
-                sa = x;
-                const u32 q2 = ++q;
-                x = 0;
-                while (q < end && (u32)g[q] - '0' <= 9u && q - q2 < 10) { x = x * 10u + ((u32)g[q] - '0'); ++q; }
-                if (q == q2 || q - q2 > 9 || q != end || x < sa) break;
-                se = x;
+        // ---- the token: name length, key
+        u32 mp = 0, end = 0, nl = 0, mode = 0;   // mode 1: name of <= 16 bytes (its own key), 2: longer
+        u64 k0 = 0, k1 = 0;
+        if (live) {
+            mp = a.spos[s];
+            end = s + 1 < R.s0 + R.ns ? a.spos[s + 1] : R.pb;
+            const u32 na = mp + 1, tl = end - na;
+            bool scan = true;
+            u32 e = na;
+            if ((u64)mp + 28 <= a.n) {   // the first 16 bytes in registers: ':' by SWAR
+                const u32* q = reinterpret_cast<const u32*>(g + (na & ~3u));
+                const u32 sh = (na & 3u) * 8u;
+                const u32 x0 = __ldg(q), x1 = __ldg(q + 1), x2 = __ldg(q + 2), x3 = __ldg(q + 3), x4 = __ldg(q + 4);
+                u32 w0 = __funnelshift_r(x0, x1, sh), w1 = __funnelshift_r(x1, x2, sh), w2 = __funnelshift_r(x2, x3, sh), w3 = __funnelshift_r(x3, x4, sh);
+                u32 cm = movemask4(zero_bytes(w0 ^ 0x3A3A3A3Au)) | (movemask4(zero_bytes(w1 ^ 0x3A3A3A3Au)) << 4) |
+                         (movemask4(zero_bytes(w2 ^ 0x3A3A3A3Au)) << 8) | (movemask4(zero_bytes(w3 ^ 0x3A3A3A3Au)) << 12);
+                cm &= tl >= 16 ? 0xffffu : ((1u << tl) - 1u);
+                if (cm || tl <= 16) {
+                    nl = cm ? (u32)__ffs((int)cm) - 1u : tl;
+                    w0 = keep_bytes(w0, (int)nl); w1 = keep_bytes(w1, (int)nl - 4); w2 = keep_bytes(w2, (int)nl - 8); w3 = keep_bytes(w3, (int)nl - 12);
+                    k0 = (u64)w0 | ((u64)w1 << 32); k1 = (u64)w2 | ((u64)w3 << 32);
+                    mode = nl ? 1u : 0u;
+                    scan = false;
+                } else e = na + 16;
             }
-            slen = se - sa;
-            v = make_uint4((u32)tl64, sa, se, nl | ((u32)(g[mp] == '<') << 16));
-            ok = true;
-        } while (0);
+            if (scan) {
+                while (e < end && g[e] != ':') ++e;
+                nl = e - na;
+                mode = nl != 0 && nl <= 255 ? 2u : 0u;
+            }
+        }
+        // ---- the probe
+        i64 tl64 = 0;
+        bool found = false;
+        if (mode == 1) found = table_lookup_key16(a.T, k0, k1, nl, tl64);
+        else if (mode == 2) found = table_lookup(a.T, g + mp + 1, nl, tl64);
+        bool ok = found && tl64 >= 0 && tl64 <= 0x7fffffffLL;
+        // ---- ":start-end" (gafkluge.hpp:131-146), plain digits only
+        u32 sa = 0, se = (u32)tl64;
+        const u32 e = mp + 1 + nl;
+        if (ok && e < end) {
+            u32 q = e + 1, x = 0;
+            const u32 q1 = q;
+            while (q < end && (u32)g[q] - '0' <= 9u && q - q1 < 10) { x = x * 10u + ((u32)g[q] - '0'); ++q; }
+            const bool ok1 = q != q1 && q - q1 <= 9 && q < end && g[q] == '-';
+            sa = x;
+            const u32 q2 = ++q;
+            x = 0;
+            while (ok1 && q < end && (u32)g[q] - '0' <= 9u && q - q2 < 10) { x = x * 10u + ((u32)g[q] - '0'); ++q; }
+            ok = ok1 && q != q2 && q - q2 <= 9 && q == end && x >= sa;
+            se = x;
+        }
+        const u32 slen = ok ? se - sa : 0u;
         if (live && !ok) atomicExch(&R.status, 1u);
         par_sum64(&R.sum_steps, k, slen, live && ok);
-        if (in) { a.sval[s] = v; a.sx[s] = make_uint4(ok ? slen : 0u, 0, 0, 0); }
-    }
-}
-// one CIGAR op: digits between the previous letter and this one (for_each_cg, gafkluge.hpp:226-239)
-__global__ void __launch_bounds__(128) k_par_ops(const ParArgs a) {
-    const u32 nround = (a.nops + 31u) & ~31u;
-    for (u32 o = blockIdx.x * blockDim.x + threadIdx.x; o < nround; o += gridDim.x * blockDim.x) {
-        const bool in = o < a.nops;
-        const u32 k = in ? a.orec[o] : 0u;
-        ParRec& R = a.recs[k];
-        uint4 v = make_uint4(0, 0, 0, 0);
-        const bool live = in && !R.status;
-        bool ok = false;
-        if (live) {
-            const u8* g = a.gaf;
-            const u32 lp = a.opos[o];
-            const u32 ds = o > R.g0 ? a.opos[o - 1] + 1u : R.ca;
-            const u32 nd = lp - ds;
-            const u32 kc = (u32)g[lp] - '=';
-            ok = kc < 28u && ((kOpMask >> kc) & 1u) && nd != 0 && nd <= 7 && !(nd > 1 && g[ds] == '0');
-            u32 x = 0;
-            if (ok) { for (u32 q = ds; q < lp; ++q) x = x * 10u + ((u32)g[q] - '0'); ok = x != 0; }
-            if (ok && o + 1 == R.g0 + R.no && lp != R.cb - 1) ok = false;   // digits after the last op letter
-            if (!ok) atomicExch(&R.status, 1u);
-            else v = make_uint4(((kTargetMask >> kc) & 1u) ? x : 0u, ((kQueryMask >> kc) & 1u) ? x : 0u, ((kMatchMask >> kc) & 1u) ? x : 0u, x);
+        if (in) {
+            a.sval[s] = ok ? make_uint4((u32)tl64, sa, se, nl | ((u32)(g[mp] == '<') << 16)) : make_uint4(0, 0, 0, 0);
+            a.sx[s] = slen;
         }
-        par_sum64(&R.sum_ops, k, v.w, live && ok);
-        if (in) a.ox[o] = v;
     }
 }
 // summed step lengths; flip_gaf's mirrored path interval (gaf2paf_main.cpp:111-131)
@@ -432,34 +538,85 @@ __global__ void __launch_bounds__(256) k_par_totals(const ParArgs a) {
 
 // normalised views of the scanned arrays of one record
 struct ParView {
-    const uint4* sx; const uint4* ox; const u32* opos;
+    const u64* sx; const uint4* ox; const u32* ot; const u32* opos;
     u32 s0, ns, g0, no, total;
     uint4 obase, ototal;
     bool minus;
     // cumulative step length before normalised step i (0 <= i <= ns)
-    __device__ __forceinline__ u32 cum_steps(u32 i) const { return minus ? total - (sx[s0 + ns - i].x - sx[s0].x) : sx[s0 + i].x - sx[s0].x; }
+    __device__ __forceinline__ u32 cum_steps(u32 i) const { return minus ? total - (u32)(sx[s0 + ns - i] - sx[s0]) : (u32)(sx[s0 + i] - sx[s0]); }
     // inclusive prefix sums over the ops in normalised order, op j (0 <= j < no)
     __device__ __forceinline__ uint4 incl(u32 j) const {
         if (!minus) return sub4(ox[g0 + j + 1], obase);
         return sub4(ototal, sub4(ox[g0 + no - 1 - j], obase));   // total - exclusive prefix of the original op no-1-j
     }
+    // ... its target component alone, from the compact array
+    __device__ __forceinline__ u32 incl_t(u32 j) const {
+        if (!minus) return __ldg(ot + g0 + j + 1) - obase.x;
+        return ototal.x - (__ldg(ot + g0 + no - 1 - j) - obase.x);
+    }
     __device__ __forceinline__ u32 orig(u32 j) const { return minus ? no - 1 - j : j; }
 };
 struct ParBoundary { u32 j, t, cq, cm, cb; bool cut, exh; };
-// boundary B of the cumulative target length -> position in the op stream (as k_short's phase 5)
-__device__ __forceinline__ ParBoundary par_boundary(const ParView& V, const u8* gaf, u32 B) {
+// first op (normalised order) in [lo, hi) whose cumulative target length reaches B, else hi
+__device__ __forceinline__ u32 par_lower_bound(const ParView& V, u32 B, u32 lo, u32 hi) {
+    while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (V.incl_t(mid) >= B) hi = mid; else lo = mid + 1; }
+    return lo;
+}
+// two of them side by side (independent loads in every round)
+__device__ __forceinline__ void par_lower_bound2(const ParView& V, u32 B0, u32 B1, u32 lo, u32 hi, u32& r0, u32& r1) {
+    u32 l0 = lo, h0 = hi, l1 = lo, h1 = hi;
+    while (l0 < h0 || l1 < h1) {
+        const u32 m0 = (l0 + h0) >> 1, m1 = (l1 + h1) >> 1;
+        const u32 t0 = l0 < h0 ? V.incl_t(m0) : 0u, t1 = l1 < h1 ? V.incl_t(m1) : 0u;
+        if (l0 < h0) { if (t0 >= B0) h0 = m0; else l0 = m0 + 1; }
+        if (l1 < h1) { if (t1 >= B1) h1 = m1; else l1 = m1 + 1; }
+    }
+    r0 = l0; r1 = l1;
+}
+// the same for a whole warp that shares V, B0 and B1: 32 probes per round and bound, ~log32(no) rounds
+__device__ __forceinline__ void par_lower_bound2_warp(const ParView& V, u32 B0, u32 B1, u32& r0, u32& r1) {
+    const u32 FULL = 0xffffffffu, lane = threadIdx.x & 31u;
+    u32 l0 = 0, h0 = V.no, l1 = 0, h1 = V.no;
+    while (l0 < h0 || l1 < h1) {   // (uniform)
+        const u32 s0 = (h0 - l0 + 31u) >> 5, s1 = (h1 - l1 + 31u) >> 5;
+        u32 p0 = l0 + (lane + 1u) * s0 - 1u, p1 = l1 + (lane + 1u) * s1 - 1u;
+        p0 = p0 < h0 ? p0 : h0 - 1u; p1 = p1 < h1 ? p1 : h1 - 1u;
+        const bool a0 = l0 < h0, a1 = l1 < h1;
+        const u32 t0 = a0 ? V.incl_t(p0) : 0u, t1 = a1 ? V.incl_t(p1) : 0u;
+        const u32 m0 = __ballot_sync(FULL, a0 && t0 >= B0), m1 = __ballot_sync(FULL, a1 && t1 >= B1);
+        if (a0) {
+            if (m0 == 0) l0 = h0;   // no op of [l0, h0) reaches B0
+            else {
+                const int f = __ffs((int)m0) - 1;
+                const u32 pf = __shfl_sync(FULL, p0, f), pp = __shfl_sync(FULL, p0, f ? f - 1 : 0);
+                if (f) l0 = pp + 1u;
+                h0 = pf;            // the answer lies in [l0, pf]
+            }
+        }
+        if (a1) {
+            if (m1 == 0) l1 = h1;
+            else {
+                const int f = __ffs((int)m1) - 1;
+                const u32 pf = __shfl_sync(FULL, p1, f), pp = __shfl_sync(FULL, p1, f ? f - 1 : 0);
+                if (f) l1 = pp + 1u;
+                h1 = pf;
+            }
+        }
+    }
+    r0 = l0; r1 = l1;
+}
+// boundary B of the cumulative target length, j = its lower bound in the op stream -> the sums up to it (as k_short's phase 5)
+__device__ __forceinline__ ParBoundary par_boundary(const ParView& V, const u8* gaf, u32 B, u32 j) {
     ParBoundary b;
     b.j = b.t = b.cq = b.cm = b.cb = 0; b.cut = b.exh = false;
     if (B == 0) return b;
-    u32 lo = 0, hi = V.no;
-    while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (V.incl(mid).x >= B) hi = mid; else lo = mid + 1; }
-    b.j = lo;
-    if (lo == V.no) { b.exh = true; return b; }
-    const uint4 E = V.incl(lo);
-    const uint4 P = lo ? V.incl(lo - 1) : make_uint4(0, 0, 0, 0);
+    b.j = j;
+    if (j == V.no) { b.exh = true; return b; }
+    const uint4 E = V.incl(j);
+    const uint4 P = j ? V.incl(j - 1) : make_uint4(0, 0, 0, 0);
     b.t = P.x;
     const u32 off = B - P.x;
-    const u32 kc = (u32)gaf[V.opos[V.g0 + V.orig(lo)]] - '=';
+    const u32 kc = (u32)gaf[V.opos[V.g0 + V.orig(j)]] - '=';
     b.cq = P.y + (((kQueryMask >> kc) & 1u) ? off : 0u);
     b.cm = P.z + (((kMatchMask >> kc) & 1u) ? off : 0u);
     b.cb = P.w + off;
@@ -469,77 +626,107 @@ __device__ __forceinline__ ParBoundary par_boundary(const ParView& V, const u8* 
 
 // one PAF line per path step (gaf2paf_main.cpp:157-263 in the closed form of SURVEY.md Appendix B)
 __global__ void __launch_bounds__(128) k_par_lines(const ParArgs a) {
+    const u32 FULL = 0xffffffffu;
     __shared__ u32 p10[10];
     if (threadIdx.x < 10) { u32 v = 1; for (u32 i = 0; i < threadIdx.x; ++i) v *= 10u; p10[threadIdx.x] = v; }
     __syncthreads();
-    for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < a.nsteps; s += gridDim.x * blockDim.x) {
-        ParRec& R = a.recs[a.srec[s]];
-        if (R.nslots == 0) { a.lx[s] = 0; continue; }   // rejected before it got a descriptor run (every step of it writes one zero)
+    const u32 nround = (a.nsteps + 31u) & ~31u;
+    const u32 lane = threadIdx.x & 31u;
+    for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < nround; s += gridDim.x * blockDim.x) {
+        const bool in = s < a.nsteps;
+        const u32 k = in ? a.srec[s] : 0xffffffffu;
+        ParRec& R = a.recs[in ? k : 0u];
+        const bool has_run = in && R.nslots != 0;   // else: rejected before it got a descriptor run
         const bool rminus = R.minus != 0;
         // this thread owns ORIGINAL step s - s0; its normalised index:
         const u32 jo = s - R.s0, i = rminus ? R.ns - 1 - jo : jo;
         u32 line = 0, emit = 0;
         LineDesc* slot = a.desc + R.slot0 + i;
-        if (!R.status) {
-            ParView V;
-            V.sx = a.sx; V.ox = a.ox; V.opos = a.opos;
-            V.s0 = R.s0; V.ns = R.ns; V.g0 = R.g0; V.no = R.no; V.total = R.total; V.minus = rminus;
+        ParView V;
+        V.sx = a.sx; V.ox = a.ox; V.ot = a.ot; V.opos = a.opos;
+        V.s0 = R.s0; V.ns = R.ns; V.g0 = R.g0; V.no = R.no; V.total = R.total; V.minus = rminus;
+        V.obase = V.ototal = make_uint4(0, 0, 0, 0);
+        i32 sa = 0, se = 0, tlen = 0, so = 0, eo = 0, quota = 0;
+        u32 nl = 0, B = 0, eB = 0;
+        bool rev = false, bad = false;
+        const bool live = has_run && !R.status;
+        if (has_run) {   // (also for lanes whose record was rejected meanwhile: the warp-wide search below reads through every lane's view)
             V.obase = a.ox[R.g0];
             V.ototal = sub4(a.ox[R.g0 + R.no], V.obase);
+        }
+        if (live) {
             const uint4 sv = a.sval[s];
-            const i32 tlen = (i32)sv.x, sa = (i32)sv.y, se = (i32)sv.z;
-            const u32 nl = sv.w & 0xffffu;
-            const bool rev = ((sv.w >> 16) & 1u) != (u32)rminus;
+            tlen = (i32)sv.x; sa = (i32)sv.y; se = (i32)sv.z;
+            nl = sv.w & 0xffffu;
+            rev = ((sv.w >> 16) & 1u) != (u32)rminus;
             const i32 slen = se - sa;
             const i32 W = R.pe - R.ps;
-            const i32 so = i == 0 ? R.ps : 0;
+            so = i == 0 ? R.ps : 0;
             const bool last = i + 1 == R.ns;
             // B_i = cumulative quota of the steps before i: B_0 = 0, B_i = cum_steps(i) - ps, B_ns = W   (Appendix B.3)
             const u32 cs = i == 0 ? 0u : V.cum_steps(i);
-            bool bad = i > 0 && cs < (u32)R.ps;
-            const u32 B = i == 0 || bad ? 0u : cs - (u32)R.ps;
-            i32 quota = slen - so, eo = 0;
+            bad = i > 0 && cs < (u32)R.ps;
+            B = i == 0 || bad ? 0u : cs - (u32)R.ps;
+            quota = slen - so;
             if (last) { quota = W - (i32)B; eo = slen - so - quota; }
             if (so < 0 || quota < 0 || eo < 0) bad = true;   // :178 assert / negative quota
-            if (!bad && quota > 0) {
-                const u32 eB = B + (u32)quota;
-                const ParBoundary b0 = par_boundary(V, a.gaf, B), b1 = par_boundary(V, a.gaf, eB);
-                if (b0.exh || b1.exh) bad = true;   // :80 assert(cur_len > target_len): CIGAR shorter than the path
-                else {
-                    const u32 q = b1.cq - b0.cq, nm = b1.cm - b0.cm, nb = b1.cb - b0.cb;
-                    if (nm > 0) {   // gaf2paf_main.cpp:225
-                        LineStep L;
-                        L.rev = rev;
-                        L.q0 = (u32)R.qs + b0.cq; L.q1 = L.q0 + q;
-                        L.name_a = a.spos[s] + 1u - R.s; L.nl = nl; L.tlen = (u32)tlen;
-                        L.ts = (u32)(sa + (rev ? eo : so)); L.te = (u32)(se - (rev ? so : eo));
-                        L.nm = nm; L.nb = nb;
-                        L.lenS = 0; L.codeS = 0; L.codeE = 0; L.mid_a = L.mid_b = 0;
-                        L.mid_fwd = rev == rminus;   // text order == output order
-                        L.lenE = eB - (b1.t > B ? b1.t : B);
-                        const u32 jS = B == 0 ? 0u : (b0.cut ? b0.j : b0.j + 1u);
-                        const bool cutS = B != 0 && b0.cut;
-                        const u32 jE = b1.j;
-                        u32 mS = jS;   // verbatim middle tokens: [mS, jE)
-                        if (jS < jE) {
-                            if (cutS) { L.lenS = V.incl(jS).x - B; L.codeS = a.gaf[a.opos[R.g0 + V.orig(jS)]]; mS = jS + 1; }
-                            if (mS < jE) {
-                                const u32 o1 = rminus ? R.no - jE : mS, o2 = rminus ? R.no - 1 - mS : jE - 1;   // original index range [o1, o2]
-                                L.mid_a = (o1 ? a.opos[R.g0 + o1 - 1] + 1u : R.ca) - R.s;
-                                L.mid_b = a.opos[R.g0 + o2] + 1u - R.s;
-                            }
+            eB = B + (u32)(quota > 0 ? quota : 0);
+        }
+        const bool need = live && !bad && quota > 0;
+        // 32 consecutive steps of one record: their boundaries lie between those of the first and the last of them.  The
+        // warp brackets them together (32 probes per round), then every lane searches its two boundaries in the bracket
+        // (a few hundred bytes of `ot`), side by side.
+        u32 lo = 0, hi = V.no;
+        if (__all_sync(FULL, k == __shfl_sync(FULL, k, 0)) && __any_sync(FULL, need)) {
+            u32 bmin = need ? B : 0xffffffffu, bmax = need ? eB : 0u;
+            for (int o = 16; o > 0; o >>= 1) {
+                const u32 x0 = __shfl_xor_sync(FULL, bmin, o), x1 = __shfl_xor_sync(FULL, bmax, o);
+                bmin = x0 < bmin ? x0 : bmin;
+                bmax = x1 > bmax ? x1 : bmax;
+            }
+            par_lower_bound2_warp(V, bmin, bmax, lo, hi);
+        }
+        if (need) {
+            u32 j0, j1;
+            par_lower_bound2(V, B, eB, lo, hi, j0, j1);
+            const ParBoundary b0 = par_boundary(V, a.gaf, B, j0), b1 = par_boundary(V, a.gaf, eB, j1);
+            if (b0.exh || b1.exh) bad = true;   // :80 assert(cur_len > target_len): CIGAR shorter than the path
+            else {
+                const u32 q = b1.cq - b0.cq, nm = b1.cm - b0.cm, nb = b1.cb - b0.cb;
+                if (nm > 0) {   // gaf2paf_main.cpp:225
+                    LineStep L;
+                    L.rev = rev;
+                    L.q0 = (u32)R.qs + b0.cq; L.q1 = L.q0 + q;
+                    L.name_a = a.spos[s] + 1u - R.s; L.nl = nl; L.tlen = (u32)tlen;
+                    L.ts = (u32)(sa + (rev ? eo : so)); L.te = (u32)(se - (rev ? so : eo));
+                    L.nm = nm; L.nb = nb;
+                    L.lenS = 0; L.codeS = 0; L.codeE = 0; L.mid_a = L.mid_b = 0;
+                    L.mid_fwd = rev == rminus;   // text order == output order
+                    L.lenE = eB - (b1.t > B ? b1.t : B);
+                    const u32 jS = B == 0 ? 0u : (b0.cut ? b0.j : b0.j + 1u);
+                    const bool cutS = B != 0 && b0.cut;
+                    const u32 jE = b1.j;
+                    u32 mS = jS;   // verbatim middle tokens: [mS, jE)
+                    if (jS < jE) {
+                        if (cutS) { L.lenS = V.incl_t(jS) - B; L.codeS = a.gaf[a.opos[R.g0 + V.orig(jS)]]; mS = jS + 1; }
+                        if (mS < jE) {
+                            const u32 o1 = rminus ? R.no - jE : mS, o2 = rminus ? R.no - 1 - mS : jE - 1;   // original index range [o1, o2]
+                            L.mid_a = (o1 ? a.opos[R.g0 + o1 - 1] + 1u : R.ca) - R.s;
+                            L.mid_b = a.opos[R.g0 + o2] + 1u - R.s;
                         }
-                        L.codeE = a.gaf[a.opos[R.g0 + V.orig(jE)]];
-                        line = R.rconst + line_step_len(L, p10);
-                        emit = 1;
-                        store_line_desc(slot, R.r, 0u, line, L);   // loff: k_par_place
                     }
+                    L.codeE = a.gaf[a.opos[R.g0 + V.orig(jE)]];
+                    line = R.rconst + line_step_len(L, p10);
+                    emit = 1;
+                    store_line_desc(slot, R.r, 0u, line, L);   // loff: k_par_place
                 }
             }
-            if (bad) atomicExch(&R.status, 1u);
         }
-        if (!emit) slot->rec = kDescInvalid;
-        a.lx[R.s0 + i] = (u64)line | ((u64)emit << 32);
+        if (live && bad) atomicExch(&R.status, 1u);
+        if (has_run) {
+            if (!emit) slot->rec = kDescInvalid;
+            a.lx[R.s0 + i] = (u64)line | ((u64)emit << 32);
+        } else if (in) a.lx[s] = 0;   // (every step of the record writes one zero)
     }
 }
 

@@ -939,6 +939,56 @@ __global__ void __launch_bounds__(kEThreads, DENSE ? 3 : 4) k_emit_lines(const E
         }
         stage_text(t0, t1);
     }
+    // A record too long to be staged whole (a warp of a k_par run: 32 consecutive path steps of ONE record): stage the
+    // pieces its lines are made of -- query name, tp / rc values (the same for all lanes), the span of the lanes' node
+    // names in the path column and the span of their verbatim CIGAR pieces in the cg tag.
+    bool parts = false;
+    LineSrc PS;
+    PS.qname = PS.name = PS.tp = PS.rc = PS.mid = nullptr;
+    if (DENSE && !text_staged && kETextCap != 0) {
+        const u32 rec0 = __shfl_sync(FULL, d.rec, first);
+        if (__all_sync(FULL, !valid || d.rec == rec0)) {
+            const u32 rs0 = __shfl_sync(FULL, rs, first);
+            const u32 qn = __shfl_sync(FULL, R.qn_b, first);
+            const u32 tpa = __shfl_sync(FULL, R.tp_a, first), tpb = __shfl_sync(FULL, R.tp_b, first);
+            const u32 rca = __shfl_sync(FULL, R.rc_a, first), rcb = __shfl_sync(FULL, R.rc_b, first);
+            u32 n0 = valid ? L.name_a : 0xffffffffu, n1 = valid ? L.name_a + L.nl : 0u;
+            const bool has_mid = valid && L.mid_b > L.mid_a;
+            u32 m0 = has_mid ? L.mid_a : 0xffffffffu, m1 = has_mid ? L.mid_b : 0u;
+            for (int o2 = 16; o2 > 0; o2 >>= 1) {
+                const u32 x0 = __shfl_xor_sync(FULL, n0, o2), x1 = __shfl_xor_sync(FULL, n1, o2);
+                const u32 y0 = __shfl_xor_sync(FULL, m0, o2), y1 = __shfl_xor_sync(FULL, m1, o2);
+                n0 = x0 < n0 ? x0 : n0; n1 = x1 > n1 ? x1 : n1;
+                m0 = y0 < m0 ? y0 : m0; m1 = y1 > m1 ? y1 : m1;
+            }
+            // regions (record-relative [from, to)): query name, tp, rc, names, CIGAR pieces
+            const u32 from[5] = {0u, tpa, rca, n0, m0};
+            const u32 to[5] = {qn, tpb, rcb, n1, m1};
+            u32 base[5], al[5], off = 0;
+#pragma unroll
+            for (int r = 0; r < 5; ++r) {
+                base[r] = off;
+                al[r] = (rs0 + from[r]) & ~15u;   // absolute, 16-byte aligned start of the copy
+                if (to[r] > from[r]) off += ((rs0 + to[r] - al[r]) + 15u) & ~15u;
+            }
+            if (off <= kETextCap) {
+#pragma unroll
+                for (int r = 0; r < 5; ++r) {
+                    if (to[r] > from[r]) {
+                        const u32 nvec = ((rs0 + to[r] - al[r]) + 15u) >> 4;
+                        for (u32 v = lane; v < nvec; v += 32) reinterpret_cast<uint4*>(sm_text + base[r])[v] = ldg_vec_guarded(a.gaf, (u64)al[r] + 16u * v, a.n);
+                    }
+                }
+                __syncwarp();
+                parts = true;
+                PS.qname = sm_text + base[0] + (rs0 - al[0]);
+                PS.tp = sm_text + base[1] + (rs0 + tpa - al[1]);
+                PS.rc = sm_text + base[2] + (rs0 + rca - al[2]);
+                PS.name = sm_text + base[3] + (rs0 + L.name_a - al[3]);
+                PS.mid = sm_text + base[4] + (rs0 + L.mid_a - al[4]);
+            }
+        }
+    }
     if (text_staged) {
 #if !defined(G2P_HOSTSIM)
         if (text_tma) {
@@ -959,7 +1009,7 @@ __global__ void __launch_bounds__(kEThreads, DENSE ? 3 : 4) k_emit_lines(const E
     const u64 o1 = __shfl_sync(FULL, end, last);
     // short records: one run that fits the buffer (32 lines of ~130 bytes); anything else goes straight to global
     if (__any_sync(FULL, gap) || holes || (!DENSE && (o1 - __shfl_sync(FULL, o, first)) + 15u > kEOutCap)) {
-        if (valid) write_line(a.out + o + d.len, line_src(rt, R, L), R, L);
+        if (valid) write_line(a.out + o + d.len, parts ? PS : line_src(rt, R, L), R, L);
         return;
     }
     // The warp's lines are one contiguous run of the output.  It goes through the staging buffer in
@@ -973,7 +1023,7 @@ __global__ void __launch_bounds__(kEThreads, DENSE ? 3 : 4) k_emit_lines(const E
         const bool fits = DENSE ? ((todo >> lane) & 1u) != 0 && (end - ob) + pad <= kEOutCap : valid;
         const u32 in = DENSE ? __ballot_sync(FULL, fits) : vmask;   // a prefix of `todo`: the lines are in output order
         if (DENSE && in == 0) {   // one line longer than the buffer
-            if ((int)lane == f) write_line(a.out + o + d.len, line_src(rt, R, L), R, L);
+            if ((int)lane == f) write_line(a.out + o + d.len, parts ? PS : line_src(rt, R, L), R, L);
             todo &= todo - 1u;
             continue;
         }
@@ -982,6 +1032,7 @@ __global__ void __launch_bounds__(kEThreads, DENSE ? 3 : 4) k_emit_lines(const E
             // two instantiations so that the common one (staged lines, staged text) works on pointers the
             // compiler can prove to be shared memory: LDS / STS instead of generic 64-bit LD / ST
             if (text_staged) write_line(sm + pad + (u32)(o - ob) + d.len, line_src(sm_text + (rs - A), R, L), R, L);
+            else if (DENSE && parts) write_line(sm + pad + (u32)(o - ob) + d.len, PS, R, L);
             else write_line(sm + pad + (u32)(o - ob) + d.len, line_src(a.gaf + rs, R, L), R, L);   // long records: text from global
         }
         const u32 total = pad + (u32)(oe - ob);

@@ -197,7 +197,8 @@ int main(int argc, char** argv) {
         if (ptiles == 0 || ptiles > 0xFFFFFF00ULL) break;
         pa.ntiles = (u32)ptiles;
         std::vector<u64> tile_off(ptiles + 1);
-        pa.tile_off = tile_off.data();
+        std::vector<uint4> tile_osum(ptiles + 1);
+        pa.tile_off = tile_off.data(); pa.tile_osum = tile_osum.data();
         std::vector<uint2> tile_map(ptiles);
         pa.tile_map = tile_map.data();
         hs::launch(dim3(grec), dim3(256), 0, [&] { k_par_tilemap(pa); });
@@ -205,6 +206,7 @@ int main(int argc, char** argv) {
         hs::launch(dim3((npl + 127) / 128), dim3(128), 0, [&] { k_par_head(pa); });
         hs::launch(dim3(pa.ntiles), dim3(kPThreads), 0, [&] { k_par_count(pa); });
         scan64(tile_off.data(), pa.ntiles);
+        scan4(tile_osum.data(), pa.ntiles);
         hs::launch(dim3(grec), dim3(256), 0, [&] { k_par_ranges(pa); });
         scan64(slot_scan.data(), npl);
         pa.nsteps = (u32)tile_off[ptiles]; pa.nops = (u32)(tile_off[ptiles] >> 32);
@@ -216,17 +218,15 @@ int main(int argc, char** argv) {
             if (need > desc_cap) { desc_cap = (u32)need; desc.resize(desc_cap + 1); la.desc = desc.data(); la.desc_cap = desc_cap; pa.desc = desc.data(); }
         }
         pa.half = desc_cap / 2u; pa.small_max = 8;
-        std::vector<u32> spos(pa.nsteps), srec(pa.nsteps), opos(pa.nops), orec(pa.nops);
-        std::vector<uint4> sval(pa.nsteps), sx(pa.nsteps + 1), ox(pa.nops + 1);
-        std::vector<u64> lx(pa.nsteps + 1);
-        pa.spos = spos.data(); pa.srec = srec.data(); pa.opos = opos.data(); pa.orec = orec.data();
+        std::vector<u32> spos(pa.nsteps), srec(pa.nsteps), opos(pa.nops), ot(pa.nops + 1);
+        std::vector<uint4> sval(pa.nsteps), ox(pa.nops + 1);
+        std::vector<u64> lx(pa.nsteps + 1), sx(pa.nsteps + 1);
+        pa.spos = spos.data(); pa.srec = srec.data(); pa.opos = opos.data(); pa.ot = ot.data();
         pa.sval = sval.data(); pa.sx = sx.data(); pa.ox = ox.data(); pa.lx = lx.data();
         hs::launch(dim3(grec), dim3(256), 0, [&] { k_par_slots(pa); });
         hs::launch(dim3(pa.ntiles), dim3(kPThreads), 0, [&] { k_par_fill(pa); });
         hs::launch(dim3(std::min<u32>((pa.nsteps + 127) / 128, 8u)), dim3(128), 0, [&] { k_par_steps(pa); });
-        hs::launch(dim3(std::min<u32>((pa.nops + 127) / 128, 8u)), dim3(128), 0, [&] { k_par_ops(pa); });
-        scan4(sx.data(), pa.nsteps);
-        scan4(ox.data(), pa.nops);
+        scan64(sx.data(), pa.nsteps);
         hs::launch(dim3(grec), dim3(256), 0, [&] { k_par_totals(pa); });
         hs::launch(dim3(std::min<u32>((pa.nsteps + 127) / 128, 8u)), dim3(128), 0, [&] { k_par_lines(pa); });
         scan64(lx.data(), pa.nsteps);

@@ -127,3 +127,26 @@ def test_par_descriptor_room():
         rc, ref, _ = H.run_tool(CHECK, ["-", "-l", lp], gaf)
         rc1, out1, st = _simt(lp, gaf, G2P_SIMT_DESC_CAP="1024")
         assert rc == 0 and rc1 == 0 and out1 == ref and st[1] == 0 and st[3] == st[0]
+
+
+@pytest.mark.parametrize("preset,pat", [("medium", rb"s"), ("stable", rb"ctg")])
+def test_par_long_node_names(preset, pat):
+    """Names longer than 16 bytes (hashed keys verified against the arena) and of exactly 16 / 17 bytes."""
+    p = H.preset(preset, seed=9)
+    lengths = H.gen_lengths(p)
+    gaf = H.gen_records(p, 0, 120, threads=2)
+
+    def rename(m):
+        n = int(m.group(2))
+        pre = (b"chromosome_with_a_long_name_", b"exactly16b_", b"seventeen_b_", b"n")[n % 4]
+        return m.group(1) + pre + m.group(2)
+    gaf2 = re.sub(rb"([<>])" + pat + rb"(\d+)", rename, gaf)
+    len2 = re.sub(rb"(^|\n)" + pat + rb"(\d+)", rename, lengths)
+    assert gaf2 != gaf
+    with tempfile.TemporaryDirectory() as td:
+        lp = os.path.join(td, "l.tsv")
+        open(lp, "wb").write(len2)
+        rc, ref, _ = H.run_tool(CHECK, ["-", "-l", lp], gaf2)
+        assert rc == 0 and ref.count(b"\n") > 0
+        rc1, out1, st1 = _simt(lp, gaf2)
+        assert rc1 == 0 and out1 == ref and st1[0] > 0 and st1[3] == 0, st1
