@@ -146,6 +146,9 @@ struct g2p_ctx {
     bool len_sort = false;           // G2P_LEN_SORT=1: global counting sort of the records by length class before k_rec (default off: in-CTA sort only)
     bool size_kernel_short = false;  // G2P_SIZE_KERNEL=short: k_short (8 lanes per record) instead of k_rec (thread per record)
     uint32_t rec_chunks_override = 0; // G2P_REC_CHUNKS: k_rec slot capacity in 16-byte chunks
+    bool unstable_staged = false;    // G2P_UNSTABLE_STAGED=1: gaf2unstable's records and output go through shared memory (k_unstable_staged).  Measured slower
+                                     // (2.3-2.6 vs 1.9-2.1 ms per 294 k records): the per-record code is bound by SIMT divergence (4 of 32 lanes active,
+                                     // profiles/r02_k_unstable.txt), not by the latency of its byte loads, and the staging buffers cost occupancy
     bool par = true;                 // G2P_PAR=0: records k_rec does not take go straight to k_long (one warp per record) instead of the token-parallel kernels
     u32 long_small_max = 8;          // G2P_LONG_SMALL: k_long batches of at most this many lines take a small descriptor block (0: always 32 slots)
     uint64_t desc_cap_override = 0;  // G2P_DESC_CAP (tests): line-descriptor slots, to exercise the overflow fallback
@@ -253,9 +256,12 @@ int g2p_create(int device, g2p_ctx** out) {
     cudaFuncSetAttribute(k_emit_lines<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmitSmem);
     cudaFuncSetAttribute(k_long<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)long_smem<true>());
     cudaFuncSetAttribute(k_long<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)long_smem<false>());
+    cudaFuncSetAttribute(k_unstable_staged<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)unstable_smem<false>());
+    cudaFuncSetAttribute(k_unstable_staged<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)unstable_smem<true>());
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
     if (const char* c = std::getenv("G2P_ONE_PASS_INDEX")) ctx->two_pass_index = std::atoi(c) == 0;
     if (const char* c = std::getenv("G2P_PAR")) ctx->par = std::atoi(c) != 0;
+    if (const char* c = std::getenv("G2P_UNSTABLE_STAGED")) ctx->unstable_staged = std::atoi(c) != 0;
     if (const char* c = std::getenv("G2P_LONG_SMALL")) ctx->long_small_max = (u32)std::min(16, std::max(0, std::atoi(c)));
     if (const char* c = std::getenv("G2P_DESC_CAP")) ctx->desc_cap_override = std::strtoull(c, nullptr, 10);
     if (const char* c = std::getenv("G2P_FUSE")) ctx->fuse_mode = std::min(2, std::max(0, std::atoi(c)));
@@ -1059,7 +1065,9 @@ static int run_unstable(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
     u64* d_blocks = static_cast<u64*>(w.d_blocks.p);
     u32* d_list = static_cast<u32*>(w.d_list.p);
     const u32 ncta = std::min<u32>((nrec + kListThreads - 1) / kListThreads, (u32)ctx->n_sm * 32u);
-    k_unstable<false><<<ncta, kListThreads, 0, st>>>(d_gaf, d_rec, nrec, ctx->uview, d_off, d_status, nullptr, d_meta, d_list);
+    const u32 ncta_s = (nrec + kUThreads - 1) / kUThreads;
+    if (ctx->unstable_staged) k_unstable_staged<false><<<ncta_s, kUThreads, unstable_smem<false>(), st>>>(d_gaf, (u64)n, d_rec, nrec, ctx->uview, d_off, d_status, nullptr, d_meta, d_list);
+    else k_unstable<false><<<ncta, kListThreads, 0, st>>>(d_gaf, d_rec, nrec, ctx->uview, d_off, d_status, nullptr, d_meta, d_list);
     ++launches;
     G2P_CUDA(cudaEventRecord(w.ev[2], st));
     k_scan_reduce<<<nscan, kScanThreads, 0, st>>>(d_off, nrec, d_blocks);
@@ -1072,7 +1080,8 @@ static int run_unstable(g2p_ctx* ctx, Worker& w, const u8* d_gaf, size_t n, cuda
     G2P_CUDA(w.d_out.ensure(out_total + 256));
     u8* d_o = static_cast<u8*>(w.d_out.p);
     G2P_CUDA(cudaEventRecord(w.ev[3], st));
-    k_unstable<true><<<ncta, kListThreads, 0, st>>>(d_gaf, d_rec, nrec, ctx->uview, d_off, d_status, d_o, d_meta, d_list);
+    if (ctx->unstable_staged) k_unstable_staged<true><<<ncta_s, kUThreads, unstable_smem<true>(), st>>>(d_gaf, (u64)n, d_rec, nrec, ctx->uview, d_off, d_status, d_o, d_meta, d_list);
+    else k_unstable<true><<<ncta, kListThreads, 0, st>>>(d_gaf, d_rec, nrec, ctx->uview, d_off, d_status, d_o, d_meta, d_list);
     ++launches;
     G2P_CUDA(cudaEventRecord(w.ev[4], st));
     G2P_CUDA(cudaStreamSynchronize(st));

@@ -1,12 +1,15 @@
 // g2p_kernels.cuh — sm_100a kernels of the GAF -> PAF pipeline.
 //
-//   k_index1                                       newline index in one pass (TMA tiles + decoupled look-back)
-//   k_count_lines / k_scan_tiles / k_fill_lines   two-pass newline index (fallback when the index capacity guess is too small)
-//   k_rec (or k_short) / k_long<false> / k_convert_list<false>  pass 1: per-record PAF byte length, status, line descriptors
-//   k_scan_*                                       exclusive scans: byte lengths -> output offsets, line counts -> line slots
-//   k_line_map + k_emit_lines                      pass 2: one thread per PAF line writes the bytes
+//   k_fuse<Cfg> (g2p_fuse.cuh)                     the whole conversion in one pass, for blocks of canonical records of <= 1000 bytes
+//   k_count_lines / k_scan_tiles / k_fill_lines   newline index (default); k_index1: the same in one pass (G2P_ONE_PASS_INDEX=1)
+//   k_rec (or k_short) -> k_par_* (g2p_par.cuh) -> k_long<false> -> k_convert_list<false>
+//                                                  pass 1: per-record PAF byte length, status, line descriptors; every kernel
+//                                                  takes what the one before it left (<= 240 bytes / canonical / any record)
+//   k_scan_*                                       exclusive scans: byte lengths -> output offsets, line counts -> line slots + line map
+//   k_emit_lines<DENSE>                            pass 2: one thread per PAF line writes the bytes
 //   k_long<true> / k_convert_list<true>            pass 2 for records without descriptors
 //   k_diagnose                                     details of the first failing record
+//   k_unstable_staged<EMIT> (k_unstable)           gaf2unstable; k_filter_* (g2p_filter.cuh): gaffilter
 //
 // All work is byte / integer; the pipeline is bound by HBM traffic and by the
 // latency of serial per-record parsing, so the kernels stage contiguous record
@@ -513,6 +516,80 @@ __global__ void __launch_bounds__(kListThreads) k_unstable(const u8* __restrict_
             StoreSink ss(out + out_off[r]);
             unstable_record_global(gaf + s, len, V, ss, ea, eb);
         }
+    }
+}
+
+// The same with the CTA's records staged: 128 consecutive records are one contiguous piece of the input and produce one
+// contiguous piece of the output.  Both go through shared memory (coalesced 128-bit loads / stores), so the per-record
+// code -- a byte-at-a-time state machine that scans a record several times (columns, path, tags in name order) -- runs
+// at shared-memory latency instead of one L2 round trip per byte.  A CTA whose records (or output) exceed the buffers
+// reads (writes) global memory directly.
+constexpr u32 kUThreads = 128;
+#ifndef G2U_IN_CAP
+#define G2U_IN_CAP (24u << 10)
+#endif
+#ifndef G2U_OUT_CAP
+#define G2U_OUT_CAP (40u << 10)
+#endif
+constexpr u32 kUInCap = G2U_IN_CAP, kUOutCap = G2U_OUT_CAP;   // (tests build a variant with tiny buffers to reach the direct paths)
+template <bool EMIT> constexpr size_t unstable_smem() { return kUInCap + 32 + (EMIT ? kUOutCap + 32 : 0); }
+
+template <bool EMIT>
+__global__ void __launch_bounds__(kUThreads) k_unstable_staged(const u8* __restrict__ gaf, u64 n, const u32* __restrict__ rec_start, u32 nrec, UnstableView V,
+                                                               u64* __restrict__ out_off, u32* __restrict__ status, u8* __restrict__ out,
+                                                               PipelineMeta* __restrict__ meta, u32* __restrict__ warn_list) {
+    G2P_DYN_SMEM(smem);
+    u8* sm_in = smem;
+    u8* sm_out = smem + kUInCap + 32;
+    const u32 r0 = blockIdx.x * kUThreads, r1 = min(r0 + kUThreads, nrec);
+    const u32 s0 = rec_start[r0], s1 = rec_start[r1];
+    const u32 e1 = (u64)s1 < n ? s1 : (u32)n;   // (an unterminated last line ends at n)
+    const u32 A = s0 & ~15u;
+    const bool in_staged = e1 - A <= kUInCap;
+    if (in_staged) {
+        const u32 nvec = (e1 - A + 15u) >> 4;
+        for (u32 v = threadIdx.x; v < nvec; v += kUThreads) reinterpret_cast<uint4*>(sm_in)[v] = ldg_vec_guarded(gaf, (u64)A + 16u * v, n);
+    }
+    u64 o0 = 0, o1 = 0;
+    u32 opad = 0;
+    bool out_staged = false;
+    if (EMIT) {
+        o0 = out_off[r0]; o1 = out_off[r1];
+        opad = (u32)(o0 & 15u);
+        out_staged = (o1 - o0) + opad <= kUOutCap;
+    }
+    __syncthreads();
+    const u32 r = r0 + threadIdx.x;
+    if (r < r1) {
+        const u32 s = rec_start[r], len = rec_start[r + 1] - s - 1;
+        const u8* text = in_staged ? sm_in + (s - A) : gaf + s;
+        u32 ea = 0, eb = 0;
+        if (!EMIT) {
+            CountSink cs;
+            const u32 st = unstable_record_global(text, len, V, cs, ea, eb);
+            out_off[r] = (st_is_abort(st) || (st & 0xff) == ST_SKIP) ? 0 : cs.n;
+            status[r] = st;
+            if (st_is_error(st)) atomicMin(&meta->first_err, r);
+            else if ((st & 0xff) == ST_WARN_MULTIREF) warn_list[atomicAdd(&meta->n_deleg, 1u)] = r;
+        } else {
+            const u32 st = status[r];
+            if (!(st_is_abort(st) || (st & 0xff) == ST_SKIP)) {
+                const u64 o = out_off[r];
+                StoreSink ss(out_staged ? sm_out + opad + (u32)(o - o0) : out + o);
+                unstable_record_global(text, len, V, ss, ea, eb);
+            }
+        }
+    }
+    if (EMIT && out_staged) {
+        __syncthreads();
+        const u32 total = opad + (u32)(o1 - o0);
+        u8* gb = out + (o0 - opad);
+        const u32 full_b = total >> 4;
+        for (u32 u = (opad ? 1u : 0u) + threadIdx.x; u < full_b; u += kUThreads) reinterpret_cast<uint4*>(gb)[u] = reinterpret_cast<const uint4*>(sm_out)[u];
+        const u32 head_end = opad ? (total < 16u ? total : 16u) : 0u;
+        for (u32 b = opad + threadIdx.x; b < head_end; b += kUThreads) gb[b] = sm_out[b];
+        const u32 tail_a = full_b * 16u > head_end ? full_b * 16u : head_end;
+        for (u32 b = tail_a + threadIdx.x; b < total; b += kUThreads) gb[b] = sm_out[b];
     }
 }
 

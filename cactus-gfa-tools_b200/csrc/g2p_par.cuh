@@ -631,7 +631,6 @@ __global__ void __launch_bounds__(128) k_par_lines(const ParArgs a) {
     if (threadIdx.x < 10) { u32 v = 1; for (u32 i = 0; i < threadIdx.x; ++i) v *= 10u; p10[threadIdx.x] = v; }
     __syncthreads();
     const u32 nround = (a.nsteps + 31u) & ~31u;
-    const u32 lane = threadIdx.x & 31u;
     for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < nround; s += gridDim.x * blockDim.x) {
         const bool in = s < a.nsteps;
         const u32 k = in ? a.srec[s] : 0xffffffffu;

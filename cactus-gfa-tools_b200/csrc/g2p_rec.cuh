@@ -25,9 +25,9 @@
 //     split and its remainder starts the next step.
 //
 // Outputs are exactly k_short's: per record the PAF byte count, line count, status and a RecDesc,
-// per PAF line a LineDesc in the record's own kSMaxLines slots; k_line_map / k_emit_lines are
+// per PAF line a LineDesc in the record's own kSMaxLines slots; the line map and k_emit_lines are
 // unchanged.  Only canonical records are converted (same definition as k_short, see g2p_short.cuh);
-// anything else is appended to the delegate list for k_long / the general kernel.
+// anything else is appended to the delegate list for k_par / k_long / the general kernel.
 #pragma once
 #include "g2p_short.cuh"
 

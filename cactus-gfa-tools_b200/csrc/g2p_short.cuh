@@ -845,22 +845,8 @@ struct EmitArgs {
     u8* out;
 };
 
-// Line map of k_short's records (after the scans): record r's lines are descriptors
-// r * kSMaxLines + j, its first line slot is line_off[r].
-__global__ void __launch_bounds__(256) k_line_map(const u64* __restrict__ line_off, const u32* __restrict__ rec_start,
-                                                  const u64* __restrict__ out_off, u32 nrec, LineMapEnt* __restrict__ map) {
-    const u32 r = blockIdx.x * 256u + threadIdx.x;
-    if (r >= nrec) return;
-    const u64 b = line_off[r], e = line_off[r + 1];
-    if (b == e) return;
-    LineMapEnt m;
-    m.rec_start = rec_start[r];
-    m.out_off = out_off[r];
-    for (u64 k = b; k < e; ++k) { m.desc_idx = r * kSMaxLines + (u32)(k - b); map[k] = m; }
-}
-
-// DENSE = false: the lines of k_rec / k_short records through the line map (a.map); DENSE = true: k_long's
-// 32-slot descriptor blocks (a.map == null).
+// DENSE = false: the lines of k_rec / k_short records through the line map (a.map, written by k_scan_apply2);
+// DENSE = true: the dense descriptor array of k_par's runs and k_long's blocks (a.map == null).
 template <bool DENSE>
 __global__ void __launch_bounds__(kEThreads, DENSE ? 3 : 4) k_emit_lines(const EmitArgs a) {
     G2P_DYN_SMEM(smem);

@@ -69,15 +69,16 @@ G2P_HD u32 u_parse_header(const u8* r, u32 len, URecHdr& h) {
     h.path_a = a; h.path_b = b;
     h.prefixed = (r[a] == '<' || r[a] == '>');
     h.empty_path = (!h.prefixed && b - a == 1 && r[a] == '*');
-    if (h.prefixed) {
-        u32 p = a;
-        while (p < b) {
+    if (h.prefixed) {   // (no return from inside a loop, here and below: on the device a return there moves the point where the
+        u32 p = a;      // warp's lanes meet again to the end of the function, and they run one after the other until then)
+        st = ST_OK;
+        while (p < b && st == ST_OK) {
             u32 q = next_marker(r, p + 1, b);
             StepTok t;
             st = parse_step_token<true>(r, p, q, t);
-            if (st) return st;
             p = q;
         }
+        if (st) return st;
     }
     G2U_NEXT_COL(7); st = gaf_int(r, a, b, h.plen); if (st) return st;
     G2U_NEXT_COL(8); st = gaf_int(r, a, b, h.ps); if (st) return st;
@@ -96,7 +97,8 @@ G2P_HD u32 u_parse_header(const u8* r, u32 len, URecHdr& h) {
     h.tags_from = pos;
     // optional fields: syntax + duplicate names (exact, pairwise: records carry a handful)
     u32 p1 = pos;
-    while (!eof) {
+    u32 tag_st = ST_OK;
+    while (!eof && tag_st == ST_OK) {
         a = p1; b = a;
         while (b < len && r[b] != '\t') ++b;
         if (b < len) p1 = b + 1; else { p1 = len; eof = true; }
@@ -105,10 +107,10 @@ G2P_HD u32 u_parse_header(const u8* r, u32 len, URecHdr& h) {
         while (c1 < b && r[c1] != ':') ++c1;
         u32 c2 = c1 + 1;
         while (c2 < b && r[c2] != ':') ++c2;
-        if (b - a < 5 || c1 >= b || c2 >= b) return ST_ABORT_TAG;
+        if (b - a < 5 || c1 >= b || c2 >= b) { tag_st = ST_ABORT_TAG; break; }
         // compare with every earlier field
         u32 p0 = h.tags_from;
-        while (p0 < a) {
+        while (p0 < a && tag_st == ST_OK) {
             u32 e0 = p0;
             while (r[e0] != '\t') ++e0;
             if (e0 > p0) {
@@ -117,13 +119,13 @@ G2P_HD u32 u_parse_header(const u8* r, u32 len, URecHdr& h) {
                 if (k0 - p0 == c1 - a) {
                     bool same = true;
                     for (u32 i = 0; i < c1 - a; ++i) if (r[p0 + i] != r[a + i]) { same = false; break; }
-                    if (same) return ST_ABORT_DUPTAG;
+                    if (same) tag_st = ST_ABORT_DUPTAG;
                 }
             }
             p0 = e0 + 1;
         }
     }
-    return ST_OK;
+    return tag_st;
 }
 
 // get_unstable_interval (gaf2unstable_main.cpp:70-107): node index range [i0, i1) of the
@@ -186,6 +188,7 @@ G2P_HD u32 unstable_record(const u8* r, u32 len, const UnstableView& V, Sink& S,
     i32 ref_first = -1;
     bool multi = false;
     bool any_step = false;
+    u32 fail = ST_OK;   // (set instead of returning from inside the loops: see u_parse_header)
     if (h.empty_path) {
         for (int k = 0; k < 6; ++k) { S.ch('*'); S.ch('\t'); }
     } else {
@@ -200,41 +203,44 @@ G2P_HD u32 unstable_record(const u8* r, u32 len, const UnstableView& V, Sink& S,
                 u32 q = next_marker(r, p + 1, h.path_b);
                 parse_step_token<false>(r, p, q, t);
                 is_last = q >= h.path_b;
-                if (!t.is_interval && !(p == h.path_a && is_last)) return ST_ABORT_ASSERT;   // :116 assert(path.size() == 1)
+                if (!t.is_interval && !(p == h.path_a && is_last)) { fail = ST_ABORT_ASSERT; break; }   // :116 assert(path.size() == 1)
                 p = q;
             }
-            u32 i0, i1;
+            u32 i0 = 0, i1 = 0;
             if (!t.is_interval) {
                 st = u_interval(V, r + t.name_a, t.name_b - t.name_a, h.ps, h.pe, i0, i1);
-                if (st) return st;
-                const i64 path_len = h.pe - h.ps;                     // :119-127
-                h.ps -= V.nodes[i0].offset;
-                h.pe = h.ps + path_len;
-                const UNode& last = V.nodes[i1 - 1];
-                h.plen = (last.cum + (i64)last.length) - V.nodes[i0].cum;
+                if (st == ST_OK) {
+                    const i64 path_len = h.pe - h.ps;                     // :119-127
+                    h.ps -= V.nodes[i0].offset;
+                    h.pe = h.ps + path_len;
+                    const UNode& last = V.nodes[i1 - 1];
+                    h.plen = (last.cum + (i64)last.length) - V.nodes[i0].cum;
+                }
             } else {
                 st = u_interval(V, r + t.name_a, t.name_b - t.name_a, t.start, t.end, i0, i1);
-                if (st) return st;
             }
+            if (st) { fail = st; break; }
             const u32 cnt = i1 - i0;
             for (u32 k = 0; k < cnt; ++k) {
                 const UNode& nd = V.nodes[t.rev ? i1 - 1 - k : i0 + k];   // :135-137
                 S.ch(t.rev ? '<' : '>');
                 S.bytes(V.node_names + nd.name_off, nd.name_len);
-                if (nd.ref < 0) return ST_ABORT_ASSERT;                    // :160-161 node_id / partition lookup
+                if (nd.ref < 0) { fail = ST_ABORT_ASSERT; break; }        // :160-161 node_id / partition lookup
                 if (!any_step) { ref_first = nd.ref; any_step = true; }
                 else if (nd.ref != ref_first) multi = true;
             }
-            if (is_last) break;
+            if (fail || is_last) break;
         }
-        S.ch('\t');
-        u_put_int(S, h.plen); S.ch('\t');
-        u_put_int(S, h.ps); S.ch('\t');
-        u_put_int(S, h.pe); S.ch('\t');
-        u_put_int(S, h.m); S.ch('\t');
-        u_put_int(S, h.b); S.ch('\t');
+        if (!fail) {
+            S.ch('\t');
+            u_put_int(S, h.plen); S.ch('\t');
+            u_put_int(S, h.ps); S.ch('\t');
+            u_put_int(S, h.pe); S.ch('\t');
+            u_put_int(S, h.m); S.ch('\t');
+            u_put_int(S, h.b); S.ch('\t');
+        }
     }
-    S.dec(h.mapq == -1 ? 255 : (i64)h.mapq);
+    if (!fail) S.dec(h.mapq == -1 ? 255 : (i64)h.mapq);
 
     // optional fields in tag-name order, rc overridden when exactly one reference contig (:172-174)
     const bool set_rc = any_step && !multi;
@@ -242,7 +248,7 @@ G2P_HD u32 unstable_record(const u8* r, u32 len, const UnstableView& V, Sink& S,
     bool rc_done = !set_rc;
     u32 last_a = 0, last_n = 0;
     bool have_last = false;
-    for (;;) {
+    while (!fail) {
         // smallest key strictly greater than the last one printed
         bool found = false;
         u32 best_a = 0, best_b = 0, best_k = 0;
@@ -276,7 +282,7 @@ G2P_HD u32 unstable_record(const u8* r, u32 len, const UnstableView& V, Sink& S,
         last_a = best_a; last_n = best_k; have_last = true;
     }
     S.ch('\n');
-    return multi ? (u32)ST_WARN_MULTIREF : (u32)ST_OK;
+    return fail ? fail : (multi ? (u32)ST_WARN_MULTIREF : (u32)ST_OK);
 }
 
 }  // namespace g2p

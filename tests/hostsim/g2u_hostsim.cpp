@@ -6,6 +6,13 @@
 // the rewrite against the reference binary and the golden vectors.
 //
 // usage: g2u_hostsim -g graph.gfa [-o node-lengths.tsv] <gaf|->      (stdout / exit code as gaf2unstable)
+// Built with -DG2U_SIMT (build/g2u_simt): the staged kernels k_unstable_staged<false/true> themselves, run by the SIMT
+// emulator (cuda_shim.hpp) over the whole input -- size pass, scan, emit pass, like run_unstable.
+#if defined(G2U_SIMT)
+#define HS_IMPLEMENTATION
+#include "cuda_shim.hpp"
+#include "../../cactus-gfa-tools_b200/csrc/g2p_kernels.cuh"
+#endif
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -83,6 +90,37 @@ int main(int argc, char** argv) {
     V.contig_begin = begin.data(); V.nodes = nodes.data(); V.node_names = names.data();
     V.ref_off = refoff.data(); V.ref_names = refnames.data();
 
+#if defined(G2U_SIMT)
+    {
+        const u64 n = gaf.size();
+        std::vector<uint4> buf((n + 15) / 16 + 4);
+        u8* text = reinterpret_cast<u8*>(buf.data());
+        std::memcpy(text, gaf.data(), n);
+        std::vector<u32> rec{0};
+        for (u64 i = 0; i < n; ++i) if (text[i] == '\n') rec.push_back((u32)i + 1);
+        if (n && text[n - 1] != '\n') rec.push_back((u32)n + 1);   // unterminated last line: virtual newline, as the line index does
+        const u32 nrec = (u32)rec.size() - 1;
+        if (nrec == 0) return 0;
+        rec.push_back(0);
+        std::vector<u64> off(nrec + 1, 0);
+        std::vector<u32> status(nrec), wl(nrec);
+        PipelineMeta meta;
+        std::memset(&meta, 0, sizeof meta);
+        meta.first_err = 0xFFFFFFFFu;
+        const u32 ncta = (nrec + kUThreads - 1) / kUThreads;
+        hs::launch(dim3(ncta), dim3(kUThreads), unstable_smem<false>(), [&] { k_unstable_staged<false>(text, n, rec.data(), nrec, V, off.data(), status.data(), nullptr, &meta, wl.data()); });
+        u64 run = 0;
+        for (u32 r = 0; r <= nrec; ++r) { const u64 c = r < nrec ? off[r] : 0; off[r] = run; run += c; }
+        std::vector<u8> outb(run + 64, 0xEE);
+        hs::launch(dim3(ncta), dim3(kUThreads), unstable_smem<true>(), [&] { k_unstable_staged<true>(text, n, rec.data(), nrec, V, off.data(), status.data(), outb.data(), &meta, wl.data()); });
+        const u32 stop = meta.first_err == 0xFFFFFFFFu ? nrec : meta.first_err;
+        std::fwrite(outb.data(), 1, off[stop], stdout);
+        std::fflush(stdout);
+        for (u32 r = 0; r < stop; ++r) if ((status[r] & 0xff) == ST_WARN_MULTIREF) std::fprintf(stderr, "[gaf2unstable] warning: Target path spans multiple reference contigs\n");
+        if (stop != nrec) { std::fprintf(stderr, "abort: status %u\n", status[stop] & 0xff); return 134; }
+        return 0;
+    }
+#endif
     if (!gaf.empty() && gaf.back() != '\n') gaf.push_back('\n');
     const u8* base = reinterpret_cast<const u8*>(gaf.data());
     std::string out;

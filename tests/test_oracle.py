@@ -97,11 +97,12 @@ def test_unterminated_last_line_and_two_files():
 
 # ---- gaf2unstable (config 2) ---------------------------------------------------------------
 G2U_HOSTSIM = os.path.join(H.BUILD, "g2u_hostsim")
+G2U_SIMT = os.path.join(H.BUILD, "g2u_simt")   # k_unstable_staged<> itself under the SIMT emulator
 G2U_REF = os.path.join(H.REF_BIN, "gaf2unstable")
 G2U_PORT = os.path.join(H.ORACLE_BIN, "gaf2unstable_oracle")
 
 
-@pytest.mark.parametrize("binary", [G2U_HOSTSIM, G2U_PORT])
+@pytest.mark.parametrize("binary", [G2U_HOSTSIM, G2U_SIMT, G2U_PORT])
 def test_gaf2unstable_host_code_matches_golden(binary):
     """the device code on the host, and the independent oracle restatement, against the golden vectors"""
     d = H.golden("gaf2unstable_kat.json")
@@ -126,9 +127,10 @@ def test_gaf2unstable_differential(seed, aligned):
     with tempfile.TemporaryDirectory() as td:
         gp, lp = os.path.join(td, "g.gfa"), os.path.join(td, "nl.tsv")
         open(gp, "wb").write(rgfa)
-        rc, out, serr = H.run_tool(G2U_HOSTSIM, ["-g", gp, "-o", lp, "-"], gaf)
-        assert rc == 0 and out == ref and open(lp, "rb").read() == nl
-        assert serr.count("warning") == err.count("[gaf2unstable] warning")
+        for binary in (G2U_HOSTSIM, G2U_SIMT, G2U_SIMT + "_small"):   # _small: tiny staging buffers, so that some CTAs read / write global memory directly
+            rc, out, serr = H.run_tool(binary, ["-g", gp, "-o", lp, "-"], gaf)
+            assert rc == 0 and out == ref and open(lp, "rb").read() == nl, binary
+            assert serr.count("warning") == err.count("[gaf2unstable] warning"), binary
         rc, out, serr = H.run_tool(G2U_PORT, ["-g", gp, "-o", lp, "-"], gaf)   # oracle restatement: stderr verbatim too
         assert rc == 0 and out == ref and open(lp, "rb").read() == nl and serr == err
 
