@@ -37,11 +37,18 @@ struct UnstableView {
     const u8* ref_names;
 };
 
+constexpr u32 kUMaxTags = 16;
 struct URecHdr {
     i64 qlen, qs, qe, plen, ps, pe, m, b;
     i32 mapq;
     u32 qn_b, path_a, path_b, tags_from;
     u8 strand, prefixed, empty_path;
+    // the optional fields, collected while they are validated (so that neither the duplicate check nor the output in
+    // name order has to scan the text again for every field); ntags > kUMaxTags: more than fit, the text is rescanned
+    u32 ntags;
+    u32 tag_a[kUMaxTags];
+    u16 tag_n[kUMaxTags];   // bytes of the whole field
+    u8 tag_k[kUMaxTags];    // bytes of its name
 };
 
 // Columns 1-12 and validation of the optional fields: parse_gaf_record (gafkluge.hpp:84-204).
@@ -98,6 +105,7 @@ G2P_HD u32 u_parse_header(const u8* r, u32 len, URecHdr& h) {
     // optional fields: syntax + duplicate names (exact, pairwise: records carry a handful)
     u32 p1 = pos;
     u32 tag_st = ST_OK;
+    h.ntags = 0;
     while (!eof && tag_st == ST_OK) {
         a = p1; b = a;
         while (b < len && r[b] != '\t') ++b;
@@ -109,6 +117,21 @@ G2P_HD u32 u_parse_header(const u8* r, u32 len, URecHdr& h) {
         while (c2 < b && r[c2] != ':') ++c2;
         if (b - a < 5 || c1 >= b || c2 >= b) { tag_st = ST_ABORT_TAG; break; }
         // compare with every earlier field
+        const u32 kn = c1 - a;
+        if (h.ntags <= kUMaxTags) {
+            for (u32 j = 0; j < h.ntags && j < kUMaxTags; ++j) {
+                if (h.tag_k[j] == kn) {
+                    bool same = true;
+                    for (u32 i = 0; i < kn; ++i) if (r[h.tag_a[j] + i] != r[a + i]) { same = false; break; }
+                    if (same) tag_st = ST_ABORT_DUPTAG;
+                }
+            }
+            if (h.ntags < kUMaxTags && kn <= 255u && b - a <= 65535u) {
+                h.tag_a[h.ntags] = a; h.tag_n[h.ntags] = (u16)(b - a); h.tag_k[h.ntags] = (u8)kn;
+                ++h.ntags;
+            } else h.ntags = kUMaxTags + 1;
+            continue;
+        }
         u32 p0 = h.tags_from;
         while (p0 < a && tag_st == ST_OK) {
             u32 e0 = p0;
@@ -253,6 +276,17 @@ G2P_HD u32 unstable_record(const u8* r, u32 len, const UnstableView& V, Sink& S,
         bool found = false;
         u32 best_a = 0, best_b = 0, best_k = 0;
         u32 p0 = h.tags_from;
+        if (h.ntags <= kUMaxTags) {   // from the collected fields
+            for (u32 j = 0; j < h.ntags; ++j) {
+                const u32 ta = h.tag_a[j], kn = h.tag_k[j];
+                const bool is_rc = set_rc && kn == 2 && r[ta] == 'r' && r[ta + 1] == 'c';
+                if (!is_rc && (!have_last || u_key_cmp(r + ta, kn, r + last_a, last_n) > 0) &&
+                    (!found || u_key_cmp(r + ta, kn, r + best_a, best_k) < 0)) {
+                    found = true; best_a = ta; best_b = ta + h.tag_n[j]; best_k = kn;
+                }
+            }
+            p0 = len;
+        }
         while (p0 < len) {
             u32 e0 = p0;
             while (e0 < len && r[e0] != '\t') ++e0;

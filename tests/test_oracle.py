@@ -180,3 +180,38 @@ def test_late_delegation_under_emulator(reverse):
                 got_rc = p.returncode if p.returncode >= 0 else 128 - p.returncode
                 assert got_rc == rc, name
                 assert (p.stdout == ref) if rc != 134 else ref.startswith(p.stdout), name
+
+
+@pytest.mark.skipif(not os.path.exists(G2U_REF), reason="reference build (oracle/_ref) not present")
+def test_gaf2unstable_many_tags():
+    """Optional fields: none, more than the 16 the per-record code collects (it rescans the text then), duplicates before
+    and after that limit, long names, an rc tag that is replaced -- each record alone, stdout / exit code as the reference."""
+    rgfa, gaf = H.gen_rgfa_case(4, n_records=40, aligned=True)
+    base = [l for l in gaf.split(b"\n") if l and not l.startswith(b"*") and l.split(b"\t")[5] != b"*"][:6]
+    assert len(base) >= 4
+
+    def with_tags(line, tags):
+        return b"\t".join(line.split(b"\t")[:12] + tags)
+    many = [("%c%c:i:%d" % (97 + i // 5, 97 + i % 5, i)).encode() for i in range(22)]
+    cases = [
+        with_tags(base[0], []),
+        with_tags(base[1], many[:16][::-1]),
+        with_tags(base[2], many[:17][::-1]),
+        with_tags(base[3], many[::-1] + [b"rc:Z:old", b"longname:Z:x", b"lo:Z:y"]),
+        with_tags(base[0], many[:10] + [many[3]]),                    # duplicate among the collected fields
+        with_tags(base[1], many[:20] + [many[2]]),                    # duplicate of a collected field after the limit
+        with_tags(base[2], many[:20] + [many[18]]),                   # duplicate of a field beyond the limit
+        with_tags(base[3], [b"ab:i:1", b"abc:i:2", b"a:i:3x", b"ab:Z:dup"]),
+        with_tags(base[0], [b"zz:i:1", b"", b"aa:i:2", b""]),           # empty fields
+        with_tags(base[1], [b"bad"]),
+    ]
+    with tempfile.TemporaryDirectory() as td:
+        gp = os.path.join(td, "g.gfa")
+        open(gp, "wb").write(rgfa)
+        for c in cases:
+            data = base[4] + b"\n" + c + b"\n" + base[5] + b"\n"
+            rc, ref, err = H.run_tool(G2U_REF, ["-g", gp, "-"], data)
+            for binary in (G2U_HOSTSIM, G2U_SIMT, G2U_PORT):
+                rc1, out1, _ = H.run_tool(binary, ["-g", gp, "-"], data)
+                assert rc1 == rc, (binary, c)
+                assert (out1 == ref) if rc == 0 else ref.startswith(out1) or out1.startswith(ref), (binary, c)
