@@ -147,8 +147,8 @@ struct g2p_ctx {
     bool size_kernel_short = false;  // G2P_SIZE_KERNEL=short: k_short (8 lanes per record) instead of k_rec (thread per record)
     uint32_t rec_chunks_override = 0; // G2P_REC_CHUNKS: k_rec slot capacity in 16-byte chunks
     bool unstable_staged = false;    // G2P_UNSTABLE_STAGED=1: gaf2unstable's records and output go through shared memory (k_unstable_staged).  Measured slower
-                                     // (2.3-2.6 vs 1.9-2.1 ms per 294 k records): the per-record code is bound by SIMT divergence (4 of 32 lanes active,
-                                     // profiles/r02_k_unstable.txt), not by the latency of its byte loads, and the staging buffers cost occupancy
+                                     // (1.10 vs 0.97 ms per 294 k records): the per-record code is bound by SIMT divergence (profiles/r02_k_unstable.txt),
+                                     // not by the latency of its byte loads, and the staging buffers cost occupancy
     bool par = true;                 // G2P_PAR=0: records k_rec does not take go straight to k_long (one warp per record) instead of the token-parallel kernels
     u32 long_small_max = 8;          // G2P_LONG_SMALL: k_long batches of at most this many lines take a small descriptor block (0: always 32 slots)
     uint64_t desc_cap_override = 0;  // G2P_DESC_CAP (tests): line-descriptor slots, to exercise the overflow fallback

@@ -491,30 +491,60 @@ __global__ void __launch_bounds__(kListThreads) k_convert_list(const u8* __restr
 // spans several reference contigs are listed for the host, which prints the reference's
 // warning for them.
 // ------------------------------------------------------------------------------
+// unstable_record's phases (g2u_core.cuh) for the 32 records of a warp at once: a warp barrier after every phase of the
+// parse, the two data-dependent loops (path steps, optional fields) as warp-uniform loops.  Every lane of the warp must
+// call it; `act` says whether the lane has a record.
 template <class Sink>
-__device__ G2P_NOINLINE u32 unstable_record_global(const u8* r, u32 len, const UnstableView& V, Sink& S, u32& ea, u32& eb) {
-    return unstable_record(r, len, V, S, ea, eb);
+__device__ __forceinline__ u32 unstable_record_warp(bool act, const u8* r, u32 len, const UnstableView& V, Sink& S) {
+    const u32 FULL = 0xffffffffu;
+    URecHdr h;
+    UParse c;
+    URun u;
+    u32 st = act ? (u32)ST_OK : (u32)ST_SKIP;
+    if (st == ST_OK) st = u_hdr_a(r, len, h, c);
+    __syncwarp();
+    if (st == ST_OK) st = u_hdr_b(r, len, h, c);
+    __syncwarp();
+    if (st == ST_OK) st = u_hdr_c(r, len, h, c);
+    __syncwarp();
+    if (st == ST_OK) st = u_hdr_d(r, len, h, c);
+    __syncwarp();
+    const bool go = st == ST_OK;
+    u.steps_left = u.tags_left = false;
+    if (go) u_out_head(r, h, u, S);
+    while (__any_sync(FULL, go && u.steps_left)) {
+        if (go && u.steps_left) u_out_step(r, V, h, u, S);
+    }
+    if (go) u_out_mid(h, u, S);
+    while (__any_sync(FULL, go && u.tags_left)) {
+        if (go && u.tags_left) u_out_tag(r, len, V, h, u, S);
+    }
+    if (go) st = u_out_end(u, S);
+    return st;
 }
 
 template <bool EMIT>
 __global__ void __launch_bounds__(kListThreads) k_unstable(const u8* __restrict__ gaf, const u32* __restrict__ rec_start, u32 nrec, UnstableView V,
                                                            u64* __restrict__ out_off, u32* __restrict__ status, u8* __restrict__ out,
                                                            PipelineMeta* __restrict__ meta, u32* __restrict__ warn_list) {
-    for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < nrec; r += gridDim.x * blockDim.x) {
-        const u32 s = rec_start[r], len = rec_start[r + 1] - s - 1;
-        u32 ea = 0, eb = 0;
+    for (u32 base = blockIdx.x * blockDim.x; base < nrec; base += gridDim.x * blockDim.x) {   // (uniform: every lane of a warp takes part)
+        const u32 r = base + threadIdx.x;
+        const bool in = r < nrec;
+        const u32 s = in ? rec_start[r] : 0u, len = in ? rec_start[r + 1] - s - 1 : 0u;
         if (!EMIT) {
             CountSink cs;
-            const u32 st = unstable_record_global(gaf + s, len, V, cs, ea, eb);
-            out_off[r] = (st_is_abort(st) || (st & 0xff) == ST_SKIP) ? 0 : cs.n;
-            status[r] = st;
-            if (st_is_error(st)) atomicMin(&meta->first_err, r);
-            else if ((st & 0xff) == ST_WARN_MULTIREF) warn_list[atomicAdd(&meta->n_deleg, 1u)] = r;
+            const u32 st = unstable_record_warp(in, gaf + s, len, V, cs);
+            if (in) {
+                out_off[r] = (st_is_abort(st) || (st & 0xff) == ST_SKIP) ? 0 : cs.n;
+                status[r] = st;
+                if (st_is_error(st)) atomicMin(&meta->first_err, r);
+                else if ((st & 0xff) == ST_WARN_MULTIREF) warn_list[atomicAdd(&meta->n_deleg, 1u)] = r;
+            }
         } else {
-            const u32 st = status[r];
-            if (st_is_abort(st) || (st & 0xff) == ST_SKIP) continue;
-            StoreSink ss(out + out_off[r]);
-            unstable_record_global(gaf + s, len, V, ss, ea, eb);
+            const u32 st = in ? status[r] : (u32)ST_SKIP;
+            const bool act = in && !(st_is_abort(st) || (st & 0xff) == ST_SKIP);
+            StoreSink ss(out + (act ? out_off[r] : 0));
+            unstable_record_warp(act, gaf + s, len, V, ss);
         }
     }
 }
@@ -560,24 +590,25 @@ __global__ void __launch_bounds__(kUThreads) k_unstable_staged(const u8* __restr
     }
     __syncthreads();
     const u32 r = r0 + threadIdx.x;
-    if (r < r1) {
-        const u32 s = rec_start[r], len = rec_start[r + 1] - s - 1;
+    const bool in = r < r1;
+    {
+        const u32 s = in ? rec_start[r] : s0, len = in ? rec_start[r + 1] - s - 1 : 0u;
         const u8* text = in_staged ? sm_in + (s - A) : gaf + s;
-        u32 ea = 0, eb = 0;
         if (!EMIT) {
             CountSink cs;
-            const u32 st = unstable_record_global(text, len, V, cs, ea, eb);
-            out_off[r] = (st_is_abort(st) || (st & 0xff) == ST_SKIP) ? 0 : cs.n;
-            status[r] = st;
-            if (st_is_error(st)) atomicMin(&meta->first_err, r);
-            else if ((st & 0xff) == ST_WARN_MULTIREF) warn_list[atomicAdd(&meta->n_deleg, 1u)] = r;
-        } else {
-            const u32 st = status[r];
-            if (!(st_is_abort(st) || (st & 0xff) == ST_SKIP)) {
-                const u64 o = out_off[r];
-                StoreSink ss(out_staged ? sm_out + opad + (u32)(o - o0) : out + o);
-                unstable_record_global(text, len, V, ss, ea, eb);
+            const u32 st = unstable_record_warp(in, text, len, V, cs);
+            if (in) {
+                out_off[r] = (st_is_abort(st) || (st & 0xff) == ST_SKIP) ? 0 : cs.n;
+                status[r] = st;
+                if (st_is_error(st)) atomicMin(&meta->first_err, r);
+                else if ((st & 0xff) == ST_WARN_MULTIREF) warn_list[atomicAdd(&meta->n_deleg, 1u)] = r;
             }
+        } else {
+            const u32 st = in ? status[r] : (u32)ST_SKIP;
+            const bool act = in && !(st_is_abort(st) || (st & 0xff) == ST_SKIP);
+            const u64 o = act ? out_off[r] : o0;
+            StoreSink ss(out_staged ? sm_out + opad + (u32)(o - o0) : out + o);
+            unstable_record_warp(act, text, len, V, ss);
         }
     }
     if (EMIT && out_staged) {

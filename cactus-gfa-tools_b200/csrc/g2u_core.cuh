@@ -52,19 +52,29 @@ struct URecHdr {
 };
 
 // Columns 1-12 and validation of the optional fields: parse_gaf_record (gafkluge.hpp:84-204).
-G2P_HD u32 u_parse_header(const u8* r, u32 len, URecHdr& h) {
-    if (len > 0 && r[0] == '*') return ST_SKIP;
-    u32 pos = 0, a = 0, b = 0, st;
-    bool eof = false;
-    i64 tmp;
+//
+// The parse -- and, below, the output of a record -- is cut into PHASES that carry their state in a struct.  On the
+// host (and for one record at a time) they simply run one after the other: u_parse_header, unstable_record.  The
+// kernels (k_unstable*, g2p_kernels.cuh) call the same phases with a warp barrier after each and run the two
+// data-dependent loops (path steps, optional fields) as warp-uniform loops: per-record code like this diverges a
+// little more with every data-dependent inner loop, and the lanes of a warp only meet again where ALL of them arrive
+// -- without the barriers 4 of 32 lanes were active per instruction (profiles/r02_k_unstable.txt).
+struct UParse { u32 pos; bool eof; };
+
 #define G2U_NEXT_COL(col)                                             \
     do {                                                              \
-        if (eof) return ST_ABORT_COLUMN | ((col) << 8);               \
-        a = pos; b = a;                                               \
+        if (c.eof) return ST_ABORT_COLUMN | ((col) << 8);             \
+        a = c.pos; b = a;                                             \
         while (b < len && r[b] != '\t') ++b;                          \
-        if (b < len) pos = b + 1; else { pos = len; eof = true; }     \
+        if (b < len) c.pos = b + 1; else { c.pos = len; c.eof = true; } \
         if (b == a) return ST_ABORT_COLUMN | ((col) << 8);            \
     } while (0)
+
+// '*' lines, columns 1-5
+G2P_HD u32 u_hdr_a(const u8* r, u32 len, URecHdr& h, UParse& c) {
+    if (len > 0 && r[0] == '*') return ST_SKIP;
+    c.pos = 0; c.eof = false;
+    u32 a = 0, b = 0, st;
     G2U_NEXT_COL(1); h.qn_b = b;
     G2U_NEXT_COL(2); st = gaf_int(r, a, b, h.qlen); if (st) return st;
     G2U_NEXT_COL(3); st = gaf_int(r, a, b, h.qs); if (st) return st;
@@ -72,21 +82,30 @@ G2P_HD u32 u_parse_header(const u8* r, u32 len, URecHdr& h) {
     G2U_NEXT_COL(5);
     if (b - a != 1 || (r[a] != '+' && r[a] != '-' && r[a] != '*')) return ST_ABORT_STRAND;
     h.strand = r[a];
+    return ST_OK;
+}
+// column 6: the path and the syntax of its steps
+G2P_HD u32 u_hdr_b(const u8* r, u32 len, URecHdr& h, UParse& c) {
+    u32 a = 0, b = 0, st = ST_OK;
     G2U_NEXT_COL(6);
     h.path_a = a; h.path_b = b;
     h.prefixed = (r[a] == '<' || r[a] == '>');
     h.empty_path = (!h.prefixed && b - a == 1 && r[a] == '*');
     if (h.prefixed) {   // (no return from inside a loop, here and below: on the device a return there moves the point where the
-        u32 p = a;      // warp's lanes meet again to the end of the function, and they run one after the other until then)
-        st = ST_OK;
+        u32 p = a;      // warp's lanes meet again to the end of the function)
         while (p < b && st == ST_OK) {
             u32 q = next_marker(r, p + 1, b);
             StepTok t;
             st = parse_step_token<true>(r, p, q, t);
             p = q;
         }
-        if (st) return st;
     }
+    return st;
+}
+// columns 7-12
+G2P_HD u32 u_hdr_c(const u8* r, u32 len, URecHdr& h, UParse& c) {
+    u32 a = 0, b = 0, st;
+    i64 tmp;
     G2U_NEXT_COL(7); st = gaf_int(r, a, b, h.plen); if (st) return st;
     G2U_NEXT_COL(8); st = gaf_int(r, a, b, h.ps); if (st) return st;
     G2U_NEXT_COL(9); st = gaf_int(r, a, b, h.pe); if (st) return st;
@@ -100,10 +119,15 @@ G2P_HD u32 u_parse_header(const u8* r, u32 len, URecHdr& h) {
         if (tmp > 2147483647LL || tmp < -2147483648LL) return ST_ABORT_STOL_RANGE;
         h.mapq = tmp >= 255 ? -1 : (i32)tmp;
     }
+    h.tags_from = c.pos;
+    return ST_OK;
+}
 #undef G2U_NEXT_COL
-    h.tags_from = pos;
-    // optional fields: syntax + duplicate names (exact, pairwise: records carry a handful)
-    u32 p1 = pos;
+// optional fields: syntax + duplicate names (exact, pairwise: records carry a handful)
+G2P_HD u32 u_hdr_d(const u8* r, u32 len, URecHdr& h, UParse& c) {
+    u32 a = 0, b = 0;
+    bool eof = c.eof;
+    u32 p1 = c.pos;
     u32 tag_st = ST_OK;
     h.ntags = 0;
     while (!eof && tag_st == ST_OK) {
@@ -150,6 +174,14 @@ G2P_HD u32 u_parse_header(const u8* r, u32 len, URecHdr& h) {
     }
     return tag_st;
 }
+G2P_HD u32 u_parse_header(const u8* r, u32 len, URecHdr& h) {
+    UParse c;
+    u32 st = u_hdr_a(r, len, h, c);
+    if (st == ST_OK) st = u_hdr_b(r, len, h, c);
+    if (st == ST_OK) st = u_hdr_c(r, len, h, c);
+    if (st == ST_OK) st = u_hdr_d(r, len, h, c);
+    return st;
+}
 
 // get_unstable_interval (gaf2unstable_main.cpp:70-107): node index range [i0, i1) of the
 // contig covering [start, end), with the reference's assertions.
@@ -194,129 +226,158 @@ G2P_HD void u_put_int(Sink& S, i64 v) {   // gafkluge.hpp:27-29 int_to_string
     if (v == -1) S.ch('*'); else S.dec(v);
 }
 
-// gaf2unstable (gaf2unstable_main.cpp:109-175) + operator<<(GafRecord) (gafkluge.hpp:288-323)
+// gaf2unstable (gaf2unstable_main.cpp:109-175) + operator<<(GafRecord) (gafkluge.hpp:288-323), in phases (see above)
+struct URun {
+    u32 p;                 // next step token of a prefixed path
+    u32 fail;              // first failure (the record aborts the reference)
+    i32 ref_first;
+    bool multi, any_step;
+    bool steps_left, tags_left;
+    bool set_rc, rc_done, have_last;
+    u32 last_a, last_n;
+};
+
+// columns 1-5; an empty path prints its six '*' columns here
+template <class Sink>
+G2P_HD void u_out_head(const u8* r, URecHdr& h, URun& u, Sink& S) {
+    S.bytes(r, h.qn_b); S.ch('\t');
+    u_put_int(S, h.qlen); S.ch('\t');
+    u_put_int(S, h.qs); S.ch('\t');
+    u_put_int(S, h.qe); S.ch('\t');
+    S.ch(h.strand); S.ch('\t');
+    u.p = h.path_a; u.fail = ST_OK; u.ref_first = -1; u.multi = false; u.any_step = false;
+    u.steps_left = !h.empty_path; u.tags_left = false;
+    if (h.empty_path) for (int k = 0; k < 6; ++k) { S.ch('*'); S.ch('\t'); }
+}
+// one path step -> its nodes
+template <class Sink>
+G2P_HD void u_out_step(const u8* r, const UnstableView& V, URecHdr& h, URun& u, Sink& S) {
+    StepTok t;
+    bool is_last;
+    u32 st = ST_OK;
+    if (!h.prefixed) {
+        t.name_a = h.path_a; t.name_b = h.path_b; t.rev = 0; t.is_interval = 0; t.start = t.end = 0;
+        is_last = true;
+    } else {
+        u32 q = next_marker(r, u.p + 1, h.path_b);
+        parse_step_token<false>(r, u.p, q, t);
+        is_last = q >= h.path_b;
+        if (!t.is_interval && !(u.p == h.path_a && is_last)) st = ST_ABORT_ASSERT;   // :116 assert(path.size() == 1)
+        u.p = q;
+    }
+    u32 i0 = 0, i1 = 0;
+    if (st == ST_OK) {
+        if (!t.is_interval) {
+            st = u_interval(V, r + t.name_a, t.name_b - t.name_a, h.ps, h.pe, i0, i1);
+            if (st == ST_OK) {
+                const i64 path_len = h.pe - h.ps;                     // :119-127
+                h.ps -= V.nodes[i0].offset;
+                h.pe = h.ps + path_len;
+                const UNode& last = V.nodes[i1 - 1];
+                h.plen = (last.cum + (i64)last.length) - V.nodes[i0].cum;
+            }
+        } else {
+            st = u_interval(V, r + t.name_a, t.name_b - t.name_a, t.start, t.end, i0, i1);
+        }
+    }
+    if (st == ST_OK) {
+        const u32 cnt = i1 - i0;
+        for (u32 k = 0; k < cnt; ++k) {
+            const UNode& nd = V.nodes[t.rev ? i1 - 1 - k : i0 + k];   // :135-137
+            S.ch(t.rev ? '<' : '>');
+            S.bytes(V.node_names + nd.name_off, nd.name_len);
+            if (nd.ref < 0) { st = ST_ABORT_ASSERT; break; }          // :160-161 node_id / partition lookup
+            if (!u.any_step) { u.ref_first = nd.ref; u.any_step = true; }
+            else if (nd.ref != u.ref_first) u.multi = true;
+        }
+    }
+    if (st != ST_OK) u.fail = st;
+    if (st != ST_OK || is_last) u.steps_left = false;
+}
+// columns 7-12
+template <class Sink>
+G2P_HD void u_out_mid(URecHdr& h, URun& u, Sink& S) {
+    if (u.fail) return;
+    if (!h.empty_path) {
+        S.ch('\t');
+        u_put_int(S, h.plen); S.ch('\t');
+        u_put_int(S, h.ps); S.ch('\t');
+        u_put_int(S, h.pe); S.ch('\t');
+        u_put_int(S, h.m); S.ch('\t');
+        u_put_int(S, h.b); S.ch('\t');
+    }
+    S.dec(h.mapq == -1 ? 255 : (i64)h.mapq);
+    // optional fields in tag-name order, rc overridden when exactly one reference contig (:172-174)
+    u.set_rc = u.any_step && !u.multi;
+    u.rc_done = !u.set_rc;
+    u.last_a = 0; u.last_n = 0; u.have_last = false;
+    u.tags_left = true;
+}
+// the next optional field in name order (or the synthetic rc tag)
+template <class Sink>
+G2P_HD void u_out_tag(const u8* r, u32 len, const UnstableView& V, URecHdr& h, URun& u, Sink& S) {
+    const u8 rc_key[2] = {'r', 'c'};
+    // smallest key strictly greater than the last one printed
+    bool found = false;
+    u32 best_a = 0, best_b = 0, best_k = 0;
+    u32 p0 = h.tags_from;
+    if (h.ntags <= kUMaxTags) {   // from the collected fields
+        for (u32 j = 0; j < h.ntags; ++j) {
+            const u32 ta = h.tag_a[j], kn = h.tag_k[j];
+            const bool is_rc = u.set_rc && kn == 2 && r[ta] == 'r' && r[ta + 1] == 'c';
+            if (!is_rc && (!u.have_last || u_key_cmp(r + ta, kn, r + u.last_a, u.last_n) > 0) &&
+                (!found || u_key_cmp(r + ta, kn, r + best_a, best_k) < 0)) {
+                found = true; best_a = ta; best_b = ta + h.tag_n[j]; best_k = kn;
+            }
+        }
+        p0 = len;
+    }
+    while (p0 < len) {
+        u32 e0 = p0;
+        while (e0 < len && r[e0] != '\t') ++e0;
+        if (e0 > p0) {
+            u32 k0 = p0;
+            while (r[k0] != ':') ++k0;
+            const u32 kn = k0 - p0;
+            const bool is_rc = u.set_rc && kn == 2 && r[p0] == 'r' && r[p0 + 1] == 'c';
+            if (!is_rc && (!u.have_last || u_key_cmp(r + p0, kn, r + u.last_a, u.last_n) > 0) &&
+                (!found || u_key_cmp(r + p0, kn, r + best_a, best_k) < 0)) {
+                found = true; best_a = p0; best_b = e0; best_k = kn;
+            }
+        }
+        p0 = e0 + 1;
+    }
+    // does the synthetic rc tag come before the candidate?
+    if (!u.rc_done && (!found || u_key_cmp(rc_key, 2, r + best_a, best_k) < 0)) {
+        S.ch('\t'); S.ch('r'); S.ch('c'); S.ch(':'); S.ch('Z'); S.ch(':');
+        const u32 o0 = V.ref_off[u.ref_first], o1 = V.ref_off[u.ref_first + 1];
+        S.bytes(V.ref_names + o0, o1 - o0);
+        u.rc_done = true;
+        return;   // `last` unchanged: rc never equals an input key here (input rc is skipped)
+    }
+    if (!found) { u.tags_left = false; return; }
+    S.ch('\t');
+    S.bytes(r + best_a, best_b - best_a);
+    u.last_a = best_a; u.last_n = best_k; u.have_last = true;
+}
+template <class Sink>
+G2P_HD u32 u_out_end(URun& u, Sink& S) {
+    S.ch('\n');
+    return u.fail ? u.fail : (u.multi ? (u32)ST_WARN_MULTIREF : (u32)ST_OK);
+}
+
 template <class Sink>
 G2P_HD u32 unstable_record(const u8* r, u32 len, const UnstableView& V, Sink& S, u32& ea, u32& eb) {
     ea = eb = 0;
     URecHdr h;
     u32 st = u_parse_header(r, len, h);
     if (st != ST_OK) return st;
-
-    S.bytes(r, h.qn_b); S.ch('\t');
-    u_put_int(S, h.qlen); S.ch('\t');
-    u_put_int(S, h.qs); S.ch('\t');
-    u_put_int(S, h.qe); S.ch('\t');
-    S.ch(h.strand); S.ch('\t');
-
-    i32 ref_first = -1;
-    bool multi = false;
-    bool any_step = false;
-    u32 fail = ST_OK;   // (set instead of returning from inside the loops: see u_parse_header)
-    if (h.empty_path) {
-        for (int k = 0; k < 6; ++k) { S.ch('*'); S.ch('\t'); }
-    } else {
-        u32 p = h.path_a;
-        for (;;) {
-            StepTok t;
-            bool is_last;
-            if (!h.prefixed) {
-                t.name_a = h.path_a; t.name_b = h.path_b; t.rev = 0; t.is_interval = 0; t.start = t.end = 0;
-                is_last = true;
-            } else {
-                u32 q = next_marker(r, p + 1, h.path_b);
-                parse_step_token<false>(r, p, q, t);
-                is_last = q >= h.path_b;
-                if (!t.is_interval && !(p == h.path_a && is_last)) { fail = ST_ABORT_ASSERT; break; }   // :116 assert(path.size() == 1)
-                p = q;
-            }
-            u32 i0 = 0, i1 = 0;
-            if (!t.is_interval) {
-                st = u_interval(V, r + t.name_a, t.name_b - t.name_a, h.ps, h.pe, i0, i1);
-                if (st == ST_OK) {
-                    const i64 path_len = h.pe - h.ps;                     // :119-127
-                    h.ps -= V.nodes[i0].offset;
-                    h.pe = h.ps + path_len;
-                    const UNode& last = V.nodes[i1 - 1];
-                    h.plen = (last.cum + (i64)last.length) - V.nodes[i0].cum;
-                }
-            } else {
-                st = u_interval(V, r + t.name_a, t.name_b - t.name_a, t.start, t.end, i0, i1);
-            }
-            if (st) { fail = st; break; }
-            const u32 cnt = i1 - i0;
-            for (u32 k = 0; k < cnt; ++k) {
-                const UNode& nd = V.nodes[t.rev ? i1 - 1 - k : i0 + k];   // :135-137
-                S.ch(t.rev ? '<' : '>');
-                S.bytes(V.node_names + nd.name_off, nd.name_len);
-                if (nd.ref < 0) { fail = ST_ABORT_ASSERT; break; }        // :160-161 node_id / partition lookup
-                if (!any_step) { ref_first = nd.ref; any_step = true; }
-                else if (nd.ref != ref_first) multi = true;
-            }
-            if (fail || is_last) break;
-        }
-        if (!fail) {
-            S.ch('\t');
-            u_put_int(S, h.plen); S.ch('\t');
-            u_put_int(S, h.ps); S.ch('\t');
-            u_put_int(S, h.pe); S.ch('\t');
-            u_put_int(S, h.m); S.ch('\t');
-            u_put_int(S, h.b); S.ch('\t');
-        }
-    }
-    if (!fail) S.dec(h.mapq == -1 ? 255 : (i64)h.mapq);
-
-    // optional fields in tag-name order, rc overridden when exactly one reference contig (:172-174)
-    const bool set_rc = any_step && !multi;
-    const u8 rc_key[2] = {'r', 'c'};
-    bool rc_done = !set_rc;
-    u32 last_a = 0, last_n = 0;
-    bool have_last = false;
-    while (!fail) {
-        // smallest key strictly greater than the last one printed
-        bool found = false;
-        u32 best_a = 0, best_b = 0, best_k = 0;
-        u32 p0 = h.tags_from;
-        if (h.ntags <= kUMaxTags) {   // from the collected fields
-            for (u32 j = 0; j < h.ntags; ++j) {
-                const u32 ta = h.tag_a[j], kn = h.tag_k[j];
-                const bool is_rc = set_rc && kn == 2 && r[ta] == 'r' && r[ta + 1] == 'c';
-                if (!is_rc && (!have_last || u_key_cmp(r + ta, kn, r + last_a, last_n) > 0) &&
-                    (!found || u_key_cmp(r + ta, kn, r + best_a, best_k) < 0)) {
-                    found = true; best_a = ta; best_b = ta + h.tag_n[j]; best_k = kn;
-                }
-            }
-            p0 = len;
-        }
-        while (p0 < len) {
-            u32 e0 = p0;
-            while (e0 < len && r[e0] != '\t') ++e0;
-            if (e0 > p0) {
-                u32 k0 = p0;
-                while (r[k0] != ':') ++k0;
-                const u32 kn = k0 - p0;
-                const bool is_rc = set_rc && kn == 2 && r[p0] == 'r' && r[p0 + 1] == 'c';
-                if (!is_rc && (!have_last || u_key_cmp(r + p0, kn, r + last_a, last_n) > 0) &&
-                    (!found || u_key_cmp(r + p0, kn, r + best_a, best_k) < 0)) {
-                    found = true; best_a = p0; best_b = e0; best_k = kn;
-                }
-            }
-            p0 = e0 + 1;
-        }
-        // does the synthetic rc tag come before the candidate?
-        if (!rc_done && (!found || u_key_cmp(rc_key, 2, r + best_a, best_k) < 0)) {
-            S.ch('\t'); S.ch('r'); S.ch('c'); S.ch(':'); S.ch('Z'); S.ch(':');
-            const u32 o0 = V.ref_off[ref_first], o1 = V.ref_off[ref_first + 1];
-            S.bytes(V.ref_names + o0, o1 - o0);
-            rc_done = true;
-            continue;   // `last` unchanged: rc never equals an input key here (input rc is skipped)
-        }
-        if (!found) break;
-        S.ch('\t');
-        S.bytes(r + best_a, best_b - best_a);
-        last_a = best_a; last_n = best_k; have_last = true;
-    }
-    S.ch('\n');
-    return fail ? fail : (multi ? (u32)ST_WARN_MULTIREF : (u32)ST_OK);
+    URun u;
+    u_out_head(r, h, u, S);
+    while (u.steps_left) u_out_step(r, V, h, u, S);
+    u_out_mid(h, u, S);
+    while (u.tags_left) u_out_tag(r, len, V, h, u, S);
+    return u_out_end(u, S);
 }
 
 }  // namespace g2p

@@ -2,7 +2,7 @@
 """Mutation fuzzer: a converter binary vs the reference gaf2paf on single malformed
 or unusual records.  Compares exit code and stdout (and stderr text for rc 1).
 
-    python tests/fuzz_vs_ref.py [--n 2000] [--seed 1] [--bin build/g2p_hostsim]
+    python tests/fuzz_vs_ref.py [--n 2000] [--seed 1] [--bin build/g2p_hostsim] [--long]
 
 Development tool (needs oracle/_ref, i.e. the build container).  CIGAR text outside the SAM
 grammar that std::stol accepts is handled like the reference does; the only tolerated class is
@@ -133,6 +133,7 @@ def main():
     ap.add_argument("--n", type=int, default=2000)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--bin", default=os.path.join(ROOT, "build", "g2p_hostsim"))
+    ap.add_argument("--long", action="store_true", help="append a 300-byte tag to every case: the records take the long-record kernels (k_par, k_long)")
     a = ap.parse_args()
     rnd = random.Random(a.seed)
     bad = 0
@@ -145,6 +146,8 @@ def main():
             for _ in range(rnd.randrange(1, 3)):
                 line = mutate(rnd, line.replace("\t", " "))
             data = line.replace(" ", "\t") if "\t" not in line else line
+            if a.long:
+                data += "\tzy:Z:" + "p" * 300
             data = data.encode("latin-1") + b"\n"
             ref = run(REF, lp, data)
             got = run(a.bin, lp, data)
