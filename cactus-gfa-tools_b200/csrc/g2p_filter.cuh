@@ -393,14 +393,46 @@ __global__ void __launch_bounds__(128) k_filter_sweep(const u64* __restrict__ ke
 }
 
 // ---- printing a kept record ---------------------------------------------------------------------------
-// tags of [from, len) in name order (std::map iteration): repeated selection of the smallest key above the last one
+// tags of [from, len) in name order (std::map iteration): repeated selection of the smallest key above the last one.
+// The fields are collected in one scan (FTags); with more than kUMaxTags of them the text is rescanned for every field.
+struct FTags {
+    u32 n;                  // > kUMaxTags: more than fit
+    u32 a[kUMaxTags];
+    u16 len[kUMaxTags];     // bytes of the whole field
+    u8 k[kUMaxTags];        // bytes of its name
+    u32 last_a, last_n;
+    bool have_last, left;
+};
+G2P_HD void filter_tags_collect(const u8* r, u32 from, u32 len, FTags& T) {
+    T.n = 0; T.last_a = T.last_n = 0; T.have_last = false; T.left = true;
+    u32 p0 = from;
+    while (p0 < len && T.n <= kUMaxTags) {
+        u32 e0 = p0;
+        while (e0 < len && r[e0] != '\t') ++e0;
+        if (e0 > p0) {
+            u32 k0 = p0;
+            while (k0 < e0 && r[k0] != ':') ++k0;
+            if (T.n < kUMaxTags && k0 - p0 <= 255u && e0 - p0 <= 65535u) { T.a[T.n] = p0; T.len[T.n] = (u16)(e0 - p0); T.k[T.n] = (u8)(k0 - p0); ++T.n; }
+            else T.n = kUMaxTags + 1;
+        }
+        p0 = e0 + 1;
+    }
+}
+// prints the next tag in name order; T.left = false when there is none
 template <class Sink>
-G2P_HD void filter_put_tags_sorted(const u8* r, u32 from, u32 len, bool last_wins, Sink& S) {
-    u32 last_a = 0, last_n = 0;
-    bool have_last = false;
-    for (;;) {
-        bool found = false;
-        u32 best_a = 0, best_b = 0, best_k = 0;
+G2P_HD void filter_tags_next(const u8* r, u32 from, u32 len, bool last_wins, FTags& T, Sink& S) {
+    bool found = false;
+    u32 best_a = 0, best_b = 0, best_k = 0;
+    if (T.n <= kUMaxTags) {
+        for (u32 j = 0; j < T.n; ++j) {
+            const u32 p0 = T.a[j], kn = T.k[j];
+            // (PAF mode: a repeated tag name overwrites the earlier one in the reference's std::map -- the last one is printed)
+            const int cb = found ? u_key_cmp(r + p0, kn, r + best_a, best_k) : -1;
+            if ((!T.have_last || u_key_cmp(r + p0, kn, r + T.last_a, T.last_n) > 0) && (cb < 0 || (cb == 0 && last_wins))) {
+                found = true; best_a = p0; best_b = p0 + T.len[j]; best_k = kn;
+            }
+        }
+    } else {
         u32 p0 = from;
         while (p0 < len) {
             u32 e0 = p0;
@@ -409,24 +441,29 @@ G2P_HD void filter_put_tags_sorted(const u8* r, u32 from, u32 len, bool last_win
                 u32 k0 = p0;
                 while (k0 < e0 && r[k0] != ':') ++k0;
                 const u32 kn = k0 - p0;
-                // (PAF mode: a repeated tag name overwrites the earlier one in the reference's std::map -- the last one is printed)
                 const int cb = found ? u_key_cmp(r + p0, kn, r + best_a, best_k) : -1;
-                if ((!have_last || u_key_cmp(r + p0, kn, r + last_a, last_n) > 0) && (cb < 0 || (cb == 0 && last_wins))) {
+                if ((!T.have_last || u_key_cmp(r + p0, kn, r + T.last_a, T.last_n) > 0) && (cb < 0 || (cb == 0 && last_wins))) {
                     found = true; best_a = p0; best_b = e0; best_k = kn;
                 }
             }
             p0 = e0 + 1;
         }
-        if (!found) break;
-        S.ch('\t');
-        S.bytes(r + best_a, best_b - best_a);
-        last_a = best_a; last_n = best_k; have_last = true;
     }
+    if (!found) { T.left = false; return; }
+    S.ch('\t');
+    S.bytes(r + best_a, best_b - best_a);
+    T.last_a = best_a; T.last_n = best_k; T.have_last = true;
+}
+template <class Sink>
+G2P_HD void filter_put_tags_sorted(const u8* r, u32 from, u32 len, bool last_wins, Sink& S) {
+    FTags T;
+    filter_tags_collect(r, from, len, T);
+    while (T.left) filter_tags_next(r, from, len, last_wins, T, S);
 }
 
 // operator<<(GafRecord) (gafkluge.hpp:288-323) of an unchanged record
 template <class Sink>
-G2P_HD void filter_print_gaf(const u8* r, u32 len, Sink& S) {
+G2P_HD u32 filter_print_gaf_head(const u8* r, u32 len, Sink& S) {   // the 12 columns; returns where the optional fields begin
     URecHdr h;
     u_parse_header(r, len, h);
     S.bytes(r, h.qn_b); S.ch('\t');
@@ -445,13 +482,18 @@ G2P_HD void filter_print_gaf(const u8* r, u32 len, Sink& S) {
         u_put_int(S, h.b); S.ch('\t');
     }
     S.dec(h.mapq == -1 ? 255 : (i64)h.mapq);
-    filter_put_tags_sorted(r, h.tags_from, len, false, S);
+    return h.tags_from;
+}
+template <class Sink>
+G2P_HD void filter_print_gaf(const u8* r, u32 len, Sink& S) {
+    const u32 from = filter_print_gaf_head(r, len, S);
+    filter_put_tags_sorted(r, from, len, false, S);
     S.ch('\n');
 }
 
 // operator<<(PafLine) (paf.hpp:83-95): 12 columns (numbers through stol), then every tag -- cg included, see the header -- in name order
 template <class Sink>
-G2P_HD void filter_print_paf(const u8* r, u32 len, Sink& S) {
+G2P_HD u32 filter_print_paf_head(const u8* r, u32 len, Sink& S) {
     u32 p = 0, k = 0, tags_from = len;
     while (p <= len && k < 12) {
         u32 e = p;
@@ -465,22 +507,47 @@ G2P_HD void filter_print_paf(const u8* r, u32 len, Sink& S) {
         }
         p = e + 1;
     }
-    filter_put_tags_sorted(r, tags_from, len, true, S);
+    return tags_from;
+}
+template <class Sink>
+G2P_HD void filter_print_paf(const u8* r, u32 len, Sink& S) {
+    const u32 from = filter_print_paf_head(r, len, S);
+    filter_put_tags_sorted(r, from, len, true, S);
     S.ch('\n');
+}
+
+// One record per thread, in phases with the warp meeting after each (as unstable_record_warp): the 12 columns, the
+// collection of the optional fields, then one field per round of a warp-uniform loop.
+template <class Sink>
+__device__ __forceinline__ void filter_print_warp(bool act, const u8* r, u32 len, u32 is_paf, Sink& S) {
+    const u32 FULL = 0xffffffffu;
+    u32 from = 0;
+    if (act) from = is_paf ? filter_print_paf_head(r, len, S) : filter_print_gaf_head(r, len, S);
+    __syncwarp();
+    FTags T;
+    T.left = false;
+    if (act) filter_tags_collect(r, from, len, T);
+    __syncwarp();
+    while (__any_sync(FULL, act && T.left)) {
+        if (act && T.left) filter_tags_next(r, from, len, is_paf != 0, T, S);
+    }
+    if (act) S.ch('\n');
 }
 
 template <bool EMIT>
 __global__ void __launch_bounds__(128) k_filter_emit(const u8* __restrict__ text, const u32* __restrict__ rec_start, u32 nrec, u32 is_paf,
                                                      const u8* __restrict__ keep, u64* __restrict__ out_off, u8* __restrict__ out) {
-    for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < nrec; r += gridDim.x * blockDim.x) {
-        const u32 s = rec_start[r], len = rec_start[r + 1] - s - 1;
+    for (u32 base = blockIdx.x * blockDim.x; base < nrec; base += gridDim.x * blockDim.x) {   // (uniform: every lane takes part)
+        const u32 r = base + threadIdx.x;
+        const bool act = r < nrec && keep[r] != 0;
+        const u32 s = act ? rec_start[r] : 0u, len = act ? rec_start[r + 1] - s - 1 : 0u;
         if (!EMIT) {
             CountSink cs;
-            if (keep[r]) { if (is_paf) filter_print_paf(text + s, len, cs); else filter_print_gaf(text + s, len, cs); }
-            out_off[r] = cs.n;
-        } else if (keep[r]) {
-            StoreSink ss(out + out_off[r]);
-            if (is_paf) filter_print_paf(text + s, len, ss); else filter_print_gaf(text + s, len, ss);
+            filter_print_warp(act, text + s, len, is_paf, cs);
+            if (r < nrec) out_off[r] = cs.n;
+        } else {
+            StoreSink ss(out + (act ? out_off[r] : 0));
+            filter_print_warp(act, text + s, len, is_paf, ss);
         }
     }
 }

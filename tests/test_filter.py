@@ -131,3 +131,26 @@ def test_gpu_gaffilter_cli(g2p):
             rc, out, err = H.run_tool(exe, args)
             rrc, rout, rerr = H.run_tool(REF, args)
             assert rc == rrc and out == rout and err.replace(exe, "X") == rerr.replace(REF, "X")
+
+
+@needs_ref
+def test_emulated_filter_many_tags():
+    """More optional fields than the emit kernels collect (16: the text is rescanned then), repeated names in PAF mode
+    (the last one is printed) among and beyond the collected ones, long names."""
+    many = [("%c%c:i:%d" % (97 + i // 5, 97 + i % 5, i)).encode() for i in range(22)]
+    gaf = b"\n".join([
+        b"\t".join([b"q1\t100\t5\t40\t+\t>a\t50\t0\t35\t35\t35\t60"] + many[:16][::-1] + [b"cg:Z:35M"]),
+        b"\t".join([b"q1\t100\t50\t90\t+\t>a\t50\t0\t40\t40\t40\t60"] + many[::-1] + [b"cg:Z:40M", b"longname:Z:v"]),
+        b"\t".join([b"q2\t100\t0\t40\t-\t>b\t50\t0\t40\t40\t40\t60", b"tp:A:P", b"cg:Z:40M"]),
+    ]) + b"\n"
+    rc, out, err = H.run_gaffilter_ref(gaf, ["-r", "2"])
+    src, sout, serr = simt(gaf, ["-r", "2"])
+    assert rc == src == 0 and sout == out and out.count(b"\n") == 3 and last_line(serr) == last_line(err)
+    paf = b"\n".join([
+        b"\t".join([b"q1\t100\t5\t40\t+\ta\t50\t0\t35\t35\t35\t60"] + many[:10] + [b"ac:i:99", b"cg:Z:35M", b"ab:Z:again"]),
+        b"\t".join([b"q1\t100\t50\t90\t+\ta\t50\t0\t40\t40\t40\t60"] + many + [b"ab:i:77", b"ea:i:78", b"cg:Z:40M", b"cg:Z:39M1X"]),
+        b"\t".join([b"q2\t100\t0\t40\t-\tb\t50\t0\t40\t40\t40\t60", b"cg:Z:40M"]),
+    ]) + b"\n"
+    rc, out, err = H.run_gaffilter_ref(paf, ["-p", "-r", "2"])
+    src, sout, serr = simt(paf, ["-p", "-r", "2"])
+    assert rc == src == 0 and sout == out and out.count(b"\n") == 3 and last_line(serr) == last_line(err)
