@@ -89,7 +89,7 @@ struct PinBuf {
 struct Worker {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[10] = {};  // 0..4: general pipeline (index, size, scan, emit), 5..6: k_fuse, 8..9: k_par
-    DevBuf f_rows, f_keys, f_keys2, f_vals, f_vals2, f_pmax, f_keep, f_hist, f_meta;   // gaffilter
+    DevBuf f_rows, f_keys, f_keys2, f_vals, f_vals2, f_pmax, f_keep, f_hist, f_meta, f_seg;   // gaffilter
     DevBuf d_mid, d_in, d_tiles, d_rec, d_status, d_off, d_blocks, d_out, d_meta, d_list, d_list2, d_desc, d_rdesc, d_sdesc, d_loff, d_map, d_lsort, d_perm, d_fuse;
     DevBuf p_recs, p_tb, p_toff, p_bs, p_step, p_op, d_list3;   // k_par (g2p_par.cuh)
     PinBuf h_meta, h_fmeta, h_par;
@@ -100,7 +100,7 @@ struct Worker {
                h_fmeta.ensure(sizeof(FuseMeta)) == cudaSuccess && h_par.ensure(64) == cudaSuccess;
     }
     void release() {
-        for (DevBuf* b : {&f_rows, &f_keys, &f_keys2, &f_vals, &f_vals2, &f_pmax, &f_keep, &f_hist, &f_meta, &d_mid, &d_in, &d_tiles, &d_rec, &d_status, &d_off, &d_blocks, &d_out, &d_meta, &d_list, &d_list2, &d_desc, &d_rdesc, &d_sdesc, &d_loff, &d_map, &d_lsort, &d_perm, &d_fuse, &p_recs, &p_tb, &p_toff, &p_bs, &p_step, &p_op, &d_list3}) b->release();
+        for (DevBuf* b : {&f_rows, &f_keys, &f_keys2, &f_vals, &f_vals2, &f_pmax, &f_keep, &f_hist, &f_meta, &f_seg, &d_mid, &d_in, &d_tiles, &d_rec, &d_status, &d_off, &d_blocks, &d_out, &d_meta, &d_list, &d_list2, &d_desc, &d_rdesc, &d_sdesc, &d_loff, &d_map, &d_lsort, &d_perm, &d_fuse, &p_recs, &p_tb, &p_toff, &p_bs, &p_step, &p_op, &d_list3}) b->release();
         h_meta.release();
         h_fmeta.release();
         h_par.release();
@@ -1336,7 +1336,18 @@ static int run_filter(g2p_ctx* ctx, Worker& w, const u8* d_text, size_t n, const
     }
     i64* pmax = static_cast<i64*>(w.f_pmax.p);
     u8* keep = static_cast<u8*>(w.f_keep.p);
-    k_filter_prefmax<<<grid, 256, 0, st>>>(keys, vals, rows, nrec, pmax);
+    {   // segmented max-scan of the interval ends over the sorted order
+        const u32 nseg = (nrec + kSegTile - 1) / kSegTile;
+        G2P_CUDA(w.f_seg.ensure((size_t)nseg * 24 + 64));
+        i64* tile_val = static_cast<i64*>(w.f_seg.p);
+        i64* carry = tile_val + nseg;
+        u32* tile_flag = reinterpret_cast<u32*>(carry + nseg);
+        k_filter_ends<<<grid, 256, 0, st>>>(keys, vals, rows, nrec, pmax);
+        k_segmax<false><<<nseg, kSegThreads, 0, st>>>(keys, nrec, pmax, tile_val, tile_flag, nullptr);
+        k_segmax_tiles<<<1, 32, 0, st>>>(tile_val, tile_flag, nseg, carry);
+        k_segmax<true><<<nseg, kSegThreads, 0, st>>>(keys, nrec, pmax, tile_val, tile_flag, carry);
+        launches += 3;
+    }
     G2P_CUDA(cudaMemsetAsync(keep, 0, nrec, st));
     k_filter_sweep<<<grid, 128, 0, st>>>(keys, vals, rows, pmax, nrec, P, keep, d_fm);
     u64* d_off = static_cast<u64*>(w.d_off.p);

@@ -10,7 +10,9 @@
 //                       gafkluge.hpp:84-204, or parse_paf_line, paf.hpp:48-80) -> one 80-byte row; 128-bit hash of the
 //                       query name; sort key = hash32 << 32 | query_start
 //   k_rs_hist / scatter LSD radix sort of (key, record) pairs, 4 bits per pass, stable
-//   k_filter_prefmax    per run of equal hash32: running maximum of the interval ends (bounds the backward scan)
+//   k_filter_ends, k_segmax<>, k_segmax_tiles
+//                       per run of equal hash32: running maximum of the interval ends (segmented max-scan; bounds the
+//                       backward scan)
 //   k_filter_sweep      one thread per record: forwards while start_j <= stop_i, backwards while the running maximum
 //                       of the ends reaches start_i; same qualifiers and the same double arithmetic as dominates()
 //   k_filter_emit       size pass / scan / write pass of the kept records, re-serialised like the reference prints
@@ -292,22 +294,85 @@ G2P_HD void filter_interval(const FRow& r, i64& lo, i64& hi) {
     hi = a < b ? b : a;
 }
 
-// Running maximum of the interval ends inside each run of equal hash32 (one thread per run; runs are short except for
-// assembly contigs, where one thread walks ~10^5 entries).
-__global__ void __launch_bounds__(256) k_filter_prefmax(const u64* __restrict__ keys, const u32* __restrict__ vals, const FRow* __restrict__ rows,
-                                                        u32 n, i64* __restrict__ prefmax) {
+// Running maximum of the interval ends inside each run of equal hash32: a segmented inclusive max-scan over the sorted
+// order (a run is one query sequence -- with assembly contigs as queries a single run holds 10^5 alignments, so nothing
+// here may walk a run serially).  k_filter_ends writes every entry's end, k_segmax<false> reduces 2048-entry tiles to
+// (does a run start inside the tile?, maximum after the last start), k_segmax_tiles turns those into the value carried
+// into every tile, k_segmax<true> rescans the tiles with their carry.
+constexpr int kSegThreads = 256, kSegItems = 8;
+constexpr u32 kSegTile = kSegThreads * kSegItems;
+__device__ __forceinline__ bool filter_run_head(const u64* __restrict__ keys, u32 p) {
+    const u64 k = keys[p];
+    return p == 0 || k == ~0ULL || (u32)(keys[p - 1] >> 32) != (u32)(k >> 32);   // ('*' and failed lines: each one alone)
+}
+__global__ void __launch_bounds__(256) k_filter_ends(const u64* __restrict__ keys, const u32* __restrict__ vals, const FRow* __restrict__ rows,
+                                                     u32 n, i64* __restrict__ prefmax) {
     for (u32 p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
-        if (keys[p] == ~0ULL) { prefmax[p] = 0; continue; }
-        const u32 h = (u32)(keys[p] >> 32);
-        if (p > 0 && (u32)(keys[p - 1] >> 32) == h) continue;   // not the head of its run
-        i64 m = INT64_MIN;
-        for (u32 q = p; q < n && (u32)(keys[q] >> 32) == h; ++q) {
-            i64 lo, hi;
-            filter_interval(rows[vals[q]], lo, hi);
-            m = hi > m ? hi : m;
-            prefmax[q] = m;
-        }
+        i64 hi = 0;
+        if (keys[p] != ~0ULL) { i64 lo; filter_interval(rows[vals[p]], lo, hi); }
+        prefmax[p] = hi;
     }
+}
+// (flag, value) of a sequence followed by another: the value after the last run start
+__device__ __forceinline__ void segmax_join(bool& f, i64& v, bool f2, i64 v2) {
+    v = f2 ? v2 : (v > v2 ? v : v2);
+    f = f || f2;
+}
+template <bool APPLY>
+__global__ void __launch_bounds__(kSegThreads) k_segmax(const u64* __restrict__ keys, u32 n, i64* __restrict__ x, i64* __restrict__ tile_val, u32* __restrict__ tile_flag,
+                                                        const i64* __restrict__ carry_val) {
+    __shared__ i64 wv[kSegThreads / 32];
+    __shared__ u32 wf[kSegThreads / 32];
+    const u32 base = blockIdx.x * kSegTile + threadIdx.x * kSegItems;
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    // the thread's items
+    bool f = false;
+    i64 v = INT64_MIN;
+    bool hf[kSegItems];
+    i64 hv[kSegItems];
+#pragma unroll
+    for (int i = 0; i < kSegItems; ++i) {
+        const u32 p = base + i;
+        hf[i] = p < n && filter_run_head(keys, p);
+        hv[i] = p < n ? x[p] : INT64_MIN;
+        if (p < n) segmax_join(f, v, hf[i], hv[i]);
+    }
+    // inclusive scan over the threads of the warp, then over the warps
+    bool sf = f;
+    i64 sv = v;
+    for (int d = 1; d < 32; d <<= 1) {
+        const u32 pf = __shfl_up_sync(0xffffffffu, (u32)sf, d);
+        const i64 pv = __shfl_up_sync(0xffffffffu, sv, d);
+        if (lane >= (u32)d) { bool nf = pf != 0; i64 nv = pv; segmax_join(nf, nv, sf, sv); sf = nf; sv = nv; }
+    }
+    if (lane == 31) { wv[warp] = sv; wf[warp] = sf; }
+    __syncthreads();
+    // what arrives at this thread from the left: the tile's carry, the warps before, the lanes before
+    bool cf = false;
+    i64 cv = APPLY ? carry_val[blockIdx.x] : INT64_MIN;
+    for (u32 w = 0; w < warp; ++w) segmax_join(cf, cv, wf[w] != 0, wv[w]);
+    {
+        const u32 pf = __shfl_up_sync(0xffffffffu, (u32)sf, 1);
+        const i64 pv = __shfl_up_sync(0xffffffffu, sv, 1);
+        if (lane > 0) segmax_join(cf, cv, pf != 0, pv);
+    }
+    if (APPLY) {
+#pragma unroll
+        for (int i = 0; i < kSegItems; ++i) {
+            const u32 p = base + i;
+            if (p < n) { segmax_join(cf, cv, hf[i], hv[i]); x[p] = cv; }
+        }
+    } else if (threadIdx.x == kSegThreads - 1) {
+        segmax_join(cf, cv, f, v);
+        tile_val[blockIdx.x] = cv;
+        tile_flag[blockIdx.x] = cf;
+    }
+}
+__global__ void k_segmax_tiles(const i64* __restrict__ tile_val, const u32* __restrict__ tile_flag, u32 ntiles, i64* __restrict__ carry_val) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    bool f = false;
+    i64 v = INT64_MIN;
+    for (u32 t = 0; t < ntiles; ++t) { carry_val[t] = v; segmax_join(f, v, tile_flag[t] != 0, tile_val[t]); }
 }
 
 // dominates() of the reference (gaffilter_main.cpp:31-60), same operations in the same order (no contraction: the

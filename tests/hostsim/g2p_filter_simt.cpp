@@ -72,7 +72,15 @@ int main(int argc, char** argv) {
             std::swap(vals, vals2);
         }
         for (u32 i = 1; i < nrec; ++i) if (keys[i - 1] > keys[i]) { std::fprintf(stderr, "g2p_filter_simt: sort order broken at %u\n", i); return 99; }
-        hs::launch(dim3(4), dim3(256), 0, [&] { k_filter_prefmax(keys, vals, rows.data(), nrec, pmax.data()); });
+        {
+            const u32 nseg = (nrec + kSegTile - 1) / kSegTile;
+            std::vector<i64> tile_val(nseg), carry(nseg);
+            std::vector<u32> tile_flag(nseg);
+            hs::launch(dim3(4), dim3(256), 0, [&] { k_filter_ends(keys, vals, rows.data(), nrec, pmax.data()); });
+            hs::launch(dim3(nseg), dim3(kSegThreads), 0, [&] { k_segmax<false>(keys, nrec, pmax.data(), tile_val.data(), tile_flag.data(), nullptr); });
+            hs::launch(dim3(1), dim3(32), 0, [&] { k_segmax_tiles(tile_val.data(), tile_flag.data(), nseg, carry.data()); });
+            hs::launch(dim3(nseg), dim3(kSegThreads), 0, [&] { k_segmax<true>(keys, nrec, pmax.data(), tile_val.data(), tile_flag.data(), carry.data()); });
+        }
         hs::launch(dim3(4), dim3(128), 0, [&] { k_filter_sweep(keys, vals, rows.data(), pmax.data(), nrec, P, keep.data(), &fm); });
         hs::launch(dim3(4), dim3(128), 0, [&] { k_filter_emit<false>(text, rec.data(), nrec, P.is_paf, keep.data(), off.data(), nullptr); });
         hs::launch(dim3(nscan_r), dim3(kScanThreads), 0, [&] { k_scan_reduce(off.data(), nrec, blocks.data()); });
