@@ -154,9 +154,9 @@ struct g2p_ctx {
     uint64_t desc_cap_override = 0;  // G2P_DESC_CAP (tests): line-descriptor slots, to exercise the overflow fallback
     int fuse_mode = 1;               // G2P_FUSE: 0 never run the one-pass kernel k_fuse; 2 always try it first; 1 (default) when it pays:
                                      // k_fuse takes records of up to 1000 bytes at one speed, the two-pass pipeline is faster on records its
-                                     // thread-per-record size pass k_rec takes (<= 240 bytes: 7.2 vs 9.3 ms per 10 M records) and ~9x slower on
-                                     // longer ones (k_long) -- so: mean record length > 200 bytes, or the previous call sent > 1/32 of its
-                                     // records to k_long
+                                     // thread-per-record size pass k_rec takes (<= 240 bytes: 7.2 vs 9.3 ms per 10 M records) and slower on longer
+                                     // ones (k_par; ~9x slower with k_long) -- so: mean record length > 200 bytes, or k_rec left > 1/32 of the
+                                     // previous call's records to the long-record kernels
     std::atomic<int> prefer_fuse{0};
     int fuse_cfg = 6;                // k_fuse configuration (tile bytes, table sizes; g2p_fuse.cuh); moves to a denser one, and stays there, when a tile
                                      // holds more records / path steps than its tables (G2P_FUSE_CFG picks the first one)
