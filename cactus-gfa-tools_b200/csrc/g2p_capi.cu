@@ -1309,6 +1309,7 @@ static int run_filter(g2p_ctx* ctx, Worker& w, const u8* d_text, size_t n, const
     FilterMeta init;
     std::memset(&init, 0, sizeof init);
     init.first_err = 0xFFFFFFFFu;
+    init.assert_rec = 0xFFFFFFFFu;
     G2P_CUDA(cudaMemcpyAsync(d_fm, &init, sizeof init, cudaMemcpyHostToDevice, st));
     FilterParams P{gp->ratio, gp->min_overlap_pct, gp->min_identity, gp->min_overlap_len, gp->min_block_len, gp->min_mapq, gp->is_paf ? 1u : 0u};
     u64* keys = static_cast<u64*>(w.f_keys.p);
@@ -1361,12 +1362,18 @@ static int run_filter(g2p_ctx* ctx, Worker& w, const u8* d_text, size_t n, const
     G2P_CUDA(cudaMemcpyAsync(&hm, d_fm, sizeof hm, cudaMemcpyDeviceToHost, st));
     G2P_CUDA(cudaStreamSynchronize(st));
     G2P_CUDA(cudaGetLastError());
-    if (hm.unsupported) { ctx->set_err("gaffilter: a query_start outside [0, 2^32) is not supported by the device sort"); return G2P_E_ARG; }
     res->n_loaded = hm.n_loaded;
+    if (hm.first_err == 0xFFFFFFFFu && hm.unsupported) { ctx->set_err("gaffilter: a query_start >= 2^32 is not supported by the device sort"); return G2P_E_ARG; }
     if (hm.first_err != 0xFFFFFFFFu) {   // the reference dies while it loads the records: nothing is printed
         res->rec_status = hm.err_status & 0xff;
         if (res->rec_status < G2P_REC_ABORT) res->rec_status = G2P_REC_ABORT + 8;
         res->err_record = hm.first_err;
+        res->gpu_launches = launches;
+        return G2P_OK;
+    }
+    if (hm.assert_rec != 0xFFFFFFFFu) {   // an assertion of the reference's filter loop (gaffilter_main.cpp:68, :289): it aborts
+        res->rec_status = G2P_REC_ABORT + 9;
+        res->err_record = hm.assert_rec;
         res->gpu_launches = launches;
         return G2P_OK;
     }

@@ -52,8 +52,8 @@ struct FilterMeta {
     u32 n_filtered;
     u64 filtered_len;    // "total block lengths filtered"
     u64 out_total;
-    u32 unsupported;     // a query_start outside [0, 2^32): not sortable here
-    u32 pad;
+    u32 unsupported;     // a query_start >= 2^32: not sortable here
+    u32 assert_rec;      // smallest record on which an assertion of the reference's filter loop fires (0xFFFFFFFF: none)
 };
 
 // ---- stof of a tag value (gi:f:0.978): decimal digits, optional fraction and exponent; anything else -> false -----
@@ -211,9 +211,11 @@ __global__ void __launch_bounds__(128) k_filter_parse(const FilterArgs a) {
         else if (st != ST_OK) { row.flags |= kFRowSkip; atomicMin(&a.meta->first_err, r); }
         else {
             atomicAdd(&a.meta->n_loaded, 1u);
-            if (row.qs < 0 || row.qs > 0xFFFFFFF0LL) atomicExch(&a.meta->unsupported, 1u);
+            if (row.qs > 0xFFFFFFF0LL) atomicExch(&a.meta->unsupported, 1u);
             const u32 h32 = (u32)(row.h0 ^ (row.h0 >> 32) ^ row.h1 ^ (row.h1 >> 32));
-            key = ((u64)(h32 == 0xffffffffu ? 0xfffffffeu : h32) << 32) | (u64)(u32)row.qs;
+            // (negative starts -- no real aligner writes them, std::stol reads them -- sort together with start 0: the
+            // forward scan of k_filter_sweep never stops on a start <= 0)
+            key = ((u64)(h32 == 0xffffffffu ? 0xfffffffeu : h32) << 32) | (u64)(row.qs < 0 ? 0u : (u32)row.qs);
         }
         a.rows[r] = row;
         a.keys[r] = key;
@@ -407,15 +409,23 @@ G2P_HD bool filter_dominates(const FRow& g1, const FRow& g2, double ratio) {
 G2P_HD bool filter_dominates_mz(const FRow& g1, const FRow& g2, i64 thr) {   // dominates_mzgaf2paf (:63-66)
     return (g1.block_length >= thr && g2.block_length < thr) || (g1.block_length < thr && g2.block_length < thr);
 }
-// one overlapping record j against record i: false = i is filtered out (gaffilter_main.cpp:263-312)
-G2P_HD bool filter_pair_ok(const FRow& ri, const FRow& rj, const FilterParams& P) {
+// assert(identity >= 0) of the visit lambda (gaffilter_main.cpp:289): evaluated for EVERY interval the tree reports,
+// the record's own included
+G2P_HD bool filter_identity_negative(const FRow& rj) {
+    return rj.matches != 0 && f_div((double)rj.block_length, (double)rj.matches) < 0.0;
+}
+// one overlapping record j against record i: false = i is filtered out (gaffilter_main.cpp:263-312); `boom`: one of the
+// reference's assertions fires on this pair (identity >= 0, :289; oend >= ostart in overlap_size, :68) -- it aborts
+G2P_HD bool filter_pair_ok(const FRow& ri, const FRow& rj, const FilterParams& P, bool& boom) {
     if (rj.h0 != ri.h0 || rj.h1 != ri.h1 || rj.name_len != ri.name_len) return true;   // another query sequence (hash32 collision)
     double identity = rj.matches ? f_div((double)rj.block_length, (double)rj.matches) : 0.0;
+    if (identity < 0.0) boom = true;
     if (rj.flags & kFRowHasGi) { const double g = (double)rj.gi; identity = g < identity ? g : identity; }
     if (!(rj.mapq >= P.min_mapq && (rj.qlen <= P.min_block_len || rj.block_length >= P.min_block_len) && identity >= P.min_identity)) return true;
     if (!(ri.rc == rj.rc || ri.rc == 0 || rj.rc == 0)) return true;   // they map to different reference contigs
     const i64 ostart = ri.qs > rj.qs ? ri.qs : rj.qs, oend = ri.qe < rj.qe ? ri.qe : rj.qe;
     const i64 overlap = oend - ostart;
+    if (overlap < 0) boom = true;
     if (!(ri.block_length == 0 || f_div((double)overlap, (double)ri.block_length) >= P.min_overlap_pct)) return true;
     bool dom = true;
     if (P.ratio != 0.0) dom = filter_dominates(ri, rj, P.ratio);
@@ -432,23 +442,31 @@ __global__ void __launch_bounds__(128) k_filter_sweep(const u64* __restrict__ ke
         const u32 h = (u32)(keys[p] >> 32);
         // query of visit_overlapping(query_start, end_point): end_point = query_end - 1 if query_end > query_start else query_end
         const i64 qstart = ri.qs, qstop = ri.qe > ri.qs ? ri.qe - 1 : ri.qe;
-        bool ok = true;
+        bool ok = true, boom = false;
+        // (The reference collects ALL overlapping intervals -- its assertions run on every one of them, the record's own
+        // included -- and only then looks for one that is not dominated: the scans do not stop at the first such one.)
+        {
+            i64 lo, hi;
+            filter_interval(ri, lo, hi);
+            if (hi >= qstart && lo <= qstop && filter_identity_negative(ri)) boom = true;
+        }
         // forwards: starts are ascending (the stored interval's lower end can be query_end - 1 < query_start only for
         // empty / inverted records, whose lower end is within one of their start)
-        for (u32 q = p + 1; ok && q < n && (u32)(keys[q] >> 32) == h; ++q) {
+        for (u32 q = p + 1; q < n && (u32)(keys[q] >> 32) == h; ++q) {
             const FRow rj = rows[vals[q]];
             i64 lo, hi;
             filter_interval(rj, lo, hi);
-            if (rj.qs > qstop + 1) break;
-            if (hi >= qstart && lo <= qstop) ok = filter_pair_ok(ri, rj, P);
+            if (rj.qs > qstop + 1 && rj.qs > 0) break;
+            if (hi >= qstart && lo <= qstop) { const bool d = filter_pair_ok(ri, rj, P, boom); ok = ok && d; }
         }
-        for (u32 q = p; ok && q-- > 0 && (u32)(keys[q] >> 32) == h;) {
+        for (u32 q = p; q-- > 0 && (u32)(keys[q] >> 32) == h;) {
             if (prefmax[q] < qstart) break;   // nothing at or before q reaches the query
             const FRow rj = rows[vals[q]];
             i64 lo, hi;
             filter_interval(rj, lo, hi);
-            if (hi >= qstart && lo <= qstop) ok = filter_pair_ok(ri, rj, P);
+            if (hi >= qstart && lo <= qstop) { const bool d = filter_pair_ok(ri, rj, P, boom); ok = ok && d; }
         }
+        if (boom) atomicMin(&meta->assert_rec, i);
         keep[i] = ok ? 1 : 0;
         if (!ok) {
             atomicAdd(&meta->n_filtered, 1u);
@@ -538,8 +556,23 @@ G2P_HD u32 filter_print_gaf_head(const u8* r, u32 len, Sink& S) {   // the 12 co
     S.ch(h.strand); S.ch('\t');
     if (h.empty_path) { for (int k = 0; k < 6; ++k) { S.ch('*'); S.ch('\t'); } }
     else {
-        // steps are re-serialised token by token: ">name" / ">name:start-end" / a bare stable name
-        S.bytes(r + h.path_a, h.path_b - h.path_a); S.ch('\t');
+        // steps are re-serialised token by token (operator<<(GafStep), gafkluge.hpp:274-283): ">name", or
+        // ">name:start-end" with the two numbers as std::stol read them (">a:007-10:9" prints ">a:7-10"); a bare stable
+        // name is printed as it is
+        if (!h.prefixed) S.bytes(r + h.path_a, h.path_b - h.path_a);
+        else {
+            u32 p = h.path_a;
+            while (p < h.path_b) {
+                const u32 q = next_marker(r, p + 1, h.path_b);
+                StepTok t;
+                parse_step_token<false>(r, p, q, t);
+                S.ch(r[p]);
+                S.bytes(r + t.name_a, t.name_b - t.name_a);
+                if (t.is_interval) { S.ch(':'); S.dec(t.start); S.ch('-'); S.dec(t.end); }
+                p = q;
+            }
+        }
+        S.ch('\t');
         u_put_int(S, h.plen); S.ch('\t');
         u_put_int(S, h.ps); S.ch('\t');
         u_put_int(S, h.pe); S.ch('\t');

@@ -108,7 +108,7 @@ int main(int argc, char** argv) {
     cerr << "[gaffilter]: Loaded " << res.n_loaded << (P.is_paf ? " PAF" : " GAF") << " records" << endl;
     cerr << "[gaffilter]: Constructed interval trees" << endl;
     cli::write_seq(1, out, res.out_bytes);
-    cerr << "[gaffilter]: filtered " << res.n_filtered << " / " << res.n_loaded << ". total block lengths filtered: " << res.filtered_len << endl;
+    cerr << "[gaffilter]: filtered " << res.n_filtered << " / " << res.n_loaded << ". total block lengths filtered: " << (long long)res.filtered_len << endl;   // (an int64_t in the reference: a sum beyond 2^63 prints negative)
     g2p_destroy(ctx);
     return 0;
 }

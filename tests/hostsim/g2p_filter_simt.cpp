@@ -50,6 +50,7 @@ int main(int argc, char** argv) {
     FilterMeta fm;
     std::memset(&fm, 0, sizeof fm);
     fm.first_err = 0xFFFFFFFFu;
+    fm.assert_rec = 0xFFFFFFFFu;
     if (nrec) {
         const u32 nblk = (nrec + kRsTile - 1) / kRsTile, nh = 16u * nblk;
         const u32 nscan_h = (nh + kScanTile - 1) / kScanTile, nscan_r = (nrec + kScanTile - 1) / kScanTile;
@@ -86,17 +87,18 @@ int main(int argc, char** argv) {
         hs::launch(dim3(nscan_r), dim3(kScanThreads), 0, [&] { k_scan_reduce(off.data(), nrec, blocks.data()); });
         hs::launch(dim3(1), dim3(1024), 0, [&] { k_scan_blocks(blocks.data(), nscan_r, &fm.out_total); });
         hs::launch(dim3(nscan_r), dim3(kScanThreads), 0, [&] { k_scan_apply(off.data(), nrec, blocks.data(), &fm.out_total); });
-        if (fm.unsupported) { std::fprintf(stderr, "unsupported query_start\n"); return 98; }
+        if (fm.first_err == 0xFFFFFFFFu && fm.unsupported) { std::fprintf(stderr, "unsupported query_start\n"); return 98; }
         if (fm.first_err != 0xFFFFFFFFu) {
             hs::launch(dim3(1), dim3(1), 0, [&] { k_filter_diagnose(fa); });
             std::fprintf(stderr, "abort: line %u status %u\n", fm.first_err, fm.err_status & 0xff);
             return 134;
         }
+        if (fm.assert_rec != 0xFFFFFFFFu) { std::fprintf(stderr, "abort: assertion of the filter loop on record %u\n", fm.assert_rec); return 134; }
         std::vector<u8> out(fm.out_total + 64);
         hs::launch(dim3(4), dim3(128), 0, [&] { k_filter_emit<true>(text, rec.data(), nrec, P.is_paf, keep.data(), off.data(), out.data()); });
         std::fprintf(stderr, "[gaffilter]: Loaded %u %s records\n[gaffilter]: Constructed interval trees\n", fm.n_loaded, P.is_paf ? "PAF" : "GAF");
         std::fwrite(out.data(), 1, fm.out_total, stdout);
     } else std::fprintf(stderr, "[gaffilter]: Loaded 0 %s records\n[gaffilter]: Constructed interval trees\n", P.is_paf ? "PAF" : "GAF");
-    std::fprintf(stderr, "[gaffilter]: filtered %u / %u. total block lengths filtered: %llu\n", fm.n_filtered, fm.n_loaded, (unsigned long long)fm.filtered_len);
+    std::fprintf(stderr, "[gaffilter]: filtered %u / %u. total block lengths filtered: %lld\n", fm.n_filtered, fm.n_loaded, (long long)fm.filtered_len);
     return 0;
 }
