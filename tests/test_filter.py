@@ -154,3 +154,30 @@ def test_emulated_filter_many_tags():
     rc, out, err = H.run_gaffilter_ref(paf, ["-p", "-r", "2"])
     src, sout, serr = simt(paf, ["-p", "-r", "2"])
     assert rc == src == 0 and sout == out and out.count(b"\n") == 3 and last_line(serr) == last_line(err)
+
+
+@needs_ref
+def test_emulated_filter_reference_quirks():
+    """Found by tests/fuzz_filter_vs_ref.py: the assertions of the reference's filter loop (identity >= 0 on every
+    visited interval, oend >= ostart in overlap_size) abort it; path steps are printed from their parsed form; negative
+    query starts are accepted; the summed block length is a signed 64-bit number."""
+    base = (b"q1\t100\t5\t40\t+\t>a\t50\t0\t35\t35\t35\t60\ttp:A:P\tcg:Z:35M\n"
+            b"q1\t100\t9\t31\t-\t>b\t50\t0\t22\t20\t22\t60\ttp:A:P\tcg:Z:22M\n"
+            b"q2\t100\t0\t40\t+\t>a\t50\t0\t40\t40\t40\t60\tcg:Z:40M\n")
+    cases = [
+        (base.replace(b"\t20\t22\t60", b"\t-20\t22\t60"), ["-r", "2"]),                     # matches < 0: identity < 0
+        (base.replace(b"q2\t100\t0\t40\t+\t>a\t50\t0\t40\t40\t40", b"q2\t100\t0\t40\t+\t>a\t50\t0\t40\t-4\t40"), ["-o", "5"]),   # ... on a record alone on its query
+        (base.replace(b"q1\t100\t9\t31", b"q1\t100\t39\t7"), ["-r", "2"]),                  # inverted interval: oend < ostart
+        (base.replace(b">b\t", b">b:007-10:9<c: 2-8\t"), ["-r", "2"]),                      # steps re-serialised
+        (base.replace(b"q1\t100\t9\t31", b"q1\t100\t-9\t31"), ["-r", "2"]),                 # negative query start
+        (base.replace(b"q1\t100\t9\t31", b"q1\t100\t-9\t-3"), ["-o", "3"]),
+        (base.replace(b"\t20\t22\t60", b"\t20\t9223372036854775807\t60").replace(b"35\t35\t35\t60", b"35\t35\t9223372036854775800\t60"), ["-r", "1.0001"]),
+    ]
+    for data, args in cases:
+        rc, out, err = H.run_gaffilter_ref(data, args)
+        src, sout, serr = simt(data, args)
+        assert src == rc, (data, args)
+        if rc == 0:
+            assert sout == out and last_line(serr) == last_line(err), (data, args)
+        else:
+            assert sout == b""
